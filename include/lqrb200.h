@@ -1,0 +1,203 @@
+/*
+ * lqrb200.h — C ABI of liblqrb200.so, the B200 (sm_100a) batched LQR / KKT solver.
+ *
+ * This is the drop-in boundary for the hot path of bjack205/LQR.jl.  The reference is pure Julia
+ * with no FFI of its own, so each entry point below names the Julia function(s) it
+ * replaces; the Julia `ccall` shim that re-exposes the reference's names on top of this header is
+ * lqr.jl_b200/julia/LQRB200.jl, and INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every array is caller-owned (host OR device pointer, detected with
+ *     cudaPointerGetAttributes); the library owns only its handle and internal scratch.
+ *   - every function returns int32: 0 ok; -i = argument i (1-based) invalid (LAPACK style);
+ *     >0 = 1000 + cudaError_t.  Nothing throws across the ABI.  lqrb_last_error_string() explains.
+ *   - numerical failure never aborts a batch: per-instance `info[batch]` mirrors the potrf `info`
+ *     the reference surfaces at src/cholesky_solve.jl:1-3:
+ *         0 ok;  otherwise (knot+1)*1000 + stage*100 + (1-based pivot index),
+ *         stage 0 = cost-Hessian / Riccati E block, 1 = Schur B block, 2 = Schur C block.
+ *   - one handle per host thread / GPU, stream ordered, no global state (SURVEY §8b threading).
+ *
+ * Two data layouts
+ *   INSTANCE-MAJOR ("Julia order"): what LQR.jl holds — one instance contiguous, every small matrix
+ *     column-major, knot index next, batch index outermost.  E.g. A is Float64[n, n, N-1, batch].
+ *   PACKED batch-minor SoA (device resident, the layout the kernels stream): a 2-D array
+ *     [rows][ldb] where consecutive instances are consecutive doubles (coalesced, TMA-tileable) and
+ *     `ldb = lqrb_padded_batch(batch)`.  Row maps are given by the *_layout functions below.
+ */
+#ifndef LQRB200_H
+#define LQRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQRB_VERSION 100 /* 0.1.0 */
+
+/* Hessian storage modes = the three BlockCholesky modes, src/block_cholesky.jl:55-91 */
+#define LQRB_HESS_DENSE 0     /* H_k = [Q Hux'; Hux R], whole-matrix potrf (:55-66)            */
+#define LQRB_HESS_BLOCKDIAG 1 /* Hux = 0, separate potrf of Q and R (:69-77)                   */
+#define LQRB_HESS_DIAG 2      /* Diagonal storage: stores the inverse, solve = multiply (:82-91) */
+
+/* flags */
+#define LQRB_FLAG_SOC 1     /* Ginv=false: H=I, g=0 (second_order_correction!, src/cholesky_solver.jl:254-273) */
+#define LQRB_FLAG_LTI 2     /* Riccati: A,B,Q,R,q,r carry no knot axis (LQRProblem, src/lqr_problem.jl:1-11) */
+#define LQRB_FLAG_NO_AFFINE 4 /* Riccati: q, r, qf are absent/zero (the reference's DPSolver form) */
+
+typedef struct lqrb_context *lqrb_handle_t;
+
+/* ---------------------------------------------------------------- library / handle ---------- */
+int32_t lqrb_version(void);
+int32_t lqrb_device_count(int32_t *count);
+int32_t lqrb_create(lqrb_handle_t *handle, int32_t device);
+int32_t lqrb_destroy(lqrb_handle_t handle);
+const char *lqrb_last_error_string(lqrb_handle_t handle);
+/* cudaStream_t to order all work of this handle on (NULL = the handle's own stream). */
+int32_t lqrb_set_stream(lqrb_handle_t handle, void *cuda_stream);
+int32_t lqrb_synchronize(lqrb_handle_t handle);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches). */
+int64_t lqrb_launch_count(lqrb_handle_t handle);
+/* kernel variant used by the last solve on this handle ("riccati_tpi<4,1>", ...). */
+const char *lqrb_last_kernel_name(lqrb_handle_t handle);
+/* tuning knob: 0 = default choice, otherwise force a variant. */
+int32_t lqrb_set_option(lqrb_handle_t handle, const char *name, int64_t value);
+
+/* ---------------------------------------------------------------- layouts -------------------- */
+int64_t lqrb_padded_batch(int64_t batch); /* ldb: batch rounded up to a multiple of 32 */
+
+/* LQRProblem / Primals sizes: src/lqr_problem.jl:21-25 (num_vars = N*n + (N-1)*m). */
+int64_t lqrb_num_vars(int32_t n, int32_t m, int32_t N);
+/* number of constraint rows P = sum(p) + (N-1)*n   (src/conblocks.jl:74-96 with dynamics coupling). */
+int64_t lqrb_num_cons(int32_t n, int32_t N, const int32_t *p);
+
+/* Riccati packed rows.
+ *   knots : [(LTI ? 1 : N-1)][F][ldb]  per knot: A (n*n col-major) | B (n*m) | Q (upper packed,
+ *           idx(i,j)=j(j+1)/2+i) | R (upper packed) | q (n) | r (m);  F = rows_per_knot
+ *   term  : [n(n+1)/2 + 2n][ldb]       Qf (upper packed) | qf (n) | x0 (n)
+ *   Z     : [N*n+(N-1)*m][ldb]         Primals order [x1;u1;x2;u2;...;xN] (src/lqr_problem.jl:46-73)
+ *   K     : [(N-1)*(m*n+m)][ldb]       per knot: K (m*n col-major) | kff (m)                      */
+typedef struct {
+    int64_t rows_per_knot, knot_count, term_rows, z_rows, gain_rows;
+} lqrb_riccati_layout_t;
+int32_t lqrb_riccati_layout(int32_t n, int32_t m, int32_t N, int32_t flags,
+                            lqrb_riccati_layout_t *out);
+
+/* KKT packed rows (one "data" array, knot after knot; offsets in the layout struct).
+ *   knot k: H_k (DIAG: w | BLOCKDIAG: tri(n)+tri(m_k) | DENSE: tri(w), upper packed) | g_k (w)
+ *           | [k<N-1] D1_k=[A_k B_k] (n*w col-major) | d_k (n)
+ *           | [k>0 and explicit D2] D2_k (n*w col-major)
+ *           | C_k (p_k*w col-major) | c_k (p_k)                 with w = n + (k<N-1 ? m : 0)
+ *   outputs: dz [NN][ldb] Primals order; mult [P][ldb] order [mu_1;lam_1;...;mu_N]
+ *            (src/jacobian_blocks.jl:181-195); res [NN][ldb] = D1'lam+C'mu+D2'lam_prev+g
+ *            (src/cholesky_solver.jl:201-236).                                                   */
+int64_t lqrb_kkt_data_rows(int32_t n, int32_t m, int32_t N, const int32_t *p, int32_t hess_mode,
+                           int32_t explicit_d2);
+/* row offset of knot k in the packed data array (k = N gives the total). */
+int64_t lqrb_kkt_knot_offset(int32_t n, int32_t m, int32_t N, const int32_t *p, int32_t hess_mode,
+                             int32_t explicit_d2, int32_t k);
+
+/* ---------------------------------------------------------------- Riccati ------------------- */
+/* Replaces DPSolver solve! : src/dynamic_programming.jl:54-72 (compute_gain! :37-43,
+ * compute_ctg! :48-52, chol_solve! :28-31) and the rollout of src/least_squares.jl:195-202,
+ * generalised to per-knot (LTV) data and affine cost terms.
+ *
+ * Instance-major arrays (host or device; all the same kind):
+ *   A[n,n,Kn,batch] B[n,m,Kn,batch] Q[n,n,Kn,batch] R[m,m,Kn,batch] q[n,Kn,batch] r[m,Kn,batch]
+ *   Qf[n,n,batch] qf[n,batch] x0[n,batch]       Kn = (flags & LTI) ? 1 : N-1; q, r, qf may be NULL
+ * Outputs: Z[NN,batch] (Primals order), optional K[m,n,N-1,batch], kff[m,N-1,batch], info[batch].
+ * With host pointers the call does H2D -> pack -> solve -> unpack -> D2H, chunked over two
+ * streams so copies overlap compute.                                                             */
+int32_t lqrb_riccati_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                         int32_t flags, const double *A, const double *B, const double *Q,
+                         const double *R, const double *q, const double *r, const double *Qf,
+                         const double *qf, const double *x0, double *Z, double *K, double *kff,
+                         int32_t *info);
+
+/* Device-resident split of the same call (all pointers are DEVICE pointers). */
+int32_t lqrb_riccati_pack_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                              int32_t flags, const double *A, const double *B, const double *Q,
+                              const double *R, const double *q, const double *r, const double *Qf,
+                              const double *qf, const double *x0, double *knots, double *term);
+/* gains may be NULL (internal scratch is used); info may be NULL. */
+int32_t lqrb_riccati_solve_packed_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N,
+                                      int64_t batch, int32_t flags, const double *knots,
+                                      const double *term, double *Z, double *gains, int32_t *info);
+/* packed [rows][ldb] -> instance-major [rows, batch] (and back); device pointers. */
+int32_t lqrb_unpack_rows_f64(lqrb_handle_t handle, int64_t rows, int64_t batch, const double *packed,
+                             double *instance_major);
+int32_t lqrb_pack_rows_f64(lqrb_handle_t handle, int64_t rows, int64_t batch,
+                           const double *instance_major, double *packed);
+
+/* forward simulate with given controls: rollout!, src/least_squares.jl:195-202.
+ * Instance-major, host or device: A,B as above, x0[n,batch], U[m,N-1,batch] -> X[n,N,batch]. */
+int32_t lqrb_rollout_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                         int32_t flags, const double *A, const double *B, const double *x0,
+                         const double *U, double *X);
+
+/* ---------------------------------------------------------------- BlockCholesky ------------- */
+/* Replaces cholesky!(chol, A, B[, C]) : src/block_cholesky.jl:55-91.  Instance-major:
+ *   A[n,n,batch] B[m,m,batch] C[m,n,batch] (C NULL unless DENSE) -> M[(n+m),(n+m),batch]
+ * M holds the upper factor (strict lower untouched = zero here), or for DIAG the reciprocals on
+ * its diagonal, exactly as the reference's `chol.M`.                                            */
+int32_t lqrb_block_cholesky_f64(lqrb_handle_t handle, int32_t n, int32_t m, int64_t batch,
+                                int32_t hess_mode, const double *A, const double *B,
+                                const double *C, double *M, int32_t *info);
+/* Replaces ldiv!(chol, b) and chol \ b : src/block_cholesky.jl:93-101.
+ *   M as produced above, b[(n+m), nrhs, batch] overwritten with the solution.                    */
+int32_t lqrb_block_ldiv_f64(lqrb_handle_t handle, int32_t n, int32_t m, int64_t batch,
+                            int32_t hess_mode, const double *M, int32_t nrhs, double *b);
+
+/* ---------------------------------------------------------------- constrained KKT solve ------ */
+/* Replaces _solve!(::CholeskySolver) : src/cholesky_solver.jl:166-182, i.e.
+ *   calculate_shur_factors! (src/jacobian_blocks.jl:220-286), cholesky!(chol, shur)
+ *   (src/cholesky_solve.jl:28-67), forward/backward_substitution! (:93-143) and
+ *   calculate_primals! (src/cholesky_solver.jl:185-236); with LQRB_FLAG_SOC it is
+ *   second_order_correction!'s chain (:254-273).
+ *
+ * Instance-major arrays (host or device):
+ *   Q[n,n,N,batch] R[m,m,N-1,batch] Hux[m,n,N-1,batch]|NULL q[n,N,batch] r[m,N-1,batch]
+ *   A[n,n,N-1,batch] B[n,m,N-1,batch] d[n,N-1,batch]           (D1_k = [A_k B_k], y_k = [c_k; d_k])
+ *   D2: NULL => D2_k = [-I 0] (test/cartpole.jl:34-42); else concat over k=2..N of [n,w_k] blocks
+ *   p[N] (host int32): stage-constraint rows per knot; C: concat over k of C_k[p_k,w_k]; c likewise
+ * Outputs (instance-major): dz[NN,batch], mult[P,batch], res[NN,batch]|NULL, info[batch]|NULL.  */
+int32_t lqrb_kkt_solve_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                           const int32_t *p, int32_t hess_mode, int32_t flags, const double *Q,
+                           const double *R, const double *Hux, const double *q, const double *r,
+                           const double *A, const double *B, const double *d, const double *D2,
+                           const double *C, const double *c, double *dz, double *mult, double *res,
+                           int32_t *info);
+
+/* Device-resident split (DEVICE pointers; `data` has lqrb_kkt_data_rows() x ldb doubles). */
+int32_t lqrb_kkt_pack_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                          const int32_t *p, int32_t hess_mode, const double *Q, const double *R,
+                          const double *Hux, const double *q, const double *r, const double *A,
+                          const double *B, const double *d, const double *D2, const double *C,
+                          const double *c, double *data);
+int32_t lqrb_kkt_solve_packed_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N,
+                                  int64_t batch, const int32_t *p, int32_t hess_mode,
+                                  int32_t explicit_d2, int32_t flags, const double *data,
+                                  double *dz, double *mult, double *res, int32_t *info);
+
+/* ---------------------------------------------------------------- Dubins SQP ---------------- */
+/* Fixed-count SQP outer loop (solve!/step!, src/cholesky_solver.jl:109-153, globalised as the
+ * in-repo spec src/sqp.jl:72-94: L1 merit, eta=1e-4, rho=0.5, <=10 trials, SOC tried at alpha=1)
+ * on the Dubins car turn problem, everything on device: RK3 linearisation, cost expansion
+ * (dt-scaled, test/sparse_solver.jl:67-72), one constrained KKT solve per iteration.
+ *   x0[3,batch] xf[3,batch] (host or device), Z[NN,batch] in/out (initial guess -> solution),
+ *   feas_p[batch], feas_d[batch] out, iters_done[batch] out, kkt_solves (host) total KKT solves. */
+typedef struct {
+    int32_t N, iters;
+    double dt, q_diag, r_diag, qf_diag;
+    double eps_p, eps_d; /* convergence: 1e-5 each, src/cholesky_solver.jl:131-132 */
+    int32_t line_search; /* 0 = full steps, 1 = L1 merit back-tracking + SOC */
+} lqrb_sqp_options_t;
+int32_t lqrb_sqp_dubins_f64(lqrb_handle_t handle, int64_t batch, const lqrb_sqp_options_t *opts,
+                            const double *x0, const double *xf, double *Z, double *feas_p,
+                            double *feas_d, int32_t *iters_done, int64_t *kkt_solves);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQRB200_H */

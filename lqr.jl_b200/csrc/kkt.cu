@@ -1,0 +1,377 @@
+// kkt.cu — host side of the batched constrained KKT solve (row maps, dispatch, host-buffer path).
+#include <algorithm>
+#include <cstdio>
+
+#include "kkt_coop.cuh"
+#include "kkt_kernels.cuh"
+
+// ------------------------------------------------------------------ size classes --------------
+// thread-per-instance instantiations: (n, m, P1, PM, PN) with p = [P1, PM, ..., PM, PN].
+//   cartpole (test/problems.jl:58-88): 4,1 init+goal          dubins: 3,2 init+goal (+1 mid row)
+//   DoubleIntegrator(3) (test/problems.jl:14-56): 6,3 init, 1 mid row, goal;  D=1: 2,1
+#define KKT_TPI_SIZES(X) \
+    X(4, 1, 4, 0, 4) X(3, 2, 3, 0, 3) X(3, 2, 3, 1, 3) X(2, 1, 2, 0, 2) X(2, 1, 2, 1, 2) X(6, 3, 6, 1, 6)
+
+struct KktShape {
+    int n, m, N, hess, d2x;
+    const int32_t *p;
+    bool uniform;  // p = [P1, PM.., PN]
+    int P1, PM, PN;
+};
+
+static KktShape make_shape(int n, int m, int N, const int32_t *p, int hess, int d2x) {
+    KktShape s{n, m, N, hess, d2x, p, true, p[0], N > 2 ? p[1] : 0, p[N - 1]};
+    for (int k = 1; k < N - 1; ++k)
+        if (p[k] != s.PM) s.uniform = false;
+    return s;
+}
+
+static bool kkt_has_tpi(const KktShape &s) {
+    if (!s.uniform || s.d2x) return false;
+#define X(N_, M_, A_, B_, C_) \
+    if (s.n == N_ && s.m == M_ && s.P1 == A_ && (s.N == 2 || s.PM == B_) && s.PN == C_) return true;
+    KKT_TPI_SIZES(X)
+#undef X
+    return false;
+}
+
+int lqrb_kkt_tile(const lqrb_context *h, int n, int m, int N, const int32_t *p, int hess_mode,
+                  int explicit_d2) {
+    if (h->opt("kkt_variant", 0) == 2) return 1;
+    return kkt_has_tpi(make_shape(n, m, N, p, hess_mode, explicit_d2)) ? LQRB_TILE : 1;
+}
+
+// ------------------------------------------------------------------ layout queries ------------
+static int64_t knot_rows(int n, int m, int N, const int32_t *p, int hess, int d2x, int k) {
+    const int mk = k < N - 1 ? m : 0, w = n + mk, p2 = k < N - 1 ? n : 0;
+    return hess_rows(n, mk, hess) + w + (int64_t)p2 * w + p2 + ((d2x && k > 0) ? (int64_t)n * w : 0) +
+           (int64_t)p[k] * w + p[k];
+}
+
+extern "C" int64_t lqrb_kkt_knot_offset(int32_t n, int32_t m, int32_t N, const int32_t *p,
+                                        int32_t hess_mode, int32_t explicit_d2, int32_t k) {
+    int64_t off = 0;
+    for (int j = 0; j < k && j < N; ++j) off += knot_rows(n, m, N, p, hess_mode, explicit_d2, j);
+    return off;
+}
+
+extern "C" int64_t lqrb_kkt_data_rows(int32_t n, int32_t m, int32_t N, const int32_t *p,
+                                      int32_t hess_mode, int32_t explicit_d2) {
+    return lqrb_kkt_knot_offset(n, m, N, p, hess_mode, explicit_d2, N);
+}
+
+// source array ids: 0 Q, 1 R, 2 Hux, 3 q, 4 r, 5 A, 6 B, 7 d, 8 D2, 9 C, 10 c
+static std::vector<RowMap> kkt_data_map(const KktShape &s) {
+    const int n = s.n, m = s.m, N = s.N;
+    std::vector<RowMap> map;
+    int Coff = 0, coff = 0, D2off = 0;
+    for (int k = 0; k < N; ++k) {
+        const int mk = k < N - 1 ? m : 0, w = n + mk, p2 = k < N - 1 ? n : 0, ps = s.p[k];
+        // H
+        if (s.hess == LQRB_HESS_DIAG) {
+            for (int i = 0; i < n; ++i) map.push_back({0, k * n * n + i + i * n, 0.0});
+            for (int i = 0; i < mk; ++i) map.push_back({1, k * m * m + i + i * m, 0.0});
+        } else if (s.hess == LQRB_HESS_BLOCKDIAG) {
+            for (int j = 0; j < n; ++j)
+                for (int i = 0; i <= j; ++i) map.push_back({0, k * n * n + i + j * n, 0.0});
+            for (int j = 0; j < mk; ++j)
+                for (int i = 0; i <= j; ++i) map.push_back({1, k * m * m + i + j * m, 0.0});
+        } else {
+            for (int j = 0; j < w; ++j)
+                for (int i = 0; i <= j; ++i) {
+                    if (j < n)
+                        map.push_back({0, k * n * n + i + j * n, 0.0});
+                    else if (i < n)
+                        map.push_back({2, k * m * n + (j - n) + i * m, 0.0});  // Hux'(i, j-n)
+                    else
+                        map.push_back({1, k * m * m + (i - n) + (j - n) * m, 0.0});
+                }
+        }
+        // g
+        for (int i = 0; i < n; ++i) map.push_back({3, k * n + i, 0.0});
+        for (int i = 0; i < mk; ++i) map.push_back({4, k * m + i, 0.0});
+        // D1 = [A B], d
+        if (p2) {
+            for (int j = 0; j < w; ++j)
+                for (int i = 0; i < n; ++i) {
+                    if (j < n)
+                        map.push_back({5, k * n * n + i + j * n, 0.0});
+                    else
+                        map.push_back({6, k * n * m + i + (j - n) * n, 0.0});
+                }
+            for (int i = 0; i < n; ++i) map.push_back({7, k * n + i, 0.0});
+        }
+        if (s.d2x && k > 0) {
+            for (int e = 0; e < n * w; ++e) map.push_back({8, D2off + e, 0.0});
+            D2off += n * w;
+        }
+        for (int e = 0; e < ps * w; ++e) map.push_back({9, Coff + e, 0.0});
+        for (int e = 0; e < ps; ++e) map.push_back({10, coff + e, 0.0});
+        Coff += ps * w;
+        coff += ps;
+    }
+    return map;
+}
+
+static std::vector<RowMap> identity_rows(int64_t rows) {
+    std::vector<RowMap> map((size_t)rows);
+    for (int64_t r = 0; r < rows; ++r) map[(size_t)r] = RowMap{0, (int32_t)r, 0.0};
+    return map;
+}
+
+static std::string shape_key(const char *tag, const KktShape &s) {
+    std::string k = tag;
+    char buf[64];
+    snprintf(buf, sizeof buf, ":%d:%d:%d:%d:%d:", s.n, s.m, s.N, s.hess, s.d2x);
+    k += buf;
+    for (int i = 0; i < s.N; ++i) k += std::to_string(s.p[i]) + ",";
+    return k;
+}
+
+static int32_t check_kkt(lqrb_context *h, int n, int m, int N, int64_t batch, const int32_t *p, int hess) {
+    if (!h) return -1;
+    if (n < 1 || n > 128) return lqrb_fail(h, -2, "n out of range [1,128]");
+    if (m < 1 || m > n) return lqrb_fail(h, -3, "m out of range [1,n]");
+    if (N < 2) return lqrb_fail(h, -4, "N must be >= 2");
+    if (batch < 0) return lqrb_fail(h, -5, "batch must be >= 0");
+    if (!p) return lqrb_fail(h, -6, "p is NULL");
+    for (int k = 0; k < N; ++k)
+        if (p[k] < 0 || p[k] > n + m) return lqrb_fail(h, -6, "p[k] out of range [0, n+m]");
+    if (hess < 0 || hess > 2) return lqrb_fail(h, -7, "hess_mode must be 0, 1 or 2");
+    return 0;
+}
+
+struct KktSizes {
+    int64_t NN, P, data_rows, rec_rows;
+    int64_t sC, sc, sD2;
+};
+
+static KktSizes kkt_sizes(const KktShape &s) {
+    KktSizes z{};
+    z.NN = lqrb_num_vars(s.n, s.m, s.N);
+    z.P = lqrb_num_cons(s.n, s.N, s.p);
+    z.data_rows = lqrb_kkt_data_rows(s.n, s.m, s.N, s.p, s.hess, s.d2x);
+    for (int k = 0; k < s.N; ++k) {
+        const int w = s.n + (k < s.N - 1 ? s.m : 0);
+        z.sC += (int64_t)s.p[k] * w;
+        z.sc += s.p[k];
+        if (k > 0) z.sD2 += (int64_t)s.n * w;
+    }
+    z.rec_rows = kkt_coop_rec_rows(s.n, s.m, s.N, s.p);  // an upper bound that also fits the TPI records
+    return z;
+}
+
+// ------------------------------------------------------------------ solve (packed, device) ----
+template <int n, int m, int P1, int PM, int PN>
+static int32_t launch_kkt_tpi(lqrb_context *h, const KktShape &s, int64_t batch, int flags,
+                              const double *data, double *scratch, double *dz, double *mult,
+                              double *res, int32_t *info, cudaStream_t st) {
+    constexpr int THREADS = 64;
+    const unsigned grid = (unsigned)((batch + THREADS - 1) / THREADS);
+    const bool soc = (flags & LQRB_FLAG_SOC) != 0;
+#define LAUNCH(HESS, SOC) \
+    kkt_tpi_kernel<n, m, P1, PM, PN, HESS, SOC, THREADS><<<grid, THREADS, 0, st>>>(data, scratch, dz, mult, res, info, s.N, batch)
+    if (soc) {
+        // H and g are ignored: any HESS instantiation reads the same rows layout it was packed with
+        if (s.hess == LQRB_HESS_DIAG) LAUNCH(LQRB_HESS_DIAG, true);
+        else if (s.hess == LQRB_HESS_BLOCKDIAG) LAUNCH(LQRB_HESS_BLOCKDIAG, true);
+        else LAUNCH(LQRB_HESS_DENSE, true);
+    } else {
+        if (s.hess == LQRB_HESS_DIAG) LAUNCH(LQRB_HESS_DIAG, false);
+        else if (s.hess == LQRB_HESS_BLOCKDIAG) LAUNCH(LQRB_HESS_BLOCKDIAG, false);
+        else LAUNCH(LQRB_HESS_DENSE, false);
+    }
+#undef LAUNCH
+    char nm[96];
+    snprintf(nm, sizeof nm, "kkt_tpi<%d,%d,p=%d/%d/%d,hess=%d%s>", n, m, P1, PM, PN, s.hess, soc ? ",soc" : "");
+    h->kernel_name = nm;
+    LQRB_LAUNCH_CHECK(h, "kkt_tpi_kernel");
+    return 0;
+}
+
+static int32_t kkt_solve_on(lqrb_context *h, const KktShape &s, int64_t batch, int flags,
+                            const double *data, double *scratch, double *dz, double *mult, double *res,
+                            int32_t *info, cudaStream_t st) {
+    if (batch == 0) return 0;
+    if (lqrb_kkt_tile(h, s.n, s.m, s.N, s.p, s.hess, s.d2x) == LQRB_TILE) {
+#define X(N_, M_, A_, B_, C_)                                                                       \
+    if (s.n == N_ && s.m == M_ && s.P1 == A_ && (s.N == 2 || s.PM == B_) && s.PN == C_)            \
+        return launch_kkt_tpi<N_, M_, A_, B_, C_>(h, s, batch, flags, data, scratch, dz, mult, res, info, st);
+        KKT_TPI_SIZES(X)
+#undef X
+    }
+    return launch_kkt_coop(h, s.n, s.m, s.N, s.p, s.hess, s.d2x, flags, batch, data, scratch, dz, mult, res,
+                           info, st);
+}
+
+extern "C" int32_t lqrb_kkt_solve_packed_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N,
+                                             int64_t batch, const int32_t *p, int32_t hess_mode,
+                                             int32_t explicit_d2, int32_t flags, const double *data,
+                                             double *dz, double *mult, double *res, int32_t *info) {
+    int32_t rc = check_kkt(h, n, m, N, batch, p, hess_mode);
+    if (rc) return rc;
+    if (!data) return lqrb_fail(h, -11, "data is NULL");
+    if (!dz) return lqrb_fail(h, -12, "dz is NULL");
+    if (!mult) return lqrb_fail(h, -13, "mult is NULL");
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    const KktShape s = make_shape(n, m, N, p, hess_mode, explicit_d2);
+    const KktSizes z = kkt_sizes(s);
+    double *scratch = (double *)lqrb_scratch(h, SCR_FACT, (size_t)lqrb_padded_batch(batch) * z.rec_rows * 8);
+    if (!scratch) return 1000 + (int)cudaErrorMemoryAllocation;
+    return kkt_solve_on(h, s, batch, flags, data, scratch, dz, mult, res, info, h->stream);
+}
+
+// ------------------------------------------------------------------ pack / unpack -------------
+static int32_t kkt_pack_on(lqrb_context *h, const KktShape &s, const KktSizes &z, int64_t batch,
+                           const double *const src[11], double *data, cudaStream_t st) {
+    const int n = s.n, m = s.m, N = s.N;
+    const int64_t strides[11] = {(int64_t)n * n * N, (int64_t)m * m * (N - 1), (int64_t)m * n * (N - 1),
+                                 (int64_t)n * N,     (int64_t)m * (N - 1),     (int64_t)n * n * (N - 1),
+                                 (int64_t)n * m * (N - 1), (int64_t)n * (N - 1), z.sD2, z.sC, z.sc};
+    ArrayTable t = {};
+    for (int i = 0; i < 11; ++i) {
+        t.ptr[i] = src[i];
+        t.stride[i] = strides[i];
+    }
+    const int tile = lqrb_kkt_tile(h, n, m, N, s.p, s.hess, s.d2x);
+    return lqrb_gather_pack(h, lqrb_get_map(h, shape_key("kd", s), kkt_data_map(s)), t, batch, tile, data, st);
+}
+
+extern "C" int32_t lqrb_kkt_pack_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N, int64_t batch,
+                                     const int32_t *p, int32_t hess_mode, const double *Q,
+                                     const double *R, const double *Hux, const double *q,
+                                     const double *r, const double *A, const double *B,
+                                     const double *d, const double *D2, const double *C,
+                                     const double *c, double *data) {
+    int32_t rc = check_kkt(h, n, m, N, batch, p, hess_mode);
+    if (rc) return rc;
+    if (!Q || !R || !q || !r || !A || !B || !d) return lqrb_fail(h, -8, "a required input array is NULL");
+    if (!data) return lqrb_fail(h, -19, "data is NULL");
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    const KktShape s = make_shape(n, m, N, p, hess_mode, D2 != nullptr);
+    const KktSizes z = kkt_sizes(s);
+    if (z.sC > 0 && (!C || !c)) return lqrb_fail(h, -17, "C/c is NULL but p has non-zero entries");
+    const double *src[11] = {Q, R, Hux, q, r, A, B, d, D2, C, c};
+    return kkt_pack_on(h, s, z, batch, src, data, h->stream);
+}
+
+static int32_t kkt_unpack_on(lqrb_context *h, const KktShape &s, const KktSizes &z, int64_t batch,
+                             const double *dzp, const double *multp, const double *resp, double *dz,
+                             double *mult, double *res, cudaStream_t st) {
+    const int tile = lqrb_kkt_tile(h, s.n, s.m, s.N, s.p, s.hess, s.d2x);
+    ArrayTableOut t = {};
+    t.ptr[0] = dz;
+    t.stride[0] = z.NN;
+    int32_t rc = lqrb_scatter_unpack(h, lqrb_get_map(h, "id" + std::to_string(z.NN), identity_rows(z.NN)), t,
+                                     batch, tile, dzp, st);
+    if (rc) return rc;
+    t.ptr[0] = mult;
+    t.stride[0] = z.P;
+    rc = lqrb_scatter_unpack(h, lqrb_get_map(h, "id" + std::to_string(z.P), identity_rows(z.P)), t, batch,
+                             tile, multp, st);
+    if (rc || !res) return rc;
+    t.ptr[0] = res;
+    t.stride[0] = z.NN;
+    return lqrb_scatter_unpack(h, lqrb_get_map(h, "id" + std::to_string(z.NN), identity_rows(z.NN)), t, batch,
+                               tile, resp, st);
+}
+
+// ------------------------------------------------------------------ full call -----------------
+extern "C" int32_t lqrb_kkt_solve_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N, int64_t batch,
+                                      const int32_t *p, int32_t hess_mode, int32_t flags,
+                                      const double *Q, const double *R, const double *Hux,
+                                      const double *q, const double *r, const double *A,
+                                      const double *B, const double *d, const double *D2,
+                                      const double *C, const double *c, double *dz, double *mult,
+                                      double *res, int32_t *info) {
+    int32_t rc = check_kkt(h, n, m, N, batch, p, hess_mode);
+    if (rc) return rc;
+    if (!Q || !R || !q || !r || !A || !B || !d) return lqrb_fail(h, -9, "a required input array is NULL");
+    if (!dz) return lqrb_fail(h, -20, "dz is NULL");
+    if (!mult) return lqrb_fail(h, -21, "mult is NULL");
+    if (batch == 0) return 0;
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    const KktShape s = make_shape(n, m, N, p, hess_mode, D2 != nullptr);
+    const KktSizes z = kkt_sizes(s);
+    if (z.sC > 0 && (!C || !c)) return lqrb_fail(h, -18, "C/c is NULL but p has non-zero entries");
+    const int64_t K1 = N - 1;
+    const int64_t per[11] = {(int64_t)n * n * N, (int64_t)m * m * K1, Hux ? (int64_t)m * n * K1 : 0,
+                             (int64_t)n * N,     (int64_t)m * K1,     (int64_t)n * n * K1,
+                             (int64_t)n * m * K1, (int64_t)n * K1,    D2 ? z.sD2 : 0, z.sC, z.sc};
+    const double *src[11] = {Q, R, Hux, q, r, A, B, d, D2, C, c};
+    const bool on_device = lqrb_is_device_ptr(Q);
+
+    if (on_device) {
+        const int64_t ldb = lqrb_padded_batch(batch);
+        double *data = (double *)lqrb_scratch(h, SCR_PACK_IN, (size_t)ldb * z.data_rows * 8);
+        double *dzp = (double *)lqrb_scratch(h, SCR_PACK_OUT, (size_t)ldb * z.NN * 8);
+        double *mp = (double *)lqrb_scratch(h, SCR_PACK_OUT2, (size_t)ldb * z.P * 8);
+        double *rp = res ? (double *)lqrb_scratch(h, SCR_PACK_OUT3, (size_t)ldb * z.NN * 8) : nullptr;
+        double *scr = (double *)lqrb_scratch(h, SCR_FACT, (size_t)ldb * z.rec_rows * 8);
+        if (!data || !dzp || !mp || !scr || (res && !rp)) return 1000 + (int)cudaErrorMemoryAllocation;
+        rc = kkt_pack_on(h, s, z, batch, src, data, h->stream);
+        if (rc) return rc;
+        rc = kkt_solve_on(h, s, batch, flags, data, scr, dzp, mp, rp, info, h->stream);
+        if (rc) return rc;
+        return kkt_unpack_on(h, s, z, batch, dzp, mp, rp, dz, mult, res, h->stream);
+    }
+
+    // ---- host buffers: chunked over two streams ----
+    int64_t in_per = 0;
+    for (int i = 0; i < 11; ++i) in_per += per[i];
+    int64_t chunk = h->opt("host_chunk", 0);
+    if (chunk <= 0) chunk = std::max<int64_t>(LQRB_TILE, (64ll << 20) / (in_per * 8) / LQRB_TILE * LQRB_TILE);
+    chunk = std::min<int64_t>(round_up(chunk, LQRB_TILE), lqrb_padded_batch(batch));
+    const int64_t out_per = z.NN + z.P + (res ? z.NN : 0);
+    const size_t in_bytes = (size_t)chunk * in_per * 8, out_bytes = (size_t)chunk * out_per * 8;
+    const size_t pk_bytes = (size_t)chunk * z.data_rows * 8;
+    const size_t po_bytes = (size_t)chunk * (2 * z.NN + z.P) * 8;
+    const size_t sc_bytes = (size_t)chunk * z.rec_rows * 8;
+    char *stage_in = (char *)lqrb_scratch(h, SCR_STAGE_A, 2 * in_bytes);
+    char *stage_out = (char *)lqrb_scratch(h, SCR_STAGE_B, 2 * out_bytes);
+    char *pk = (char *)lqrb_scratch(h, SCR_PACK_IN, 2 * pk_bytes);
+    char *po = (char *)lqrb_scratch(h, SCR_PACK_OUT, 2 * po_bytes);
+    char *sc = (char *)lqrb_scratch(h, SCR_FACT, 2 * sc_bytes);
+    int32_t *dinfo = (int32_t *)lqrb_scratch(h, SCR_INFO, 2 * (size_t)chunk * sizeof(int32_t));
+    if (!stage_in || !stage_out || !pk || !po || !sc || !dinfo) return 1000 + (int)cudaErrorMemoryAllocation;
+
+    LQRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    for (int i = 0; i < 2; ++i) LQRB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[i], h->ev[0], 0));
+    int which = 0;
+    for (int64_t first = 0; first < batch; first += chunk, which ^= 1) {
+        const int64_t cb = std::min(chunk, batch - first);
+        cudaStream_t st = h->copy_stream[which];
+        double *cur = (double *)(stage_in + which * in_bytes);
+        const double *dsrc[11];
+        for (int i = 0; i < 11; ++i) {
+            if (!src[i] || per[i] == 0) {
+                dsrc[i] = nullptr;
+                continue;
+            }
+            LQRB_CUDA(h, cudaMemcpyAsync(cur, src[i] + first * per[i], (size_t)cb * per[i] * 8,
+                                         cudaMemcpyHostToDevice, st));
+            dsrc[i] = cur;
+            cur += cb * per[i];
+        }
+        double *data = (double *)(pk + which * pk_bytes);
+        double *dzp = (double *)(po + which * po_bytes), *mp = dzp + chunk * z.NN, *rp = mp + chunk * z.P;
+        double *scr = (double *)(sc + which * sc_bytes);
+        int32_t *di = dinfo + which * chunk;
+        rc = kkt_pack_on(h, s, z, cb, dsrc, data, st);
+        if (rc) return rc;
+        rc = kkt_solve_on(h, s, cb, flags, data, scr, dzp, mp, res ? rp : nullptr, di, st);
+        if (rc) return rc;
+        double *so = (double *)(stage_out + which * out_bytes);
+        double *odz = so, *om = odz + cb * z.NN, *ores = om + cb * z.P;
+        rc = kkt_unpack_on(h, s, z, cb, dzp, mp, rp, odz, om, res ? ores : nullptr, st);
+        if (rc) return rc;
+        LQRB_CUDA(h, cudaMemcpyAsync(dz + first * z.NN, odz, (size_t)cb * z.NN * 8, cudaMemcpyDeviceToHost, st));
+        LQRB_CUDA(h, cudaMemcpyAsync(mult + first * z.P, om, (size_t)cb * z.P * 8, cudaMemcpyDeviceToHost, st));
+        if (res)
+            LQRB_CUDA(h, cudaMemcpyAsync(res + first * z.NN, ores, (size_t)cb * z.NN * 8, cudaMemcpyDeviceToHost, st));
+        if (info)
+            LQRB_CUDA(h, cudaMemcpyAsync(info + first, di, (size_t)cb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < 2; ++i) LQRB_CUDA(h, cudaStreamSynchronize(h->copy_stream[i]));
+    return 0;
+}

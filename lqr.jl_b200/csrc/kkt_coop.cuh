@@ -1,0 +1,24 @@
+// kkt_coop.cuh — declarations of the cooperative KKT path (kernel in kkt_coop.cu).
+#pragma once
+#include "common.cuh"
+
+// rows of one knot's factor record (full-storage blocks): B^ | D^ | E^ | F^ | mu~ | C^_{k-1} | lam~_{k-1}
+__host__ __device__ inline int64_t kkt_coop_rec_knot_rows(int p1, int ps, int p2) {
+    return (int64_t)ps * ps + (int64_t)p1 * ps + (int64_t)ps * p2 + (int64_t)p1 * p2 + ps + (int64_t)p1 * p1 + p1;
+}
+
+static inline int64_t kkt_coop_rec_rows(int n, int m, int N, const int32_t *p) {
+    int64_t r = 0;
+    for (int k = 0; k < N; ++k) r += kkt_coop_rec_knot_rows(k > 0 ? n : 0, p[k], k < N - 1 ? n : 0);
+    return r;
+}
+
+__host__ __device__ inline size_t kkt_coop_ws_doubles(int n, int m, int P) {
+    const size_t w = n + m;
+    return w * w + 3 * w + 2 * n * w + P * w + 2 * w * n + w * P + 3 * (size_t)n * n + (size_t)P * P +
+           2 * (size_t)n * P + 4 * n + 3 * P + 16;
+}
+
+int32_t launch_kkt_coop(lqrb_context *h, int n, int m, int N, const int32_t *p, int hess, int d2x,
+                        int flags, int64_t batch, const double *data, double *scratch, double *dz,
+                        double *mult, double *res, int32_t *info, cudaStream_t st);

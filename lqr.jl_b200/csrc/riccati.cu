@@ -1,0 +1,404 @@
+// riccati.cu — host side of the batched Riccati entry points (dispatch, packing, host-buffer path).
+#include <algorithm>
+#include <cstdio>
+
+#include "riccati_kernels.cuh"
+
+// ------------------------------------------------------------------ size classes --------------
+// thread-per-instance instantiations (registers only).  Everything else -> cooperative kernel.
+#define RICCATI_TPI_SIZES(X) X(2, 1) X(3, 2) X(4, 1) X(4, 2) X(6, 3)
+
+static bool riccati_has_tpi(int n, int m) {
+#define X(N_, M_) \
+    if (n == N_ && m == M_) return true;
+    RICCATI_TPI_SIZES(X)
+#undef X
+    return false;
+}
+
+int lqrb_riccati_tile(const lqrb_context *h, int n, int m) {
+    const int64_t force = h->opt("riccati_variant", 0);  // 1 = tpi, 2 = coop
+    if (force == 2) return 1;
+    return riccati_has_tpi(n, m) ? LQRB_TILE : 1;
+}
+
+// ------------------------------------------------------------------ row maps ------------------
+// source array ids: 0 A, 1 B, 2 Q, 3 R, 4 q, 5 r, 6 Qf, 7 qf, 8 x0
+static std::vector<RowMap> riccati_knot_map(int n, int m, int N, int flags) {
+    const int Kn = (flags & LQRB_FLAG_LTI) ? 1 : N - 1;
+    std::vector<RowMap> map;
+    map.reserve((size_t)Kn * (n * n + n * m + tri(n) + tri(m) + n + m));
+    for (int k = 0; k < Kn; ++k) {
+        for (int e = 0; e < n * n; ++e) map.push_back({0, k * n * n + e, 0.0});
+        for (int e = 0; e < n * m; ++e) map.push_back({1, k * n * m + e, 0.0});
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i <= j; ++i) map.push_back({2, k * n * n + i + j * n, 0.0});
+        for (int j = 0; j < m; ++j)
+            for (int i = 0; i <= j; ++i) map.push_back({3, k * m * m + i + j * m, 0.0});
+        for (int e = 0; e < n; ++e) map.push_back({4, k * n + e, 0.0});
+        for (int e = 0; e < m; ++e) map.push_back({5, k * m + e, 0.0});
+    }
+    return map;
+}
+
+static std::vector<RowMap> riccati_term_map(int n) {
+    std::vector<RowMap> map;
+    for (int j = 0; j < n; ++j)
+        for (int i = 0; i <= j; ++i) map.push_back({6, i + j * n, 0.0});
+    for (int e = 0; e < n; ++e) map.push_back({7, e, 0.0});
+    for (int e = 0; e < n; ++e) map.push_back({8, e, 0.0});
+    return map;
+}
+
+// gains packed rows -> K (array 0), kff (array 1)
+static std::vector<RowMap> riccati_gain_map(int n, int m, int N) {
+    std::vector<RowMap> map;
+    for (int k = 0; k < N - 1; ++k) {
+        for (int e = 0; e < m * n; ++e) map.push_back({0, k * m * n + e, 0.0});
+        for (int e = 0; e < m; ++e) map.push_back({1, k * m + e, 0.0});
+    }
+    return map;
+}
+
+static std::vector<RowMap> identity_rows(int64_t rows) {
+    std::vector<RowMap> map((size_t)rows);
+    for (int64_t r = 0; r < rows; ++r) map[(size_t)r] = RowMap{0, (int32_t)r, 0.0};
+    return map;
+}
+
+static std::string key(const char *tag, int a, int b, int c, int d) {
+    char buf[96];
+    snprintf(buf, sizeof buf, "%s:%d:%d:%d:%d", tag, a, b, c, d);
+    return buf;
+}
+
+static int32_t check_dims(lqrb_context *h, int n, int m, int N, int64_t batch) {
+    if (!h) return -1;
+    if (n < 1 || n > 128) return lqrb_fail(h, -2, "n out of range [1,128]");
+    if (m < 1 || m > n) return lqrb_fail(h, -3, "m out of range [1,n]");
+    if (N < 2) return lqrb_fail(h, -4, "N must be >= 2");
+    if (batch < 0) return lqrb_fail(h, -5, "batch must be >= 0");
+    return 0;
+}
+
+// ------------------------------------------------------------------ solve (packed, device) ----
+template <int n, int m>
+static int32_t launch_tpi(lqrb_context *h, int N, int64_t batch, int lti, const double *knots,
+                          const double *term, double *Z, double *gains, int32_t *info,
+                          cudaStream_t s) {
+    constexpr int THREADS = 128;
+    const unsigned grid = (unsigned)((batch + THREADS - 1) / THREADS);
+    if (lti)
+        riccati_tpi_kernel<n, m, true, THREADS, 1><<<grid, THREADS, 0, s>>>(knots, term, Z, gains, info, N, batch);
+    else
+        riccati_tpi_kernel<n, m, false, THREADS, 1><<<grid, THREADS, 0, s>>>(knots, term, Z, gains, info, N, batch);
+    char nm[64];
+    snprintf(nm, sizeof nm, "riccati_tpi<%d,%d>%s", n, m, lti ? "[lti]" : "");
+    h->kernel_name = nm;
+    LQRB_LAUNCH_CHECK(h, "riccati_tpi_kernel");
+    return 0;
+}
+
+static int32_t launch_coop(lqrb_context *h, int n, int m, int N, int64_t batch, int lti,
+                           const double *knots, const double *term, double *Z, double *gains,
+                           int32_t *info, cudaStream_t s) {
+    const size_t per = riccati_coop_smem_doubles(n, m) * sizeof(double);
+    char nm[64];
+    if (n + m <= 24) {
+        constexpr int G = 32, THREADS = 128;
+        const size_t smem = per * (THREADS / G);
+        auto kern = riccati_coop_kernel<G, THREADS>;
+        LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)((batch + THREADS / G - 1) / (THREADS / G));
+        kern<<<grid, THREADS, smem, s>>>(knots, term, Z, gains, info, n, m, N, lti, batch);
+        snprintf(nm, sizeof nm, "riccati_coop<G=32>(n=%d,m=%d)", n, m);
+    } else {
+        constexpr int G = 256, THREADS = 256;
+        if (per > 227 * 1024) return lqrb_fail(h, -2, "n,m too large for the shared-memory Riccati kernel");
+        auto kern = riccati_coop_kernel<G, THREADS>;
+        LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)per));
+        kern<<<(unsigned)batch, THREADS, per, s>>>(knots, term, Z, gains, info, n, m, N, lti, batch);
+        snprintf(nm, sizeof nm, "riccati_coop<G=256>(n=%d,m=%d)", n, m);
+    }
+    h->kernel_name = nm;
+    LQRB_LAUNCH_CHECK(h, "riccati_coop_kernel");
+    return 0;
+}
+
+static int32_t riccati_solve_on(lqrb_context *h, int n, int m, int N, int64_t batch, int flags,
+                                const double *knots, const double *term, double *Z, double *gains,
+                                int32_t *info, cudaStream_t s) {
+    if (batch == 0) return 0;
+    const int lti = (flags & LQRB_FLAG_LTI) ? 1 : 0;
+    const int tile = lqrb_riccati_tile(h, n, m);
+    if (tile == LQRB_TILE) {
+#define X(N_, M_) \
+    if (n == N_ && m == M_) return launch_tpi<N_, M_>(h, N, batch, lti, knots, term, Z, gains, info, s);
+        RICCATI_TPI_SIZES(X)
+#undef X
+    }
+    return launch_coop(h, n, m, N, batch, lti, knots, term, Z, gains, info, s);
+}
+
+extern "C" int32_t lqrb_riccati_solve_packed_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N,
+                                                 int64_t batch, int32_t flags, const double *knots,
+                                                 const double *term, double *Z, double *gains,
+                                                 int32_t *info) {
+    int32_t rc = check_dims(h, n, m, N, batch);
+    if (rc) return rc;
+    if (!knots) return lqrb_fail(h, -7, "knots is NULL");
+    if (!term) return lqrb_fail(h, -8, "term is NULL");
+    if (!Z) return lqrb_fail(h, -9, "Z is NULL");
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    if (!gains) {
+        const size_t bytes = (size_t)lqrb_padded_batch(batch) * (N - 1) * (m * n + m) * sizeof(double);
+        gains = (double *)lqrb_scratch(h, SCR_GAINS, bytes);
+        if (!gains) return 1000 + (int)cudaErrorMemoryAllocation;
+    }
+    return riccati_solve_on(h, n, m, N, batch, flags, knots, term, Z, gains, info, h->stream);
+}
+
+// ------------------------------------------------------------------ pack (device) -------------
+static int32_t riccati_pack_on(lqrb_context *h, int n, int m, int N, int64_t batch, int flags,
+                               const double *A, const double *B, const double *Q, const double *R,
+                               const double *q, const double *r, const double *Qf, const double *qf,
+                               const double *x0, double *knots, double *term, cudaStream_t s) {
+    const int Kn = (flags & LQRB_FLAG_LTI) ? 1 : N - 1;
+    const int tile = lqrb_riccati_tile(h, n, m);
+    ArrayTable t = {};
+    const double *ptrs[9] = {A, B, Q, R, q, r, Qf, qf, x0};
+    const int64_t strides[9] = {(int64_t)Kn * n * n, (int64_t)Kn * n * m, (int64_t)Kn * n * n,
+                                (int64_t)Kn * m * m, (int64_t)Kn * n,     (int64_t)Kn * m,
+                                (int64_t)n * n,      n,                   n};
+    for (int i = 0; i < 9; ++i) {
+        t.ptr[i] = ptrs[i];
+        t.stride[i] = strides[i];
+    }
+    DevMap km = lqrb_get_map(h, key("rk", n, m, N, flags & LQRB_FLAG_LTI), riccati_knot_map(n, m, N, flags));
+    DevMap tm = lqrb_get_map(h, key("rt", n, 0, 0, 0), riccati_term_map(n));
+    int32_t rc = lqrb_gather_pack(h, km, t, batch, tile, knots, s);
+    if (rc) return rc;
+    return lqrb_gather_pack(h, tm, t, batch, tile, term, s);
+}
+
+extern "C" int32_t lqrb_riccati_pack_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N,
+                                         int64_t batch, int32_t flags, const double *A,
+                                         const double *B, const double *Q, const double *R,
+                                         const double *q, const double *r, const double *Qf,
+                                         const double *qf, const double *x0, double *knots,
+                                         double *term) {
+    int32_t rc = check_dims(h, n, m, N, batch);
+    if (rc) return rc;
+    if (!A) return lqrb_fail(h, -7, "A is NULL");
+    if (!B) return lqrb_fail(h, -8, "B is NULL");
+    if (!Q) return lqrb_fail(h, -9, "Q is NULL");
+    if (!R) return lqrb_fail(h, -10, "R is NULL");
+    if (!Qf) return lqrb_fail(h, -13, "Qf is NULL");
+    if (!x0) return lqrb_fail(h, -15, "x0 is NULL");
+    if (!knots) return lqrb_fail(h, -16, "knots is NULL");
+    if (!term) return lqrb_fail(h, -17, "term is NULL");
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    return riccati_pack_on(h, n, m, N, batch, flags, A, B, Q, R, q, r, Qf, qf, x0, knots, term, h->stream);
+}
+
+// ------------------------------------------------------------------ unpack helpers ------------
+static int32_t riccati_unpack_on(lqrb_context *h, int n, int m, int N, int64_t batch,
+                                 const double *Zp, const double *gains, double *Z, double *K,
+                                 double *kff, cudaStream_t s) {
+    const int tile = lqrb_riccati_tile(h, n, m);
+    const int64_t NN = lqrb_num_vars(n, m, N);
+    ArrayTableOut t = {};
+    t.ptr[0] = Z;
+    t.stride[0] = NN;
+    int32_t rc = lqrb_scatter_unpack(h, lqrb_get_map(h, "id" + std::to_string(NN), identity_rows(NN)), t,
+                                     batch, tile, Zp, s);
+    if (rc) return rc;
+    if (K || kff) {
+        ArrayTableOut g = {};
+        g.ptr[0] = K;
+        g.stride[0] = (int64_t)(N - 1) * m * n;
+        g.ptr[1] = kff;
+        g.stride[1] = (int64_t)(N - 1) * m;
+        rc = lqrb_scatter_unpack(h, lqrb_get_map(h, key("rg", n, m, N, 0), riccati_gain_map(n, m, N)), g,
+                                 batch, tile, gains, s);
+    }
+    return rc;
+}
+
+// ------------------------------------------------------------------ full call -----------------
+extern "C" int32_t lqrb_riccati_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N, int64_t batch,
+                                    int32_t flags, const double *A, const double *B, const double *Q,
+                                    const double *R, const double *q, const double *r,
+                                    const double *Qf, const double *qf, const double *x0, double *Z,
+                                    double *K, double *kff, int32_t *info) {
+    int32_t rc = check_dims(h, n, m, N, batch);
+    if (rc) return rc;
+    if (!A) return lqrb_fail(h, -7, "A is NULL");
+    if (!B) return lqrb_fail(h, -8, "B is NULL");
+    if (!Q) return lqrb_fail(h, -9, "Q is NULL");
+    if (!R) return lqrb_fail(h, -10, "R is NULL");
+    if (!Qf) return lqrb_fail(h, -13, "Qf is NULL");
+    if (!x0) return lqrb_fail(h, -15, "x0 is NULL");
+    if (!Z) return lqrb_fail(h, -16, "Z is NULL");
+    if (batch == 0) return 0;
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+
+    lqrb_riccati_layout_t L;
+    lqrb_riccati_layout(n, m, N, flags, &L);
+    const int64_t Kn = L.knot_count;
+    const bool on_device = lqrb_is_device_ptr(A);
+
+    // per-instance record lengths of the instance-major arrays
+    const int64_t sA = Kn * n * n, sB = Kn * n * m, sQ = Kn * n * n, sR = Kn * m * m, sq = Kn * n,
+                  sr = Kn * m, sQf = (int64_t)n * n;
+    const int64_t in_per = sA + sB + sQ + sR + sq + sr + sQf + 2 * n;
+    const int64_t NN = L.z_rows, GRN = L.gain_rows;
+
+    if (on_device) {
+        const int64_t ldb = lqrb_padded_batch(batch);
+        double *knots = (double *)lqrb_scratch(h, SCR_PACK_IN, (size_t)ldb * Kn * L.rows_per_knot * 8);
+        double *term = (double *)lqrb_scratch(h, SCR_PACK_IN2, (size_t)ldb * L.term_rows * 8);
+        double *Zp = (double *)lqrb_scratch(h, SCR_PACK_OUT, (size_t)ldb * NN * 8);
+        double *gains = (double *)lqrb_scratch(h, SCR_GAINS, (size_t)ldb * GRN * 8);
+        if (!knots || !term || !Zp || !gains) return 1000 + (int)cudaErrorMemoryAllocation;
+        rc = riccati_pack_on(h, n, m, N, batch, flags, A, B, Q, R, q, r, Qf, qf, x0, knots, term, h->stream);
+        if (rc) return rc;
+        rc = riccati_solve_on(h, n, m, N, batch, flags, knots, term, Zp, gains, info, h->stream);
+        if (rc) return rc;
+        return riccati_unpack_on(h, n, m, N, batch, Zp, gains, Z, K, kff, h->stream);
+    }
+
+    // ---- host buffers: chunked H2D -> pack -> solve -> unpack -> D2H over two streams ----
+    int64_t chunk = h->opt("host_chunk", 0);
+    if (chunk <= 0) {
+        // ~64 MB of input per chunk keeps both copy engines and the SMs busy
+        chunk = std::max<int64_t>(LQRB_TILE, (64ll << 20) / (in_per * 8) / LQRB_TILE * LQRB_TILE);
+    }
+    chunk = std::min<int64_t>(round_up(chunk, LQRB_TILE), lqrb_padded_batch(batch));
+    const int64_t out_per = NN + ((K || kff) ? GRN : 0);
+    const size_t in_bytes = (size_t)chunk * in_per * 8, out_bytes = (size_t)chunk * out_per * 8;
+    const size_t pk_bytes = (size_t)chunk * (Kn * L.rows_per_knot + L.term_rows) * 8;
+    const size_t po_bytes = (size_t)chunk * (NN + GRN) * 8;
+    char *stage_in = (char *)lqrb_scratch(h, SCR_STAGE_A, 2 * in_bytes);
+    char *stage_out = (char *)lqrb_scratch(h, SCR_STAGE_B, 2 * out_bytes);
+    char *pk = (char *)lqrb_scratch(h, SCR_PACK_IN, 2 * pk_bytes);
+    char *po = (char *)lqrb_scratch(h, SCR_PACK_OUT, 2 * po_bytes);
+    int32_t *dinfo = (int32_t *)lqrb_scratch(h, SCR_INFO, 2 * (size_t)chunk * sizeof(int32_t));
+    if (!stage_in || !stage_out || !pk || !po || !dinfo) return 1000 + (int)cudaErrorMemoryAllocation;
+
+    LQRB_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    for (int i = 0; i < 2; ++i) LQRB_CUDA(h, cudaStreamWaitEvent(h->copy_stream[i], h->ev[0], 0));
+
+    int which = 0;
+    for (int64_t first = 0; first < batch; first += chunk, which ^= 1) {
+        const int64_t cb = std::min(chunk, batch - first);
+        cudaStream_t s = h->copy_stream[which];
+        double *si = (double *)(stage_in + which * in_bytes);
+        // carve the instance-major stage
+        double *dA = si, *dB = dA + cb * sA, *dQ = dB + cb * sB, *dR = dQ + cb * sQ,
+               *dq = dR + cb * sR, *dr = dq + cb * sq, *dQf = dr + cb * sr, *dqf = dQf + cb * sQf,
+               *dx0 = dqf + cb * n;
+        auto h2d = [&](double *dst, const double *src, int64_t per) -> cudaError_t {
+            if (!src) return cudaMemsetAsync(dst, 0, (size_t)cb * per * 8, s);
+            return cudaMemcpyAsync(dst, src + first * per, (size_t)cb * per * 8, cudaMemcpyHostToDevice, s);
+        };
+        LQRB_CUDA(h, h2d(dA, A, sA));
+        LQRB_CUDA(h, h2d(dB, B, sB));
+        LQRB_CUDA(h, h2d(dQ, Q, sQ));
+        LQRB_CUDA(h, h2d(dR, R, sR));
+        LQRB_CUDA(h, h2d(dq, q, sq));
+        LQRB_CUDA(h, h2d(dr, r, sr));
+        LQRB_CUDA(h, h2d(dQf, Qf, sQf));
+        LQRB_CUDA(h, h2d(dqf, qf, n));
+        LQRB_CUDA(h, h2d(dx0, x0, n));
+        double *knots = (double *)(pk + which * pk_bytes);
+        double *term = knots + chunk * Kn * L.rows_per_knot;
+        double *Zp = (double *)(po + which * po_bytes);
+        double *gains = Zp + chunk * NN;
+        int32_t *di = dinfo + which * chunk;
+        rc = riccati_pack_on(h, n, m, N, cb, flags, dA, dB, dQ, dR, dq, dr, dQf, dqf, dx0, knots, term, s);
+        if (rc) return rc;
+        rc = riccati_solve_on(h, n, m, N, cb, flags, knots, term, Zp, gains, di, s);
+        if (rc) return rc;
+        double *so = (double *)(stage_out + which * out_bytes);
+        double *oZ = so, *oK = so + cb * NN, *okff = oK + cb * (int64_t)(N - 1) * m * n;
+        rc = riccati_unpack_on(h, n, m, N, cb, Zp, gains, oZ, K ? oK : nullptr, kff ? okff : nullptr, s);
+        if (rc) return rc;
+        LQRB_CUDA(h, cudaMemcpyAsync(Z + first * NN, oZ, (size_t)cb * NN * 8, cudaMemcpyDeviceToHost, s));
+        if (K)
+            LQRB_CUDA(h, cudaMemcpyAsync(K + first * (int64_t)(N - 1) * m * n, oK,
+                                         (size_t)cb * (N - 1) * m * n * 8, cudaMemcpyDeviceToHost, s));
+        if (kff)
+            LQRB_CUDA(h, cudaMemcpyAsync(kff + first * (int64_t)(N - 1) * m, okff,
+                                         (size_t)cb * (N - 1) * m * 8, cudaMemcpyDeviceToHost, s));
+        if (info)
+            LQRB_CUDA(h, cudaMemcpyAsync(info + first, di, (size_t)cb * sizeof(int32_t),
+                                         cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < 2; ++i) LQRB_CUDA(h, cudaStreamSynchronize(h->copy_stream[i]));
+    return 0;
+}
+
+// ------------------------------------------------------------------ rollout -------------------
+// rollout!(X, U) : src/least_squares.jl:195-202.  Instance-major, one thread per instance, the state
+// lives in the output array (not a hot path; used by callers that supply their own controls).
+__global__ void rollout_kernel(const double *__restrict__ A, const double *__restrict__ B,
+                               const double *__restrict__ x0, const double *__restrict__ U,
+                               double *__restrict__ X, int n, int m, int N, int lti, int64_t batch) {
+    const int64_t inst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= batch) return;
+    const int Kn = lti ? 1 : N - 1;
+    const double *Ai = A + inst * (int64_t)Kn * n * n, *Bi = B + inst * (int64_t)Kn * n * m;
+    const double *Ui = U + inst * (int64_t)(N - 1) * m;
+    double *Xi = X + inst * (int64_t)N * n;
+    for (int i = 0; i < n; ++i) Xi[i] = x0[inst * n + i];
+    for (int k = 0; k < N - 1; ++k) {
+        const double *Ak = Ai + (int64_t)(lti ? 0 : k) * n * n, *Bk = Bi + (int64_t)(lti ? 0 : k) * n * m;
+        const double *xk = Xi + (int64_t)k * n, *uk = Ui + (int64_t)k * m;
+        double *xn = Xi + (int64_t)(k + 1) * n;
+        for (int i = 0; i < n; ++i) {
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = fma(Ak[i + l * n], xk[l], s);
+            for (int l = 0; l < m; ++l) s = fma(Bk[i + l * n], uk[l], s);
+            xn[i] = s;
+        }
+    }
+}
+
+extern "C" int32_t lqrb_rollout_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N, int64_t batch,
+                                    int32_t flags, const double *A, const double *B, const double *x0,
+                                    const double *U, double *X) {
+    int32_t rc = check_dims(h, n, m, N, batch);
+    if (rc) return rc;
+    if (!A) return lqrb_fail(h, -7, "A is NULL");
+    if (!B) return lqrb_fail(h, -8, "B is NULL");
+    if (!x0) return lqrb_fail(h, -9, "x0 is NULL");
+    if (!U) return lqrb_fail(h, -10, "U is NULL");
+    if (!X) return lqrb_fail(h, -11, "X is NULL");
+    if (batch == 0) return 0;
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    const int lti = (flags & LQRB_FLAG_LTI) ? 1 : 0;
+    const int64_t Kn = lti ? 1 : N - 1;
+    const bool dev = lqrb_is_device_ptr(A);
+    const double *dA = A, *dB = B, *dx0 = x0, *dU = U;
+    double *dX = X;
+    if (!dev) {
+        const size_t tot = (size_t)batch * (Kn * n * n + Kn * n * m + n + (N - 1) * m + (size_t)N * n) * 8;
+        double *buf = (double *)lqrb_scratch(h, SCR_STAGE_A, tot);
+        if (!buf) return 1000 + (int)cudaErrorMemoryAllocation;
+        double *a = buf, *b = a + batch * Kn * n * n, *x = b + batch * Kn * n * m, *u = x + batch * n;
+        dX = u + batch * (int64_t)(N - 1) * m;
+        LQRB_CUDA(h, cudaMemcpyAsync(a, A, (size_t)batch * Kn * n * n * 8, cudaMemcpyHostToDevice, h->stream));
+        LQRB_CUDA(h, cudaMemcpyAsync(b, B, (size_t)batch * Kn * n * m * 8, cudaMemcpyHostToDevice, h->stream));
+        LQRB_CUDA(h, cudaMemcpyAsync(x, x0, (size_t)batch * n * 8, cudaMemcpyHostToDevice, h->stream));
+        LQRB_CUDA(h, cudaMemcpyAsync(u, U, (size_t)batch * (N - 1) * m * 8, cudaMemcpyHostToDevice, h->stream));
+        dA = a; dB = b; dx0 = x; dU = u;
+    }
+    rollout_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, h->stream>>>(dA, dB, dx0, dU, dX, n, m, N, lti, batch);
+    LQRB_LAUNCH_CHECK(h, "rollout_kernel");
+    if (!dev) {
+        LQRB_CUDA(h, cudaMemcpyAsync(X, dX, (size_t)batch * N * n * 8, cudaMemcpyDeviceToHost, h->stream));
+        LQRB_CUDA(h, cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}

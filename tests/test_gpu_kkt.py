@@ -1,0 +1,123 @@
+"""GPU parity: batched constrained KKT solve (C ABI -> CUDA) against the CPU oracle (the reference's
+block algorithm) and the refined global KKT solve, on the reference's fixtures and the configs.
+
+Tolerances: relative error of dz and of the multipliers, stationarity residual and
+primal residual all <= 1e-10 unless a per-case value is written below."""
+import numpy as np
+import pytest
+
+from lqr_b200 import ops, problems
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _check(prob, handle, oracle_mod, tol=TOL, truth_instances=(0,), soc=False, res_tol=TOL):
+    from oracle import dense_kkt
+    dz, lam, info, res = ops.kkt_solve_problem(prob, soc=soc, want_res=True, handle=handle)
+    dzo, lamo, infoo, reso = oracle_mod.kkt_solve(prob, soc=soc, want_res=True)
+    assert (info == 0).all() and (infoo == 0).all(), handle.last_kernel
+    b = dz.shape[0]
+    for i in range(b):
+        assert _rel(dz[i], dzo[i]) <= tol, (i, _rel(dz[i], dzo[i]), handle.last_kernel)
+        assert _rel(lam[i], lamo[i]) <= tol, (i, _rel(lam[i], lamo[i]), handle.last_kernel)
+        assert np.linalg.norm(res[i] - reso[i]) <= tol * max(1.0, np.linalg.norm(reso[i]))
+    for i in truth_instances:
+        zt, lt = dense_kkt.kkt_truth(prob, i, soc=soc)
+        assert _rel(dz[i], zt) <= tol and _rel(lam[i], lt) <= tol
+        rs, rp = dense_kkt.kkt_residuals(prob, i, dz[i], lam[i], soc=soc)
+        assert rs <= res_tol and rp <= res_tol, (rs, rp)
+    return dz, lam
+
+
+def test_config1_cartpole_fixture(handle, oracle_mod):
+    """config 1: single cartpole instance, block-Cholesky vs sparse/dense KKT (test/cartpole.jl)."""
+    _check(problems.cartpole_fixture(), handle, oracle_mod)
+    assert handle.last_kernel.startswith("kkt_tpi<4,1")
+
+
+@pytest.mark.parametrize("dense_cost", [False, True])
+def test_double_integrator_fixture(handle, oracle_mod, dense_cost):
+    """test/cholesky_solve.jl:7-44 on DoubleIntegrator(3,101): ||D dz + d||, ||H dz + g + D'lam|| and
+    equality with the dense KKT solve."""
+    _check(problems.double_integrator_fixture(dense_cost=dense_cost), handle, oracle_mod)
+    assert handle.last_kernel.startswith("kkt_tpi<6,3")
+
+
+def test_second_order_correction_chain(handle, oracle_mod):
+    """Ginv=false chain (src/cholesky_solver.jl:254-273): dz = -D'(DD')^-1 d.  cond(DD') of the double
+    integrator is ~1e7, so this case is held to 1e-8."""
+    _check(problems.cartpole_fixture(), handle, oracle_mod, soc=True)
+    _check(problems.double_integrator_fixture(), handle, oracle_mod, soc=True, tol=1e-8, res_tol=1e-8)
+
+
+@pytest.mark.parametrize("mid_p", [0, 1])
+@pytest.mark.parametrize("batch", [1, 33, 130])
+def test_config3_dubins(handle, oracle_mod, mid_p, batch):
+    prob = problems.dubins_kkt_batch(batch, seed=batch, N=201, mid_p=mid_p)
+    _check(prob, handle, oracle_mod, truth_instances=(0, batch - 1))
+    assert handle.last_kernel.startswith("kkt_tpi<3,2")
+
+
+@pytest.mark.parametrize("hess", [0, 1, 2])
+@pytest.mark.parametrize("n,m,N,mid_p", [(2, 1, 9, 0), (2, 1, 9, 1), (4, 1, 30, 0), (3, 2, 2, 0), (6, 3, 12, 1)])
+def test_tpi_hessian_modes(handle, oracle_mod, n, m, N, mid_p, hess):
+    prob = problems.random_lqr_kkt(n, m, N, 37, seed=7 * n + hess, mid_p=mid_p, hess_mode=hess)
+    _check(prob, handle, oracle_mod)
+    assert handle.last_kernel.startswith("kkt_tpi")
+
+
+@pytest.mark.parametrize("hess", [0, 1, 2])
+@pytest.mark.parametrize("n,m,N,mid_p,d2x", [(5, 2, 10, 2, False), (4, 1, 12, 0, True), (3, 2, 8, 1, True),
+                                            (12, 4, 40, 0, False), (12, 4, 9, 3, True), (20, 6, 6, 0, False)])
+def test_cooperative_kernel(handle, oracle_mod, n, m, N, mid_p, d2x, hess):
+    prob = problems.random_lqr_kkt(n, m, N, 6, seed=n + hess, mid_p=mid_p, hess_mode=hess, explicit_D2=d2x)
+    _check(prob, handle, oracle_mod)
+    assert handle.last_kernel.startswith("kkt_coop")
+
+
+def test_irregular_stage_pattern(handle, oracle_mod):
+    """A waypoint constraint on a single interior knot: p is not [P1, PM.., PN] -> cooperative kernel."""
+    prob = problems.random_lqr_kkt(4, 1, 16, 5, seed=3, mid_p=1)
+    p = prob["p"].copy()
+    for k in range(1, 15):
+        if k != 8:
+            p[k] = 0
+            prob["C"][k] = np.zeros((5, 0, 5))
+            prob["c"][k] = np.zeros((5, 0))
+    prob["p"] = p
+    _check(prob, handle, oracle_mod)
+    assert handle.last_kernel.startswith("kkt_coop")
+
+
+def test_large_dense_schur_variant(handle, oracle_mod):
+    """config 5b shape (n=64, m=16) at a short horizon."""
+    prob = problems.random_lqr_kkt(64, 16, 6, 2, seed=4)
+    _check(prob, handle, oracle_mod, tol=1e-9, res_tol=1e-9)
+
+
+def test_info_flags_bad_hessian(handle):
+    prob = problems.dubins_kkt_batch(40, seed=1, N=21)
+    prob["R"][5, 3] = -np.eye(2)
+    _, _, info = ops.kkt_solve_problem(prob, handle=handle)
+    assert info[5] == 4 * 1000 + 3 + 1 and (np.delete(info, 5) == 0).all()
+
+
+def test_idempotent_full_width_batch(handle):
+    """Size-independent check at a large batch: the step computed from the solution point has zero
+    primal residual (D dz + d = 0 row by row), evaluated block-wise on the host for every instance."""
+    b = 4096
+    prob = problems.dubins_kkt_batch(b, seed=2, N=201)
+    dz, lam, info = ops.kkt_solve_problem(prob, handle=handle)
+    assert (info == 0).all()
+    n, m, N = 3, 2, 201
+    X, U = ops.split_primals(dz, n, m, N)
+    dyn = np.einsum("bkij,bkj->bki", prob["A"], X[:, :-1]) + np.einsum("bkij,bkj->bki", prob["B"], U) \
+        - X[:, 1:] + prob["d"]
+    assert np.abs(dyn).max() <= 1e-10
+    assert np.abs(X[:, 0] + prob["c"][0]).max() <= 1e-10
+    assert np.abs(X[:, -1] + prob["c"][-1]).max() <= 1e-10

@@ -1,0 +1,128 @@
+"""GPU parity: batched Riccati (C ABI -> CUDA) against the CPU oracle and the refined KKT truth.
+
+Tolerance (BASELINE.json north_star): relative solution error <= 1e-10 in FP64."""
+import numpy as np
+import pytest
+
+from lqr_b200 import _lib, ops, problems
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def _check(prob, handle, oracle_mod, tol=TOL):
+    X, U, K, kff, info = ops.riccati_solve_problem(prob, handle=handle)
+    Xo, Uo, Ko, kffo, infoo = oracle_mod.riccati(prob)
+    assert (info == 0).all() and (infoo == 0).all()
+    b = X.shape[0]
+    worst = max(max(_rel(X[i], Xo[i]), _rel(U[i], Uo[i]), _rel(K[i], Ko[i]), _rel(kff[i], kffo[i]))
+                for i in range(b))
+    assert worst <= tol, (worst, handle.last_kernel)
+    return X, U
+
+
+@pytest.mark.parametrize("batch", [1, 31, 32, 33, 257])
+def test_cartpole_ltv_vs_oracle(handle, oracle_mod, batch):
+    prob = problems.riccati_cartpole_batch(batch, seed=batch)
+    _check(prob, handle, oracle_mod)
+    assert handle.last_kernel.startswith("riccati_tpi<4,1>")
+
+
+def test_cartpole_vs_refined_kkt_truth(handle, oracle_mod):
+    """config 2 parity: Riccati == KKT solution with only init + dynamics constraints."""
+    from oracle import dense_kkt
+    prob = problems.riccati_cartpole_batch(8, seed=0)
+    X, U = _check(prob, handle, oracle_mod)
+    kp = dense_kkt.riccati_as_kkt(prob)
+    n, m, N = 4, 1, 101
+    for i in range(8):
+        zt, _ = dense_kkt.kkt_truth(kp, i)
+        Xt, Ut = ops.split_primals(zt[None], n, m, N)
+        assert _rel(X[i], Xt[0]) <= TOL and _rel(U[i], Ut[0]) <= TOL
+
+
+@pytest.mark.parametrize("n,m,N", [(2, 1, 11), (3, 2, 201), (4, 2, 50), (6, 3, 31)])
+@pytest.mark.parametrize("lti", [False, True])
+def test_tpi_sizes(handle, oracle_mod, n, m, N, lti):
+    prob = problems.random_lqr_riccati(n, m, N, 70, seed=n * 10 + m, lti=lti)
+    _check(prob, handle, oracle_mod)
+    assert handle.last_kernel.startswith("riccati_tpi")
+
+
+@pytest.mark.parametrize("n,m,N,batch", [(5, 2, 20, 9), (12, 4, 101, 10), (7, 7, 15, 5), (32, 8, 12, 3), (64, 16, 11, 2)])
+def test_cooperative_sizes(handle, oracle_mod, n, m, N, batch):
+    prob = problems.random_lqr_riccati(n, m, N, batch, seed=n)
+    _check(prob, handle, oracle_mod)
+    assert handle.last_kernel.startswith("riccati_coop")
+
+
+def test_no_affine_terms_reference_form(handle, oracle_mod):
+    """The reference DPSolver form: LTI, no q/r/qf (src/dynamic_programming.jl:54-72)."""
+    prob = problems.random_lqr_riccati(4, 1, 101, 40, seed=5, lti=True)
+    prob["q"] = prob["r"] = prob["qf"] = None
+    _check(prob, handle, oracle_mod)
+
+
+def test_device_resident_path_matches_host_path(handle):
+    import torch
+    prob = problems.riccati_cartpole_batch(100, seed=3)
+    f = ops.riccati_flatten(prob)
+    n, m, N, b = 4, 1, 101, 100
+    L = _lib.riccati_layout(n, m, N)
+    ldb = _lib.padded_batch(b)
+    dev = {k: torch.from_numpy(f[k]).cuda() for k in ("A", "B", "Q", "R", "q", "r", "Qf", "qf", "x0")}
+    knots = torch.zeros(ldb * L.knot_count * L.rows_per_knot, dtype=torch.float64, device="cuda")
+    term = torch.zeros(ldb * L.term_rows, dtype=torch.float64, device="cuda")
+    Zp = torch.zeros(ldb * L.z_rows, dtype=torch.float64, device="cuda")
+    Z = torch.zeros(b, L.z_rows, dtype=torch.float64, device="cuda")
+    handle.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        ops.riccati_pack(handle, n, m, N, b, 0, dev["A"], dev["B"], dev["Q"], dev["R"], dev["q"], dev["r"],
+                         dev["Qf"], dev["qf"], dev["x0"], knots, term)
+        ops.riccati_solve_packed(handle, n, m, N, b, 0, knots, term, Zp)
+        ops.unpack_rows(handle, L.z_rows, b, Zp, Z)
+        torch.cuda.synchronize()
+    finally:
+        handle.set_stream(None)
+    X, U, _, _, _ = ops.riccati_solve_problem(prob, handle=handle)
+    Xd, Ud = ops.split_primals(Z.cpu().numpy(), n, m, N)
+    assert np.array_equal(Xd, X) and np.array_equal(Ud, U)
+
+
+def test_info_reports_nonpositive_pivot(handle):
+    prob = problems.riccati_cartpole_batch(40, seed=9)
+    prob["R"][7] = -1e6          # E = R + B'PB becomes negative at instance 7
+    _, _, _, _, info = ops.riccati_solve_problem(prob, handle=handle)
+    assert info[7] != 0 and (np.delete(info, 7) == 0).all()
+
+
+def test_linearity_full_size(handle):
+    """Size-independent property at the BASELINE batch (65,536): with q=r=qf=0 the trajectory is linear
+    in x0, so solve(2*x0) == 2*solve(x0) up to rounding."""
+    b = 65536
+    base = problems.riccati_cartpole_batch(256, seed=11)
+    rep = b // 256
+    prob = {k: (np.tile(v, (rep,) + (1,) * (v.ndim - 1)) if isinstance(v, np.ndarray) else v)
+            for k, v in base.items()}
+    prob["q"] = prob["r"] = prob["qf"] = None
+    rng = np.random.default_rng(0)
+    prob["x0"] = rng.standard_normal((b, 4))
+    X1, U1, _, _, info = ops.riccati_solve_problem(prob, want_gains=False, handle=handle)
+    prob["x0"] = 2.0 * prob["x0"]
+    X2, U2, _, _, _ = ops.riccati_solve_problem(prob, want_gains=False, handle=handle)
+    assert (info == 0).all()
+    assert np.abs(X2 - 2 * X1).max() <= 1e-9 * max(1.0, np.abs(X1).max())
+    assert np.abs(U2 - 2 * U1).max() <= 1e-9 * max(1.0, np.abs(U1).max())
+
+
+def test_rollout_entry_point(handle, oracle_mod):
+    prob = problems.riccati_cartpole_batch(50, seed=2)
+    X, U, _, _, _ = ops.riccati_solve_problem(prob, handle=handle)
+    f = ops.riccati_flatten(prob)
+    Xr = np.zeros((50, 101, 4))
+    ops.rollout(handle, 4, 1, 101, 50, 0, f["A"], f["B"], f["x0"], np.ascontiguousarray(U), Xr)
+    assert _rel(Xr, X) <= 1e-12
