@@ -8,9 +8,9 @@
 // ------------------------------------------------------------------ size classes --------------
 // thread-per-instance instantiations: (n, m, P1, PM, PN) with p = [P1, PM, ..., PM, PN].
 //   cartpole (test/problems.jl:58-88): 4,1 init+goal          dubins: 3,2 init+goal (+1 mid row)
-//   DoubleIntegrator(3) (test/problems.jl:14-56): 6,3 init, 1 mid row, goal;  D=1: 2,1
+//   DoubleIntegrator(3) (test/problems.jl:14-56): 6,3 init, 1 mid row, goal;  D=2: 4,2
 #define KKT_TPI_SIZES(X) \
-    X(4, 1, 4, 0, 4) X(3, 2, 3, 0, 3) X(3, 2, 3, 1, 3) X(2, 1, 2, 0, 2) X(2, 1, 2, 1, 2) X(6, 3, 6, 1, 6)
+    X(4, 1, 4, 0, 4) X(3, 2, 3, 0, 3) X(3, 2, 3, 1, 3) X(2, 1, 2, 0, 2) X(4, 2, 4, 1, 4) X(6, 3, 6, 1, 6)
 
 struct KktShape {
     int n, m, N, hess, d2x;

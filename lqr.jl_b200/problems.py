@@ -212,7 +212,7 @@ def random_lqr_kkt(n, m, N, batch, seed=3, dt=0.01, mid_p=0, hess_mode=HESS_BLOC
     R = _spd(rng, (batch, N - 1), m, 1.0 / np.sqrt(m), 1e-1)
     Hux = None
     if hess_mode == HESS_DENSE:
-        Hux = 0.05 * rng.standard_normal((batch, N - 1, m, n))
+        Hux = 0.05 / (np.sqrt(m) + np.sqrt(n)) * rng.standard_normal((batch, N - 1, m, n))  # keeps H > 0
     q = rng.standard_normal((batch, N, n))
     r = rng.standard_normal((batch, N - 1, m))
     d = 0.1 * rng.standard_normal((batch, N - 1, n))

@@ -186,7 +186,7 @@ def block_ldiv(n, m, mode, M, b):
     w = n + m
     bb = np.asarray(b, dtype=np.float64)
     vec = bb.ndim == 1
-    buf = np.ascontiguousarray(bb.reshape(w, -1).T)  # column-major w x nrhs
+    buf = np.array(bb.reshape(w, -1).T, dtype=np.float64, order="C", copy=True)  # column-major w x nrhs
     lib().lqro_block_ldiv(C.c_int(n), C.c_int(m), C.c_int(mode), _p(_cm(M)), C.c_int(buf.shape[0]),
                           _p(buf), C.c_int(w))
     out = buf.T.copy()

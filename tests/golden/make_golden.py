@@ -1,0 +1,46 @@
+"""Generates tests/golden/*.npz: refined-truth outputs of the global KKT solve (oracle/dense_kkt.py, the
+analogue of src/sparse_solver.jl:267-292 / test/cholesky_solve.jl:42) on seeded inputs.
+
+The reference itself keeps no golden vectors and cannot be executed here (Julia absent), so these vectors
+are NOT reference outputs; they freeze the refined truth so that later edits to the oracle or kernels are
+caught.  Re-generate with:  python -m tests.golden.make_golden
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from lqr_b200 import problems  # noqa: E402
+
+KKT_CASES = {
+    "cartpole_kkt": lambda: problems.cartpole_fixture(),
+    "double_integrator_kkt": lambda: problems.double_integrator_fixture(),
+    "dubins_kkt": lambda: problems.dubins_kkt_batch(2, seed=1, N=201),
+}
+
+
+def main():
+    from oracle import dense_kkt
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name, make in KKT_CASES.items():
+        prob = make()
+        dz, lam = dense_kkt.kkt_truth(prob, 0)
+        np.savez_compressed(os.path.join(here, name + ".npz"), dz=dz, mult=lam)
+    prob = problems.riccati_cartpole_batch(4, seed=0)
+    kp = dense_kkt.riccati_as_kkt(prob)
+    n, m, N = 4, 1, 101
+    X = np.zeros((4, N, n))
+    U = np.zeros((4, N - 1, m))
+    for i in range(4):
+        zt, _ = dense_kkt.kkt_truth(kp, i)
+        body = zt[:(N - 1) * (n + m)].reshape(N - 1, n + m)
+        X[i, :-1], U[i], X[i, -1] = body[:, :n], body[:, n:], zt[(N - 1) * (n + m):]
+    np.savez_compressed(os.path.join(here, "cartpole_riccati.npz"), X=X, U=U, batch=4, seed=0)
+
+
+if __name__ == "__main__":
+    main()
