@@ -82,18 +82,32 @@ static int32_t check_dims(lqrb_context *h, int n, int m, int N, int64_t batch) {
 }
 
 // ------------------------------------------------------------------ solve (packed, device) ----
+// Launch shapes.  The headline batch (65,536 = 2,048 warps) must fit in ONE wave: 148 SMs x 16 warps
+// = 2,368 resident warps needs <= 128 registers per thread (ncu, round 1: at 154 registers only 12
+// warps/SM fit -> 1.15 waves and a tail that ran at 1/7 occupancy).  Small sizes take the tight
+// bound; the register-heavy sizes keep the loose one.
+template <int n, int m, bool LTI, int THREADS, int MINB>
+static void launch_tpi_cfg(int N, int64_t batch, const double *knots, const double *term, double *Z,
+                           double *gains, int32_t *info, cudaStream_t s) {
+    const unsigned grid = (unsigned)((batch + THREADS - 1) / THREADS);
+    riccati_tpi_kernel<n, m, LTI, THREADS, MINB><<<grid, THREADS, 0, s>>>(knots, term, Z, gains, info, N, batch);
+}
+
 template <int n, int m>
 static int32_t launch_tpi(lqrb_context *h, int N, int64_t batch, int lti, const double *knots,
                           const double *term, double *Z, double *gains, int32_t *info,
                           cudaStream_t s) {
-    constexpr int THREADS = 128;
-    const unsigned grid = (unsigned)((batch + THREADS - 1) / THREADS);
-    if (lti)
-        riccati_tpi_kernel<n, m, true, THREADS, 1><<<grid, THREADS, 0, s>>>(knots, term, Z, gains, info, N, batch);
-    else
-        riccati_tpi_kernel<n, m, false, THREADS, 1><<<grid, THREADS, 0, s>>>(knots, term, Z, gains, info, N, batch);
+    constexpr bool SMALL = (n * n + n * m) <= 20;
+    const bool tight = SMALL && h->opt("riccati_tpi_cfg", 0) != 1;
+    if (SMALL && tight) {
+        if (lti) launch_tpi_cfg<n, m, true, 64, 8>(N, batch, knots, term, Z, gains, info, s);
+        else launch_tpi_cfg<n, m, false, 64, 8>(N, batch, knots, term, Z, gains, info, s);
+    } else {
+        if (lti) launch_tpi_cfg<n, m, true, 128, 1>(N, batch, knots, term, Z, gains, info, s);
+        else launch_tpi_cfg<n, m, false, 128, 1>(N, batch, knots, term, Z, gains, info, s);
+    }
     char nm[64];
-    snprintf(nm, sizeof nm, "riccati_tpi<%d,%d>%s", n, m, lti ? "[lti]" : "");
+    snprintf(nm, sizeof nm, "riccati_tpi<%d,%d>%s%s", n, m, lti ? "[lti]" : "", tight ? "[64x8]" : "[128x1]");
     h->kernel_name = nm;
     LQRB_LAUNCH_CHECK(h, "riccati_tpi_kernel");
     return 0;

@@ -1,0 +1,124 @@
+"""GPU tests of the reference-interface mirror (lqr_b200.*): same call sequences as the reference's
+scripts, checked with the identities those scripts state."""
+import numpy as np
+import pytest
+
+import lqr_b200 as LQR
+from lqr_b200 import problems
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_dpsolver_like_test_dp(handle, oracle_mod):
+    """test/dp.jl: prob -> DPSolver -> solve!(sol, solver, prob); X[1] == x0 and the closed loop holds."""
+    pr = problems.random_lqr_riccati(4, 1, 101, 16, seed=1, lti=True)
+    prob = LQR.LQRProblem(pr["Qf"], pr["Q"], pr["R"], pr["A"], pr["B"], pr["x0"], N=101)
+    solver = LQR.DPSolver(prob, handle=handle)
+    sol = LQR.LQRSolution(prob)
+    LQR.solve_(sol, solver, prob)
+    assert (sol.info == 0).all() and np.array_equal(sol.X[:, 0], pr["x0"])
+    u = -np.einsum("bkij,bkj->bki", sol.K, sol.X[:, :-1])
+    assert _rel(u, sol.U) < 1e-12
+    xn = np.einsum("bij,bkj->bki", pr["A"], sol.X[:, :-1]) + np.einsum("bij,bkj->bki", pr["B"], sol.U)
+    assert _rel(xn, sol.X[:, 1:]) < 1e-12
+    pr["q"] = pr["r"] = pr["qf"] = None
+    Xo, Uo, Ko, _, _ = oracle_mod.riccati(pr)
+    assert _rel(sol.X, Xo) < 1e-10 and _rel(sol.K, Ko) < 1e-10
+    X2 = np.zeros_like(sol.X)
+    LQR.rollout_(X2, sol.U, prob, handle=handle)
+    assert _rel(X2, sol.X) < 1e-12
+
+
+def test_block_cholesky_like_reference_test(handle):
+    """test/block_cholesky.jl:11-67 (n=10, m=5, C = 1e-3*rand), batched over 7 instances."""
+    rng = np.random.default_rng(0)
+    n, m, b = 10, 5, 7
+    A = rng.random((b, n, n)); A = np.einsum("bki,bkj->bij", A, A)
+    B = rng.random((b, m, m)); B = np.einsum("bki,bkj->bij", B, B)
+    C = rng.random((b, m, n)) * 1e-3
+    rhs = rng.random((b, n + m))
+    M = np.block([[A, np.swapaxes(C, 1, 2)], [C, B]])
+    chol = LQR.BlockCholesky(n, m, batch=b, handle=handle)
+    assert not chol.block_diag                                                     # :20
+    LQR.cholesky_(chol, A, B, C)
+    assert (chol.info == 0).all()
+    for i in range(b):
+        assert np.allclose(chol.U[i], np.linalg.cholesky(M[i]).T, rtol=1e-9, atol=1e-11)  # :24
+    x = LQR.ldiv(chol, rhs)
+    assert _rel(x, np.linalg.solve(M, rhs[..., None])[..., 0]) < 1e-8               # :26
+    b1 = rhs.copy(); LQR.ldiv_(chol, b1)
+    assert np.array_equal(b1, x)                                                   # :27-29
+    # block diagonal (:36-49)
+    chol = LQR.BlockCholesky(n, m, batch=b, block_diag=True, handle=handle)
+    assert chol.block_diag
+    LQR.cholesky_(chol, A, B)
+    Md = M.copy(); Md[:, n:, :n] = 0; Md[:, :n, n:] = 0
+    for i in range(b):
+        assert np.allclose(chol.U[i], np.linalg.cholesky(Md[i]).T, rtol=1e-9, atol=1e-11)
+    assert _rel(LQR.ldiv(chol, rhs), np.linalg.solve(Md, rhs[..., None])[..., 0]) < 1e-8
+    # diagonal (:56-67): stores the inverse
+    Ad, Bd = rng.random((b, n)) + 0.1, rng.random((b, m)) + 0.1
+    chol = LQR.BlockCholesky(n, m, batch=b, diag=True, handle=handle)
+    LQR.cholesky_(chol, Ad[..., None] * np.eye(n), Bd[..., None] * np.eye(m))
+    dd = np.concatenate([Ad, Bd], axis=1)
+    assert np.allclose(np.diagonal(chol.M, axis1=1, axis2=2), 1.0 / dd)
+    assert np.allclose(LQR.ldiv(chol, rhs), rhs / dd)
+    # potrf info on an indefinite block (src/cholesky_solve.jl:1-3)
+    Abad = A.copy(); Abad[3] = -np.eye(n)
+    chol = LQR.BlockCholesky(n, m, batch=b, block_diag=True, handle=handle)
+    LQR.cholesky_(chol, Abad, B)
+    assert chol.info[3] == 1 and (np.delete(chol.info, 3) == 0).all()
+
+
+def test_inverted_quadratic_update(handle):
+    """InvertedQuadratic / update_cost! / gradient (src/block_cholesky.jl:107-153)."""
+    rng = np.random.default_rng(1)
+    n, m, b = 3, 2, 4
+    Q = np.einsum("bki,bkj->bij", *(2 * [rng.random((b, n, n))])) + np.eye(n)
+    R = np.einsum("bki,bkj->bij", *(2 * [rng.random((b, m, m))])) + np.eye(m)
+    q, r = rng.random((b, n)), rng.random((b, m))
+    ic = LQR.InvertedQuadratic(n, m, batch=b, handle=handle)
+    LQR.update_cholesky_([ic], [dict(Q=Q, R=R, q=q, r=r)])
+    g = LQR.gradient(ic)
+    assert np.array_equal(g, np.concatenate([q, r], axis=1))
+    H = np.zeros((b, n + m, n + m)); H[:, :n, :n] = Q; H[:, n:, n:] = R
+    assert _rel(LQR.ldiv(ic.chol, g), np.linalg.solve(H, g[..., None])[..., 0]) < 1e-10
+
+
+def test_cholesky_solver_step_sequence_like_reference_script(handle):
+    """test/cholesky_solve.jl:7-44, the step-by-step script, on DoubleIntegrator(3,101)."""
+    prob = problems.double_integrator_fixture()
+    solver = LQR.CholeskySolver(prob, handle=handle)
+    LQR.calculate_shur_factors_(solver.shur_blocks, None, None)        # :14
+    LQR.cholesky_(solver.chol_blocks, solver.shur_blocks)               # :22
+    LQR.forward_substitution_(solver.chol_blocks)                       # :28
+    LQR.backward_substitution_(solver.chol_blocks)                      # :29
+    lam = LQR.get_multipliers(solver)[0]                                # :30
+    dZ = np.zeros_like(solver.dZ)
+    LQR.calculate_primals_(dZ, None, solver.chol_blocks, None)          # :34
+    dZ = LQR.get_step(solver)[0]                                        # :35
+    D, d = LQR.get_linearized_constraints(solver)                       # :17
+    H, g = LQR.get_cost_expansion(solver)
+    S = D @ np.linalg.solve(H, D.T)
+    r = D @ np.linalg.solve(H, g) - d
+    assert _rel(lam, -np.linalg.solve(S, r)) < 1e-7                     # :31
+    assert _rel(dZ, -np.linalg.solve(H, D.T @ lam + g)) < 1e-10         # :36
+    assert np.linalg.norm(D @ dZ + d) < 1e-10                           # :39
+    assert np.linalg.norm(H @ dZ + g + D.T @ lam) < 1e-10               # :40
+    NN, P = H.shape[0], D.shape[0]
+    sol = np.linalg.solve(np.block([[H, D.T], [D, np.zeros((P, P))]]), -np.concatenate([g, d]))  # :42
+    assert _rel(dZ, sol[:NN]) < 1e-8 and _rel(lam, sol[NN:]) < 1e-7     # :43-44
+    # residual(solver) = ||g + D'lam|| knot-wise (src/cholesky_solver.jl:238-252; test/cholesky_comp.jl:45)
+    res = LQR.residual(solver)[0]
+    assert abs(res - np.linalg.norm(g + D.T @ lam)) < 1e-9 * max(1.0, res)
+    assert _rel(LQR.get_residual(solver)[0], g + D.T @ lam) < 1e-10
+    # _solve! gives the same thing in one call (:166-182)
+    s2 = LQR.CholeskySolver(prob, handle=handle)._solve_()
+    assert np.array_equal(s2.dZ, solver.dZ) and np.array_equal(s2.lam, solver.lam)
+    # second_order_correction!: dz^ = -D'(DD')^-1 d (:254-273); cond(DD') ~ 1e7 here
+    dzh = LQR.second_order_correction_(solver)[0]
+    assert _rel(dzh, -D.T @ np.linalg.solve(D @ D.T, d)) < 1e-6 or np.linalg.norm(d) == 0
