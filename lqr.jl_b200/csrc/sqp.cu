@@ -1,9 +1,480 @@
-// sqp.cu — batched Dubins SQP driver (placeholder until the device linearisation lands).
+// sqp.cu — batched Dubins SQP driver, everything on device.
+//
+// Outer loop      solve!/step!            src/cholesky_solver.jl:109-153  (<= iters steps, converge at
+//                                         feas_p, feas_d < eps, :131-137)
+// Linearisation   update!                 src/cholesky_solver.jl:155-164  (third-party numerics in the
+//                                         reference; re-derived here for the Dubins car, RK3 as
+//                                         test/cartpole.jl:38, cost expansion scaled by dt on non-terminal
+//                                         knots as test/sparse_solver.jl:67-72 pins)
+// QP step         _solve!                 src/cholesky_solver.jl:166-182  (the batched KKT kernel)
+// Globalisation   line_search (spec)      src/sqp.jl:72-94: L1 merit phi = f + mu*||c||_1,
+//                                         phi' = grad f'dx - mu*||c||_1, eta = 1e-4, rho = 0.5, <= 10
+//                                         trials, second-order correction tried only at alpha = 1:
+//                                         dx^ = -A'(AA')^-1 c(x+dx)  (= second_order_correction!,
+//                                         src/cholesky_solver.jl:254-273, the Ginv=false chain)
+// The merit penalty rule (TO.update_penalty!, third-party, unpinned) is mu <- max(mu, 1.1*||lambda||_inf).
+//
+// One thread per instance; every per-instance array is tiled batch-minor [tile][row][32].
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
+
+namespace {
+
+constexpr int n = 3, m = 2, w = n + m;
+// packed KKT rows for p = [3, 0, ..., 0, 3], HESS_DIAG (see lqrb200.h)
+constexpr int ROWS_FIRST = w + w + n * w + n + n * w + n;  // H g D1 d C c = 46
+constexpr int ROWS_MID = w + w + n * w + n;                // 28
+constexpr int ROWS_LAST = n + n + n * n + n;               // 18
+
+struct Opts {
+    int N;
+    double dt, qd, rd, qfd;
+};
+
+__device__ __forceinline__ int64_t knot_row(int k, int N) {
+    return k == 0 ? 0 : (int64_t)ROWS_FIRST + (int64_t)(k - 1) * ROWS_MID;
+}
+__device__ __forceinline__ int64_t data_rows(int N) { return ROWS_FIRST + (int64_t)(N - 2) * ROWS_MID + ROWS_LAST; }
+__device__ __forceinline__ int64_t mult_row(int k) { return k == 0 ? 0 : (int64_t)n + n + (int64_t)(k - 1) * n; }
+
+// RK3 step of the Dubins car (x, y, theta; v, omega) and the averaged heading terms.
+__device__ __forceinline__ void dubins_avg(double th, double om, double dt, double &cb, double &sb, double &dcb,
+                                           double &dsb) {
+    const double t2 = th + 0.5 * dt * om, t3 = th + dt * om;
+    double s1, c1, s2, c2, s3, c3;
+    sincos(th, &s1, &c1);
+    sincos(t2, &s2, &c2);
+    sincos(t3, &s3, &c3);
+    cb = (c1 + 4.0 * c2 + c3) / 6.0;
+    sb = (s1 + 4.0 * s2 + s3) / 6.0;
+    dcb = (-4.0 * s2 * 0.5 * dt - s3 * dt) / 6.0;  // d cb / d omega
+    dsb = (4.0 * c2 * 0.5 * dt + c3 * dt) / 6.0;
+}
+
+struct Stats {  // per-instance scalars, stored as rows of a [S_COUNT][32]-tiled array
+    enum { F0 = 0, C1, CINF, FEASD, MU, PHI0, DPHI0, ALPHA, DONE, CONV, ITERS, S_COUNT };
+};
+
+// ---------------------------------------------------------------------------------------------
+// linearise at Z: writes the packed KKT data and per-instance f, ||c||_1, ||c||_inf, feas_d.
+// feas_d = || (||g_k + D1_k'lam_k + C_k'mu_k + D2_k'lam_{k-1}||)_k ||  with the previous multipliers
+// (residual(solver, recalculate=false), src/cholesky_solver.jl:130,238-252).
+__global__ void __launch_bounds__(64) dubins_linearize_kernel(const double *__restrict__ Z, const double *__restrict__ x0,
+                                                              const double *__restrict__ xf, const double *__restrict__ mult,
+                                                              double *__restrict__ data, double *__restrict__ stats,
+                                                              Opts o, int64_t batch, int check_conv, double eps_p,
+                                                              double eps_d) {
+    const int64_t inst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= batch) return;
+    const int64_t tile = inst >> 5;
+    const int lane = (int)(inst & 31);
+    const int N = o.N;
+    const int64_t NN = (int64_t)N * n + (int64_t)(N - 1) * m, P = (int64_t)(N - 1) * n + 2 * n;
+    const double *zb = Z + tile * NN * 32 + lane;
+    const double *mb = mult + tile * P * 32 + lane;
+    double *db = data + tile * data_rows(N) * 32 + lane;
+    double *sb = stats + tile * Stats::S_COUNT * 32 + lane;
+    const double *x0b = x0 + tile * n * 32 + lane, *xfb = xf + tile * n * 32 + lane;
+    double xg[n];
+    for (int i = 0; i < n; ++i) xg[i] = xfb[i * 32];
+
+    double f = 0.0, c1 = 0.0, cinf = 0.0, fd2 = 0.0;
+    double x[n], xn[n], lam_prev[n] = {0.0, 0.0, 0.0};
+    for (int i = 0; i < n; ++i) x[i] = zb[i * 32];
+    for (int k = 0; k < N; ++k) {
+        double *kp = db + knot_row(k, N) * 32;
+        const bool last = k == N - 1;
+        const double qs = last ? o.qfd : o.qd * o.dt, rs = o.rd * o.dt;
+        double g[w], res[w];
+        // cost expansion (diagonal): H = diag(Q dt, R dt), g = [Q (x - xf) dt; R u dt]
+        for (int i = 0; i < n; ++i) {
+            const double e = x[i] - xg[i];
+            kp[i * 32] = qs;
+            g[i] = qs * e;
+            f += 0.5 * qs * e * e;
+        }
+        if (last) {
+            for (int i = 0; i < n; ++i) kp[(n + i) * 32] = g[i];
+            double *Cp = kp + 2 * n * 32;  // C = I, c = x_N - xf
+            for (int j = 0; j < n; ++j)
+                for (int i = 0; i < n; ++i) Cp[(i + j * n) * 32] = (i == j) ? 1.0 : 0.0;
+            const double *mu = mb + mult_row(k) * 32;
+            for (int i = 0; i < n; ++i) {
+                const double c = x[i] - xg[i];
+                Cp[(n * n + i) * 32] = c;
+                c1 += fabs(c);
+                cinf = fmax(cinf, fabs(c));
+                res[i] = g[i] + mu[i * 32] - lam_prev[i];
+                fd2 += res[i] * res[i];
+            }
+            break;
+        }
+        double u[m];
+        for (int i = 0; i < m; ++i) {
+            u[i] = zb[((int64_t)k * w + n + i) * 32];
+            kp[(n + i) * 32] = rs;
+            g[n + i] = rs * u[i];
+            f += 0.5 * rs * u[i] * u[i];
+        }
+        for (int i = 0; i < w; ++i) kp[(w + i) * 32] = g[i];
+        // dynamics: RK3 map, Jacobians A (3x3), B (3x2); D1 = [A B] column-major 3 x 5
+        double cb, sbar, dcb, dsb;
+        dubins_avg(x[2], u[1], o.dt, cb, sbar, dcb, dsb);
+        const double v = u[0];
+        double D1[n * w];
+        for (int e = 0; e < n * w; ++e) D1[e] = 0.0;
+        D1[0 + 0 * n] = 1.0; D1[1 + 1 * n] = 1.0; D1[2 + 2 * n] = 1.0;
+        D1[0 + 2 * n] = -o.dt * v * sbar;
+        D1[1 + 2 * n] = o.dt * v * cb;
+        D1[0 + 3 * n] = o.dt * cb;
+        D1[1 + 3 * n] = o.dt * sbar;
+        D1[0 + 4 * n] = o.dt * v * dcb;
+        D1[1 + 4 * n] = o.dt * v * dsb;
+        D1[2 + 4 * n] = o.dt;
+        double *D1p = kp + 2 * w * 32;
+        for (int e = 0; e < n * w; ++e) D1p[e * 32] = D1[e];
+        for (int i = 0; i < n; ++i) xn[i] = zb[((int64_t)(k + 1) * w + i) * 32];
+        const double fx[n] = {x[0] + o.dt * v * cb, x[1] + o.dt * v * sbar, x[2] + o.dt * u[1]};
+        const double *lam = mb + (mult_row(k) + (k == 0 ? n : 0)) * 32;
+        double lk[n];
+        for (int i = 0; i < n; ++i) {
+            const double d = fx[i] - xn[i];  // d_k = f(z_k) - x_{k+1}   (test/cartpole.jl:34-42)
+            D1p[(n * w + i) * 32] = d;
+            c1 += fabs(d);
+            cinf = fmax(cinf, fabs(d));
+            lk[i] = lam[i * 32];
+        }
+        for (int j = 0; j < w; ++j) {
+            double s = g[j];
+            for (int i = 0; i < n; ++i) s = fma(D1[i + j * n], lk[i], s);
+            if (j < n && k > 0) s -= lam_prev[j];
+            res[j] = s;
+        }
+        if (k == 0) {  // C = [I 0], c = x_1 - x0
+            double *Cp = D1p + (n * w + n) * 32;
+            const double *mu = mb;
+            for (int j = 0; j < w; ++j)
+                for (int i = 0; i < n; ++i) Cp[(i + j * n) * 32] = (i == j) ? 1.0 : 0.0;
+            for (int i = 0; i < n; ++i) {
+                const double c = x[i] - x0b[i * 32];
+                Cp[(n * w + i) * 32] = c;
+                c1 += fabs(c);
+                cinf = fmax(cinf, fabs(c));
+                res[i] += mu[i * 32];
+            }
+        }
+        for (int j = 0; j < w; ++j) fd2 += res[j] * res[j];
+        for (int i = 0; i < n; ++i) {
+            lam_prev[i] = lk[i];
+            x[i] = xn[i];
+        }
+    }
+    const double feasd = sqrt(fd2);
+    sb[Stats::F0 * 32] = f;
+    sb[Stats::C1 * 32] = c1;
+    sb[Stats::CINF * 32] = cinf;
+    sb[Stats::FEASD * 32] = feasd;
+    if (check_conv && sb[Stats::CONV * 32] == 0.0 && cinf < eps_p && feasd < eps_d) sb[Stats::CONV * 32] = 1.0;
+}
+
+// cost and constraint 1-norm / values at a trial point Zt = Z + alpha*dz (+ dzh)
+template <bool WRITE_C>
+__device__ __forceinline__ void dubins_eval(const double *zb, const double *dzb, const double *dhb, double alpha,
+                                            const double *x0b, const double *xg, const Opts &o, double *db,
+                                            double &f, double &c1) {
+    const int N = o.N;
+    f = 0.0;
+    c1 = 0.0;
+    auto at = [&](int64_t row) {
+        double v = fma(alpha, dzb[row * 32], zb[row * 32]);
+        if (dhb) v += dhb[row * 32];
+        return v;
+    };
+    double x[n], xn[n];
+    for (int i = 0; i < n; ++i) x[i] = at(i);
+    for (int i = 0; i < n; ++i) {
+        const double c = x[i] - x0b[i * 32];
+        c1 += fabs(c);
+        if (WRITE_C) db[(2 * w + n * w + n + n * w + i) * 32] = c;
+    }
+    for (int k = 0; k < N - 1; ++k) {
+        double u[m];
+        for (int i = 0; i < m; ++i) u[i] = at((int64_t)k * w + n + i);
+        for (int i = 0; i < n; ++i) {
+            const double e = x[i] - xg[i];
+            f += 0.5 * o.qd * o.dt * e * e;
+        }
+        for (int i = 0; i < m; ++i) f += 0.5 * o.rd * o.dt * u[i] * u[i];
+        double cb, sbar, dcb, dsb;
+        dubins_avg(x[2], u[1], o.dt, cb, sbar, dcb, dsb);
+        const double fx[n] = {x[0] + o.dt * u[0] * cb, x[1] + o.dt * u[0] * sbar, x[2] + o.dt * u[1]};
+        for (int i = 0; i < n; ++i) xn[i] = at((int64_t)(k + 1) * w + i);
+        for (int i = 0; i < n; ++i) {
+            const double d = fx[i] - xn[i];
+            c1 += fabs(d);
+            if (WRITE_C) db[(knot_row(k, N) + 2 * w + n * w + i) * 32] = d;
+            x[i] = xn[i];
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        const double e = x[i] - xg[i];
+        f += 0.5 * o.qfd * e * e;
+        c1 += fabs(e);
+        if (WRITE_C) db[(knot_row(N - 1, N) + 2 * n + n * n + i) * 32] = e;
+    }
+}
+
+// Line search stages (src/sqp.jl:72-94).
+//   stage 0: penalty update, phi0, phi'0; trial alpha = 1; on failure write c(x+dx) into the data rows
+//            for the second-order correction solve and set need_soc.
+//   stage 1: second-order-correction trial x + dx + dx^; on failure alpha = rho.
+//   stage 2: trial at the current alpha; on failure alpha *= rho.
+// full_step != 0 skips the tests and takes alpha = 1 (line_search = 0).
+__global__ void __launch_bounds__(64) dubins_linesearch_kernel(double *__restrict__ Z, const double *__restrict__ dz,
+                                                               const double *__restrict__ dzh, const double *__restrict__ mult,
+                                                               double *__restrict__ mult_kept,
+                                                               const double *__restrict__ x0, const double *__restrict__ xf,
+                                                               double *__restrict__ data, double *__restrict__ stats, Opts o,
+                                                               int64_t batch, int stage, int full_step,
+                                                               int *__restrict__ counters) {
+    const int64_t inst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= batch) return;
+    const int64_t tile = inst >> 5;
+    const int lane = (int)(inst & 31);
+    const int N = o.N;
+    const int64_t NN = (int64_t)N * n + (int64_t)(N - 1) * m, P = (int64_t)(N - 1) * n + 2 * n;
+    double *zb = Z + tile * NN * 32 + lane;
+    const double *dzb = dz + tile * NN * 32 + lane;
+    const double *dhb = dzh ? dzh + tile * NN * 32 + lane : nullptr;
+    double *db = data + tile * data_rows(N) * 32 + lane;
+    double *sb = stats + tile * Stats::S_COUNT * 32 + lane;
+    const double *x0b = x0 + tile * n * 32 + lane, *xfb = xf + tile * n * 32 + lane;
+    if (sb[Stats::CONV * 32] != 0.0) return;  // converged instances are frozen (:135-137)
+    if (stage > 0 && sb[Stats::DONE * 32] != 0.0) return;
+    double xg[n];
+    for (int i = 0; i < n; ++i) xg[i] = xfb[i * 32];
+    const double eta = 1e-4, rho = 0.5;
+
+    auto accept = [&](double alpha, bool with_soc) {
+        for (int64_t r = 0; r < NN; ++r) {
+            double v = fma(alpha, dzb[r * 32], zb[r * 32]);
+            if (with_soc) v += dhb[r * 32];
+            zb[r * 32] = v;
+        }
+        sb[Stats::DONE * 32] = 1.0;
+        sb[Stats::ALPHA * 32] = alpha;
+    };
+
+    if (stage == 0) {
+        sb[Stats::ITERS * 32] += 1.0;
+        sb[Stats::DONE * 32] = 0.0;
+        {   // the multipliers of this QP step become the solver's current ones (converged instances keep theirs)
+            const double *mb = mult + tile * P * 32 + lane;
+            double *mk = mult_kept + tile * P * 32 + lane;
+            for (int64_t r = 0; r < P; ++r) mk[r * 32] = mb[r * 32];
+        }
+        if (full_step) {
+            accept(1.0, false);
+            return;
+        }
+        // penalty: mu <- max(mu, 1.1 ||lambda||_inf)
+        const double *mb = mult + tile * P * 32 + lane;
+        double linf = 0.0;
+        for (int64_t r = 0; r < P; ++r) linf = fmax(linf, fabs(mb[r * 32]));
+        const double mu = fmax(sb[Stats::MU * 32], 1.1 * linf);
+        sb[Stats::MU * 32] = mu;
+        // phi'(x, dx) = grad f'dx - mu ||c(x)||_1  with grad f = the g rows of the packed data
+        double gdx = 0.0;
+        for (int k = 0; k < N; ++k) {
+            const int wk = k < N - 1 ? w : n;
+            const double *gp = db + (knot_row(k, N) + wk) * 32;
+            for (int j = 0; j < wk; ++j) gdx = fma(gp[j * 32], dzb[((int64_t)k * w + j) * 32], gdx);
+        }
+        const double phi0 = sb[Stats::F0 * 32] + mu * sb[Stats::C1 * 32];
+        const double dphi0 = gdx - mu * sb[Stats::C1 * 32];
+        sb[Stats::PHI0 * 32] = phi0;
+        sb[Stats::DPHI0 * 32] = dphi0;
+        double f, c1;
+        dubins_eval<true>(zb, dzb, nullptr, 1.0, x0b, xg, o, db, f, c1);
+        if (f + mu * c1 <= phi0 + eta * dphi0) {
+            accept(1.0, false);
+        } else {
+            sb[Stats::ALPHA * 32] = 1.0;
+            atomicAdd(&counters[0], 1);  // needs the second-order correction solve
+        }
+        return;
+    }
+    const double mu = sb[Stats::MU * 32], phi0 = sb[Stats::PHI0 * 32], dphi0 = sb[Stats::DPHI0 * 32];
+    double f, c1;
+    if (stage == 1) {
+        dubins_eval<false>(zb, dzb, dhb, 1.0, x0b, xg, o, db, f, c1);
+        if (f + mu * c1 < phi0 + eta * dphi0) {
+            accept(1.0, true);
+        } else {
+            sb[Stats::ALPHA * 32] = rho;
+            atomicAdd(&counters[1], 1);
+        }
+        return;
+    }
+    const double alpha = sb[Stats::ALPHA * 32];
+    dubins_eval<false>(zb, dzb, nullptr, alpha, x0b, xg, o, db, f, c1);
+    if (f + mu * c1 <= phi0 + eta * alpha * dphi0) {
+        accept(alpha, false);
+    } else {
+        sb[Stats::ALPHA * 32] = alpha * rho;
+        atomicAdd(&counters[1], 1);
+    }
+}
+
+__global__ void stats_init_kernel(double *stats, int64_t batch) {
+    const int64_t inst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= batch) return;
+    double *sb = stats + (inst >> 5) * Stats::S_COUNT * 32 + (inst & 31);
+    for (int r = 0; r < Stats::S_COUNT; ++r) sb[r * 32] = 0.0;
+    sb[Stats::MU * 32] = 1.0;  // reset!: merit.mu = 1 (src/cholesky_solver.jl:88-94)
+}
+
+__global__ void stats_export_kernel(const double *stats, double *feas_p, double *feas_d, int32_t *iters, int64_t batch) {
+    const int64_t inst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= batch) return;
+    const double *sb = stats + (inst >> 5) * Stats::S_COUNT * 32 + (inst & 31);
+    if (feas_p) feas_p[inst] = sb[Stats::CINF * 32];
+    if (feas_d) feas_d[inst] = sb[Stats::FEASD * 32];
+    if (iters) iters[inst] = (int32_t)sb[Stats::ITERS * 32];
+}
+
+}  // namespace
 
 extern "C" int32_t lqrb_sqp_dubins_f64(lqrb_handle_t h, int64_t batch, const lqrb_sqp_options_t *opts,
                                        const double *x0, const double *xf, double *Z, double *feas_p,
                                        double *feas_d, int32_t *iters_done, int64_t *kkt_solves) {
     if (!h) return -1;
-    return lqrb_fail(h, -1, "lqrb_sqp_dubins_f64: not built yet");
+    if (batch < 0) return lqrb_fail(h, -2, "batch < 0");
+    if (!opts || opts->N < 3 || opts->iters < 0 || !(opts->dt > 0.0)) return lqrb_fail(h, -3, "bad options");
+    if (!x0) return lqrb_fail(h, -4, "x0 is NULL");
+    if (!xf) return lqrb_fail(h, -5, "xf is NULL");
+    if (!Z) return lqrb_fail(h, -6, "Z is NULL");
+    if (kkt_solves) *kkt_solves = 0;
+    if (batch == 0) return 0;
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    const int N = opts->N;
+    const int64_t NN = lqrb_num_vars(n, m, N), P = (int64_t)(N - 1) * n + 2 * n;
+    const int64_t ldb = lqrb_padded_batch(batch);
+    std::vector<int32_t> p((size_t)N, 0);
+    p[0] = n;
+    p[N - 1] = n;
+    const int64_t drows = lqrb_kkt_data_rows(n, m, N, p.data(), LQRB_HESS_DIAG, 0);
+    const bool dev = lqrb_is_device_ptr(Z);
+    cudaStream_t s = h->stream;
+
+    // device buffers: [Zp | dz | dzh | mult | multh | x0p | xfp | stats] in SQP0, data in SQP1
+    const size_t nd = (size_t)ldb * (3 * NN + 3 * P + 2 * n + Stats::S_COUNT);
+    double *buf = (double *)lqrb_scratch(h, SCR_SQP0, nd * 8);
+    double *data = (double *)lqrb_scratch(h, SCR_SQP1, (size_t)ldb * drows * 8);
+    int *counters = (int *)lqrb_scratch(h, SCR_SQP2, 64);
+    int32_t *dinfo = (int32_t *)lqrb_scratch(h, SCR_SQP3, (size_t)ldb * 4);
+    if (!buf || !data || !counters || !dinfo) return 1000 + (int)cudaErrorMemoryAllocation;
+    double *Zp = buf, *dz = Zp + ldb * NN, *dzh = dz + ldb * NN, *mult = dzh + ldb * NN, *multh = mult + ldb * P,
+           *multk = multh + ldb * P, *x0p = multk + ldb * P, *xfp = x0p + ldb * n, *stats = xfp + ldb * n;
+
+    // stage the instance-major inputs and pack them
+    const double *dZ = Z, *dx0 = x0, *dxf = xf;
+    double *stage = nullptr;
+    if (!dev) {
+        stage = (double *)lqrb_scratch(h, SCR_STAGE_A, (size_t)batch * (NN + 2 * n) * 8 + (size_t)batch * 24);
+        if (!stage) return 1000 + (int)cudaErrorMemoryAllocation;
+        LQRB_CUDA(h, cudaMemcpyAsync(stage, Z, (size_t)batch * NN * 8, cudaMemcpyHostToDevice, s));
+        LQRB_CUDA(h, cudaMemcpyAsync(stage + batch * NN, x0, (size_t)batch * n * 8, cudaMemcpyHostToDevice, s));
+        LQRB_CUDA(h, cudaMemcpyAsync(stage + batch * (NN + n), xf, (size_t)batch * n * 8, cudaMemcpyHostToDevice, s));
+        dZ = stage;
+        dx0 = stage + batch * NN;
+        dxf = stage + batch * (NN + n);
+    }
+    auto idmap = [&](int64_t rows) {
+        std::vector<RowMap> mp((size_t)rows);
+        for (int64_t r = 0; r < rows; ++r) mp[(size_t)r] = RowMap{0, (int32_t)r, 0.0};
+        return lqrb_get_map(h, "id" + std::to_string(rows), mp);
+    };
+    ArrayTable t = {};
+    t.ptr[0] = dZ; t.stride[0] = NN;
+    int32_t rc = lqrb_gather_pack(h, idmap(NN), t, batch, LQRB_TILE, Zp, s);
+    if (rc) return rc;
+    t.ptr[0] = dx0; t.stride[0] = n;
+    rc = lqrb_gather_pack(h, idmap(n), t, batch, LQRB_TILE, x0p, s);
+    if (rc) return rc;
+    t.ptr[0] = dxf;
+    rc = lqrb_gather_pack(h, idmap(n), t, batch, LQRB_TILE, xfp, s);
+    if (rc) return rc;
+    LQRB_CUDA(h, cudaMemsetAsync(multk, 0, (size_t)ldb * P * 8, s));
+
+    const Opts o{N, opts->dt, opts->q_diag, opts->r_diag, opts->qf_diag};
+    const unsigned grid = (unsigned)((batch + 63) / 64);
+    stats_init_kernel<<<grid, 64, 0, s>>>(stats, batch);
+    LQRB_LAUNCH_CHECK(h, "stats_init_kernel");
+    int64_t solves = 0;
+    int hc[2];
+    for (int it = 0; it < opts->iters; ++it) {
+        // update! + convergence check (:126-137)
+        dubins_linearize_kernel<<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, data, stats, o, batch, 1, opts->eps_p, opts->eps_d);
+        LQRB_LAUNCH_CHECK(h, "dubins_linearize_kernel");
+        // _solve! (:143)
+        rc = lqrb_kkt_solve_packed_f64(h, n, m, N, batch, p.data(), LQRB_HESS_DIAG, 0, 0, data, dz, mult, nullptr, dinfo);
+        if (rc) return rc;
+        solves += batch;
+        // line search (:146; spec src/sqp.jl:72-94)
+        LQRB_CUDA(h, cudaMemsetAsync(counters, 0, 8, s));
+        dubins_linesearch_kernel<<<grid, 64, 0, s>>>(Zp, dz, nullptr, mult, multk, x0p, xfp, data, stats, o, batch, 0,
+                                                     opts->line_search ? 0 : 1, counters);
+        LQRB_LAUNCH_CHECK(h, "dubins_linesearch_kernel");
+        if (!opts->line_search) continue;
+        LQRB_CUDA(h, cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, s));
+        LQRB_CUDA(h, cudaStreamSynchronize(s));
+        if (hc[0] == 0) continue;
+        // second-order correction: same chain with Ginv=false on c(x+dx) (:254-273)
+        rc = lqrb_kkt_solve_packed_f64(h, n, m, N, batch, p.data(), LQRB_HESS_DIAG, 0, LQRB_FLAG_SOC, data, dzh, multh,
+                                       nullptr, dinfo);
+        if (rc) return rc;
+        solves += batch;
+        int pending = hc[0];
+        for (int trial = 1; trial < 10 && pending > 0; ++trial) {
+            LQRB_CUDA(h, cudaMemsetAsync(counters, 0, 8, s));
+            dubins_linesearch_kernel<<<grid, 64, 0, s>>>(Zp, dz, dzh, mult, multk, x0p, xfp, data, stats, o, batch,
+                                                         trial == 1 ? 1 : 2, 0, counters);
+            LQRB_LAUNCH_CHECK(h, "dubins_linesearch_kernel");
+            LQRB_CUDA(h, cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, s));
+            LQRB_CUDA(h, cudaStreamSynchronize(s));
+            pending = hc[1];
+        }
+    }
+    // final feasibility numbers at the returned iterate
+    dubins_linearize_kernel<<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, data, stats, o, batch, 0, opts->eps_p, opts->eps_d);
+    LQRB_LAUNCH_CHECK(h, "dubins_linearize_kernel");
+
+    // export
+    double *oZ = Z, *ofp = feas_p, *ofd = feas_d;
+    int32_t *oit = iters_done;
+    if (!dev) {
+        oZ = stage;
+        ofp = stage + batch * NN;
+        ofd = ofp + batch;
+        oit = (int32_t *)(ofd + batch);
+    }
+    ArrayTableOut to = {};
+    to.ptr[0] = oZ; to.stride[0] = NN;
+    rc = lqrb_scatter_unpack(h, idmap(NN), to, batch, LQRB_TILE, Zp, s);
+    if (rc) return rc;
+    stats_export_kernel<<<grid, 64, 0, s>>>(stats, (feas_p || !dev) ? ofp : nullptr, (feas_d || !dev) ? ofd : nullptr,
+                                            (iters_done || !dev) ? oit : nullptr, batch);
+    LQRB_LAUNCH_CHECK(h, "stats_export_kernel");
+    if (!dev) {
+        LQRB_CUDA(h, cudaMemcpyAsync(Z, oZ, (size_t)batch * NN * 8, cudaMemcpyDeviceToHost, s));
+        if (feas_p) LQRB_CUDA(h, cudaMemcpyAsync(feas_p, ofp, (size_t)batch * 8, cudaMemcpyDeviceToHost, s));
+        if (feas_d) LQRB_CUDA(h, cudaMemcpyAsync(feas_d, ofd, (size_t)batch * 8, cudaMemcpyDeviceToHost, s));
+        if (iters_done) LQRB_CUDA(h, cudaMemcpyAsync(iters_done, oit, (size_t)batch * 4, cudaMemcpyDeviceToHost, s));
+        LQRB_CUDA(h, cudaStreamSynchronize(s));
+    }
+    if (kkt_solves) *kkt_solves = solves;
+    return 0;
 }

@@ -157,3 +157,17 @@ def split_primals(Z, n, m, N):
     body = Z[:, :(N - 1) * (n + m)].reshape(b, N - 1, n + m)
     X = np.concatenate([body[:, :, :n], Z[:, None, (N - 1) * (n + m):]], axis=1)
     return X, body[:, :, n:].copy()
+
+
+# ------------------------------------------------------------------ Dubins SQP
+def sqp_dubins(h: Handle, batch, opts: dict, x0, xf, Z, feas_p=None, feas_d=None, iters=None):
+    """lqrb_sqp_dubins_f64; Z is updated in place.  Returns the total number of KKT solves."""
+    import ctypes as C
+    o = _lib.SqpOptions(N=int(opts["N"]), iters=int(opts["iters"]), dt=float(opts["dt"]),
+                        q_diag=float(opts["q_diag"]), r_diag=float(opts["r_diag"]), qf_diag=float(opts["qf_diag"]),
+                        eps_p=float(opts.get("eps_p", 1e-5)), eps_d=float(opts.get("eps_d", 1e-5)),
+                        line_search=int(opts.get("line_search", 1)))
+    solves = C.c_int64(0)
+    h.call("lqrb_sqp_dubins_f64", batch, C.byref(o), ptr(x0), ptr(xf), ptr(Z), ptr(feas_p), ptr(feas_d), ptr(iters),
+           C.byref(solves))
+    return int(solves.value)

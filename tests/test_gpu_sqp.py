@@ -1,0 +1,56 @@
+"""GPU parity: the on-device Dubins SQP driver (config 4) against the numpy restatement of the same loop
+(oracle/sqp_dubins.py: src/cholesky_solver.jl:109-153 + src/sqp.jl:72-94)."""
+import numpy as np
+import pytest
+
+from lqr_b200.sqp import DubinsSQP
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("N,batch", [(11, 5), (11, 70), (201, 3)])
+def test_full_step_iterates_match_oracle(handle, oracle_mod, N, batch):
+    """line_search = 0: every iterate is a deterministic function of the KKT solves -> tight agreement."""
+    from oracle import sqp_dubins as S
+    Z0, x0, xf, o = S.turn90_problem(batch, N=N)
+    o["line_search"] = 0
+    Zo, fpo, fdo, ito, solves_o = S.solve(Z0, x0, xf, o)
+    s = DubinsSQP(x0, xf, N=N, tf=o["dt"] * (N - 1), iters=10, line_search=False, handle=handle)
+    Z = s.solve_(Z0)
+    assert _rel(Z, Zo) <= 1e-9
+    assert np.array_equal(s.iters, ito) and s.kkt_solves == solves_o
+    assert np.allclose(s.feas_p, fpo, rtol=1e-4, atol=1e-12) and np.allclose(s.feas_d, fdo, rtol=1e-4, atol=1e-10)
+
+
+def test_line_search_converges_like_reference_tolerances(handle, oracle_mod):
+    """With the L1-merit line search + SOC: converges within 10 iterations to feas_p, feas_d < 1e-5
+    (src/cholesky_solver.jl:111,131-137) and lands on the oracle's solution."""
+    from oracle import sqp_dubins as S
+    Z0, x0, xf, o = S.turn90_problem(64, N=11)
+    Zo, fpo, fdo, ito, _ = S.solve(Z0, x0, xf, o)
+    s = DubinsSQP(x0, xf, N=11, tf=3.0, handle=handle)
+    Z = s.solve_(Z0)
+    assert (s.feas_p < 1e-5).all() and (s.feas_d < 2e-5).all()
+    assert (s.iters <= 10).all() and s.kkt_solves >= 64 * 8
+    assert _rel(Z, Zo) <= 1e-6
+
+
+def test_hard_start_exercises_backtracking(handle, oracle_mod):
+    """A poor initial guess (large controls) forces SOC / step halving; the merit function must not
+    increase and the run must still end feasible-ish."""
+    from oracle import sqp_dubins as S
+    Z0, x0, xf, o = S.turn90_problem(32, N=21)
+    rng = np.random.default_rng(0)
+    Z0 = Z0 + 0.5 * rng.standard_normal(Z0.shape)
+    s = DubinsSQP(x0, xf, N=21, tf=3.0, iters=10, handle=handle)
+    Z = s.solve_(Z0)
+    assert np.isfinite(Z).all()
+    assert np.median(s.feas_p) < 1e-3
+    mu = 1.0
+    phi0 = S.cost(Z0, xf, o | {"N": 21, "dt": 3.0 / 20}) + mu * S.c_norm1(Z0, x0, xf, o | {"N": 21, "dt": 3.0 / 20})
+    phi1 = S.cost(Z, xf, o | {"N": 21, "dt": 3.0 / 20}) + mu * S.c_norm1(Z, x0, xf, o | {"N": 21, "dt": 3.0 / 20})
+    assert (phi1 <= phi0 + 1e-9).mean() > 0.9
