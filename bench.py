@@ -137,7 +137,11 @@ def cpu_leg(n, m, N, f, target_seconds=12.0, steps=1, warmup=0):
     """Times the oracle's OpenMP batch driver on a bounded sample.  Returns (solves/s, cores, sample, ms/step)."""
     import oracle
     oracle.build()
-    cores = oracle.num_threads()
+    # all the host cores this process may use (torchrun exports OMP_NUM_THREADS=1, so ask for them explicitly)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     total = f["x0"].shape[0]
 
     def run(cnt):
@@ -146,7 +150,7 @@ def cpu_leg(n, m, N, f, target_seconds=12.0, steps=1, warmup=0):
         info = np.zeros(cnt, dtype=np.int32)
         t0 = time.perf_counter()
         oracle.riccati_raw(n, m, N, 0, cnt, f["A"][:cnt], f["B"][:cnt], f["Q"][:cnt], f["R"][:cnt], f["q"][:cnt],
-                           f["r"][:cnt], f["Qf"][:cnt], f["qf"][:cnt], f["x0"][:cnt], X, U, K, kff, info, 0)
+                           f["r"][:cnt], f["Qf"][:cnt], f["qf"][:cnt], f["x0"][:cnt], X, U, K, kff, info, cores)
         return time.perf_counter() - t0
     probe = min(total, 2048)
     run(probe)

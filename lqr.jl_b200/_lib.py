@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblqrb200.so")
+LIB_PATH = os.environ.get("LQRB200_LIB", os.path.join(_HERE, "liblqrb200.so"))  # override: kernel A/B experiments only
 CSRC = os.path.join(_HERE, "csrc")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "lqrb200.h")
 

@@ -13,10 +13,11 @@
 //   forward  k = 0..N-1 : load knot k, factor H_k, form its Schur pieces, finish block row k-1 of S
 //                         (C_{k-1} += G_k[1,1], the A_k = C_{k-1} aliasing of
 //                         src/jacobian_blocks.jl:165-167 becomes a register carry), factor block row
-//                         k and forward-substitute; spill the factor row to a per-instance scratch
-//                         record;
-//   backward k = N-1..0 : reload knot k and its record, back-substitute, form the residual and the
-//                         primal step of knot k.
+//                         k and forward-substitute; only C^_{k-1} and lam~_{k-1} go to the per-instance
+//                         scratch record (tri(n)+n doubles per knot);
+//   backward k = N-1..0 : reload knot k and its record, RECOMPUTE the rest of block row k (cheaper
+//                         than a round trip through HBM: the kernel is DRAM-bound with the FP64 pipe
+//                         under 20 % busy), back-substitute, form the residual and the primal step.
 // D2_k = [-I 0] is structural here (test/cartpole.jl:34-42); explicit D2 goes to the cooperative kernel.
 #pragma once
 #include "smallmat.cuh"
@@ -29,13 +30,6 @@ struct KnotRows {
     static constexpr int w = n + mk;
     static constexpr int oH = 0, oG = hess_rows(n, mk, HESS), oD1 = oG + w, od = oD1 + p2 * w,
                          oC = od + p2, oc = oC + ps * w, ROWS = oc + ps;
-};
-
-// rows of one knot's factor record in the scratch array
-template <int p1, int ps, int p2>
-struct RecRows {
-    static constexpr int oB = 0, oD = tri(ps), oE = oD + p1 * ps, oF = oE + ps * p2, omu = oF + p1 * p2,
-                         oC = omu + ps, ol = oC + tri(p1), ROWS = ol + p1;
 };
 
 // ------------------------------------------------------------------ cost-Hessian factor -------
@@ -115,12 +109,159 @@ struct FwdCarry {
     double dp[n];       // pending d_k = rho2 - d - F^'lam~ - E^'mu~ (+ rho1_{k+1} next)
 };
 
+// Block row k of the factor, everything that depends only on knot k's data and on (A^ = C^_{k-1},
+// lam~_{k-1}):   F^ = A^-T F,  D^ = A^-T D,  B^ = chol(B - D^'D^),  E^ = B^-T (E - D^'F^),
+//                mu~ = B^-T (c - D^'lam~_{k-1})            (src/cholesky_solve.jl:47-67, :93-117)
+// with F = D2*WD = -WD[0:n,:], D = D2*WC = -WC[0:n,:], B = C*WC, E = C*WD  (shur!/copy_shur!,
+// src/jacobian_blocks.jl:231-286).  The forward sweep (FWD) also needs G22 = D1*WD and rho2 = D1*hg - d
+// to start the next row; the backward sweep calls the same code again instead of reading the row back
+// from HBM (the record keeps only C^_{k-1} and lam~_{k-1}).
+template <int n, int mk, int p1, int ps, int p2, int HESS, bool SOC, bool FWD>
+struct RowFactor {
+    static constexpr int w = n + mk;
+    double Fh[p1 * p2 + 1];
+    double Bh[tri(ps) + 1], Bhinv[ps + 1], Dh[p1 * ps + 1], Eh[ps * p2 + 1], mut[ps + 1];
+    double G22[FWD ? tri(p2) + 1 : 1], rho2[FWD ? p2 + 1 : 1];
+
+    __device__ __forceinline__ int compute(const double *__restrict__ kp, const HFactor<n, mk, HESS, SOC> &H,
+                                           const double *hg, const double *Ah, const double *Ahinv,
+                                           const double *lamp) {
+        using KR = KnotRows<n, mk, ps, p2, HESS>;
+        int info = 0;
+        double WD[w * p2 + 1];  // H^-1 D1'   (w x p2, column j = H^-1 * row j of D1)
+        if constexpr (p2 > 0) {
+            double D1[p2 * w];
+            SM_UNROLL
+            for (int e = 0; e < p2 * w; ++e) D1[e] = ld_keep(kp + (KR::oD1 + e) * 32);
+            SM_UNROLL
+            for (int j = 0; j < p2; ++j) {
+                SM_UNROLL
+                for (int i = 0; i < w; ++i) WD[i + j * w] = D1[j + i * p2];
+                H.solve(WD + j * w);
+            }
+            if constexpr (FWD) {
+                SM_UNROLL
+                for (int j = 0; j < p2; ++j)
+                    SM_UNROLL
+                    for (int i = 0; i <= j; ++i) {
+                        double s = 0.0;
+                        SM_UNROLL
+                        for (int l = 0; l < w; ++l) s = fma(D1[i + l * p2], WD[l + j * w], s);
+                        G22[tri_idx(i, j)] = s;
+                    }
+                SM_UNROLL
+                for (int i = 0; i < p2; ++i) {
+                    double s = -ld_stream(kp + (KR::od + i) * 32);  // d = r_[3] - d  (copy_shur! :285)
+                    SM_UNROLL
+                    for (int l = 0; l < w; ++l) s = fma(D1[i + l * p2], hg[l], s);
+                    rho2[i] = s;
+                }
+            }
+            if constexpr (p1 > 0) {
+                SM_UNROLL
+                for (int j = 0; j < p2; ++j) {
+                    SM_UNROLL
+                    for (int i = 0; i < p1; ++i) Fh[i + j * p1] = -WD[i + j * w];
+                    solve_ut<p1>(Ah, Ahinv, Fh + j * p1);  // tri_solve!(U.A, U.F, 'U', 'T')
+                }
+            }
+        }
+        if constexpr (ps > 0) {
+            double Cc[ps * w], WC[w * ps];
+            SM_UNROLL
+            for (int e = 0; e < ps * w; ++e) Cc[e] = ld_keep(kp + (KR::oC + e) * 32);
+            SM_UNROLL
+            for (int j = 0; j < ps; ++j) {
+                SM_UNROLL
+                for (int i = 0; i < w; ++i) WC[i + j * w] = Cc[j + i * ps];
+                H.solve(WC + j * w);
+            }
+            SM_UNROLL
+            for (int j = 0; j < ps; ++j)
+                SM_UNROLL
+                for (int i = 0; i <= j; ++i) {
+                    double s = 0.0;
+                    SM_UNROLL
+                    for (int l = 0; l < w; ++l) s = fma(Cc[i + l * ps], WC[l + j * w], s);
+                    Bh[tri_idx(i, j)] = s;  // B = YYt[ips,ips]
+                }
+            SM_UNROLL
+            for (int i = 0; i < ps; ++i) {
+                double s = -ld_stream(kp + (KR::oc + i) * 32);  // c = r_[2] - c  (:284)
+                SM_UNROLL
+                for (int l = 0; l < w; ++l) s = fma(Cc[i + l * ps], hg[l], s);
+                mut[i] = s;
+            }
+            if constexpr (p2 > 0) {  // E = C*WD  (ps x p2)
+                SM_UNROLL
+                for (int j = 0; j < p2; ++j)
+                    SM_UNROLL
+                    for (int i = 0; i < ps; ++i) {
+                        double s = 0.0;
+                        SM_UNROLL
+                        for (int l = 0; l < w; ++l) s = fma(Cc[i + l * ps], WD[l + j * w], s);
+                        Eh[i + j * ps] = s;
+                    }
+            }
+            if constexpr (p1 > 0) {  // D = D2*WC = -WC[0:n,:];  D^ = A^-T D
+                SM_UNROLL
+                for (int j = 0; j < ps; ++j) {
+                    SM_UNROLL
+                    for (int i = 0; i < p1; ++i) Dh[i + j * p1] = -WC[i + j * w];
+                    solve_ut<p1>(Ah, Ahinv, Dh + j * p1);
+                }
+                SM_UNROLL
+                for (int j = 0; j < ps; ++j)  // B -= D^'D^
+                    SM_UNROLL
+                    for (int i = 0; i <= j; ++i) {
+                        double s = Bh[tri_idx(i, j)];
+                        SM_UNROLL
+                        for (int l = 0; l < p1; ++l) s = fma(-Dh[l + i * p1], Dh[l + j * p1], s);
+                        Bh[tri_idx(i, j)] = s;
+                    }
+                SM_UNROLL
+                for (int i = 0; i < ps; ++i) {  // c - D^'lam~_{k-1}
+                    double s = mut[i];
+                    SM_UNROLL
+                    for (int l = 0; l < p1; ++l) s = fma(-Dh[l + i * p1], lamp[l], s);
+                    mut[i] = s;
+                }
+                if constexpr (p2 > 0) {  // E -= D^'F^
+                    SM_UNROLL
+                    for (int j = 0; j < p2; ++j)
+                        SM_UNROLL
+                        for (int i = 0; i < ps; ++i) {
+                            double s = Eh[i + j * ps];
+                            SM_UNROLL
+                            for (int l = 0; l < p1; ++l) s = fma(-Dh[l + i * p1], Fh[l + j * p1], s);
+                            Eh[i + j * ps] = s;
+                        }
+                }
+            }
+            const int st = chol_packed<ps>(Bh, Bhinv);  // chol!(U.B)
+            if (st) info = 100 + st;
+            solve_ut<ps>(Bh, Bhinv, mut);               // mu~_k
+            if constexpr (p2 > 0) {
+                SM_UNROLL
+                for (int j = 0; j < p2; ++j) solve_ut<ps>(Bh, Bhinv, Eh + j * ps);  // E^ = B^-T E
+            }
+        }
+        return info;
+    }
+};
+
+// rows of one knot's record in the scratch array: C^_{k-1} (diag = reciprocals) | lam~_{k-1}
+template <int p1>
+struct RecRows2 {
+    static constexpr int oC = 0, ol = tri(p1), ROWS = ol + p1;
+};
+
 // ------------------------------------------------------------------ forward knot --------------
 template <int n, int mk, int p1, int ps, int p2, int HESS, bool SOC>
 __device__ __forceinline__ int kkt_fwd_knot(const double *__restrict__ kp, double *__restrict__ rec,
                                             FwdCarry<n> &cy, int knot) {
     using KR = KnotRows<n, mk, ps, p2, HESS>;
-    using RR = RecRows<p1, ps, p2>;
+    using RR = RecRows2<p1>;
     constexpr int w = n + mk;
     int info = 0;
 
@@ -160,142 +301,10 @@ __device__ __forceinline__ int kkt_fwd_knot(const double *__restrict__ kp, doubl
         for (int i = 0; i < p1; ++i) rec[(RR::ol + i) * 32] = lamp[i];
     }
 
-    // ---- Schur pieces of knot k.  Y = [D2; C; D1], W = H^-1 Y'  (shur! :231-242)
-    double WD[w * p2 + 1];   // H^-1 D1'   (w x p2, column j = H^-1 * row j of D1)
-    double D1[p2 * w + 1];   // n x w col-major
-    double G22[tri(p2) + 1], rho2[p2 + 1];
-    double Fh[p1 * p2 + 1];  // F^ = A^-T F,  F = D2*WD = -WD[0:n,:]
-    if constexpr (p2 > 0) {
-        SM_UNROLL
-        for (int e = 0; e < p2 * w; ++e) D1[e] = ld_keep(kp + (KR::oD1 + e) * 32);
-        SM_UNROLL
-        for (int j = 0; j < p2; ++j) {
-            SM_UNROLL
-            for (int i = 0; i < w; ++i) WD[i + j * w] = D1[j + i * p2];
-            H.solve(WD + j * w);
-        }
-        SM_UNROLL
-        for (int j = 0; j < p2; ++j)
-            SM_UNROLL
-            for (int i = 0; i <= j; ++i) {
-                double s = 0.0;
-                SM_UNROLL
-                for (int l = 0; l < w; ++l) s = fma(D1[i + l * p2], WD[l + j * w], s);
-                G22[tri_idx(i, j)] = s;
-            }
-        SM_UNROLL
-        for (int i = 0; i < p2; ++i) {
-            double s = -ld_stream(kp + (KR::od + i) * 32);  // d = r_[3] - d  (copy_shur! :285)
-            SM_UNROLL
-            for (int l = 0; l < w; ++l) s = fma(D1[i + l * p2], hg[l], s);
-            rho2[i] = s;
-        }
-        if constexpr (p1 > 0) {
-            SM_UNROLL
-            for (int j = 0; j < p2; ++j) {
-                SM_UNROLL
-                for (int i = 0; i < p1; ++i) Fh[i + j * p1] = -WD[i + j * w];
-                solve_ut<p1>(Ah, Ahinv, Fh + j * p1);  // tri_solve!(U.A, U.F, 'U', 'T')
-            }
-        }
-    }
-
-    double Bh[tri(ps) + 1], Bhinv[ps + 1], Dh[p1 * ps + 1], Eh[ps * p2 + 1], mut[ps + 1];
-    if constexpr (ps > 0) {
-        double Cc[ps * w], WC[w * ps];
-        SM_UNROLL
-        for (int e = 0; e < ps * w; ++e) Cc[e] = ld_keep(kp + (KR::oC + e) * 32);
-        SM_UNROLL
-        for (int j = 0; j < ps; ++j) {
-            SM_UNROLL
-            for (int i = 0; i < w; ++i) WC[i + j * w] = Cc[j + i * ps];
-            H.solve(WC + j * w);
-        }
-        SM_UNROLL
-        for (int j = 0; j < ps; ++j)
-            SM_UNROLL
-            for (int i = 0; i <= j; ++i) {
-                double s = 0.0;
-                SM_UNROLL
-                for (int l = 0; l < w; ++l) s = fma(Cc[i + l * ps], WC[l + j * w], s);
-                Bh[tri_idx(i, j)] = s;  // B = YYt[ips,ips]
-            }
-        SM_UNROLL
-        for (int i = 0; i < ps; ++i) {
-            double s = -ld_stream(kp + (KR::oc + i) * 32);  // c = r_[2] - c  (:284)
-            SM_UNROLL
-            for (int l = 0; l < w; ++l) s = fma(Cc[i + l * ps], hg[l], s);
-            mut[i] = s;
-        }
-        if constexpr (p2 > 0) {  // E = C*WD  (ps x p2)
-            SM_UNROLL
-            for (int j = 0; j < p2; ++j)
-                SM_UNROLL
-                for (int i = 0; i < ps; ++i) {
-                    double s = 0.0;
-                    SM_UNROLL
-                    for (int l = 0; l < w; ++l) s = fma(Cc[i + l * ps], WD[l + j * w], s);
-                    Eh[i + j * ps] = s;
-                }
-        }
-        if constexpr (p1 > 0) {  // D = D2*WC = -WC[0:n,:];  D^ = A^-T D
-            SM_UNROLL
-            for (int j = 0; j < ps; ++j) {
-                SM_UNROLL
-                for (int i = 0; i < p1; ++i) Dh[i + j * p1] = -WC[i + j * w];
-                solve_ut<p1>(Ah, Ahinv, Dh + j * p1);
-            }
-            SM_UNROLL
-            for (int j = 0; j < ps; ++j)  // B -= D^'D^
-                SM_UNROLL
-                for (int i = 0; i <= j; ++i) {
-                    double s = Bh[tri_idx(i, j)];
-                    SM_UNROLL
-                    for (int l = 0; l < p1; ++l) s = fma(-Dh[l + i * p1], Dh[l + j * p1], s);
-                    Bh[tri_idx(i, j)] = s;
-                }
-            SM_UNROLL
-            for (int i = 0; i < ps; ++i) {  // c - D^'lam~_{k-1}
-                double s = mut[i];
-                SM_UNROLL
-                for (int l = 0; l < p1; ++l) s = fma(-Dh[l + i * p1], lamp[l], s);
-                mut[i] = s;
-            }
-            if constexpr (p2 > 0) {  // E -= D^'F^
-                SM_UNROLL
-                for (int j = 0; j < p2; ++j)
-                    SM_UNROLL
-                    for (int i = 0; i < ps; ++i) {
-                        double s = Eh[i + j * ps];
-                        SM_UNROLL
-                        for (int l = 0; l < p1; ++l) s = fma(-Dh[l + i * p1], Fh[l + j * p1], s);
-                        Eh[i + j * ps] = s;
-                    }
-            }
-        }
-        const int st = chol_packed<ps>(Bh, Bhinv);  // chol!(U.B)
-        if (st && !info) info = (knot + 1) * 1000 + 100 + st;
-        solve_ut<ps>(Bh, Bhinv, mut);               // mu~_k
-        if constexpr (p2 > 0) {
-            SM_UNROLL
-            for (int j = 0; j < p2; ++j) solve_ut<ps>(Bh, Bhinv, Eh + j * ps);  // E^ = B^-T E
-        }
-        // record
-        SM_UNROLL
-        for (int j = 0; j < ps; ++j)
-            SM_UNROLL
-            for (int i = 0; i <= j; ++i)
-                rec[(RR::oB + tri_idx(i, j)) * 32] = (i == j) ? Bhinv[i] : Bh[tri_idx(i, j)];
-        SM_UNROLL
-        for (int e = 0; e < p1 * ps; ++e) rec[(RR::oD + e) * 32] = Dh[e];
-        SM_UNROLL
-        for (int e = 0; e < ps * p2; ++e) rec[(RR::oE + e) * 32] = Eh[e];
-        SM_UNROLL
-        for (int i = 0; i < ps; ++i) rec[(RR::omu + i) * 32] = mut[i];
-    }
-    if constexpr (p1 > 0 && p2 > 0) {
-        SM_UNROLL
-        for (int e = 0; e < p1 * p2; ++e) rec[(RR::oF + e) * 32] = Fh[e];
+    RowFactor<n, mk, p1, ps, p2, HESS, SOC, true> R;
+    {
+        const int st = R.compute(kp, H, hg, Ah, Ahinv, lamp);
+        if (st && !info) info = (knot + 1) * 1000 + st;
     }
 
     // ---- pending C_k, d_k for the next knot to finish
@@ -304,27 +313,27 @@ __device__ __forceinline__ int kkt_fwd_knot(const double *__restrict__ kp, doubl
         for (int j = 0; j < p2; ++j)
             SM_UNROLL
             for (int i = 0; i <= j; ++i) {
-                double s = G22[tri_idx(i, j)];
+                double s = R.G22[tri_idx(i, j)];
                 if constexpr (p1 > 0) {
                     SM_UNROLL
-                    for (int l = 0; l < p1; ++l) s = fma(-Fh[l + i * p1], Fh[l + j * p1], s);
+                    for (int l = 0; l < p1; ++l) s = fma(-R.Fh[l + i * p1], R.Fh[l + j * p1], s);
                 }
                 if constexpr (ps > 0) {
                     SM_UNROLL
-                    for (int l = 0; l < ps; ++l) s = fma(-Eh[l + i * ps], Eh[l + j * ps], s);
+                    for (int l = 0; l < ps; ++l) s = fma(-R.Eh[l + i * ps], R.Eh[l + j * ps], s);
                 }
                 cy.Cp[tri_idx(i, j)] = s;
             }
         SM_UNROLL
         for (int i = 0; i < p2; ++i) {
-            double s = rho2[i];
+            double s = R.rho2[i];
             if constexpr (p1 > 0) {
                 SM_UNROLL
-                for (int l = 0; l < p1; ++l) s = fma(-Fh[l + i * p1], lamp[l], s);
+                for (int l = 0; l < p1; ++l) s = fma(-R.Fh[l + i * p1], lamp[l], s);
             }
             if constexpr (ps > 0) {
                 SM_UNROLL
-                for (int l = 0; l < ps; ++l) s = fma(-Eh[l + i * ps], mut[l], s);
+                for (int l = 0; l < ps; ++l) s = fma(-R.Eh[l + i * ps], R.mut[l], s);
             }
             cy.dp[i] = s;
         }
@@ -341,58 +350,67 @@ __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
                                              double *__restrict__ mult_lprev,
                                              double *__restrict__ res_out) {
     using KR = KnotRows<n, mk, ps, p2, HESS>;
-    using RR = RecRows<p1, ps, p2>;
+    using RR = RecRows2<p1>;
     constexpr int w = n + mk;
 
-    // mu'_k = B^-1 (mu~ - E^ lam'_k)      (backward_substitution! :130-134)
-    double mu[ps + 1];
-    if constexpr (ps > 0) {
-        double Bh[tri(ps)], Bhinv[ps];
-        SM_UNROLL
-        for (int j = 0; j < ps; ++j)
-            SM_UNROLL
-            for (int i = 0; i <= j; ++i) {
-                const double v = rec[(RR::oB + tri_idx(i, j)) * 32];
-                if (i == j) Bhinv[i] = v;
-                Bh[tri_idx(i, j)] = v;
-            }
-        SM_UNROLL
-        for (int i = 0; i < ps; ++i) {
-            double s = rec[(RR::omu + i) * 32];
-            if constexpr (p2 > 0) {
-                SM_UNROLL
-                for (int l = 0; l < p2; ++l) s = fma(-rec[(RR::oE + i + l * ps) * 32], lam[l], s);
-            }
-            mu[i] = s;
-        }
-        solve_un<ps>(Bh, Bhinv, mu);
+    HFactor<n, mk, HESS, SOC> H;
+    H.load_factor(kp + KR::oH * 32);
+    double g[w], hg[w];
+    SM_UNROLL
+    for (int i = 0; i < w; ++i) {
+        g[i] = SOC ? 0.0 : ld_stream(kp + (KR::oG + i) * 32);
+        hg[i] = g[i];
     }
-    // lam'_{k-1} = C^_{k-1}^-1 (lam~_{k-1} - D^ mu'_k - F^ lam'_k)   (:127-129)
-    double lprev[p1 + 1];
+    if constexpr (ps > 0) H.solve(hg);  // only mu~ needs H^-1 g here
+
+    // C^_{k-1} and lam~_{k-1} come back from the record; the rest of row k is recomputed
+    double Ah[tri(p1) + 1], Ahinv[p1 + 1], lamp[p1 + 1];
     if constexpr (p1 > 0) {
-        double Ch[tri(p1)], Chinv[p1];
         SM_UNROLL
         for (int j = 0; j < p1; ++j)
             SM_UNROLL
             for (int i = 0; i <= j; ++i) {
                 const double v = rec[(RR::oC + tri_idx(i, j)) * 32];
-                if (i == j) Chinv[i] = v;
-                Ch[tri_idx(i, j)] = v;
+                if (i == j) Ahinv[i] = v;
+                Ah[tri_idx(i, j)] = v;
             }
         SM_UNROLL
+        for (int i = 0; i < p1; ++i) lamp[i] = rec[(RR::ol + i) * 32];
+    }
+    RowFactor<n, mk, p1, ps, p2, HESS, SOC, false> R;
+    R.compute(kp, H, hg, Ah, Ahinv, lamp);
+
+    // mu'_k = B^-1 (mu~ - E^ lam'_k)      (backward_substitution! :130-134)
+    double mu[ps + 1];
+    if constexpr (ps > 0) {
+        SM_UNROLL
+        for (int i = 0; i < ps; ++i) {
+            double s = R.mut[i];
+            if constexpr (p2 > 0) {
+                SM_UNROLL
+                for (int l = 0; l < p2; ++l) s = fma(-R.Eh[i + l * ps], lam[l], s);
+            }
+            mu[i] = s;
+        }
+        solve_un<ps>(R.Bh, R.Bhinv, mu);
+    }
+    // lam'_{k-1} = C^_{k-1}^-1 (lam~_{k-1} - D^ mu'_k - F^ lam'_k)   (:127-129)
+    double lprev[p1 + 1];
+    if constexpr (p1 > 0) {
+        SM_UNROLL
         for (int i = 0; i < p1; ++i) {
-            double s = rec[(RR::ol + i) * 32];
+            double s = lamp[i];
             if constexpr (ps > 0) {
                 SM_UNROLL
-                for (int l = 0; l < ps; ++l) s = fma(-rec[(RR::oD + i + l * p1) * 32], mu[l], s);
+                for (int l = 0; l < ps; ++l) s = fma(-R.Dh[i + l * p1], mu[l], s);
             }
             if constexpr (p2 > 0) {
                 SM_UNROLL
-                for (int l = 0; l < p2; ++l) s = fma(-rec[(RR::oF + i + l * p1) * 32], lam[l], s);
+                for (int l = 0; l < p2; ++l) s = fma(-R.Fh[i + l * p1], lam[l], s);
             }
             lprev[i] = s;
         }
-        solve_un<p1>(Ch, Chinv, lprev);
+        solve_un<p1>(Ah, Ahinv, lprev);
     }
     // multipliers (negated, :140-141): mu_k and lam_{k-1}
     SM_UNROLL
@@ -405,15 +423,14 @@ __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
     double z[w];
     SM_UNROLL
     for (int j = 0; j < w; ++j) {
-        double s = 0.0;
-        if constexpr (!SOC) s = ld_stream(kp + (KR::oG + j) * 32);
+        double s = g[j];
         if constexpr (p2 > 0) {
             SM_UNROLL
-            for (int i = 0; i < p2; ++i) s = fma(-ld_stream(kp + (KR::oD1 + i + j * p2) * 32), lam[i], s);
+            for (int i = 0; i < p2; ++i) s = fma(-ld_keep(kp + (KR::oD1 + i + j * p2) * 32), lam[i], s);
         }
         if constexpr (ps > 0) {
             SM_UNROLL
-            for (int i = 0; i < ps; ++i) s = fma(-ld_stream(kp + (KR::oC + i + j * ps) * 32), mu[i], s);
+            for (int i = 0; i < ps; ++i) s = fma(-ld_keep(kp + (KR::oC + i + j * ps) * 32), mu[i], s);
         }
         if constexpr (p1 > 0) {
             if (j < n) s += lprev[j];  // D2' lam_{k-1} = -(-lam'_{k-1})
@@ -425,8 +442,6 @@ __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
         for (int j = 0; j < w; ++j) __stcs(res_out + j * 32, z[j]);
     }
     // dz_k = -H_k^-1 res_k   (calc_primals! :195-199)
-    HFactor<n, mk, HESS, SOC> H;
-    H.load_factor(kp + KR::oH * 32);
     H.solve(z);
     SM_UNROLL
     for (int j = 0; j < w; ++j) __stcs(dz + j * 32, -z[j]);
@@ -443,9 +458,9 @@ struct KktLayout {
     using KF = KnotRows<n, m, P1, n, HESS>;
     using KM = KnotRows<n, m, PM, n, HESS>;
     using KL = KnotRows<n, 0, PN, 0, HESS>;
-    using RF = RecRows<0, P1, n>;
-    using RM = RecRows<n, PM, n>;
-    using RL = RecRows<n, PN, 0>;
+    using RF = RecRows2<0>;
+    using RM = RecRows2<n>;
+    using RL = RecRows2<n>;
     __host__ __device__ static constexpr int64_t data_rows(int N) {
         return KF::ROWS + (int64_t)(N - 2) * KM::ROWS + KL::ROWS;
     }
@@ -458,8 +473,11 @@ struct KktLayout {
     __host__ __device__ static constexpr int64_t z_rows(int N) { return (int64_t)N * n + (int64_t)(N - 1) * m; }
 };
 
+// Launch bound: for w = n+m <= 5 ask for 8 CTAs of 64 threads per SM (<= 128 registers, 16 warps/SM):
+// measured on B200 (262,144 Dubins instances) 6.42 -> 6.20 ms, cartpole 1.29 -> 1.05 ms; the kernel is
+// DRAM-bound, so residency beats the few spilled bytes.  Larger sizes keep all 255 registers.
 template <int n, int m, int P1, int PM, int PN, int HESS, bool SOC, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (n + m <= 5) ? 8 : 1)
     kkt_tpi_kernel(const double *__restrict__ data, double *__restrict__ scratch,
                    double *__restrict__ dz, double *__restrict__ mult, double *__restrict__ res,
                    int32_t *__restrict__ info, int N, int64_t batch) {
