@@ -3,6 +3,7 @@
 #include <cstdio>
 
 #include "riccati_kernels.cuh"
+#include "riccati_dmma_kernels.cuh"
 
 // ------------------------------------------------------------------ size classes --------------
 // thread-per-instance instantiations (registers only).  Everything else -> cooperative kernel.
@@ -12,6 +13,17 @@ static bool riccati_has_tpi(int n, int m) {
 #define X(N_, M_) \
     if (n == N_ && m == M_) return true;
     RICCATI_TPI_SIZES(X)
+#undef X
+    return false;
+}
+
+// warp-per-instance FP64 tensor-core (DMMA) instantiations: n in {8,12}, m <= 4, even record length
+#define RICCATI_DMMA_SIZES(X) X(8, 1) X(8, 4) X(12, 1) X(12, 4)
+
+static bool riccati_has_dmma(int n, int m) {
+#define X(N_, M_) \
+    if (n == N_ && m == M_) return true;
+    RICCATI_DMMA_SIZES(X)
 #undef X
     return false;
 }
@@ -139,6 +151,24 @@ static int32_t launch_coop(lqrb_context *h, int n, int m, int N, int64_t batch, 
     return 0;
 }
 
+template <int n, int m>
+static int32_t launch_dmma(lqrb_context *h, int N, int64_t batch, int lti, const double *knots,
+                           const double *term, double *Z, double *gains, int32_t *info,
+                           cudaStream_t s) {
+    constexpr int STAGES = 4, WARPS = 4;
+    const size_t per = (rdmma::riccati_dmma_warp_smem(rdmma::Map<n, m>::F, STAGES) + 15) / 16 * 16;
+    const size_t smem = per * WARPS;
+    auto kern = rdmma::riccati_dmma_kernel<n, m, STAGES, WARPS>;
+    LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((batch + WARPS - 1) / WARPS);
+    kern<<<grid, WARPS * 32, smem, s>>>(knots, term, Z, gains, info, N, lti, batch);
+    char nm[64];
+    snprintf(nm, sizeof nm, "riccati_dmma<%d,%d>%s", n, m, lti ? "[lti]" : "");
+    h->kernel_name = nm;
+    LQRB_LAUNCH_CHECK(h, "riccati_dmma_kernel");
+    return 0;
+}
+
 static int32_t riccati_solve_on(lqrb_context *h, int n, int m, int N, int64_t batch, int flags,
                                 const double *knots, const double *term, double *Z, double *gains,
                                 int32_t *info, cudaStream_t s) {
@@ -149,6 +179,13 @@ static int32_t riccati_solve_on(lqrb_context *h, int n, int m, int N, int64_t ba
 #define X(N_, M_) \
     if (n == N_ && m == M_) return launch_tpi<N_, M_>(h, N, batch, lti, knots, term, Z, gains, info, s);
         RICCATI_TPI_SIZES(X)
+#undef X
+    }
+    // bulk copies need 16-byte aligned records
+    if (h->opt("riccati_variant", 0) != 2 && riccati_has_dmma(n, m) && ((uintptr_t)knots & 15) == 0) {
+#define X(N_, M_) \
+    if (n == N_ && m == M_) return launch_dmma<N_, M_>(h, N, batch, lti, knots, term, Z, gains, info, s);
+        RICCATI_DMMA_SIZES(X)
 #undef X
     }
     return launch_coop(h, n, m, N, batch, lti, knots, term, Z, gains, info, s);

@@ -1,0 +1,450 @@
+// riccati_dmma_kernels.cuh — warp-per-instance Riccati recursion on the FP64 tensor cores.
+//
+// Replaces solve!(sol, ::DPSolver, prob) : src/dynamic_programming.jl:54-72 for the "quadrotor-sized"
+// class (n = 8 or 12 states, m <= 4 controls), where the per-knot work really is dense contractions:
+//   compute_gain! :37-43  PB = P*B, PA = P*A, E = R + B'PB, K = E^-1 B'PA
+//   compute_ctg!  :48-52  P_ = Q + A'PA - (A'PB) K
+// written as one symmetric form:   F = [A B]  (n x w, w = n + m)
+//   T = F' * P^            (w x 16)      P^ = [P p; p' 0] embedded in a 16 x 16 "physical" tile space
+//   M = T * F + blkdiag(Q, R)            (w x w)   = [Qxx Qxu; Qux Quu]
+//   P^_ = Mxx^ - W'W,  W = L^-1 [Mux | gu],  Quu = L L'   (Schur complement of the control block)
+// One warp owns one instance for the whole horizon.  P^ lives in mma.sync m8n8k4 accumulator
+// registers across all knots:
+//   * P^ is symmetric, so its accumulator (C) fragment IS a valid B fragment of the next T = F'P^
+//     (lane (g,q) of tile (rt,ct) holds P^[8rt+g][8ct+2q+e] = P^[k][col] with k = 8ct+2q+e) once the
+//     contraction index is permuted — and the same permutation makes the T accumulators valid A
+//     fragments of M = T*F.  No shared-memory round trip, no shuffles for the two GEMMs.
+//   * the 6 (n=12) F fragments a lane loads are used as A fragments of T and B fragments of M: every
+//     entry of A_k, B_k is read from shared memory exactly once per knot.
+//   * physical positions: tile 0 = x0..x7; tile 1 = [x8 u0 x9 u1 x10 u2 x11 u3].  The control columns
+//     of M land in register e=1 of tile column 1, one control per quad lane, which is what the Schur
+//     MMA (k = 4 = one DMMA per tile) wants.  In P^ space position 9 (u0's slot) carries the affine
+//     column p, so kff / p_ come out of the same MMAs.
+// Knot records (tile width 1 layout: A | B | Q | R | q | r contiguous per knot) are streamed HBM ->
+// shared memory with cp.async.bulk + mbarrier, STAGES-1 knots ahead, by the owning warp itself.
+#pragma once
+#include "smallmat.cuh"
+
+namespace rdmma {
+
+__device__ __forceinline__ void mma884(double &d0, double &d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 1-D TMA bulk copy global -> shared (16-byte aligned addresses and size), completes on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int n, int m>
+struct Map {
+    static_assert(n == 8 || n == 12, "state tile map is written for n = 8, 12");
+    static_assert(m >= 1 && m <= 4, "one control per quad lane");
+    static constexpr int w = n + m;
+    static constexpr int KS = n / 4;  // contraction steps over the state index
+    static constexpr int oQ = n * w, oR = oQ + tri(n), oq = oR + tri(m), orr = oq + n;
+    static constexpr int F = orr + m;      // doubles per knot record
+    static constexpr int TR = tri(n) + 2 * n;
+    static constexpr int GR = m * n + m;
+    static_assert(F % 2 == 0, "bulk copies need 16-byte records");
+    // physical position -> index into z = [x; u] (M space); -1 = unused slot
+    __host__ __device__ static constexpr int zmap(int pos) {
+        if (pos < 8) return pos;
+        const int j = pos - 8;
+        if ((j & 1) == 0) return (8 + j / 2 < n) ? 8 + j / 2 : -1;
+        return ((j - 1) / 2 < m) ? n + (j - 1) / 2 : -1;
+    }
+    // physical position -> state index (P^ space); -1 = unused, -2 = the affine ("1") slot
+    __host__ __device__ static constexpr int xmap(int pos) {
+        if (pos < 8) return pos;
+        if (pos == 9) return -2;
+        const int j = pos - 8;
+        if ((j & 1) == 0) return (8 + j / 2 < n) ? 8 + j / 2 : -1;
+        return -1;
+    }
+    // contraction step s, quad lane q -> state index k (the permutation that lets C fragments be
+    // reused as operands): s = 0: tile-0 even columns, 1: tile-0 odd columns, 2: tile-1 even columns
+    __host__ __device__ static constexpr int kperm(int s, int q) { return s == 0 ? 2 * q : s == 1 ? 2 * q + 1 : 8 + q; }
+};
+
+__host__ __device__ inline size_t riccati_dmma_warp_smem(int F, int stages) {
+    return (size_t)stages * F * 8 + 32 * 8 /* z */ + 64 * 8 /* gains */ + (size_t)stages * 8 /* mbarriers */;
+}
+
+// Cholesky of the m x m control block a (symmetric, full storage a[s][t], s<=t valid) and the explicit
+// inverses the Schur step multiplies with: Linv = L^-1 (lower), Minv = a^-1.  Returns potrf-style info.
+template <int m>
+__device__ __forceinline__ int chol_inv_small(const double (&a)[4][4], double (&Linv)[4][4], double (&Minv)[4][4]) {
+    double Lm[4][4], dinv[4];
+    int info = 0;
+    SM_UNROLL
+    for (int j = 0; j < m; ++j) {
+        double s = a[j][j];
+        SM_UNROLL
+        for (int l = 0; l < j; ++l) s = fma(-Lm[j][l], Lm[j][l], s);
+        if (!(s > 0.0) && info == 0) info = j + 1;
+        const double r = rsqrt(s);
+        dinv[j] = r;
+        Lm[j][j] = s * r;
+        SM_UNROLL
+        for (int i = j + 1; i < m; ++i) {
+            double t = a[j][i];
+            SM_UNROLL
+            for (int l = 0; l < j; ++l) t = fma(-Lm[i][l], Lm[j][l], t);
+            Lm[i][j] = t * r;
+        }
+    }
+    SM_UNROLL
+    for (int j = 0; j < m; ++j) {
+        Linv[j][j] = dinv[j];
+        SM_UNROLL
+        for (int i = j + 1; i < m; ++i) {
+            double t = 0.0;
+            SM_UNROLL
+            for (int l = j; l < i; ++l) t = fma(Lm[i][l], Linv[l][j], t);
+            Linv[i][j] = -t * dinv[i];
+        }
+    }
+    SM_UNROLL
+    for (int s = 0; s < m; ++s)
+        SM_UNROLL
+        for (int t = s; t < m; ++t) {
+            double v = 0.0;
+            SM_UNROLL
+            for (int l = t; l < m; ++l) v = fma(Linv[l][s], Linv[l][t], v);
+            Minv[s][t] = v;
+            Minv[t][s] = v;
+        }
+    return info;
+}
+
+template <int n, int m, int STAGES, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+    riccati_dmma_kernel(const double *__restrict__ knots, const double *__restrict__ term,
+                        double *__restrict__ Z, double *__restrict__ gains, int32_t *__restrict__ info,
+                        int N, int lti, int64_t batch) {
+    using L = Map<n, m>;
+    constexpr int F = L::F, KS = L::KS, w = L::w, GR = L::GR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, q = lane & 3;
+    const int64_t inst = (int64_t)blockIdx.x * WARPS + warp;
+    if (inst >= batch) return;  // whole warp leaves; no CTA-wide barrier is used below
+
+    unsigned char *wbase = smem_raw + (size_t)warp * ((riccati_dmma_warp_smem(F, STAGES) + 15) / 16 * 16);
+    double *buf = reinterpret_cast<double *>(wbase);            // STAGES records
+    double *zs = buf + (size_t)STAGES * F;                      // 2 x 16 doubles: [x; u] double buffer
+    double *gs = zs + 32;                                       // staged gains of one knot
+    uint64_t *full = reinterpret_cast<uint64_t *>(gs + 64);     // STAGES mbarriers
+
+    if (lane == 0) {
+        SM_UNROLL
+        for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+
+    const int Kn = lti ? 1 : N - 1;
+    const double *rec_g = knots + inst * (int64_t)Kn * F;
+    const double *tb = term + inst * L::TR;
+    double *zb = Z + inst * ((int64_t)N * n + (int64_t)(N - 1) * m);
+    double *gb = gains + inst * (int64_t)(N - 1) * GR;
+    const int steps = N - 1;
+
+    // ---------------- per-lane constant index tables
+    // F fragment column of tile mt: z index of physical position 8*mt + g
+    const int zc0 = g;
+    const int zc1 = (g & 1) ? (((g - 1) / 2 < m) ? n + (g - 1) / 2 : -1) : ((8 + g / 2 < n) ? 8 + g / 2 : -1);
+    const int fo0 = 2 * q + n * zc0;                 // doubles; s = 0,1 pair; s = 2 at 8 + q + n*zc
+    const int fo1 = zc1 >= 0 ? 2 * q + n * zc1 : -1;
+    // cost-Hessian entry added to M accumulator (mt, nt, e): blkdiag(Q, R) in physical positions
+    int hoff[2][2][2];
+    SM_UNROLL
+    for (int mt = 0; mt < 2; ++mt)
+        SM_UNROLL
+        for (int nt = 0; nt < 2; ++nt)
+            SM_UNROLL
+            for (int e = 0; e < 2; ++e) {
+                const int zr = mt == 0 ? zc0 : zc1;
+                const int pc = 8 * nt + 2 * q + e;
+                int zc;
+                if (pc < 8) zc = pc;
+                else {
+                    const int j = pc - 8;
+                    zc = (j & 1) ? (((j - 1) / 2 < m) ? n + (j - 1) / 2 : -1) : ((8 + j / 2 < n) ? 8 + j / 2 : -1);
+                }
+                int o = -1;
+                if (zr >= 0 && zc >= 0) {
+                    if (zr < n && zc < n) o = L::oQ + (zr <= zc ? zc * (zc + 1) / 2 + zr : zr * (zr + 1) / 2 + zc);
+                    else if (zr >= n && zc >= n) {
+                        const int a = zr - n, b = zc - n;
+                        o = L::oR + (a <= b ? b * (b + 1) / 2 + a : a * (a + 1) / 2 + b);
+                    }
+                }
+                hoff[mt][nt][e] = o;
+            }
+    // gradient entry of row position 8*mt + g: q (states) | r (controls)
+    const int qo0 = L::oq + zc0;
+    const int qo1 = zc1 >= 0 ? (zc1 < n ? L::oq + zc1 : L::orr + (zc1 - n)) : -1;
+    // gain store addresses of this lane: K0 -> K[q, x_g]; K1 -> K[q, x_{8+g/2}] (g even) or kff[q] (g == 1)
+    const int go0 = q < m ? q + m * g : -1;
+    const int go1 = q < m ? ((g & 1) ? (g == 1 ? m * n + q : -1) : ((8 + g / 2 < n) ? q + m * (8 + g / 2) : -1)) : -1;
+
+    // selection fragments of the transposing MMAs (scaled by 1/2 for the symmetrisation)
+    const double hsel0 = g == 2 * q ? 0.5 : 0.0, hsel1 = g == 2 * q + 1 ? 0.5 : 0.0;
+
+    // ---------------- terminal cost-to-go  P^ = [Qf qf; qf' 0] in physical positions
+    double P[2][2][2];
+    SM_UNROLL
+    for (int rt = 0; rt < 2; ++rt)
+        SM_UNROLL
+        for (int ct = 0; ct < 2; ++ct)
+            SM_UNROLL
+            for (int e = 0; e < 2; ++e) {
+                const int pr = 8 * rt + g, pc = 8 * ct + 2 * q + e;
+                const int xr = pr < 8 ? pr : (pr == 9 ? -2 : (((pr - 8) & 1) == 0 && 8 + (pr - 8) / 2 < n ? 8 + (pr - 8) / 2 : -1));
+                const int xc = pc < 8 ? pc : (pc == 9 ? -2 : (((pc - 8) & 1) == 0 && 8 + (pc - 8) / 2 < n ? 8 + (pc - 8) / 2 : -1));
+                double v = 0.0;
+                if (xr >= 0 && xc >= 0) v = tb[xr <= xc ? xc * (xc + 1) / 2 + xr : xr * (xr + 1) / 2 + xc];
+                else if (xr >= 0 && xc == -2) v = tb[tri(n) + xr];
+                else if (xr == -2 && xc >= 0) v = tb[tri(n) + xc];
+                P[rt][ct][e] = v;
+            }
+
+    auto issue_bwd = [&](int it) {
+        const int st = it % STAGES;
+        const int k = steps - 1 - it;
+        mbar_expect_tx(full + st, F * 8);
+        bulk_g2s(buf + (size_t)st * F, rec_g + (int64_t)(lti ? 0 : k) * F, F * 8, full + st);
+    };
+    if (lane == 0) {
+        for (int it = 0; it < STAGES - 1 && it < steps; ++it) issue_bwd(it);
+    }
+
+    int st_all = 0;
+    // ---------------- backward pass: k = N-2 .. 0   (src/dynamic_programming.jl:61-64)
+    for (int it = 0; it < steps; ++it) {
+        const int k = steps - 1 - it;
+        const int st = it % STAGES;
+        if (lane == 0 && it + STAGES - 1 < steps) issue_bwd(it + STAGES - 1);
+        mbar_wait(full + st, (it / STAGES) & 1);
+        const double *rec = buf + (size_t)st * F;
+
+        // F fragments: fr[mt][s] = F[kperm(s,q)][z(8mt+g)]  (A fragment of T and B fragment of M)
+        double fr[2][3];
+        {
+            const double2 v = *reinterpret_cast<const double2 *>(rec + fo0);
+            fr[0][0] = v.x;
+            fr[0][1] = v.y;
+            fr[0][2] = KS == 3 ? rec[fo0 - 2 * q + 8 + q] : 0.0;
+            if (fo1 >= 0) {
+                const double2 u = *reinterpret_cast<const double2 *>(rec + fo1);
+                fr[1][0] = u.x;
+                fr[1][1] = u.y;
+                fr[1][2] = KS == 3 ? rec[fo1 - 2 * q + 8 + q] : 0.0;
+            } else {
+                fr[1][0] = fr[1][1] = fr[1][2] = 0.0;
+            }
+        }
+        // M accumulators start at blkdiag(Q, R); gradient entries of this lane's rows
+        double M[2][2][2];
+        SM_UNROLL
+        for (int mt = 0; mt < 2; ++mt)
+            SM_UNROLL
+            for (int nt = 0; nt < 2; ++nt)
+                SM_UNROLL
+                for (int e = 0; e < 2; ++e) M[mt][nt][e] = hoff[mt][nt][e] >= 0 ? rec[hoff[mt][nt][e]] : 0.0;
+        const double qr0 = rec[qo0];
+        const double qr1 = qo1 >= 0 ? rec[qo1] : 0.0;
+
+        // T = F' P^   (compute_gain! :38,40 — PB and PA at once, plus F'p in position 9)
+        double T[2][2][2] = {};
+        SM_UNROLL
+        for (int s = 0; s < KS; ++s)
+            SM_UNROLL
+            for (int mt = 0; mt < 2; ++mt)
+                SM_UNROLL
+                for (int nt = 0; nt < 2; ++nt) {
+                    const double pb = s == 0 ? P[nt][0][0] : s == 1 ? P[nt][0][1] : P[nt][1][0];
+                    mma884(T[mt][nt][0], T[mt][nt][1], fr[mt][s], pb);
+                }
+        // M += T F   (E = R + B'PB :39, K = B'PA :41, A'PA :50).  Tile (1,0) is never formed: the new
+        // P^(1,0) is the exact transpose of P^(0,1), see below.
+        SM_UNROLL
+        for (int s = 0; s < KS; ++s)
+            SM_UNROLL
+            for (int mt = 0; mt < 2; ++mt)
+                SM_UNROLL
+                for (int nt = mt; nt < 2; ++nt) {
+                    const double ta = s == 0 ? T[mt][0][0] : s == 1 ? T[mt][0][1] : T[mt][1][0];
+                    mma884(M[mt][nt][0], M[mt][nt][1], ta, fr[nt][s]);
+                }
+        // g^ = [q; r] + F'p : column 9 of T, held by quad lane 0
+        const double gh0 = T[0][1][1] + qr0;
+        const double gh1 = T[1][1][1] + qr1;
+
+        // ---- gather the control block Quu, gu and this row's Qxu entries
+        double a[4][4], gu[4], mx0[4], v1[4];
+        SM_UNROLL
+        for (int s = 0; s < m; ++s)
+            SM_UNROLL
+            for (int t = s; t < m; ++t) a[s][t] = __shfl_sync(0xffffffffu, M[1][1][1], 4 * (2 * s + 1) + t);
+        SM_UNROLL
+        for (int t = 0; t < m; ++t) gu[t] = __shfl_sync(0xffffffffu, gh1, 4 * (2 * t + 1));
+        SM_UNROLL
+        for (int t = 0; t < m; ++t) {
+            mx0[t] = __shfl_sync(0xffffffffu, M[0][1][1], (lane & ~3) + t);
+            const double x1 = __shfl_sync(0xffffffffu, M[1][1][1], (lane & ~3) + t);
+            v1[t] = (g & 1) ? (g == 1 ? gu[t] : 0.0) : x1;
+        }
+        double Linv[4][4], Minv[4][4];
+        const int ci = chol_inv_small<m>(a, Linv, Minv);  // chol_solve! :28-31
+        if (ci != 0 && st_all == 0) st_all = (k + 1) * 1000 + ci;
+        // rows q of L^-1 and Quu^-1
+        double W0 = 0.0, W1 = 0.0, K0 = 0.0, K1 = 0.0;
+        SM_UNROLL
+        for (int t = 0; t < m; ++t) {
+            double lq = 0.0, mq = 0.0;
+            SM_UNROLL
+            for (int s = 0; s < m; ++s) {
+                if (s >= t) lq = (q == s) ? Linv[s][t] : lq;
+                mq = (q == s) ? Minv[s][t] : mq;
+            }
+            W0 = fma(lq, mx0[t], W0);
+            W1 = fma(lq, v1[t], W1);
+            K0 = fma(mq, mx0[t], K0);
+            K1 = fma(mq, v1[t], K1);
+        }
+        double *gk = gb + (int64_t)k * GR;
+        if (go0 >= 0) gk[go0] = K0;
+        if (go1 >= 0) gk[go1] = K1;
+
+        // ---- P^_ = Mxx^ - W'W  (compute_ctg! :50-51 and the affine column in the same MMAs)
+        const double t10 = __shfl_sync(0xffffffffu, gh1, 4 * (2 * q));
+        const bool odd = g & 1;
+        double S00[2] = {M[0][0][0], M[0][0][1]};
+        double S01[2] = {M[0][1][0], q == 0 ? gh0 : 0.0};
+        double S11[2] = {odd ? (g == 1 ? t10 : 0.0) : M[1][1][0], (!odd && q == 0) ? gh1 : 0.0};
+        const double nW0 = -W0, nW1 = -W1;
+        mma884(S00[0], S00[1], nW0, W0);
+        mma884(S01[0], S01[1], nW0, W1);
+        mma884(S11[0], S11[1], nW1, W1);
+        // Exact symmetrisation.  F'P^F amplifies any antisymmetric rounding residue of P^ by the OPEN-loop
+        // dynamics (|A|^2 per knot: 1e-16 -> 5e-8 over 1000 knots of an unstable LTI system), so P^ is kept
+        // bitwise symmetric: tile^T = sum_e Sel_e * B(tile, e) with Sel_e[r][k] = (r == 2k+e) — the C
+        // fragment read as a B fragment is the transpose — 2 DMMAs per tile, all products exact.
+        P[0][0][0] = 0.5 * S00[0];
+        P[0][0][1] = 0.5 * S00[1];
+        mma884(P[0][0][0], P[0][0][1], hsel0, S00[0]);
+        mma884(P[0][0][0], P[0][0][1], hsel1, S00[1]);
+        P[1][1][0] = 0.5 * S11[0];
+        P[1][1][1] = 0.5 * S11[1];
+        mma884(P[1][1][0], P[1][1][1], hsel0, S11[0]);
+        mma884(P[1][1][0], P[1][1][1], hsel1, S11[1]);
+        P[0][1][0] = S01[0];
+        P[0][1][1] = S01[1];
+        P[1][0][0] = 0.0;
+        P[1][0][1] = 0.0;
+        mma884(P[1][0][0], P[1][0][1], hsel0 + hsel0, S01[0]);
+        mma884(P[1][0][0], P[1][0][1], hsel1 + hsel1, S01[1]);
+        __syncwarp();  // every lane is done with this stage before it is refilled
+    }
+    if (info && lane == 0) info[inst] = st_all;
+    __syncwarp();
+
+    // ---------------- forward rollout   (src/dynamic_programming.jl:66-70)
+    const int AB = n * w;  // doubles of [A B] at the head of a record
+    auto issue_fwd = [&](int it) {
+        const int st = (steps + it) % STAGES;
+        mbar_expect_tx(full + st, AB * 8);
+        bulk_g2s(buf + (size_t)st * F, rec_g + (int64_t)(lti ? 0 : it) * F, AB * 8, full + st);
+    };
+    if (lane == 0) {
+        for (int it = 0; it < STAGES - 1 && it < steps; ++it) issue_fwd(it);
+    }
+    // gains of the next two knots ride in registers (written by this warp; plain loads)
+    double ga[2][2];
+    SM_UNROLL
+    for (int d = 0; d < 2; ++d) {
+        const double *gk = gb + (int64_t)d * GR;
+        ga[d][0] = (d < steps && lane < GR) ? gk[lane] : 0.0;
+        ga[d][1] = (d < steps && lane + 32 < GR) ? gk[lane + 32] : 0.0;
+    }
+    if (lane < n) zs[lane] = tb[tri(n) + n + lane];
+    __syncwarp();
+    const int row = lane & 15, half = lane >> 4;
+    for (int it = 0; it < steps; ++it) {
+        const int git = steps + it;  // position in the stage ring continues from the backward pass
+        const int st = git % STAGES;
+        double *zc = zs + (it & 1) * 16, *zn = zs + ((it + 1) & 1) * 16;
+        if (lane == 0 && it + STAGES - 1 < steps) issue_fwd(it + STAGES - 1);
+        // stage this knot's gains, prefetch knot it+2
+        gs[lane] = ga[0][0];
+        if (lane + 32 < 64) gs[lane + 32] = ga[0][1];
+        ga[0][0] = ga[1][0];
+        ga[0][1] = ga[1][1];
+        {
+            const double *gk = gb + (int64_t)(it + 2) * GR;
+            ga[1][0] = (it + 2 < steps && lane < GR) ? gk[lane] : 0.0;
+            ga[1][1] = (it + 2 < steps && lane + 32 < GR) ? gk[lane + 32] : 0.0;
+        }
+        __syncwarp();
+        double *zk = zb + (int64_t)it * w;
+        if (lane < n) __stcs(zk + lane, zc[lane]);
+        if (lane < m) {  // u = -K x - kff
+            double acc0 = -gs[m * n + lane], acc1 = 0.0;
+            SM_UNROLL
+            for (int c = 0; c < n; c += 2) {
+                acc0 = fma(-gs[lane + m * c], zc[c], acc0);
+                acc1 = fma(-gs[lane + m * (c + 1)], zc[c + 1], acc1);
+            }
+            const double u = acc0 + acc1;
+            zc[n + lane] = u;
+            __stcs(zk + n + lane, u);
+        }
+        mbar_wait(full + st, (git / STAGES) & 1);
+        __syncwarp();
+        const double *rec = buf + (size_t)st * F;
+        // x+ = A x + B u : lane (row, half) sums 8 of the 16 columns
+        double acc0 = 0.0, acc1 = 0.0;
+        if (row < n) {
+            SM_UNROLL
+            for (int j = 0; j < 8; j += 2) {
+                const int c = 8 * half + j;
+                if (c < w) acc0 = fma(rec[row + n * c], zc[c], acc0);
+                if (c + 1 < w) acc1 = fma(rec[row + n * (c + 1)], zc[c + 1], acc1);
+            }
+        }
+        double xs = acc0 + acc1;
+        xs += __shfl_xor_sync(0xffffffffu, xs, 16);
+        if (lane < n) zn[lane] = xs;
+        __syncwarp();
+    }
+    if (lane < n) __stcs(zb + (int64_t)steps * w + lane, zs[(steps & 1) * 16 + lane]);
+}
+
+}  // namespace rdmma

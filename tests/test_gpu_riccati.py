@@ -53,11 +53,43 @@ def test_tpi_sizes(handle, oracle_mod, n, m, N, lti):
     assert handle.last_kernel.startswith("riccati_tpi")
 
 
-@pytest.mark.parametrize("n,m,N,batch", [(5, 2, 20, 9), (12, 4, 101, 10), (7, 7, 15, 5), (32, 8, 12, 3), (64, 16, 11, 2)])
+@pytest.mark.parametrize("n,m,N,batch", [(5, 2, 20, 9), (12, 3, 101, 10), (7, 7, 15, 5), (32, 8, 12, 3), (64, 16, 11, 2)])
 def test_cooperative_sizes(handle, oracle_mod, n, m, N, batch):
     prob = problems.random_lqr_riccati(n, m, N, batch, seed=n)
     _check(prob, handle, oracle_mod)
     assert handle.last_kernel.startswith("riccati_coop")
+
+
+@pytest.mark.parametrize("n,m,N,batch", [(12, 4, 101, 10), (12, 4, 2, 3), (12, 4, 7, 133), (8, 4, 60, 9), (12, 1, 40, 5),
+                                         (8, 1, 33, 6), (12, 4, 1001, 4)])
+@pytest.mark.parametrize("lti", [False, True])
+def test_dmma_sizes(handle, oracle_mod, n, m, N, batch, lti):
+    """warp-per-instance FP64 tensor-core kernel (config 5a shape and its siblings)."""
+    prob = problems.random_lqr_riccati(n, m, N, batch, seed=n + m, lti=lti)
+    _check(prob, handle, oracle_mod)
+    assert handle.last_kernel.startswith("riccati_dmma")
+
+
+def test_dmma_matches_cooperative_kernel(handle):
+    """Two independent CUDA implementations of the same recursion agree to rounding."""
+    prob = problems.random_lqr_riccati(12, 4, 301, 40, seed=77)
+    X1, U1, K1, k1, i1 = ops.riccati_solve_problem(prob, handle=handle)
+    assert handle.last_kernel.startswith("riccati_dmma")
+    handle.set_option("riccati_variant", 2)
+    try:
+        X2, U2, K2, k2, i2 = ops.riccati_solve_problem(prob, handle=handle)
+        assert handle.last_kernel.startswith("riccati_coop")
+    finally:
+        handle.set_option("riccati_variant", 0)
+    assert (i1 == 0).all() and (i2 == 0).all()
+    assert _rel(X1, X2) <= 1e-11 and _rel(U1, U2) <= 1e-11 and _rel(K1, K2) <= 1e-11 and _rel(k1, k2) <= 1e-11
+
+
+def test_dmma_info_reports_nonpositive_pivot(handle):
+    prob = problems.random_lqr_riccati(12, 4, 50, 9, seed=1)
+    prob["R"][3] = -1e6 * np.eye(4)
+    _, _, _, _, info = ops.riccati_solve_problem(prob, handle=handle)
+    assert info[3] != 0 and (np.delete(info, 3) == 0).all()
 
 
 def test_no_affine_terms_reference_form(handle, oracle_mod):
