@@ -95,51 +95,83 @@ __host__ __device__ inline size_t riccati_dmma_warp_smem(int F, int stages) {
     return (size_t)stages * F * 8 + 32 * 8 /* z */ + 64 * 8 /* gains */ + (size_t)stages * 8 /* mbarriers */;
 }
 
-// Cholesky of the m x m control block a (symmetric, full storage a[s][t], s<=t valid) and the explicit
-// inverses the Schur step multiplies with: Linv = L^-1 (lower), Minv = a^-1.  Returns potrf-style info.
+// 1/x from the hardware seed and two Newton steps (inputs here are O(1) pivots; no special cases)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+
+// Inverse of the SPD m x m control block a (full storage, upper triangle read) by 2 x 2 block
+// elimination: two dependent reciprocals instead of four dependent rsqrt.  The potrf-style info is
+// the index of the first non-positive Cholesky pivot (pivots: a00, detA/a00, s00, detS/s00).
 template <int m>
-__device__ __forceinline__ int chol_inv_small(const double (&a)[4][4], double (&Linv)[4][4], double (&Minv)[4][4]) {
-    double Lm[4][4], dinv[4];
+__device__ __forceinline__ int spd_inv_small(const double (&a)[4][4], double (&Mi)[4][4]) {
     int info = 0;
-    SM_UNROLL
-    for (int j = 0; j < m; ++j) {
-        double s = a[j][j];
-        SM_UNROLL
-        for (int l = 0; l < j; ++l) s = fma(-Lm[j][l], Lm[j][l], s);
-        if (!(s > 0.0) && info == 0) info = j + 1;
-        const double r = rsqrt(s);
-        dinv[j] = r;
-        Lm[j][j] = s * r;
-        SM_UNROLL
-        for (int i = j + 1; i < m; ++i) {
-            double t = a[j][i];
+    if constexpr (m == 1) {
+        if (!(a[0][0] > 0.0)) info = 1;
+        Mi[0][0] = fast_rcp(a[0][0]);
+        return info;
+    } else {
+        const double detA = fma(a[0][0], a[1][1], -a[0][1] * a[0][1]);
+        if (!(a[0][0] > 0.0)) info = 1;
+        else if (!(detA > 0.0)) info = 2;
+        const double rA = fast_rcp(detA);
+        const double i00 = a[1][1] * rA, i01 = -a[0][1] * rA, i11 = a[0][0] * rA;
+        if constexpr (m == 2) {
+            Mi[0][0] = i00; Mi[0][1] = Mi[1][0] = i01; Mi[1][1] = i11;
+            return info;
+        } else {
+            constexpr int r = m - 2;  // trailing block size: 1 or 2
+            double X[2][2], S[2][2];  // X = A^-1 B, S = D - B'X
             SM_UNROLL
-            for (int l = 0; l < j; ++l) t = fma(-Lm[i][l], Lm[j][l], t);
-            Lm[i][j] = t * r;
+            for (int j = 0; j < r; ++j) {
+                X[0][j] = fma(i00, a[0][2 + j], i01 * a[1][2 + j]);
+                X[1][j] = fma(i01, a[0][2 + j], i11 * a[1][2 + j]);
+            }
+            SM_UNROLL
+            for (int i = 0; i < r; ++i)
+                SM_UNROLL
+                for (int j = i; j < r; ++j)
+                    S[i][j] = a[2 + i][2 + j] - fma(a[0][2 + i], X[0][j], a[1][2 + i] * X[1][j]);
+            double s00, s01 = 0.0, s11 = 0.0;
+            if constexpr (r == 1) {
+                if (info == 0 && !(S[0][0] > 0.0)) info = 3;
+                s00 = fast_rcp(S[0][0]);
+            } else {
+                const double detS = fma(S[0][0], S[1][1], -S[0][1] * S[0][1]);
+                if (info == 0 && !(S[0][0] > 0.0)) info = 3;
+                else if (info == 0 && !(detS > 0.0)) info = 4;
+                const double rS = fast_rcp(detS);
+                s00 = S[1][1] * rS; s01 = -S[0][1] * rS; s11 = S[0][0] * rS;
+            }
+            // Minv12 = -X S^-1 ; Minv11 = A^-1 - Minv12 X'
+            double Y[2][2];
+            SM_UNROLL
+            for (int i = 0; i < 2; ++i) {
+                Y[i][0] = -fma(X[i][0], s00, r == 2 ? X[i][1] * s01 : 0.0);
+                if (r == 2) Y[i][1] = -fma(X[i][0], s01, X[i][1] * s11);
+            }
+            double m00 = i00, m01 = i01, m11 = i11;
+            SM_UNROLL
+            for (int j = 0; j < r; ++j) {
+                m00 = fma(-Y[0][j], X[0][j], m00);
+                m01 = fma(-Y[0][j], X[1][j], m01);
+                m11 = fma(-Y[1][j], X[1][j], m11);
+            }
+            Mi[0][0] = m00; Mi[0][1] = Mi[1][0] = m01; Mi[1][1] = m11;
+            SM_UNROLL
+            for (int i = 0; i < 2; ++i)
+                SM_UNROLL
+                for (int j = 0; j < r; ++j) Mi[i][2 + j] = Mi[2 + j][i] = Y[i][j];
+            Mi[2][2] = s00;
+            if (r == 2) { Mi[2][3] = Mi[3][2] = s01; Mi[3][3] = s11; }
+            return info;
         }
     }
-    SM_UNROLL
-    for (int j = 0; j < m; ++j) {
-        Linv[j][j] = dinv[j];
-        SM_UNROLL
-        for (int i = j + 1; i < m; ++i) {
-            double t = 0.0;
-            SM_UNROLL
-            for (int l = j; l < i; ++l) t = fma(Lm[i][l], Linv[l][j], t);
-            Linv[i][j] = -t * dinv[i];
-        }
-    }
-    SM_UNROLL
-    for (int s = 0; s < m; ++s)
-        SM_UNROLL
-        for (int t = s; t < m; ++t) {
-            double v = 0.0;
-            SM_UNROLL
-            for (int l = t; l < m; ++l) v = fma(Linv[l][s], Linv[l][t], v);
-            Minv[s][t] = v;
-            Minv[t][s] = v;
-        }
-    return info;
 }
 
 template <int n, int m, int STAGES, int WARPS>
@@ -160,6 +192,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     double *zs = buf + (size_t)STAGES * F;                      // 2 x 16 doubles: [x; u] double buffer
     double *gs = zs + 32;                                       // staged gains of one knot
     uint64_t *full = reinterpret_cast<uint64_t *>(gs + 64);     // STAGES mbarriers
+    double *sc = zs;  // backward pass: 72 doubles of control-block staging (zs and gs are forward-only)
 
     if (lane == 0) {
         SM_UNROLL
@@ -307,52 +340,60 @@ __global__ void __launch_bounds__(WARPS * 32)
         const double gh0 = T[0][1][1] + qr0;
         const double gh1 = T[1][1][1] + qr1;
 
-        // ---- gather the control block Quu, gu and this row's Qxu entries
-        double a[4][4], gu[4], mx0[4], v1[4];
+        // ---- stage the control columns in shared memory: every lane then reads the whole control block
+        // Quu, gu and the four Qxu entries of its own rows with broadcast 16-byte loads (no shuffles)
+        sc[lane] = M[0][1][1];       // Mxu[pos g][u_q], rows x0..x7
+        sc[32 + lane] = M[1][1][1];  // rows of tile 1 (odd g: the rows of Quu)
+        if (q == 0) sc[64 + (g & 1) * 4 + (g >> 1)] = gh1;  // [64..67]: g^ of x8..x11, [68..71]: gu
+        __syncwarp();
+        double a[4][4], gu[4], v0[4], v1[4];
         SM_UNROLL
-        for (int s = 0; s < m; ++s)
-            SM_UNROLL
-            for (int t = s; t < m; ++t) a[s][t] = __shfl_sync(0xffffffffu, M[1][1][1], 4 * (2 * s + 1) + t);
-        SM_UNROLL
-        for (int t = 0; t < m; ++t) gu[t] = __shfl_sync(0xffffffffu, gh1, 4 * (2 * t + 1));
-        SM_UNROLL
-        for (int t = 0; t < m; ++t) {
-            mx0[t] = __shfl_sync(0xffffffffu, M[0][1][1], (lane & ~3) + t);
-            const double x1 = __shfl_sync(0xffffffffu, M[1][1][1], (lane & ~3) + t);
-            v1[t] = (g & 1) ? (g == 1 ? gu[t] : 0.0) : x1;
+        for (int s = 0; s < m; ++s) {
+            const double2 lo = *reinterpret_cast<const double2 *>(sc + 32 + 4 * (2 * s + 1));
+            const double2 hi = *reinterpret_cast<const double2 *>(sc + 32 + 4 * (2 * s + 1) + 2);
+            a[s][0] = lo.x; a[s][1] = lo.y; a[s][2] = hi.x; a[s][3] = hi.y;
         }
-        double Linv[4][4], Minv[4][4];
-        const int ci = chol_inv_small<m>(a, Linv, Minv);  // chol_solve! :28-31
+        {
+            const double2 lo = *reinterpret_cast<const double2 *>(sc + 68);
+            const double2 hi = *reinterpret_cast<const double2 *>(sc + 70);
+            gu[0] = lo.x; gu[1] = lo.y; gu[2] = hi.x; gu[3] = hi.y;
+            const double2 l0 = *reinterpret_cast<const double2 *>(sc + 4 * g);
+            const double2 h0 = *reinterpret_cast<const double2 *>(sc + 4 * g + 2);
+            v0[0] = l0.x; v0[1] = l0.y; v0[2] = h0.x; v0[3] = h0.y;
+            const double2 l1 = *reinterpret_cast<const double2 *>(sc + 32 + 4 * g);
+            const double2 h1 = *reinterpret_cast<const double2 *>(sc + 32 + 4 * g + 2);
+            v1[0] = l1.x; v1[1] = l1.y; v1[2] = h1.x; v1[3] = h1.y;
+        }
+        const double t10 = sc[64 + q];
+        const bool odd = g & 1;
+        SM_UNROLL
+        for (int t = 0; t < 4; ++t) v1[t] = odd ? (g == 1 ? gu[t] : 0.0) : v1[t];
+        double Minv[4][4];
+        const int ci = spd_inv_small<m>(a, Minv);  // chol_solve! :28-31 (E^-1 applied by multiplication)
         if (ci != 0 && st_all == 0) st_all = (k + 1) * 1000 + ci;
-        // rows q of L^-1 and Quu^-1
-        double W0 = 0.0, W1 = 0.0, K0 = 0.0, K1 = 0.0;
+        // K[q][pos] = row q of Quu^-1 times [Qux | gu]   (K = E^-1 B'PA :41-43, kff in position 9)
+        double K0 = 0.0, K1 = 0.0;
         SM_UNROLL
         for (int t = 0; t < m; ++t) {
-            double lq = 0.0, mq = 0.0;
+            double mq = 0.0;
             SM_UNROLL
-            for (int s = 0; s < m; ++s) {
-                if (s >= t) lq = (q == s) ? Linv[s][t] : lq;
-                mq = (q == s) ? Minv[s][t] : mq;
-            }
-            W0 = fma(lq, mx0[t], W0);
-            W1 = fma(lq, v1[t], W1);
-            K0 = fma(mq, mx0[t], K0);
+            for (int s = 0; s < m; ++s) mq = (q == s) ? Minv[s][t] : mq;
+            K0 = fma(mq, v0[t], K0);
             K1 = fma(mq, v1[t], K1);
         }
         double *gk = gb + (int64_t)k * GR;
         if (go0 >= 0) gk[go0] = K0;
         if (go1 >= 0) gk[go1] = K1;
 
-        // ---- P^_ = Mxx^ - W'W  (compute_ctg! :50-51 and the affine column in the same MMAs)
-        const double t10 = __shfl_sync(0xffffffffu, gh1, 4 * (2 * q));
-        const bool odd = g & 1;
+        // ---- P^_ = Mxx^ - [Qxu | gu]' K  (compute_ctg! :50-51 and the affine column in the same MMAs)
         double S00[2] = {M[0][0][0], M[0][0][1]};
         double S01[2] = {M[0][1][0], q == 0 ? gh0 : 0.0};
         double S11[2] = {odd ? (g == 1 ? t10 : 0.0) : M[1][1][0], (!odd && q == 0) ? gh1 : 0.0};
-        const double nW0 = -W0, nW1 = -W1;
-        mma884(S00[0], S00[1], nW0, W0);
-        mma884(S01[0], S01[1], nW0, W1);
-        mma884(S11[0], S11[1], nW1, W1);
+        const double nV0 = -M[0][1][1];
+        const double nV1 = odd ? (g == 1 ? -(q == 0 ? gu[0] : q == 1 ? gu[1] : q == 2 ? gu[2] : gu[3]) : 0.0) : -M[1][1][1];
+        mma884(S00[0], S00[1], nV0, K0);
+        mma884(S01[0], S01[1], nV0, K1);
+        mma884(S11[0], S11[1], nV1, K1);
         // Exact symmetrisation.  F'P^F amplifies any antisymmetric rounding residue of P^ by the OPEN-loop
         // dynamics (|A|^2 per knot: 1e-16 -> 5e-8 over 1000 knots of an unstable LTI system), so P^ is kept
         // bitwise symmetric: tile^T = sum_e Sel_e * B(tile, e) with Sel_e[r][k] = (r == 2k+e) — the C
