@@ -155,10 +155,10 @@ template <int n, int m>
 static int32_t launch_dmma(lqrb_context *h, int N, int64_t batch, int lti, const double *knots,
                            const double *term, double *Z, double *gains, int32_t *info,
                            cudaStream_t s) {
-    constexpr int STAGES = 4, WARPS = 4;
-    const size_t per = (rdmma::riccati_dmma_warp_smem(rdmma::Map<n, m>::F, STAGES) + 15) / 16 * 16;
-    const size_t smem = per * WARPS;
-    auto kern = rdmma::riccati_dmma_kernel<n, m, STAGES, WARPS>;
+    // 3 stages x 4 warps: 34 KB per CTA -> 6 CTAs = 24 warps per SM (<= 85 registers per thread)
+    constexpr int STAGES = 3, WARPS = 4, MINB = 6;
+    const size_t smem = rdmma::riccati_dmma_warp_smem(rdmma::Map<n, m>::F, STAGES) * WARPS;
+    auto kern = rdmma::riccati_dmma_kernel<n, m, STAGES, WARPS, MINB>;
     LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)((batch + WARPS - 1) / WARPS);
     kern<<<grid, WARPS * 32, smem, s>>>(knots, term, Z, gains, info, N, lti, batch);

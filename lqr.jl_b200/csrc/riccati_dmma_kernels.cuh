@@ -91,8 +91,11 @@ struct Map {
     __host__ __device__ static constexpr int kperm(int s, int q) { return s == 0 ? 2 * q : s == 1 ? 2 * q + 1 : 8 + q; }
 };
 
+// per-warp shared memory: STAGES knot records | 184 doubles of staging (backward: control block with
+// duplicated rows/columns; forward: [x;u] double buffer + one knot of gains) | STAGES mbarriers
+#define RDMMA_AUX 184
 __host__ __device__ inline size_t riccati_dmma_warp_smem(int F, int stages) {
-    return (size_t)stages * F * 8 + 32 * 8 /* z */ + 64 * 8 /* gains */ + (size_t)stages * 8 /* mbarriers */;
+    return ((size_t)stages * F * 8 + RDMMA_AUX * 8 + (size_t)stages * 8 + 15) / 16 * 16;
 }
 
 // 1/x from the hardware seed and two Newton steps (inputs here are O(1) pivots; no special cases)
@@ -108,6 +111,64 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // Inverse of the SPD m x m control block a (full storage, upper triangle read) by 2 x 2 block
 // elimination: two dependent reciprocals instead of four dependent rsqrt.  The potrf-style info is
 // the index of the first non-positive Cholesky pivot (pivots: a00, detA/a00, s00, detS/s00).
+// Row 0 of the inverse of the SPD m x m block a (upper triangle read), same 2 x 2 block elimination.
+// Each quad lane q calls this on the block cyclically permuted by q, so "row 0" is its own row q and
+// nothing has to be selected afterwards.  info as above (meaningful for the unpermuted lane q = 0).
+template <int m>
+__device__ __forceinline__ int spd_inv_row0(const double (&a)[4][4], double (&mi)[4]) {
+    int info = 0;
+    if constexpr (m == 1) {
+        if (!(a[0][0] > 0.0)) info = 1;
+        mi[0] = fast_rcp(a[0][0]);
+    } else {
+        const double detA = fma(a[0][0], a[1][1], -a[0][1] * a[0][1]);
+        if (!(a[0][0] > 0.0)) info = 1;
+        else if (!(detA > 0.0)) info = 2;
+        const double rA = fast_rcp(detA);
+        const double i00 = a[1][1] * rA, i01 = -a[0][1] * rA, i11 = a[0][0] * rA;
+        if constexpr (m == 2) {
+            mi[0] = i00;
+            mi[1] = i01;
+        } else {
+            constexpr int r = m - 2;
+            double X[2][2], S[2][2];
+            SM_UNROLL
+            for (int j = 0; j < r; ++j) {
+                X[0][j] = fma(i00, a[0][2 + j], i01 * a[1][2 + j]);
+                X[1][j] = fma(i01, a[0][2 + j], i11 * a[1][2 + j]);
+            }
+            SM_UNROLL
+            for (int i = 0; i < r; ++i)
+                SM_UNROLL
+                for (int j = i; j < r; ++j)
+                    S[i][j] = a[2 + i][2 + j] - fma(a[0][2 + i], X[0][j], a[1][2 + i] * X[1][j]);
+            double y0, y1 = 0.0;
+            if constexpr (r == 1) {
+                if (info == 0 && !(S[0][0] > 0.0)) info = 3;
+                y0 = -X[0][0] * fast_rcp(S[0][0]);
+            } else {
+                const double detS = fma(S[0][0], S[1][1], -S[0][1] * S[0][1]);
+                if (info == 0 && !(S[0][0] > 0.0)) info = 3;
+                else if (info == 0 && !(detS > 0.0)) info = 4;
+                const double rS = fast_rcp(detS);
+                // -X[0][:] * S^-1,  S^-1 = rS * [S11 -S01; -S01 S00]
+                y0 = -rS * fma(X[0][0], S[1][1], -X[0][1] * S[0][1]);
+                y1 = -rS * fma(X[0][1], S[0][0], -X[0][0] * S[0][1]);
+            }
+            double m00 = fma(-y0, X[0][0], i00), m01 = fma(-y0, X[1][0], i01);
+            if constexpr (r == 2) {
+                m00 = fma(-y1, X[0][1], m00);
+                m01 = fma(-y1, X[1][1], m01);
+            }
+            mi[0] = m00;
+            mi[1] = m01;
+            mi[2] = y0;
+            if constexpr (r == 2) mi[3] = y1;
+        }
+    }
+    return info;
+}
+
 template <int m>
 __device__ __forceinline__ int spd_inv_small(const double (&a)[4][4], double (&Mi)[4][4]) {
     int info = 0;
@@ -174,31 +235,35 @@ __device__ __forceinline__ int spd_inv_small(const double (&a)[4][4], double (&M
     }
 }
 
-template <int n, int m, int STAGES, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+template <int n, int m, int STAGES, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
     riccati_dmma_kernel(const double *__restrict__ knots, const double *__restrict__ term,
                         double *__restrict__ Z, double *__restrict__ gains, int32_t *__restrict__ info,
                         int N, int lti, int64_t batch) {
     using L = Map<n, m>;
     constexpr int F = L::F, KS = L::KS, w = L::w, GR = L::GR;
+    constexpr bool HAS_X1 = n > 8;  // states live at the even positions of tile 1
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
     const int64_t inst = (int64_t)blockIdx.x * WARPS + warp;
     if (inst >= batch) return;  // whole warp leaves; no CTA-wide barrier is used below
 
-    unsigned char *wbase = smem_raw + (size_t)warp * ((riccati_dmma_warp_smem(F, STAGES) + 15) / 16 * 16);
-    double *buf = reinterpret_cast<double *>(wbase);            // STAGES records
-    double *zs = buf + (size_t)STAGES * F;                      // 2 x 16 doubles: [x; u] double buffer
-    double *gs = zs + 32;                                       // staged gains of one knot
-    uint64_t *full = reinterpret_cast<uint64_t *>(gs + 64);     // STAGES mbarriers
-    double *sc = zs;  // backward pass: 72 doubles of control-block staging (zs and gs are forward-only)
+    unsigned char *wbase = smem_raw + (size_t)warp * riccati_dmma_warp_smem(F, STAGES);
+    double *buf = reinterpret_cast<double *>(wbase);             // STAGES records
+    double *aux = buf + (size_t)STAGES * F;                      // RDMMA_AUX doubles
+    uint64_t *full = reinterpret_cast<uint64_t *>(aux + RDMMA_AUX);  // STAGES mbarriers
+    // backward-pass staging (doubles): V0d[8][8] | Qd[8][8] | V1e[4][8] | gud[8] | G1e[4] | zero[8]
+    double *V0d = aux, *Qd = aux + 64, *V1e = aux + 128, *gud = aux + 160, *G1e = aux + 168, *zero = aux + 172;
+    // forward-pass staging
+    double *zs = aux, *gs = aux + 32;
 
     if (lane == 0) {
         SM_UNROLL
         for (int s = 0; s < STAGES; ++s) mbar_init(full + s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (lane < 8) zero[lane] = 0.0;
     __syncwarp();
 
     const int Kn = lti ? 1 : N - 1;
@@ -208,45 +273,37 @@ __global__ void __launch_bounds__(WARPS * 32)
     double *gb = gains + inst * (int64_t)(N - 1) * GR;
     const int steps = N - 1;
 
-    // ---------------- per-lane constant index tables
-    // F fragment column of tile mt: z index of physical position 8*mt + g
-    const int zc0 = g;
-    const int zc1 = (g & 1) ? (((g - 1) / 2 < m) ? n + (g - 1) / 2 : -1) : ((8 + g / 2 < n) ? 8 + g / 2 : -1);
-    const int fo0 = 2 * q + n * zc0;                 // doubles; s = 0,1 pair; s = 2 at 8 + q + n*zc
-    const int fo1 = zc1 >= 0 ? 2 * q + n * zc1 : -1;
-    // cost-Hessian entry added to M accumulator (mt, nt, e): blkdiag(Q, R) in physical positions
-    int hoff[2][2][2];
-    SM_UNROLL
-    for (int mt = 0; mt < 2; ++mt)
-        SM_UNROLL
-        for (int nt = 0; nt < 2; ++nt)
-            SM_UNROLL
-            for (int e = 0; e < 2; ++e) {
-                const int zr = mt == 0 ? zc0 : zc1;
-                const int pc = 8 * nt + 2 * q + e;
-                int zc;
-                if (pc < 8) zc = pc;
-                else {
-                    const int j = pc - 8;
-                    zc = (j & 1) ? (((j - 1) / 2 < m) ? n + (j - 1) / 2 : -1) : ((8 + j / 2 < n) ? 8 + j / 2 : -1);
-                }
-                int o = -1;
-                if (zr >= 0 && zc >= 0) {
-                    if (zr < n && zc < n) o = L::oQ + (zr <= zc ? zc * (zc + 1) / 2 + zr : zr * (zr + 1) / 2 + zc);
-                    else if (zr >= n && zc >= n) {
-                        const int a = zr - n, b = zc - n;
-                        o = L::oR + (a <= b ? b * (b + 1) / 2 + a : a * (a + 1) / 2 + b);
-                    }
-                }
-                hoff[mt][nt][e] = o;
-            }
-    // gradient entry of row position 8*mt + g: q (states) | r (controls)
-    const int qo0 = L::oq + zc0;
-    const int qo1 = zc1 >= 0 ? (zc1 < n ? L::oq + zc1 : L::orr + (zc1 - n)) : -1;
-    // gain store addresses of this lane: K0 -> K[q, x_g]; K1 -> K[q, x_{8+g/2}] (g even) or kff[q] (g == 1)
+    // ---------------- per-lane constant tables (pointers into stage 0; stage s adds s*F)
+    const bool odd = g & 1;
+    const int su = (g - 1) >> 1;  // control index of an odd row of tile 1
+    // z index of physical position 8 + g (tile 1 row/column of this lane); -1 = unused slot
+    const int zc1 = odd ? (su < m ? n + su : -1) : (HAS_X1 && 8 + g / 2 < n ? 8 + g / 2 : -1);
+    const double *pf0 = buf + 2 * q + n * g;                         // F[2q..2q+1][x_g]; F[8+q][x_g] at +8-q
+    const double *pf1 = buf + 2 * q + n * (zc1 >= 0 ? zc1 : 0);
+    const bool has1 = zc1 >= 0;
+    // blkdiag(Q, R) entries of this lane's accumulator slots (packed upper storage)
+    auto qoff = [](int i, int j) { return L::oQ + (i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j); };
+    const double *ph00a = buf + qoff(g, 2 * q), *ph00b = buf + qoff(g, 2 * q + 1);
+    const double *ph01 = buf + qoff(g, HAS_X1 ? 8 + q : 0);          // column x_{8+q}
+    int o11 = L::oQ;
+    bool v11 = false;
+    if (!odd) {
+        if (HAS_X1 && 8 + g / 2 < n) { o11 = qoff(8 + g / 2, 8 + q); v11 = true; }
+    } else if (su < m && q < m) {
+        o11 = L::oR + (su <= q ? q * (q + 1) / 2 + su : su * (su + 1) / 2 + q);
+        v11 = true;
+    }
+    const double *ph11 = buf + o11;
+    const double *pq0 = buf + L::oq + g;
+    const double *pq1 = buf + (zc1 >= 0 ? (zc1 < n ? L::oq + zc1 : L::orr + (zc1 - n)) : L::oq);
+    // gain store offsets: K0 -> K[q, x_g]; K1 -> K[q, x_{8+g/2}] (g even) or kff[q] (g == 1)
     const int go0 = q < m ? q + m * g : -1;
-    const int go1 = q < m ? ((g & 1) ? (g == 1 ? m * n + q : -1) : ((8 + g / 2 < n) ? q + m * (8 + g / 2) : -1)) : -1;
-
+    const int go1 = q < m ? (odd ? (g == 1 ? m * n + q : -1) : (HAS_X1 && 8 + g / 2 < n ? q + m * (8 + g / 2) : -1)) : -1;
+    // control-block staging: this lane's permuted read bases (cyclic shift by q: row 0 = control q)
+    const int qq = q < m ? q : 0;
+    const double *rQ = Qd + 9 * qq, *rgu = gud + qq, *rv0 = V0d + 8 * g + qq;
+    const double *rv1 = (!odd) ? V1e + 8 * (g >> 1) + qq : ((g == 1 && q < m) ? gud + qq : zero);
+    const double *rt10 = g == 1 ? G1e + q : zero;
     // selection fragments of the transposing MMAs (scaled by 1/2 for the symmetrisation)
     const double hsel0 = g == 2 * q ? 0.5 : 0.0, hsel1 = g == 2 * q + 1 ? 0.5 : 0.0;
 
@@ -268,155 +325,150 @@ __global__ void __launch_bounds__(WARPS * 32)
                 P[rt][ct][e] = v;
             }
 
-    auto issue_bwd = [&](int it) {
-        const int st = it % STAGES;
+    auto issue_bwd = [&](int it, int st) {
         const int k = steps - 1 - it;
         mbar_expect_tx(full + st, F * 8);
         bulk_g2s(buf + (size_t)st * F, rec_g + (int64_t)(lti ? 0 : k) * F, F * 8, full + st);
     };
     if (lane == 0) {
-        for (int it = 0; it < STAGES - 1 && it < steps; ++it) issue_bwd(it);
+        for (int it = 0; it < STAGES - 1 && it < steps; ++it) issue_bwd(it, it);
     }
 
     int st_all = 0;
+    double *gk = gb + (int64_t)(steps - 1) * GR;
     // ---------------- backward pass: k = N-2 .. 0   (src/dynamic_programming.jl:61-64)
-    for (int it = 0; it < steps; ++it) {
-        const int k = steps - 1 - it;
-        const int st = it % STAGES;
-        if (lane == 0 && it + STAGES - 1 < steps) issue_bwd(it + STAGES - 1);
-        mbar_wait(full + st, (it / STAGES) & 1);
-        const double *rec = buf + (size_t)st * F;
+    for (int it0 = 0; it0 < steps; it0 += STAGES) {
+        const uint32_t par = (it0 / STAGES) & 1;
+        SM_UNROLL
+        for (int st = 0; st < STAGES; ++st) {
+            const int it = it0 + st;
+            if (it >= steps) break;
+            if (lane == 0 && it + STAGES - 1 < steps) issue_bwd(it + STAGES - 1, (st + STAGES - 1) % STAGES);
+            mbar_wait(full + st, par);
+            const int so = st * F;  // compile-time after unrolling: loads are [lane pointer + immediate]
 
-        // F fragments: fr[mt][s] = F[kperm(s,q)][z(8mt+g)]  (A fragment of T and B fragment of M)
-        double fr[2][3];
-        {
-            const double2 v = *reinterpret_cast<const double2 *>(rec + fo0);
-            fr[0][0] = v.x;
-            fr[0][1] = v.y;
-            fr[0][2] = KS == 3 ? rec[fo0 - 2 * q + 8 + q] : 0.0;
-            if (fo1 >= 0) {
-                const double2 u = *reinterpret_cast<const double2 *>(rec + fo1);
-                fr[1][0] = u.x;
-                fr[1][1] = u.y;
-                fr[1][2] = KS == 3 ? rec[fo1 - 2 * q + 8 + q] : 0.0;
-            } else {
-                fr[1][0] = fr[1][1] = fr[1][2] = 0.0;
+            // F fragments: fr[mt][s] = F[kperm(s,q)][z(8mt+g)]  (A fragment of T and B fragment of M)
+            double fr[2][3];
+            {
+                const double2 v = *reinterpret_cast<const double2 *>(pf0 + so);
+                fr[0][0] = v.x;
+                fr[0][1] = v.y;
+                fr[0][2] = KS == 3 ? (pf0 - 2 * q + 8 + q)[so] : 0.0;
+                const double2 u = *reinterpret_cast<const double2 *>(pf1 + so);
+                const double u2 = KS == 3 ? (pf1 - 2 * q + 8 + q)[so] : 0.0;
+                fr[1][0] = has1 ? u.x : 0.0;
+                fr[1][1] = has1 ? u.y : 0.0;
+                fr[1][2] = has1 ? u2 : 0.0;
             }
-        }
-        // M accumulators start at blkdiag(Q, R); gradient entries of this lane's rows
-        double M[2][2][2];
-        SM_UNROLL
-        for (int mt = 0; mt < 2; ++mt)
-            SM_UNROLL
-            for (int nt = 0; nt < 2; ++nt)
-                SM_UNROLL
-                for (int e = 0; e < 2; ++e) M[mt][nt][e] = hoff[mt][nt][e] >= 0 ? rec[hoff[mt][nt][e]] : 0.0;
-        const double qr0 = rec[qo0];
-        const double qr1 = qo1 >= 0 ? rec[qo1] : 0.0;
+            // M accumulators start at blkdiag(Q, R); tile (1,0) is never formed
+            double M00[2] = {ph00a[so], ph00b[so]};
+            double M01[2] = {HAS_X1 ? ph01[so] : 0.0, 0.0};
+            const double h11 = ph11[so];
+            double M11[2] = {(!odd && v11) ? h11 : 0.0, (odd && v11) ? h11 : 0.0};
+            const double qr0 = pq0[so];
+            const double qr1 = has1 ? pq1[so] : 0.0;
 
-        // T = F' P^   (compute_gain! :38,40 — PB and PA at once, plus F'p in position 9)
-        double T[2][2][2] = {};
-        SM_UNROLL
-        for (int s = 0; s < KS; ++s)
+            // T = F' P^   (compute_gain! :38,40 — PB and PA at once, plus F'p in position 9)
+            double T[2][2][2] = {};
             SM_UNROLL
-            for (int mt = 0; mt < 2; ++mt)
+            for (int s = 0; s < KS; ++s)
                 SM_UNROLL
-                for (int nt = 0; nt < 2; ++nt) {
-                    const double pb = s == 0 ? P[nt][0][0] : s == 1 ? P[nt][0][1] : P[nt][1][0];
-                    mma884(T[mt][nt][0], T[mt][nt][1], fr[mt][s], pb);
+                for (int mt = 0; mt < 2; ++mt)
+                    SM_UNROLL
+                    for (int nt = 0; nt < 2; ++nt) {
+                        const double pb = s == 0 ? P[nt][0][0] : s == 1 ? P[nt][0][1] : P[nt][1][0];
+                        mma884(T[mt][nt][0], T[mt][nt][1], fr[mt][s], pb);
+                    }
+            // M += T F   (E = R + B'PB :39, K = B'PA :41, A'PA :50)
+            SM_UNROLL
+            for (int s = 0; s < KS; ++s) {
+                const double ta0 = s == 0 ? T[0][0][0] : s == 1 ? T[0][0][1] : T[0][1][0];
+                const double ta1 = s == 0 ? T[1][0][0] : s == 1 ? T[1][0][1] : T[1][1][0];
+                mma884(M00[0], M00[1], ta0, fr[0][s]);
+                mma884(M01[0], M01[1], ta0, fr[1][s]);
+                mma884(M11[0], M11[1], ta1, fr[1][s]);
+            }
+            // g^ = [q; r] + F'p : column 9 of T, held by quad lane 0
+            const double gh0 = T[0][1][1] + qr0;
+            const double gh1 = T[1][1][1] + qr1;
+
+            // ---- stage the control columns (rows/columns duplicated with period m so that lane q reads
+            // the block cyclically shifted by q with immediate offsets)
+            if (q < m) {
+                V0d[8 * g + q] = M01[1];  // Mxu[x_g][u_q]
+                V0d[8 * g + q + m] = M01[1];
+                if (!odd) {
+                    V1e[8 * (g >> 1) + q] = M11[1];  // Mxu[x_{8+g/2}][u_q]
+                    V1e[8 * (g >> 1) + q + m] = M11[1];
+                } else if (su < m) {
+                    Qd[8 * su + q] = M11[1];  // Quu[su][q]
+                    Qd[8 * su + q + m] = M11[1];
+                    Qd[8 * (su + m) + q] = M11[1];
+                    Qd[8 * (su + m) + q + m] = M11[1];
                 }
-        // M += T F   (E = R + B'PB :39, K = B'PA :41, A'PA :50).  Tile (1,0) is never formed: the new
-        // P^(1,0) is the exact transpose of P^(0,1), see below.
-        SM_UNROLL
-        for (int s = 0; s < KS; ++s)
+            }
+            if (q == 0) {
+                if (!odd) G1e[g >> 1] = gh1;
+                else if (su < m) { gud[su] = gh1; gud[su + m] = gh1; }
+            }
+            __syncwarp();
+            double a[4][4], v0[4], v1[4];
             SM_UNROLL
-            for (int mt = 0; mt < 2; ++mt)
+            for (int s = 0; s < m; ++s)
                 SM_UNROLL
-                for (int nt = mt; nt < 2; ++nt) {
-                    const double ta = s == 0 ? T[mt][0][0] : s == 1 ? T[mt][0][1] : T[mt][1][0];
-                    mma884(M[mt][nt][0], M[mt][nt][1], ta, fr[nt][s]);
-                }
-        // g^ = [q; r] + F'p : column 9 of T, held by quad lane 0
-        const double gh0 = T[0][1][1] + qr0;
-        const double gh1 = T[1][1][1] + qr1;
-
-        // ---- stage the control columns in shared memory: every lane then reads the whole control block
-        // Quu, gu and the four Qxu entries of its own rows with broadcast 16-byte loads (no shuffles)
-        sc[lane] = M[0][1][1];       // Mxu[pos g][u_q], rows x0..x7
-        sc[32 + lane] = M[1][1][1];  // rows of tile 1 (odd g: the rows of Quu)
-        if (q == 0) sc[64 + (g & 1) * 4 + (g >> 1)] = gh1;  // [64..67]: g^ of x8..x11, [68..71]: gu
-        __syncwarp();
-        double a[4][4], gu[4], v0[4], v1[4];
-        SM_UNROLL
-        for (int s = 0; s < m; ++s) {
-            const double2 lo = *reinterpret_cast<const double2 *>(sc + 32 + 4 * (2 * s + 1));
-            const double2 hi = *reinterpret_cast<const double2 *>(sc + 32 + 4 * (2 * s + 1) + 2);
-            a[s][0] = lo.x; a[s][1] = lo.y; a[s][2] = hi.x; a[s][3] = hi.y;
-        }
-        {
-            const double2 lo = *reinterpret_cast<const double2 *>(sc + 68);
-            const double2 hi = *reinterpret_cast<const double2 *>(sc + 70);
-            gu[0] = lo.x; gu[1] = lo.y; gu[2] = hi.x; gu[3] = hi.y;
-            const double2 l0 = *reinterpret_cast<const double2 *>(sc + 4 * g);
-            const double2 h0 = *reinterpret_cast<const double2 *>(sc + 4 * g + 2);
-            v0[0] = l0.x; v0[1] = l0.y; v0[2] = h0.x; v0[3] = h0.y;
-            const double2 l1 = *reinterpret_cast<const double2 *>(sc + 32 + 4 * g);
-            const double2 h1 = *reinterpret_cast<const double2 *>(sc + 32 + 4 * g + 2);
-            v1[0] = l1.x; v1[1] = l1.y; v1[2] = h1.x; v1[3] = h1.y;
-        }
-        const double t10 = sc[64 + q];
-        const bool odd = g & 1;
-        SM_UNROLL
-        for (int t = 0; t < 4; ++t) v1[t] = odd ? (g == 1 ? gu[t] : 0.0) : v1[t];
-        double Minv[4][4];
-        const int ci = spd_inv_small<m>(a, Minv);  // chol_solve! :28-31 (E^-1 applied by multiplication)
-        if (ci != 0 && st_all == 0) st_all = (k + 1) * 1000 + ci;
-        // K[q][pos] = row q of Quu^-1 times [Qux | gu]   (K = E^-1 B'PA :41-43, kff in position 9)
-        double K0 = 0.0, K1 = 0.0;
-        SM_UNROLL
-        for (int t = 0; t < m; ++t) {
-            double mq = 0.0;
+                for (int t = s; t < m; ++t) a[s][t] = rQ[8 * s + t];
             SM_UNROLL
-            for (int s = 0; s < m; ++s) mq = (q == s) ? Minv[s][t] : mq;
-            K0 = fma(mq, v0[t], K0);
-            K1 = fma(mq, v1[t], K1);
-        }
-        double *gk = gb + (int64_t)k * GR;
-        if (go0 >= 0) gk[go0] = K0;
-        if (go1 >= 0) gk[go1] = K1;
+            for (int t = 0; t < m; ++t) {
+                v0[t] = rv0[t];
+                v1[t] = rv1[t];
+            }
+            const double t10 = rt10[0];
+            double mi[4];
+            const int ci = spd_inv_row0<m>(a, mi);  // chol_solve! :28-31 (E^-1 applied by multiplication)
+            if (ci != 0 && st_all == 0) st_all = (steps - it) * 1000 + ci;
+            // K[q][pos] = row q of Quu^-1 times [Qux | gu]   (K = E^-1 B'PA :41-43, kff in position 9)
+            double K0 = 0.0, K1 = 0.0;
+            SM_UNROLL
+            for (int t = 0; t < m; ++t) {
+                K0 = fma(mi[t], v0[t], K0);
+                K1 = fma(mi[t], v1[t], K1);
+            }
+            if (go0 >= 0) gk[go0] = K0;
+            if (go1 >= 0) gk[go1] = K1;
+            gk -= GR;
 
-        // ---- P^_ = Mxx^ - [Qxu | gu]' K  (compute_ctg! :50-51 and the affine column in the same MMAs)
-        double S00[2] = {M[0][0][0], M[0][0][1]};
-        double S01[2] = {M[0][1][0], q == 0 ? gh0 : 0.0};
-        double S11[2] = {odd ? (g == 1 ? t10 : 0.0) : M[1][1][0], (!odd && q == 0) ? gh1 : 0.0};
-        const double nV0 = -M[0][1][1];
-        const double nV1 = odd ? (g == 1 ? -(q == 0 ? gu[0] : q == 1 ? gu[1] : q == 2 ? gu[2] : gu[3]) : 0.0) : -M[1][1][1];
-        mma884(S00[0], S00[1], nV0, K0);
-        mma884(S01[0], S01[1], nV0, K1);
-        mma884(S11[0], S11[1], nV1, K1);
-        // Exact symmetrisation.  F'P^F amplifies any antisymmetric rounding residue of P^ by the OPEN-loop
-        // dynamics (|A|^2 per knot: 1e-16 -> 5e-8 over 1000 knots of an unstable LTI system), so P^ is kept
-        // bitwise symmetric: tile^T = sum_e Sel_e * B(tile, e) with Sel_e[r][k] = (r == 2k+e) — the C
-        // fragment read as a B fragment is the transpose — 2 DMMAs per tile, all products exact.
-        P[0][0][0] = 0.5 * S00[0];
-        P[0][0][1] = 0.5 * S00[1];
-        mma884(P[0][0][0], P[0][0][1], hsel0, S00[0]);
-        mma884(P[0][0][0], P[0][0][1], hsel1, S00[1]);
-        P[1][1][0] = 0.5 * S11[0];
-        P[1][1][1] = 0.5 * S11[1];
-        mma884(P[1][1][0], P[1][1][1], hsel0, S11[0]);
-        mma884(P[1][1][0], P[1][1][1], hsel1, S11[1]);
-        P[0][1][0] = S01[0];
-        P[0][1][1] = S01[1];
-        P[1][0][0] = 0.0;
-        P[1][0][1] = 0.0;
-        mma884(P[1][0][0], P[1][0][1], hsel0 + hsel0, S01[0]);
-        mma884(P[1][0][0], P[1][0][1], hsel1 + hsel1, S01[1]);
-        __syncwarp();  // every lane is done with this stage before it is refilled
+            // ---- P^_ = Mxx^ - [Qxu | gu]' K  (compute_ctg! :50-51 and the affine column in the same MMAs)
+            double S00[2] = {M00[0], M00[1]};
+            double S01[2] = {M01[0], q == 0 ? gh0 : 0.0};
+            double S11[2] = {odd ? t10 : M11[0], (!odd && q == 0) ? gh1 : 0.0};
+            const double nV0 = q < m ? -M01[1] : 0.0;
+            const double nV1 = q < m ? -v1[0] : 0.0;
+            mma884(S00[0], S00[1], nV0, K0);
+            mma884(S01[0], S01[1], nV0, K1);
+            mma884(S11[0], S11[1], nV1, K1);
+            // Exact symmetrisation.  F'P^F amplifies any antisymmetric rounding residue of P^ by the
+            // OPEN-loop dynamics (|A|^2 per knot: 1e-16 -> 5e-8 over 1000 knots of an unstable LTI system),
+            // so P^ is kept bitwise symmetric: tile^T = sum_e Sel_e * B(tile, e), Sel_e[r][k] = (r == 2k+e)
+            // — a C fragment read as a B fragment is the transpose — 2 DMMAs per tile, all products exact.
+            P[0][0][0] = 0.5 * S00[0];
+            P[0][0][1] = 0.5 * S00[1];
+            mma884(P[0][0][0], P[0][0][1], hsel0, S00[0]);
+            mma884(P[0][0][0], P[0][0][1], hsel1, S00[1]);
+            P[1][1][0] = 0.5 * S11[0];
+            P[1][1][1] = 0.5 * S11[1];
+            mma884(P[1][1][0], P[1][1][1], hsel0, S11[0]);
+            mma884(P[1][1][0], P[1][1][1], hsel1, S11[1]);
+            P[0][1][0] = S01[0];
+            P[0][1][1] = S01[1];
+            P[1][0][0] = 0.0;
+            P[1][0][1] = 0.0;
+            mma884(P[1][0][0], P[1][0][1], hsel0 + hsel0, S01[0]);
+            mma884(P[1][0][0], P[1][0][1], hsel1 + hsel1, S01[1]);
+            __syncwarp();  // every lane is done with this stage and the staging area
+        }
     }
     if (info && lane == 0) info[inst] = st_all;
     __syncwarp();
-
     // ---------------- forward rollout   (src/dynamic_programming.jl:66-70)
     const int AB = n * w;  // doubles of [A B] at the head of a record
     auto issue_fwd = [&](int it) {
