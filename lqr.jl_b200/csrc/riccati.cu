@@ -4,6 +4,7 @@
 
 #include "riccati_kernels.cuh"
 #include "riccati_dmma_kernels.cuh"
+#include "riccati_cta_kernels.cuh"
 
 // ------------------------------------------------------------------ size classes --------------
 // thread-per-instance instantiations (registers only).  Everything else -> cooperative kernel.
@@ -24,6 +25,17 @@ static bool riccati_has_dmma(int n, int m) {
 #define X(N_, M_) \
     if (n == N_ && m == M_) return true;
     RICCATI_DMMA_SIZES(X)
+#undef X
+    return false;
+}
+
+// CTA-per-instance FP64 tensor-core instantiations (large state)
+#define RICCATI_CTA_SIZES(X) X(32, 8) X(64, 16)
+
+static bool riccati_has_cta(int n, int m) {
+#define X(N_, M_) \
+    if (n == N_ && m == M_) return true;
+    RICCATI_CTA_SIZES(X)
 #undef X
     return false;
 }
@@ -169,6 +181,20 @@ static int32_t launch_dmma(lqrb_context *h, int N, int64_t batch, int lti, const
     return 0;
 }
 
+template <int n, int m>
+static int32_t launch_cta(lqrb_context *h, int N, int64_t batch, int lti, const double *knots,
+                          const double *term, double *Z, double *gains, int32_t *info, cudaStream_t s) {
+    using C = rcta::Cfg<n, m>;
+    auto kern = rcta::riccati_cta_kernel<n, m>;
+    LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    kern<<<(unsigned)batch, C::THREADS, C::SMEM, s>>>(knots, term, Z, gains, info, N, lti, batch);
+    char nm[64];
+    snprintf(nm, sizeof nm, "riccati_cta_dmma<%d,%d>%s", n, m, lti ? "[lti]" : "");
+    h->kernel_name = nm;
+    LQRB_LAUNCH_CHECK(h, "riccati_cta_kernel");
+    return 0;
+}
+
 static int32_t riccati_solve_on(lqrb_context *h, int n, int m, int N, int64_t batch, int flags,
                                 const double *knots, const double *term, double *Z, double *gains,
                                 int32_t *info, cudaStream_t s) {
@@ -186,6 +212,12 @@ static int32_t riccati_solve_on(lqrb_context *h, int n, int m, int N, int64_t ba
 #define X(N_, M_) \
     if (n == N_ && m == M_) return launch_dmma<N_, M_>(h, N, batch, lti, knots, term, Z, gains, info, s);
         RICCATI_DMMA_SIZES(X)
+#undef X
+    }
+    if (h->opt("riccati_variant", 0) != 2 && riccati_has_cta(n, m) && ((uintptr_t)knots & 15) == 0) {
+#define X(N_, M_) \
+    if (n == N_ && m == M_) return launch_cta<N_, M_>(h, N, batch, lti, knots, term, Z, gains, info, s);
+        RICCATI_CTA_SIZES(X)
 #undef X
     }
     return launch_coop(h, n, m, N, batch, lti, knots, term, Z, gains, info, s);

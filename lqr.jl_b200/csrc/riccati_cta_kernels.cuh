@@ -1,0 +1,424 @@
+// riccati_cta_kernels.cuh — CTA-per-instance Riccati recursion for the large-state class (n = 32, 64;
+// m = 8, 16) where the per-knot updates are real dense contractions: everything of order n^3 runs on the
+// FP64 tensor cores (mma.sync m8n8k4 DMMA).
+//
+// Replaces solve!(sol, ::DPSolver, prob) : src/dynamic_programming.jl:54-72
+//   compute_gain! :37-43  PB, PA, E = R + B'PB, K = E^-1 B'PA      compute_ctg! :48-52  P_ = Q + A'PA - A'PB K
+// in the same symmetric form as riccati_dmma_kernels.cuh:  F = [A B],  T = F'P,  M = T F + blkdiag(Q,R),
+//   K = Muu^-1 Mux,  P_ = Mxx - Mxu K,   plus the affine terms  g^ = [q;r] + F'p, kff = Muu^-1 g^u,
+//   p_ = g^x - Mxu kff.
+// Work split: warp w of the n/8 warps owns state rows 8w..8w+7.
+//   * T row tile w (8 x n) = F[:,rows w]' P stays in its accumulators and is fed straight back as the
+//     A operand of M = T F (a C fragment is an A fragment under a permuted contraction index).
+//   * M is symmetric: warp w forms only the tiles (w, w+j), j = 0..NT/2, plus its 8 x m slice of Mxu; the
+//     new P tile is written to shared memory together with its mirror image, which also keeps P bitwise
+//     symmetric (an antisymmetric rounding residue would be amplified by the open-loop |A|^2 per knot).
+//   * Muu = B'PB is reduced over the warps (each contributes the contraction over its 8 states), warp 0
+//     inverts it (Gauss-Jordan, one column per lane), then K's slice for tile w is Muu^-1 times the
+//     warp's own Mxu accumulators read as a (transposed) B fragment.
+// Shared memory per CTA (n=64: 96 KB -> 2 CTAs per SM, so one CTA's serial phases hide under the other's
+// DMMAs): P (ld n+4), K' (n x (m+4)), F = [A B] column-wise with ld n+4 (bank-conflict-free fragment
+// loads; filled by one 512-byte cp.async.bulk per column), R|q|r, and small vectors.  Q is read once per
+// knot straight from global memory into the M accumulators (only the owned tiles).
+#pragma once
+#include "riccati_dmma_kernels.cuh"
+
+namespace rcta {
+using rdmma::bulk_g2s;
+using rdmma::mbar_expect_tx;
+using rdmma::mbar_init;
+using rdmma::mbar_wait;
+using rdmma::mma884;
+
+template <int n, int m>
+struct Cfg {
+    static_assert(n % 8 == 0 && m % 8 == 0 && m <= 16 && n >= 32 && n <= 64, "tile map: n = 32..64, m = 8, 16");
+    static constexpr int NT = n / 8, UT = m / 8, WARPS = NT, THREADS = WARPS * 32, w = n + m;
+    static constexpr int JT = NT / 2 + 1;  // owned column tiles of M per warp: (w + j) % NT, j < JT
+    static constexpr int LP = n + 4, LF = n + 4, LK = m + 4, LM = m + 4;
+    static constexpr int oQ = n * w, oR = oQ + tri(n), oq = oR + tri(m), orr = oq + n, F = orr + m;
+    static constexpr int HS = tri(m) + n + m;  // R | q | r  (one bulk copy)
+    static constexpr int TR = tri(n) + 2 * n, GR = m * n + m;
+    static_assert(F % 2 == 0 && oR % 2 == 0 && HS % 2 == 0, "bulk copies need 16-byte pieces");
+    // shared memory map (doubles)
+    static constexpr int sP = 0, sK = sP + n * LP, sF = sK + n * LK, sH = sF + w * LF, sPv = sH + HS, sG = sPv + n,
+                         sKff = sG + w, sMi = sKff + m, sCol = sMi + m * LM, sSlot = sCol + m,
+                         sZ = sSlot + (WARPS / 2) * m * m, sRed = sZ + 2 * w, sBar = sRed + WARPS * m + 4 * n,
+                         TOTAL = sBar + 2;
+    static_assert(sK + n * LK - sP >= w * LF, "forward pass double-buffers [A B] in the P|K' region");
+    static constexpr size_t SMEM = (size_t)TOTAL * 8;
+};
+
+// Is column tile ct = (wp + j) % NT of row tile wp formed by warp wp?  (each unordered tile pair once)
+template <int NT>
+__device__ __forceinline__ bool owns_j(int wp, int j) {
+    return j < NT / 2 || (j == NT / 2 && wp < NT / 2);
+}
+
+template <int n, int m>
+__global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
+    riccati_cta_kernel(const double *__restrict__ knots, const double *__restrict__ term,
+                       double *__restrict__ Z, double *__restrict__ gains, int32_t *__restrict__ info,
+                       int N, int lti, int64_t batch) {
+    using C = Cfg<n, m>;
+    constexpr int NT = C::NT, UT = C::UT, JT = C::JT, WARPS = C::WARPS, THREADS = C::THREADS, w = C::w;
+    constexpr int LP = C::LP, LF = C::LF, LK = C::LK, LM = C::LM, F = C::F, GR = C::GR;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    double *Ps = sm + C::sP, *Kt = sm + C::sK, *Fs = sm + C::sF, *Hs = sm + C::sH, *pv = sm + C::sPv,
+           *gh = sm + C::sG, *kffs = sm + C::sKff, *Mi = sm + C::sMi, *colb = sm + C::sCol,
+           *slot = sm + C::sSlot, *zs = sm + C::sZ, *red = sm + C::sRed;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + C::sBar);
+    const double *Rs = Hs, *qs = Hs + tri(m), *rs = qs + n;
+
+    const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int64_t inst = blockIdx.x;
+    const int Kn = lti ? 1 : N - 1;
+    const int steps = N - 1;
+    const double *rec_g = knots + inst * (int64_t)Kn * F;
+    const double *tb = term + inst * C::TR;
+    double *zb = Z + inst * ((int64_t)N * n + (int64_t)(N - 1) * m);
+    double *gb = gains + inst * (int64_t)(N - 1) * GR;
+
+    // ---------------- terminal cost-to-go: P = Qf (full storage), p = qf
+    for (int e = tid; e < n * n; e += THREADS) {
+        const int i = e % n, j = e / n;
+        Ps[i * LP + j] = tb[sym_idx(i, j)];
+    }
+    if (tid < n) pv[tid] = tb[tri(n) + tid];
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // one warp streams a knot into shared memory: [A B] column by column (padded ld), then R|q|r
+    auto issue_knot = [&](int k, double *Fdst, bool with_cost, uint64_t *b) {
+        const double *src = rec_g + (int64_t)(lti ? 0 : k) * F;
+        if (lane == 0) mbar_expect_tx(b, (uint32_t)((w * n + (with_cost ? C::HS : 0)) * 8));
+        __syncwarp();
+        for (int c = lane; c < w; c += 32) bulk_g2s(Fdst + c * LF, src + c * n, n * 8, b);
+        if (with_cost && lane == 0) bulk_g2s(Hs, src + C::oR, C::HS * 8, b);
+    };
+    if (wp == 0) issue_knot(steps - 1, Fs, true, bar);
+
+    int st_all = 0;
+    uint32_t ph0 = 0, ph1 = 0;  // phase parities of the two mbarriers (every thread waits on every use)
+    const int xr = 8 * wp + g;  // the state row this lane's accumulator rows belong to
+    // ---------------- backward pass: k = N-2 .. 0   (src/dynamic_programming.jl:61-64)
+    for (int it = 0; it < steps; ++it) {
+        const int k = steps - 1 - it;
+        const double *recg = rec_g + (int64_t)(lti ? 0 : k) * F;
+        // M accumulators start at Q (owned tiles, read once from global) and 0 (control columns)
+        double M[JT][2], Mu[UT][2];
+        SM_UNROLL
+        for (int j = 0; j < JT; ++j) {
+            const int ct = (wp + j) % NT;
+            SM_UNROLL
+            for (int e = 0; e < 2; ++e) {
+                const int c = 8 * ct + 2 * q + e;
+                M[j][e] = owns_j<NT>(wp, j) ? __ldg(recg + C::oQ + (xr <= c ? c * (c + 1) / 2 + xr : xr * (xr + 1) / 2 + c)) : 0.0;
+            }
+        }
+        SM_UNROLL
+        for (int ut = 0; ut < UT; ++ut) Mu[ut][0] = Mu[ut][1] = 0.0;
+
+        mbar_wait(bar, ph0);
+        ph0 ^= 1;
+
+        // ---- T row tile = F[:, rows]' P  (compute_gain! :38,40) and this warp's column slice of B'P
+        double T[NT][2], Tu[UT][2];
+        SM_UNROLL
+        for (int ct = 0; ct < NT; ++ct) T[ct][0] = T[ct][1] = 0.0;
+        SM_UNROLL
+        for (int ut = 0; ut < UT; ++ut) Tu[ut][0] = Tu[ut][1] = 0.0;
+        double gacc = 0.0, guacc[UT];
+        SM_UNROLL
+        for (int ut = 0; ut < UT; ++ut) guacc[ut] = 0.0;
+        {
+            const double *fa = Fs + xr * LF + q;          // F[4s+q][x row]
+            const double *fu = Fs + (n + g) * LF + q;      // F[4s+q][u = 8ut+g]
+            const double *pb = Ps + q * LP + g;            // P[4s+q][8ct+g]
+#pragma unroll 4
+            for (int s = 0; s < n / 4; ++s) {
+                const double a = fa[4 * s];
+                const double pk = pv[4 * s + q];
+                gacc = fma(a, pk, gacc);
+                double au[UT];
+                SM_UNROLL
+                for (int ut = 0; ut < UT; ++ut) {
+                    au[ut] = fu[4 * s + 8 * ut * LF];
+                    guacc[ut] = fma(au[ut], pk, guacc[ut]);
+                }
+                const double *prow = pb + 4 * s * LP;
+                SM_UNROLL
+                for (int ct = 0; ct < NT; ++ct) mma884(T[ct][0], T[ct][1], a, prow[8 * ct]);
+                const double bw = prow[8 * wp];
+                SM_UNROLL
+                for (int ut = 0; ut < UT; ++ut) mma884(Tu[ut][0], Tu[ut][1], au[ut], bw);
+            }
+        }
+        // g^ = [q; r] + F'p  (quad lanes hold partial sums over their contraction indices)
+        gacc += __shfl_xor_sync(0xffffffffu, gacc, 1);
+        gacc += __shfl_xor_sync(0xffffffffu, gacc, 2);
+        if (q == 0) gh[xr] = gacc + qs[xr];
+        SM_UNROLL
+        for (int ut = 0; ut < UT; ++ut) {
+            guacc[ut] += __shfl_xor_sync(0xffffffffu, guacc[ut], 1);
+            guacc[ut] += __shfl_xor_sync(0xffffffffu, guacc[ut], 2);
+            if (wp == 0 && q == 0) gh[n + 8 * ut + g] = guacc[ut] + rs[8 * ut + g];
+        }
+
+        // ---- M += T F : owned state tiles and the control columns  (E :39, K :41, A'PA :50)
+        SM_UNROLL
+        for (int cp = 0; cp < NT; ++cp) {
+            const double ta0 = T[cp][0], ta1 = T[cp][1];
+            const double *fb = Fs + g * LF + 8 * cp + 2 * q;  // F[8cp+2q+e][z = 8ct+g]
+            SM_UNROLL
+            for (int j = 0; j < JT; ++j) {
+                if (owns_j<NT>(wp, j)) {
+                    const int ct = (wp + j) % NT;
+                    const double2 b = *reinterpret_cast<const double2 *>(fb + 8 * ct * LF);
+                    mma884(M[j][0], M[j][1], ta0, b.x);
+                    mma884(M[j][0], M[j][1], ta1, b.y);
+                }
+            }
+            SM_UNROLL
+            for (int ut = 0; ut < UT; ++ut) {
+                const double2 b = *reinterpret_cast<const double2 *>(fb + (n + 8 * ut) * LF);
+                mma884(Mu[ut][0], Mu[ut][1], ta0, b.x);
+                mma884(Mu[ut][0], Mu[ut][1], ta1, b.y);
+            }
+        }
+        // ---- this warp's share of Muu = R + B'PB: contraction over its own 8 states
+        double Mp[UT][UT][2];
+        SM_UNROLL
+        for (int ut = 0; ut < UT; ++ut)
+            SM_UNROLL
+            for (int vt = 0; vt < UT; ++vt) {
+                SM_UNROLL
+                for (int e = 0; e < 2; ++e) {
+                    const int a = 8 * ut + g, b = 8 * vt + 2 * q + e;
+                    Mp[ut][vt][e] = wp == 0 ? Rs[a <= b ? b * (b + 1) / 2 + a : a * (a + 1) / 2 + b] : 0.0;
+                }
+                const double2 b = *reinterpret_cast<const double2 *>(Fs + (n + 8 * vt + g) * LF + 8 * wp + 2 * q);
+                mma884(Mp[ut][vt][0], Mp[ut][vt][1], Tu[ut][0], b.x);
+                mma884(Mp[ut][vt][0], Mp[ut][vt][1], Tu[ut][1], b.y);
+            }
+        // two-round reduction over the warps through WARPS/2 slots (deterministic order)
+        if (wp >= WARPS / 2) {
+            double *sl = slot + (wp - WARPS / 2) * m * m;
+            SM_UNROLL
+            for (int ut = 0; ut < UT; ++ut)
+                SM_UNROLL
+                for (int vt = 0; vt < UT; ++vt)
+                    *reinterpret_cast<double2 *>(sl + (8 * ut + g) * m + 8 * vt + 2 * q) = make_double2(Mp[ut][vt][0], Mp[ut][vt][1]);
+        }
+        __syncthreads();
+        if (wp < WARPS / 2) {
+            double *sl = slot + wp * m * m;
+            SM_UNROLL
+            for (int ut = 0; ut < UT; ++ut)
+                SM_UNROLL
+                for (int vt = 0; vt < UT; ++vt) {
+                    double2 *p2 = reinterpret_cast<double2 *>(sl + (8 * ut + g) * m + 8 * vt + 2 * q);
+                    const double2 o = *p2;
+                    *p2 = make_double2(o.x + Mp[ut][vt][0], o.y + Mp[ut][vt][1]);
+                }
+        }
+        __syncthreads();  // every warp is done with F, R|q|r and the partial slots are complete
+
+        if (wp == 1 && it + 1 < steps) issue_knot(k - 1, Fs, true, bar);  // overlaps the phases below
+        if (wp == 0) {
+            // ---- Muu^-1 by Gauss-Jordan, lane j < m owns column j  (chol_solve! :28-31 applied by
+            // multiplication); pivots are the squared Cholesky pivots, so the sign test is potrf's
+            double a[m];
+            const int j = lane < m ? lane : 0;
+            SM_UNROLL
+            for (int i = 0; i < m; ++i) {
+                double s = 0.0;
+                SM_UNROLL
+                for (int sl = 0; sl < WARPS / 2; ++sl) s += slot[sl * m * m + i * m + j];
+                a[i] = s;
+            }
+            int bad = 0;
+            SM_UNROLL
+            for (int kk = 0; kk < m; ++kk) {
+                if (lane == kk) {
+                    SM_UNROLL
+                    for (int i = 0; i < m; ++i) colb[i] = a[i];
+                }
+                __syncwarp();
+                double c[m];
+                SM_UNROLL
+                for (int i = 0; i < m; i += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(colb + i);
+                    c[i] = v.x;
+                    c[i + 1] = v.y;
+                }
+                __syncwarp();
+                if (!(c[kk] > 0.0) && bad == 0) bad = kk + 1;
+                const double p = rdmma::fast_rcp(c[kk]);
+                const bool piv = lane == kk;
+                const double f = piv ? -p : a[kk] * p;
+                SM_UNROLL
+                for (int i = 0; i < m; ++i) {
+                    if (i == kk) a[i] = piv ? p : f;
+                    else a[i] = piv ? c[i] * f : fma(-c[i], f, a[i]);
+                }
+            }
+            if (bad != 0 && st_all == 0) st_all = (k + 1) * 1000 + bad;
+            if (lane < m) {
+                double kf = 0.0;
+                SM_UNROLL
+                for (int i = 0; i < m; ++i) {
+                    Mi[i * LM + lane] = a[i];
+                    kf = fma(a[i], gh[n + i], kf);  // Muu^-1 symmetric: column j dotted with g^u
+                }
+                kffs[lane] = kf;
+                gb[(int64_t)k * GR + m * n + lane] = kf;
+            }
+        }
+        __syncthreads();
+
+        // ---- K[:, own tile] = Muu^-1 Mux[:, own tile]; Mux is this warp's Mxu accumulators transposed
+        SM_UNROLL
+        for (int rt = 0; rt < UT; ++rt) {
+            double acc[2] = {0.0, 0.0};
+            SM_UNROLL
+            for (int ut = 0; ut < UT; ++ut) {
+                const double2 av = *reinterpret_cast<const double2 *>(Mi + (8 * rt + g) * LM + 8 * ut + 2 * q);
+                mma884(acc[0], acc[1], av.x, Mu[ut][0]);
+                mma884(acc[0], acc[1], av.y, Mu[ut][1]);
+            }
+            // acc = K[u = 8rt+g][x = 8wp+2q+e]
+            SM_UNROLL
+            for (int e = 0; e < 2; ++e) {
+                const int x = 8 * wp + 2 * q + e, u = 8 * rt + g;
+                Kt[x * LK + u] = acc[e];
+                gb[(int64_t)k * GR + u + m * x] = acc[e];
+            }
+        }
+        __syncthreads();
+
+        // ---- P_ = Mxx - Mxu K (owned tiles), p_ = g^x - Mxu kff   (compute_ctg! :50-51)
+        SM_UNROLL
+        for (int ut = 0; ut < UT; ++ut) {
+            const double na0 = -Mu[ut][0], na1 = -Mu[ut][1];
+            SM_UNROLL
+            for (int j = 0; j < JT; ++j) {
+                if (owns_j<NT>(wp, j)) {
+                    const int ct = (wp + j) % NT;
+                    const double2 b = *reinterpret_cast<const double2 *>(Kt + (8 * ct + g) * LK + 8 * ut + 2 * q);
+                    mma884(M[j][0], M[j][1], na0, b.x);
+                    mma884(M[j][0], M[j][1], na1, b.y);
+                }
+            }
+        }
+        {
+            double s = 0.0;
+            SM_UNROLL
+            for (int ut = 0; ut < UT; ++ut) {
+                const double2 kf = *reinterpret_cast<const double2 *>(kffs + 8 * ut + 2 * q);
+                s = fma(Mu[ut][0], kf.x, s);
+                s = fma(Mu[ut][1], kf.y, s);
+            }
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            if (q == 0) pv[xr] = gh[xr] - s;
+        }
+        SM_UNROLL
+        for (int j = 0; j < JT; ++j) {
+            if (owns_j<NT>(wp, j)) {
+                const int ct = (wp + j) % NT;
+                SM_UNROLL
+                for (int e = 0; e < 2; ++e) {
+                    const int c = 8 * ct + 2 * q + e;
+                    if (j > 0 || xr <= c) {  // diagonal tile: the upper triangle is the value, mirrored
+                        Ps[xr * LP + c] = M[j][e];
+                        Ps[c * LP + xr] = M[j][e];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (info && tid == 0) info[inst] = st_all;
+
+    // ---------------- forward rollout   (src/dynamic_programming.jl:66-70)
+    // [A B] of knot `it` alternates between the F region and the (now free) P|K' region
+    double *Fb[2] = {Fs, Ps};
+    if (wp == 0) {
+        issue_knot(0, Fb[0], false, bar);
+        if (steps > 1) issue_knot(1, Fb[1], false, bar + 1);
+    }
+    if (tid < n) zs[tid] = tb[tri(n) + n + tid];
+    __syncthreads();
+    constexpr int UP = THREADS / m, XP = THREADS / n;  // partial sums per control / per state
+    constexpr int UX = n / UP, XZ = w / XP;
+    static_assert(UP * m == THREADS && XP * n == THREADS && UX * UP == n && XZ * XP == w, "forward pass split");
+    const int ut_ = tid % m, up_ = tid / m, xi_ = tid % n, xp_ = tid / n;
+    double gk[UX];
+    SM_UNROLL
+    for (int i = 0; i < UX; ++i) gk[i] = gb[ut_ + m * (UX * up_ + i)];
+    double kf = tid < m ? gb[m * n + tid] : 0.0;
+    for (int it = 0; it < steps; ++it) {
+        double *zc = zs + (it & 1) * w, *zn = zs + ((it + 1) & 1) * w;
+        // u = -K x - kff : UP partial sums per control
+        double acc = 0.0;
+        SM_UNROLL
+        for (int i = 0; i < UX; ++i) acc = fma(gk[i], zc[UX * up_ + i], acc);
+        const double kfc = kf;
+        if (it + 1 < steps) {
+            SM_UNROLL
+            for (int i = 0; i < UX; ++i) gk[i] = gb[(int64_t)(it + 1) * GR + ut_ + m * (UX * up_ + i)];
+            if (tid < m) kf = gb[(int64_t)(it + 1) * GR + m * n + tid];
+        }
+        if (m < 32) {
+            SM_UNROLL
+            for (int o = m; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        }
+        if (lane < m) red[wp * m + lane] = acc;
+        __syncthreads();
+        double *zk = zb + (int64_t)it * w;
+        if (tid < m) {
+            double s = kfc;
+            SM_UNROLL
+            for (int ww = 0; ww < WARPS; ++ww) s += red[ww * m + tid];
+            zc[n + tid] = -s;
+            __stcs(zk + n + tid, -s);
+        }
+        if (tid < n) __stcs(zk + tid, zc[tid]);
+        // this knot's [A B]: forward knot j completes on bar[j & 1]
+        if (it & 1) {
+            mbar_wait(bar + 1, ph1);
+            ph1 ^= 1;
+        } else {
+            mbar_wait(bar, ph0);
+            ph0 ^= 1;
+        }
+        __syncthreads();
+        // x+ = A x + B u : XP partial sums per state
+        const double *Fc = Fb[it & 1];
+        double xa = 0.0;
+        SM_UNROLL
+        for (int zz = 0; zz < XZ; ++zz) {
+            const int zi = XZ * xp_ + zz;
+            xa = fma(Fc[zi * LF + xi_], zc[zi], xa);
+        }
+        red[WARPS * m + xp_ * n + xi_] = xa;
+        __syncthreads();
+        if (tid < n) {
+            double s = 0.0;
+            SM_UNROLL
+            for (int pp = 0; pp < XP; ++pp) s += red[WARPS * m + pp * n + tid];
+            zn[tid] = s;
+        }
+        if (wp == 0 && it + 2 < steps) issue_knot(it + 2, Fb[it & 1], false, bar + (it & 1));
+        __syncthreads();
+    }
+    if (tid < n) __stcs(zb + (int64_t)steps * w + tid, zs[(steps & 1) * w + tid]);
+}
+
+}  // namespace rcta

@@ -53,7 +53,7 @@ def test_tpi_sizes(handle, oracle_mod, n, m, N, lti):
     assert handle.last_kernel.startswith("riccati_tpi")
 
 
-@pytest.mark.parametrize("n,m,N,batch", [(5, 2, 20, 9), (12, 3, 101, 10), (7, 7, 15, 5), (32, 8, 12, 3), (64, 16, 11, 2)])
+@pytest.mark.parametrize("n,m,N,batch", [(5, 2, 20, 9), (12, 3, 101, 10), (7, 7, 15, 5), (32, 7, 12, 3), (40, 16, 11, 2)])
 def test_cooperative_sizes(handle, oracle_mod, n, m, N, batch):
     prob = problems.random_lqr_riccati(n, m, N, batch, seed=n)
     _check(prob, handle, oracle_mod)
@@ -68,6 +68,36 @@ def test_dmma_sizes(handle, oracle_mod, n, m, N, batch, lti):
     prob = problems.random_lqr_riccati(n, m, N, batch, seed=n + m, lti=lti)
     _check(prob, handle, oracle_mod)
     assert handle.last_kernel.startswith("riccati_dmma")
+
+
+@pytest.mark.parametrize("n,m,N,batch", [(32, 8, 12, 3), (64, 16, 11, 2), (64, 16, 2, 3), (64, 16, 101, 5), (32, 8, 300, 7)])
+@pytest.mark.parametrize("lti", [False, True])
+def test_cta_dmma_sizes(handle, oracle_mod, n, m, N, batch, lti):
+    """CTA-per-instance FP64 tensor-core kernel (config 5b shape and its smaller sibling)."""
+    prob = problems.random_lqr_riccati(n, m, N, batch, seed=n + m, lti=lti)
+    _check(prob, handle, oracle_mod)
+    assert handle.last_kernel.startswith("riccati_cta_dmma")
+
+
+def test_cta_dmma_matches_cooperative_kernel(handle):
+    prob = problems.random_lqr_riccati(64, 16, 60, 6, seed=78)
+    X1, U1, K1, k1, i1 = ops.riccati_solve_problem(prob, handle=handle)
+    assert handle.last_kernel.startswith("riccati_cta_dmma")
+    handle.set_option("riccati_variant", 2)
+    try:
+        X2, U2, K2, k2, i2 = ops.riccati_solve_problem(prob, handle=handle)
+        assert handle.last_kernel.startswith("riccati_coop")
+    finally:
+        handle.set_option("riccati_variant", 0)
+    assert (i1 == 0).all() and (i2 == 0).all()
+    assert _rel(X1, X2) <= 1e-11 and _rel(U1, U2) <= 1e-11 and _rel(K1, K2) <= 1e-11 and _rel(k1, k2) <= 1e-11
+
+
+def test_cta_dmma_info_reports_nonpositive_pivot(handle):
+    prob = problems.random_lqr_riccati(64, 16, 20, 4, seed=2)
+    prob["R"][1] = -1e6 * np.eye(16)
+    _, _, _, _, info = ops.riccati_solve_problem(prob, handle=handle)
+    assert info[1] != 0 and (np.delete(info, 1) == 0).all()
 
 
 def test_dmma_matches_cooperative_kernel(handle):
