@@ -283,7 +283,11 @@ DevMap lqrb_get_map(lqrb_context *h, const std::string &key, const std::vector<R
     void *p = nullptr;
     const size_t bytes = map.size() * sizeof(RowMap) + 16;
     if (cudaMalloc(&p, bytes) != cudaSuccess ||
-        cudaMemcpy(p, map.data(), map.size() * sizeof(RowMap), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaMemcpy(p, map.data(), map.size() * sizeof(RowMap), cudaMemcpyHostToDevice) != cudaSuccess ||
+        // a pageable-source cudaMemcpy may return while the DMA from its staging buffer is still in flight on
+        // the legacy stream; the kernels that read the map run on non-blocking streams, so wait for it here
+        // (once per map shape)
+        cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) {
         lqrb_fail(h, 1000 + (int)cudaGetLastError(), "row map upload failed");
         return DevMap();
     }

@@ -385,6 +385,7 @@ static int32_t get_tables(lqrb_context *h, int n, int m, int N, const int32_t *p
         void *d = nullptr;
         LQRB_CUDA(h, cudaMalloc(&d, host.size()));
         LQRB_CUDA(h, cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice));
+        LQRB_CUDA(h, cudaStreamSynchronize(cudaStreamLegacy));  // pageable source: wait for the staged DMA
         h->blobs[key] = d;
         blob = (char *)d;
     }

@@ -14,11 +14,11 @@
 //     new P tile is written to shared memory together with its mirror image, which also keeps P bitwise
 //     symmetric (an antisymmetric rounding residue would be amplified by the open-loop |A|^2 per knot).
 //   * Muu = B'PB is reduced over the warps (each contributes the contraction over its 8 states), warp 0
-//     inverts it (Gauss-Jordan, one column per lane), then K's slice for tile w is Muu^-1 times the
-//     warp's own Mxu accumulators read as a (transposed) B fragment.
-// Shared memory per CTA (n=64: 96 KB -> 2 CTAs per SM, so one CTA's serial phases hide under the other's
-// DMMAs): P (ld n+4), K' (n x (m+4)), F = [A B] column-wise with ld n+4 (bank-conflict-free fragment
-// loads; filled by one 512-byte cp.async.bulk per column), R|q|r, and small vectors.  Q is read once per
+//     inverts it (Gauss-Jordan, one column per lane) while warp 1 already streams the next knot in, then
+//     K's slice for tile w is Muu^-1 times the warp's own Mxu accumulators read as a (transposed) B fragment.
+// Shared memory per CTA (n=64: 102 KB -> 2 CTAs per SM, so one CTA's serial phases hide under the other's
+// DMMAs): P (ld n+8), K' (n x (m+8)), F = [A B] column-wise with ld n+8 (every fragment is one
+// conflict-free 16-byte load; filled by one 512-byte cp.async.bulk per column), R|q|r, and small vectors.  Q is read once per
 // knot straight from global memory into the M accumulators (only the owned tiles).
 #pragma once
 #include "riccati_dmma_kernels.cuh"
@@ -34,25 +34,35 @@ template <int n, int m>
 struct Cfg {
     static_assert(n % 8 == 0 && m % 8 == 0 && m <= 16 && n >= 32 && n <= 64, "tile map: n = 32..64, m = 8, 16");
     static constexpr int NT = n / 8, UT = m / 8, WARPS = NT, THREADS = WARPS * 32, w = n + m;
-    static constexpr int JT = NT / 2 + 1;  // owned column tiles of M per warp: (w + j) % NT, j < JT
-    static constexpr int LP = n + 4, LF = n + 4, LK = m + 4, LM = m + 4;
+    static constexpr int JT = NT / 2 + 1;  // owned column tiles of M per warp (see own_ct)
+    // every fragment is read as one 16-byte load at [row g][8*blk + 2q]: leading dimensions = 8 (mod 16)
+    // doubles make each quarter-warp hit 8 distinct 16-byte bank groups
+    static constexpr int LP = n + 8, LF = n + 8, LK = m + 8, LM = m + 8;
     static constexpr int oQ = n * w, oR = oQ + tri(n), oq = oR + tri(m), orr = oq + n, F = orr + m;
     static constexpr int HS = tri(m) + n + m;  // R | q | r  (one bulk copy)
     static constexpr int TR = tri(n) + 2 * n, GR = m * n + m;
     static_assert(F % 2 == 0 && oR % 2 == 0 && HS % 2 == 0, "bulk copies need 16-byte pieces");
     // shared memory map (doubles)
-    static constexpr int sP = 0, sK = sP + n * LP, sF = sK + n * LK, sH = sF + w * LF, sPv = sH + HS, sG = sPv + n,
-                         sKff = sG + w, sMi = sKff + m, sCol = sMi + m * LM, sSlot = sCol + m,
-                         sZ = sSlot + (WARPS / 2) * m * m, sRed = sZ + 2 * w, sBar = sRed + WARPS * m + 4 * n,
-                         TOTAL = sBar + 2;
-    static_assert(sK + n * LK - sP >= w * LF, "forward pass double-buffers [A B] in the P|K' region");
+    // the WARPS partial-sum slots of Muu alias K' | z | red | pad: K' is written only after the slots are consumed,
+    // z and red belong to the forward pass
+    static constexpr int sP = 0, sK = sP + n * LP, sZ = sK + n * LK, sRed = sZ + 2 * w,
+                         sPadEnd = sK + (WARPS * m * m > n * LK + 2 * w + WARPS * m + 4 * n ? WARPS * m * m : n * LK + 2 * w + WARPS * m + 4 * n),
+                         sF = sPadEnd, sH = sF + w * LF, sPv = sH + HS, sG = sPv + n, sKff = sG + w, sMi = sKff + m,
+                         sCol = sMi + m * LM, sBar = sCol + 2 * m, TOTAL = sBar + 2, sSlot = sK;
+    static_assert(sZ - sP >= w * LF, "forward pass double-buffers [A B] in the P|K' region");
     static constexpr size_t SMEM = (size_t)TOTAL * 8;
 };
 
-// Is column tile ct = (wp + j) % NT of row tile wp formed by warp wp?  (each unordered tile pair once)
+// Which tiles of the symmetric M does warp wp form?  Tile (wp, (wp + j) % NT) for j < NT/2, plus the
+// antipodal tile j = NT/2 for the lower half of the warps: every unordered pair exactly once, and the two
+// warps that share an SM sub-partition (wp, wp + NT/2) carry NT/2 + NT/2 + 1 tiles together.
 template <int NT>
 __device__ __forceinline__ bool owns_j(int wp, int j) {
     return j < NT / 2 || (j == NT / 2 && wp < NT / 2);
+}
+template <int NT>
+__device__ __forceinline__ int own_ct(int wp, int j) {
+    return (wp + j) % NT;
 }
 
 template <int n, int m>
@@ -114,7 +124,7 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
         double M[JT][2], Mu[UT][2];
         SM_UNROLL
         for (int j = 0; j < JT; ++j) {
-            const int ct = (wp + j) % NT;
+            const int ct = own_ct<NT>(wp, j);
             SM_UNROLL
             for (int e = 0; e < 2; ++e) {
                 const int c = 8 * ct + 2 * q + e;
@@ -123,54 +133,89 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
         }
         SM_UNROLL
         for (int ut = 0; ut < UT; ++ut) Mu[ut][0] = Mu[ut][1] = 0.0;
+        // pull the next knot's record into L2 so that its bulk copies (issued after the GEMMs) are short
+        if (tid == 0 && !lti && it + 1 < steps)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(recg - F), "r"(F * 8) : "memory");
 
         mbar_wait(bar, ph0);
         ph0 ^= 1;
 
-        // ---- T row tile = F[:, rows]' P  (compute_gain! :38,40) and this warp's column slice of B'P
-        double T[NT][2], Tu[UT][2];
-        SM_UNROLL
-        for (int ct = 0; ct < NT; ++ct) T[ct][0] = T[ct][1] = 0.0;
-        SM_UNROLL
-        for (int ut = 0; ut < UT; ++ut) Tu[ut][0] = Tu[ut][1] = 0.0;
-        double gacc = 0.0, guacc[UT];
-        SM_UNROLL
-        for (int ut = 0; ut < UT; ++ut) guacc[ut] = 0.0;
+        // ---- phase 1: this warp's share of Muu = R + B'PB (contraction over its own 8 states)
         {
-            const double *fa = Fs + xr * LF + q;          // F[4s+q][x row]
-            const double *fu = Fs + (n + g) * LF + q;      // F[4s+q][u = 8ut+g]
-            const double *pb = Ps + q * LP + g;            // P[4s+q][8ct+g]
-#pragma unroll 4
-            for (int s = 0; s < n / 4; ++s) {
-                const double a = fa[4 * s];
-                const double pk = pv[4 * s + q];
-                gacc = fma(a, pk, gacc);
-                double au[UT];
+            double Tu[UT][2];
+            SM_UNROLL
+            for (int ut = 0; ut < UT; ++ut) Tu[ut][0] = Tu[ut][1] = 0.0;
+            double gua[UT][2];
+            SM_UNROLL
+            for (int ut = 0; ut < UT; ++ut) gua[ut][0] = gua[ut][1] = 0.0;
+            const double *fu = Fs + (n + g) * LF + 2 * q;       // B[8cp+2q+e][u = 8ut+g]
+            const double *pw = Ps + xr * LP + 2 * q;            // P[8cp+2q+e][8wp+g] (P symmetric)
+            SM_UNROLL
+            for (int cp = 0; cp < NT; ++cp) {
+                const double2 bw = *reinterpret_cast<const double2 *>(pw + 8 * cp);
+                const double2 pk = *reinterpret_cast<const double2 *>(pv + 8 * cp + 2 * q);
                 SM_UNROLL
                 for (int ut = 0; ut < UT; ++ut) {
-                    au[ut] = fu[4 * s + 8 * ut * LF];
-                    guacc[ut] = fma(au[ut], pk, guacc[ut]);
+                    const double2 au = *reinterpret_cast<const double2 *>(fu + 8 * ut * LF + 8 * cp);
+                    mma884(Tu[ut][0], Tu[ut][1], au.x, bw.x);
+                    mma884(Tu[ut][0], Tu[ut][1], au.y, bw.y);
+                    gua[ut][0] = fma(au.x, pk.x, gua[ut][0]);
+                    gua[ut][1] = fma(au.y, pk.y, gua[ut][1]);
                 }
-                const double *prow = pb + 4 * s * LP;
-                SM_UNROLL
-                for (int ct = 0; ct < NT; ++ct) mma884(T[ct][0], T[ct][1], a, prow[8 * ct]);
-                const double bw = prow[8 * wp];
-                SM_UNROLL
-                for (int ut = 0; ut < UT; ++ut) mma884(Tu[ut][0], Tu[ut][1], au[ut], bw);
             }
+            if (wp == 0) {  // g^u = r + B'p
+                SM_UNROLL
+                for (int ut = 0; ut < UT; ++ut) {
+                    double s = gua[ut][0] + gua[ut][1];
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    if (q == 0) gh[n + 8 * ut + g] = s + rs[8 * ut + g];
+                }
+            }
+            double *sl = slot + wp * m * m;
+            SM_UNROLL
+            for (int ut = 0; ut < UT; ++ut)
+                SM_UNROLL
+                for (int vt = 0; vt < UT; ++vt) {
+                    double mp[2];
+                    SM_UNROLL
+                    for (int e = 0; e < 2; ++e) {
+                        const int a = 8 * ut + g, b = 8 * vt + 2 * q + e;
+                        mp[e] = wp == 0 ? Rs[a <= b ? b * (b + 1) / 2 + a : a * (a + 1) / 2 + b] : 0.0;
+                    }
+                    const double2 b = *reinterpret_cast<const double2 *>(Fs + (n + 8 * vt + g) * LF + 8 * wp + 2 * q);
+                    mma884(mp[0], mp[1], Tu[ut][0], b.x);
+                    mma884(mp[0], mp[1], Tu[ut][1], b.y);
+                    *reinterpret_cast<double2 *>(sl + (8 * ut + g) * m + 8 * vt + 2 * q) = make_double2(mp[0], mp[1]);
+                }
         }
-        // g^ = [q; r] + F'p  (quad lanes hold partial sums over their contraction indices)
-        gacc += __shfl_xor_sync(0xffffffffu, gacc, 1);
-        gacc += __shfl_xor_sync(0xffffffffu, gacc, 2);
-        if (q == 0) gh[xr] = gacc + qs[xr];
+        // ---- phase 2: T row tile = F[:, rows]' P  (compute_gain! :38,40); g^x = q + A'p
+        double T[NT][2];
         SM_UNROLL
-        for (int ut = 0; ut < UT; ++ut) {
-            guacc[ut] += __shfl_xor_sync(0xffffffffu, guacc[ut], 1);
-            guacc[ut] += __shfl_xor_sync(0xffffffffu, guacc[ut], 2);
-            if (wp == 0 && q == 0) gh[n + 8 * ut + g] = guacc[ut] + rs[8 * ut + g];
+        for (int ct = 0; ct < NT; ++ct) T[ct][0] = T[ct][1] = 0.0;
+        {
+            double ga0 = 0.0, ga1 = 0.0;
+            const double *fa = Fs + xr * LF + 2 * q;  // F[8cp+2q+e][x row]
+            const double *pb = Ps + g * LP + 2 * q;   // P[8cp+2q+e][8ct+g], read through the mirror image
+            SM_UNROLL
+            for (int cp = 0; cp < NT; ++cp) {
+                const double2 a = *reinterpret_cast<const double2 *>(fa + 8 * cp);
+                const double2 pk = *reinterpret_cast<const double2 *>(pv + 8 * cp + 2 * q);
+                ga0 = fma(a.x, pk.x, ga0);
+                ga1 = fma(a.y, pk.y, ga1);
+                SM_UNROLL
+                for (int ct = 0; ct < NT; ++ct) {
+                    const double2 b = *reinterpret_cast<const double2 *>(pb + 8 * ct * LP + 8 * cp);
+                    mma884(T[ct][0], T[ct][1], a.x, b.x);
+                    mma884(T[ct][0], T[ct][1], a.y, b.y);
+                }
+            }
+            double gacc = ga0 + ga1;
+            gacc += __shfl_xor_sync(0xffffffffu, gacc, 1);
+            gacc += __shfl_xor_sync(0xffffffffu, gacc, 2);
+            if (q == 0) gh[xr] = gacc + qs[xr];
         }
-
-        // ---- M += T F : owned state tiles and the control columns  (E :39, K :41, A'PA :50)
+        // ---- phase 3: M += T F : owned state tiles and the control columns  (E :39, K :41, A'PA :50)
         SM_UNROLL
         for (int cp = 0; cp < NT; ++cp) {
             const double ta0 = T[cp][0], ta1 = T[cp][1];
@@ -178,7 +223,7 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
             SM_UNROLL
             for (int j = 0; j < JT; ++j) {
                 if (owns_j<NT>(wp, j)) {
-                    const int ct = (wp + j) % NT;
+                    const int ct = own_ct<NT>(wp, j);
                     const double2 b = *reinterpret_cast<const double2 *>(fb + 8 * ct * LF);
                     mma884(M[j][0], M[j][1], ta0, b.x);
                     mma884(M[j][0], M[j][1], ta1, b.y);
@@ -191,96 +236,77 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
                 mma884(Mu[ut][0], Mu[ut][1], ta1, b.y);
             }
         }
-        // ---- this warp's share of Muu = R + B'PB: contraction over its own 8 states
-        double Mp[UT][UT][2];
-        SM_UNROLL
-        for (int ut = 0; ut < UT; ++ut)
-            SM_UNROLL
-            for (int vt = 0; vt < UT; ++vt) {
-                SM_UNROLL
-                for (int e = 0; e < 2; ++e) {
-                    const int a = 8 * ut + g, b = 8 * vt + 2 * q + e;
-                    Mp[ut][vt][e] = wp == 0 ? Rs[a <= b ? b * (b + 1) / 2 + a : a * (a + 1) / 2 + b] : 0.0;
-                }
-                const double2 b = *reinterpret_cast<const double2 *>(Fs + (n + 8 * vt + g) * LF + 8 * wp + 2 * q);
-                mma884(Mp[ut][vt][0], Mp[ut][vt][1], Tu[ut][0], b.x);
-                mma884(Mp[ut][vt][0], Mp[ut][vt][1], Tu[ut][1], b.y);
-            }
-        // two-round reduction over the warps through WARPS/2 slots (deterministic order)
-        if (wp >= WARPS / 2) {
-            double *sl = slot + (wp - WARPS / 2) * m * m;
-            SM_UNROLL
-            for (int ut = 0; ut < UT; ++ut)
-                SM_UNROLL
-                for (int vt = 0; vt < UT; ++vt)
-                    *reinterpret_cast<double2 *>(sl + (8 * ut + g) * m + 8 * vt + 2 * q) = make_double2(Mp[ut][vt][0], Mp[ut][vt][1]);
-        }
-        __syncthreads();
-        if (wp < WARPS / 2) {
-            double *sl = slot + wp * m * m;
-            SM_UNROLL
-            for (int ut = 0; ut < UT; ++ut)
-                SM_UNROLL
-                for (int vt = 0; vt < UT; ++vt) {
-                    double2 *p2 = reinterpret_cast<double2 *>(sl + (8 * ut + g) * m + 8 * vt + 2 * q);
-                    const double2 o = *p2;
-                    *p2 = make_double2(o.x + Mp[ut][vt][0], o.y + Mp[ut][vt][1]);
-                }
-        }
-        __syncthreads();  // every warp is done with F, R|q|r and the partial slots are complete
+        __syncthreads();  // every warp is done with F and R|q|r; the Muu partial sums are in the slots
 
         if (wp == 1 && it + 1 < steps) issue_knot(k - 1, Fs, true, bar);  // overlaps the phases below
         if (wp == 0) {
-            // ---- Muu^-1 by Gauss-Jordan, lane j < m owns column j  (chol_solve! :28-31 applied by
-            // multiplication); pivots are the squared Cholesky pivots, so the sign test is potrf's
-            double a[m];
-            const int j = lane < m ? lane : 0;
+            // ---- Muu^-1 by Gauss-Jordan (chol_solve! :28-31 applied by multiplication).  Two lanes per
+            // column (lane = 16*half + column, each holds m/2 rows) keep the number of FP64 instructions low:
+            // they queue behind the other CTA's DMMAs.  Pivots are the squared Cholesky pivots (potrf's sign test).
+            constexpr int HR = m / 2;
+            const int hh = lane >> 4, j = (lane & 15) < m ? (lane & 15) : 0;
+            double a[HR];
             SM_UNROLL
-            for (int i = 0; i < m; ++i) {
-                double s = 0.0;
+            for (int i = 0; i < HR; ++i) {
+                const double *sp = slot + (HR * hh + i) * m + j;
+                double s0 = sp[0], s1 = sp[m * m];
                 SM_UNROLL
-                for (int sl = 0; sl < WARPS / 2; ++sl) s += slot[sl * m * m + i * m + j];
-                a[i] = s;
+                for (int sl = 2; sl < WARPS; sl += 2) {
+                    s0 += sp[sl * m * m];
+                    s1 += sp[(sl + 1) * m * m];
+                }
+                a[i] = s0 + s1;
             }
             int bad = 0;
             SM_UNROLL
             for (int kk = 0; kk < m; ++kk) {
-                if (lane == kk) {
+                double *cb = colb + (kk & 1) * m;  // double-buffered: one warp barrier per pivot
+                if ((lane & 15) == kk) {
                     SM_UNROLL
-                    for (int i = 0; i < m; ++i) colb[i] = a[i];
+                    for (int i = 0; i < HR; i += 2) *reinterpret_cast<double2 *>(cb + HR * hh + i) = make_double2(a[i], a[i + 1]);
                 }
+                // row kk of this lane's column lives in the half kk / HR
+                const double akk = __shfl_sync(0xffffffffu, a[kk % HR], ((kk / HR) << 4) | (lane & 15));
                 __syncwarp();
-                double c[m];
+                double c[HR];
                 SM_UNROLL
-                for (int i = 0; i < m; i += 2) {
-                    const double2 v = *reinterpret_cast<const double2 *>(colb + i);
+                for (int i = 0; i < HR; i += 2) {
+                    const double2 v = *reinterpret_cast<const double2 *>(cb + HR * hh + i);
                     c[i] = v.x;
                     c[i + 1] = v.y;
                 }
-                __syncwarp();
-                if (!(c[kk] > 0.0) && bad == 0) bad = kk + 1;
-                const double p = rdmma::fast_rcp(c[kk]);
-                const bool piv = lane == kk;
-                const double f = piv ? -p : a[kk] * p;
+                const double ckk = cb[kk];
+                if (!(ckk > 0.0) && bad == 0) bad = kk + 1;
+                const double p = rdmma::fast_rcp(ckk);
+                const bool piv = (lane & 15) == kk;
+                const double f = piv ? -p : akk * p;
                 SM_UNROLL
-                for (int i = 0; i < m; ++i) {
-                    if (i == kk) a[i] = piv ? p : f;
-                    else a[i] = piv ? c[i] * f : fma(-c[i], f, a[i]);
+                for (int i = 0; i < HR; ++i) {
+                    if (i == kk % HR) {
+                        const double upd = piv ? c[i] * f : fma(-c[i], f, a[i]);
+                        a[i] = hh == kk / HR ? (piv ? p : f) : upd;
+                    } else {
+                        a[i] = piv ? c[i] * f : fma(-c[i], f, a[i]);
+                    }
                 }
             }
             if (bad != 0 && st_all == 0) st_all = (k + 1) * 1000 + bad;
-            if (lane < m) {
+            {
                 double kf = 0.0;
                 SM_UNROLL
-                for (int i = 0; i < m; ++i) {
-                    Mi[i * LM + lane] = a[i];
-                    kf = fma(a[i], gh[n + i], kf);  // Muu^-1 symmetric: column j dotted with g^u
+                for (int i = 0; i < HR; ++i) {
+                    if ((lane & 15) < m) Mi[(HR * hh + i) * LM + j] = a[i];
+                    kf = fma(a[i], gh[n + HR * hh + i], kf);  // Muu^-1 symmetric: column j dotted with g^u
                 }
-                kffs[lane] = kf;
-                gb[(int64_t)k * GR + m * n + lane] = kf;
+                kf += __shfl_xor_sync(0xffffffffu, kf, 16);
+                if (lane < m) {
+                    kffs[lane] = kf;
+                    gb[(int64_t)k * GR + m * n + lane] = kf;
+                }
             }
         }
-        __syncthreads();
+
+        __syncthreads();  // Muu^-1 and kff are published
 
         // ---- K[:, own tile] = Muu^-1 Mux[:, own tile]; Mux is this warp's Mxu accumulators transposed
         SM_UNROLL
@@ -309,7 +335,7 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
             SM_UNROLL
             for (int j = 0; j < JT; ++j) {
                 if (owns_j<NT>(wp, j)) {
-                    const int ct = (wp + j) % NT;
+                    const int ct = own_ct<NT>(wp, j);
                     const double2 b = *reinterpret_cast<const double2 *>(Kt + (8 * ct + g) * LK + 8 * ut + 2 * q);
                     mma884(M[j][0], M[j][1], na0, b.x);
                     mma884(M[j][0], M[j][1], na1, b.y);
@@ -331,7 +357,7 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
         SM_UNROLL
         for (int j = 0; j < JT; ++j) {
             if (owns_j<NT>(wp, j)) {
-                const int ct = (wp + j) % NT;
+                const int ct = own_ct<NT>(wp, j);
                 SM_UNROLL
                 for (int e = 0; e < 2; ++e) {
                     const int c = 8 * ct + 2 * q + e;
