@@ -3,6 +3,7 @@
 #include <cstdio>
 
 #include "kkt_coop.cuh"
+#include "kkt_hw_kernels.cuh"
 #include "kkt_kernels.cuh"
 
 // ------------------------------------------------------------------ size classes --------------
@@ -31,6 +32,20 @@ static bool kkt_has_tpi(const KktShape &s) {
 #define X(N_, M_, A_, B_, C_) \
     if (s.n == N_ && s.m == M_ && s.P1 == A_ && (s.N == 2 || s.PM == B_) && s.PN == C_) return true;
     KKT_TPI_SIZES(X)
+#undef X
+    return false;
+}
+
+// half-warp-per-instance instantiations: p = [n, 0, ..., 0, n], block-diagonal Hessian, structural D2
+#define KKT_HW_SIZES(X) X(12, 4) X(8, 4)
+
+static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
+    if (h->opt("kkt_variant", 0) == 2) return false;
+    if (!s.uniform || s.d2x || s.hess != LQRB_HESS_BLOCKDIAG || (flags & LQRB_FLAG_SOC)) return false;
+    if (s.N < 3 || s.P1 != s.n || s.PM != 0 || s.PN != s.n) return false;
+#define X(N_, M_) \
+    if (s.n == N_ && s.m == M_) return true;
+    KKT_HW_SIZES(X)
 #undef X
     return false;
 }
@@ -141,6 +156,8 @@ static int32_t check_kkt(lqrb_context *h, int n, int m, int N, int64_t batch, co
     return 0;
 }
 
+static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch);
+
 struct KktSizes {
     int64_t NN, P, data_rows, rec_rows;
     int64_t sC, sc, sD2;
@@ -158,6 +175,8 @@ static KktSizes kkt_sizes(const KktShape &s) {
         if (k > 0) z.sD2 += (int64_t)s.n * w;
     }
     z.rec_rows = kkt_coop_rec_rows(s.n, s.m, s.N, s.p);  // an upper bound that also fits the TPI records
+    // the half-warp kernel keeps (U, v) records, H^-1 of every knot and a status word per instance
+    z.rec_rows = std::max<int64_t>(z.rec_rows, (int64_t)(kkt_hw_scratch_doubles(s, 2) + 1) / 2);
     return z;
 }
 
@@ -189,10 +208,52 @@ static int32_t launch_kkt_tpi(lqrb_context *h, const KktShape &s, int64_t batch,
     return 0;
 }
 
+template <int n, int m>
+static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, const double *data,
+                             double *scratch, double *dz, double *mult, double *res, int32_t *info,
+                             cudaStream_t st) {
+    using L = khw::Lay<n, m>;
+    constexpr int WARPS = 4, MINB = 3;
+    const int N = s.N;
+    // scratch: [records: batch x N x REC] [Hi: batch x N x HI] [hinfo: batch]
+    double *recs = scratch;
+    double *hinv = recs + (size_t)batch * N * L::REC;
+    int32_t *hinfo = reinterpret_cast<int32_t *>(hinv + (size_t)batch * N * L::HI);
+    LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)batch * sizeof(int32_t), st));
+    const int64_t total = batch * N;
+    khw::kkt_hinv_kernel<n, m><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(data, hinv, hinfo, N, batch);
+    LQRB_LAUNCH_CHECK(h, "kkt_hinv_kernel");
+    const size_t smem = (size_t)WARPS * (2 * L::INST + 4) * sizeof(double);
+    auto kern = khw::kkt_hw_kernel<n, m, WARPS, MINB>;
+    LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t pairs = (batch + 1) / 2;
+    kern<<<(unsigned)((pairs + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(data, hinv, hinfo, recs, dz, mult, res, info, N, batch);
+    char nm[96];
+    snprintf(nm, sizeof nm, "kkt_hw<%d,%d,p=%d/0/%d,hess=1>", n, m, n, n);
+    h->kernel_name = nm;
+    LQRB_LAUNCH_CHECK(h, "kkt_hw_kernel");
+    return 0;
+}
+
+static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch) {
+#define X(N_, M_) \
+    if (s.n == N_ && s.m == M_)   \
+        return (size_t)batch * s.N * (khw::Lay<N_, M_>::REC + khw::Lay<N_, M_>::HI) + (size_t)(batch + 1) / 2 + 2;
+    KKT_HW_SIZES(X)
+#undef X
+    return 0;
+}
+
 static int32_t kkt_solve_on(lqrb_context *h, const KktShape &s, int64_t batch, int flags,
                             const double *data, double *scratch, double *dz, double *mult, double *res,
                             int32_t *info, cudaStream_t st) {
     if (batch == 0) return 0;
+    if (kkt_has_hw(h, s, flags) && ((uintptr_t)data & 15) == 0) {
+#define X(N_, M_) \
+    if (s.n == N_ && s.m == M_) return launch_kkt_hw<N_, M_>(h, s, batch, data, scratch, dz, mult, res, info, st);
+        KKT_HW_SIZES(X)
+#undef X
+    }
     if (lqrb_kkt_tile(h, s.n, s.m, s.N, s.p, s.hess, s.d2x) == LQRB_TILE) {
 #define X(N_, M_, A_, B_, C_)                                                                       \
     if (s.n == N_ && s.m == M_ && s.P1 == A_ && (s.N == 2 || s.PM == B_) && s.PN == C_)            \

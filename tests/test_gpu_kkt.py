@@ -73,12 +73,44 @@ def test_tpi_hessian_modes(handle, oracle_mod, n, m, N, mid_p, hess):
 
 @pytest.mark.parametrize("hess", [0, 1, 2])
 @pytest.mark.parametrize("n,m,N,mid_p,d2x", [(5, 2, 10, 1, False), (4, 1, 12, 0, True), (3, 2, 8, 1, True),
-                                            (12, 4, 40, 0, False), (12, 4, 9, 2, True), (20, 6, 6, 0, False),
+                                            (12, 3, 40, 0, False), (12, 4, 9, 2, True), (20, 6, 6, 0, False),
                                             (3, 3, 2, 0, False)])
 def test_cooperative_kernel(handle, oracle_mod, n, m, N, mid_p, d2x, hess):
     prob = problems.random_lqr_kkt(n, m, N, 6, seed=n + hess, mid_p=mid_p, hess_mode=hess, explicit_D2=d2x)
     _check(prob, handle, oracle_mod)
     assert handle.last_kernel.startswith("kkt_coop")
+
+
+@pytest.mark.parametrize("n,m,N,batch", [(12, 4, 40, 6), (12, 4, 8, 5), (12, 4, 6, 1), (8, 4, 25, 7), (8, 4, 4, 3), (12, 4, 301, 9),
+                                         (12, 4, 1001, 2)])
+def test_half_warp_kernel(handle, oracle_mod, n, m, N, batch):
+    """config 5a-K shape: init + dynamics + goal, block-diagonal Hessian -> half-warp-per-instance kernel."""
+    prob = problems.random_lqr_kkt(n, m, N, batch, seed=n + N, mid_p=0, hess_mode=1)
+    _check(prob, handle, oracle_mod, truth_instances=(0, batch - 1))
+    assert handle.last_kernel.startswith("kkt_hw<")
+
+
+def test_half_warp_matches_cooperative_kernel(handle):
+    prob = problems.random_lqr_kkt(12, 4, 120, 11, seed=5, mid_p=0, hess_mode=1)
+    dz1, lam1, i1, r1 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
+    assert handle.last_kernel.startswith("kkt_hw<")
+    handle.set_option("kkt_variant", 2)
+    try:
+        dz2, lam2, i2, r2 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
+        assert handle.last_kernel.startswith("kkt_coop")
+    finally:
+        handle.set_option("kkt_variant", 0)
+    assert (i1 == 0).all() and (i2 == 0).all()
+    assert _rel(dz1, dz2) <= 1e-11 and _rel(lam1, lam2) <= 1e-11
+    assert np.abs(r1 - r2).max() <= 1e-10 * max(1.0, np.abs(r2).max())
+
+
+def test_half_warp_info_flags(handle):
+    prob = problems.random_lqr_kkt(12, 4, 30, 5, seed=9, mid_p=0, hess_mode=1)
+    prob["R"][2, 7] = -np.eye(4)
+    _, _, info = ops.kkt_solve_problem(prob, handle=handle)
+    assert handle.last_kernel.startswith("kkt_hw<")
+    assert info[2] == 8 * 1000 + 12 + 1 and (np.delete(info, 2) == 0).all()
 
 
 def test_irregular_stage_pattern(handle, oracle_mod):
