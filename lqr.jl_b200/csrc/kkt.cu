@@ -4,6 +4,7 @@
 
 #include "kkt_coop.cuh"
 #include "kkt_hw_kernels.cuh"
+#include "kkt_cta_kernels.cuh"
 #include "kkt_kernels.cuh"
 
 // ------------------------------------------------------------------ size classes --------------
@@ -46,6 +47,20 @@ static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_) return true;
     KKT_HW_SIZES(X)
+#undef X
+    return false;
+}
+
+// CTA-per-instance FP64 tensor-core instantiations (same stage pattern)
+#define KKT_CTA_SIZES(X) X(64, 16)
+
+static bool kkt_has_cta(const lqrb_context *h, const KktShape &s, int flags) {
+    if (h->opt("kkt_variant", 0) == 2) return false;
+    if (!s.uniform || s.d2x || s.hess != LQRB_HESS_BLOCKDIAG || (flags & LQRB_FLAG_SOC)) return false;
+    if (s.N < 3 || s.P1 != s.n || s.PM != 0 || s.PN != s.n) return false;
+#define X(N_, M_) \
+    if (s.n == N_ && s.m == M_) return true;
+    KKT_CTA_SIZES(X)
 #undef X
     return false;
 }
@@ -235,7 +250,38 @@ static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, 
     return 0;
 }
 
+template <int n, int m>
+static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch, const double *data,
+                              double *scratch, double *dz, double *mult, double *res, int32_t *info,
+                              cudaStream_t st) {
+    using L = kcta::Lay<n, m>;
+    const int N = s.N;
+    // scratch: [records: batch x N x REC] [pre-pass slots: batch x prep_rows] [hinfo: batch]
+    double *recs = scratch;
+    double *prep = recs + (size_t)batch * N * L::REC;
+    int32_t *hinfo = reinterpret_cast<int32_t *>(prep + (size_t)batch * L::prep_rows(N));
+    LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)batch * sizeof(int32_t), st));
+    const size_t psm = (size_t)L::PREP_TOTAL * sizeof(double), msm = (size_t)L::MAIN_TOTAL * sizeof(double);
+    auto pk = kcta::kkt_cta_prep_kernel<n, m>;
+    auto mk = kcta::kkt_cta_kernel<n, m>;
+    LQRB_CUDA(h, cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+    LQRB_CUDA(h, cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
+    pk<<<(unsigned)(batch * N), L::THREADS, psm, st>>>(data, prep, hinfo, N, batch);
+    LQRB_LAUNCH_CHECK(h, "kkt_cta_prep_kernel");
+    mk<<<(unsigned)batch, L::THREADS, msm, st>>>(data, prep, hinfo, recs, dz, mult, res, info, N, batch);
+    char nm[96];
+    snprintf(nm, sizeof nm, "kkt_cta_dmma<%d,%d,p=%d/0/%d,hess=1>", n, m, n, n);
+    h->kernel_name = nm;
+    LQRB_LAUNCH_CHECK(h, "kkt_cta_kernel");
+    return 0;
+}
+
 static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch) {
+#define X(N_, M_) \
+    if (s.n == N_ && s.m == M_)   \
+        return (size_t)batch * ((size_t)s.N * kcta::Lay<N_, M_>::REC + kcta::Lay<N_, M_>::prep_rows(s.N)) + (size_t)(batch + 1) / 2 + 2;
+    KKT_CTA_SIZES(X)
+#undef X
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_)   \
         return (size_t)batch * s.N * (khw::Lay<N_, M_>::REC + khw::Lay<N_, M_>::HI) + (size_t)(batch + 1) / 2 + 2;
@@ -248,6 +294,12 @@ static int32_t kkt_solve_on(lqrb_context *h, const KktShape &s, int64_t batch, i
                             const double *data, double *scratch, double *dz, double *mult, double *res,
                             int32_t *info, cudaStream_t st) {
     if (batch == 0) return 0;
+    if (kkt_has_cta(h, s, flags) && ((uintptr_t)data & 15) == 0 && ((uintptr_t)scratch & 15) == 0) {
+#define X(N_, M_) \
+    if (s.n == N_ && s.m == M_) return launch_kkt_cta<N_, M_>(h, s, batch, data, scratch, dz, mult, res, info, st);
+        KKT_CTA_SIZES(X)
+#undef X
+    }
     if (kkt_has_hw(h, s, flags) && ((uintptr_t)data & 15) == 0) {
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_) return launch_kkt_hw<N_, M_>(h, s, batch, data, scratch, dz, mult, res, info, st);

@@ -1,0 +1,573 @@
+// kkt_cta_kernels.cuh — constrained KKT solve for the large-state class (n = 64, m = 16): one CTA per
+// instance, everything of order n^3 on the FP64 tensor cores (mma.sync m8n8k4 DMMA).  "Dense-Schur variant"
+// of BASELINE.json config 5.
+//
+// Replaces _solve!(::CholeskySolver) : src/cholesky_solver.jl:166-182 for the stage pattern p = [n,0,..,0,n]
+// (initial condition + dynamics + goal constraint, D2 = [-I 0], block-diagonal cost Hessian) with the same
+// block-LDL' restatement as kkt_hw_kernels.cuh (see there for the algebra and the reference line numbers):
+//   pre-pass (kkt_cta_prep_kernel, one CTA per knot, fully parallel — the reference's calculate_shur_factors!,
+//     src/jacobian_blocks.jl:220-286):   Qi = Q_k^-1,  Ri = R_k^-1,  T = A Qi (= -F'),  G = A Qi A' + B Ri B',
+//     hg = Hi g,  rho = D1 hg - d           (first knot: B0 = C Hi C', -E0' and -y0 in the same slots)
+//   main kernel (kkt_cta_kernel, one CTA per instance, sequential in k — cholesky!(chol, shur) and the two
+//     substitutions, src/cholesky_solve.jl:28-143):   Sigma = Cp + Qi,  Si = Sigma^-1,  Z = T Si (= -U'),
+//     v = Si y,  Cp <- G - Z T',  dp <- rho + T v;   backward:  x_{k-1} = v_k + Z_k' x_k,  Lambda = -x,
+//     res_k, dz_k = -Hi res_k   (calculate_primals!, src/cholesky_solver.jl:185-236).
+// Both kernels invert n x n SPD blocks with an in-place block Gauss-Jordan on 8 x 8 tiles: warp w keeps row
+// tile w of the matrix in DMMA accumulator registers for all n/8 block steps; per step the pivot column panel
+// goes through shared memory, the owning warp inverts the 8 x 8 pivot (one lane per column), and the rank-8
+// update of every other tile is two DMMAs (A operand = the warp's own accumulators, a C fragment read as an
+// A fragment under the permuted contraction index; B operand = a panel tile read with one 16-byte load).
+#pragma once
+#include "kkt_hw_kernels.cuh"
+
+namespace kcta {
+using rdmma::bulk_g2s;
+using rdmma::mbar_expect_tx;
+using rdmma::mbar_init;
+using rdmma::mbar_wait;
+using rdmma::mma884;
+
+template <int n, int m>
+struct Lay {
+    static_assert(n % 8 == 0 && m % 8 == 0 && n == 64 && m <= 16, "written for n = 64, m = 8, 16");
+    static constexpr int NT = n / 8, UT = m / 8, w = n + m, WARPS = NT, THREADS = WARPS * 32;
+    // packed knot records (tile width 1), identical to kkt_hw_kernels.cuh
+    static constexpr int oQ = 0, oR = tri(n), og = oR + tri(m), oD1 = og + w, od = oD1 + n * w, CORE = od + n;
+    static constexpr int oC0 = CORE, FIRST = CORE + n * w + n, MID = CORE;
+    static constexpr int oCl = tri(n) + n, LAST = oCl + n * n + n;
+    __host__ __device__ static constexpr int64_t data_rows(int N) { return FIRST + (int64_t)(N - 2) * MID + LAST; }
+    __host__ __device__ static constexpr int64_t knot_off(int k) { return k == 0 ? 0 : FIRST + (int64_t)(k - 1) * MID; }
+    __host__ __device__ static constexpr int64_t mult_rows(int N) { return 2 * n + (int64_t)(N - 1) * n; }
+    __host__ __device__ static constexpr int64_t z_rows(int N) { return (int64_t)N * n + (int64_t)(N - 1) * m; }
+    // pre-pass output slot of one knot (doubles): Qi | T | G | hg (w) | rho (n) | Ri (m*m)
+    static constexpr int hQi = 0, hT = n * n, hG = 2 * n * n, hHg = 3 * n * n, hRho = hHg + w, hRi = hRho + n,
+                         HS = hRi + m * m;
+    static_assert(HS % 2 == 0 && hHg % 2 == 0, "16-byte pieces");
+    // per instance: N slots + the true Qi of the first knot (its slot holds B0)
+    __host__ __device__ static constexpr int64_t prep_rows(int N) { return (int64_t)N * HS + n * n; }
+    static constexpr int REC = n * n + n;  // Z (row-major) | v
+    // shared memory of the pre-pass (doubles)
+    static constexpr int LA = n + 4;  // k-major operand loads: leading dimension = 4 (mod 16)
+    static constexpr int pA = 0, pQ = pA + w * LA, pPan = pQ + n * LA, pPi = pPan + NT * 64, pCol = pPi + 64,
+                         pRi = pCol + 2 * m, pV = pRi + m * (m + 4), PREP_TOTAL = pV + 4 * w + 64;
+    // shared memory of the main kernel (doubles)
+    static constexpr int LB = n + 8;  // paired (16-byte) operand loads: leading dimension = 8 (mod 16)
+    static constexpr int mT = 0, mS = mT + n * LB, mPan = mS + n * LB, mPi = mPan + NT * 64, mCol = mPi + 64,
+                         mV = mCol + 16, mBar = mV + 8 * n + 4 * w, MAIN_TOTAL = mBar + 2;
+};
+
+// ------------------------------------------------------------------ block Gauss-Jordan ----------------
+// In place: S[ct][e] = tile (wp, ct) of an SPD n x n matrix in C-fragment layout -> the same tiles of its
+// inverse.  pan: NT*64 doubles (8 x 8 tiles, row-major), pis: 64 doubles, colb: 16 doubles.  Returns the
+// 1-based index of the first non-positive pivot (potrf semantics) or 0; identical in every thread.
+template <int NT>
+__device__ __forceinline__ int block_gj_inverse(double (&S)[NT][2], double *pan, double *pis, double *colb,
+                                                int *flag, int wp, int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    SM_UNROLL
+    for (int kb = 0; kb < NT; ++kb) {
+        *reinterpret_cast<double2 *>(pan + wp * 64 + g * 8 + 2 * q) = make_double2(S[kb][0], S[kb][1]);
+        __syncthreads();
+        if (wp == kb) {
+            // invert the 8 x 8 pivot block: lane j < 8 owns column j (symmetric: column = row)
+            double a[8];
+            const int j = lane < 8 ? lane : 0;
+            SM_UNROLL
+            for (int i = 0; i < 8; ++i) a[i] = pan[kb * 64 + i * 8 + j];
+            const int bad = khw::gj_inverse<8>(a, colb, lane < 8 ? lane : 31);
+            if (lane < 8) {
+                SM_UNROLL
+                for (int i = 0; i < 8; ++i) pis[i * 8 + lane] = a[i];
+            }
+            if (bad != 0 && lane == 0 && *flag == 0) *flag = 8 * kb + bad;
+        }
+        __syncthreads();
+        const double2 pv = *reinterpret_cast<const double2 *>(pis + g * 8 + 2 * q);  // Pi[g][2q..2q+1] (symmetric)
+        if (wp != kb) {
+            // T = A_wk Pi ; A_wj -= T A_kj ; A_wk = -T.  The pivot row A_kj is taken from the column panel:
+            // in-place Gauss-Jordan leaves A_kj = A_jk' for the columns still to be eliminated (j > kb) and
+            // A_kj = -A_jk' for the ones already done (A_ik <- -A_ik Pi but A_kj <- +Pi A_kj).
+            double t0 = 0.0, t1 = 0.0;
+            mma884(t0, t1, S[kb][0], pv.x);
+            mma884(t0, t1, S[kb][1], pv.y);
+            const double n0 = -t0, n1 = -t1;
+            SM_UNROLL
+            for (int j = 0; j < NT; ++j) {
+                if (j != kb) {
+                    const double2 b = *reinterpret_cast<const double2 *>(pan + j * 64 + g * 8 + 2 * q);
+                    mma884(S[j][0], S[j][1], j < kb ? t0 : n0, b.x);
+                    mma884(S[j][0], S[j][1], j < kb ? t1 : n1, b.y);
+                }
+            }
+            S[kb][0] = n0;
+            S[kb][1] = n1;
+        } else {
+            // the pivot row: A_kj = Pi A_kj, A_kk = Pi
+            SM_UNROLL
+            for (int j = 0; j < NT; ++j) {
+                if (j != kb) {
+                    const double2 b = *reinterpret_cast<const double2 *>(pan + j * 64 + g * 8 + 2 * q);
+                    double s0 = 0.0, s1 = 0.0;
+                    mma884(s0, s1, pv.x, b.x);
+                    mma884(s0, s1, pv.y, b.y);
+                    S[j][0] = j < kb ? -s0 : s0;
+                    S[j][1] = j < kb ? -s1 : s1;
+                }
+            }
+            S[kb][0] = pv.x;
+            S[kb][1] = pv.y;
+        }
+        __syncthreads();
+    }
+    return *flag;
+}
+
+// ------------------------------------------------------------------ pre-pass --------------------------
+// grid = batch * N CTAs of THREADS threads.  knot 0: generic scalar code for the C_1 blocks (once per instance).
+template <int n, int m>
+__global__ void __launch_bounds__(Lay<n, m>::THREADS, 2)
+    kkt_cta_prep_kernel(const double *__restrict__ data, double *__restrict__ prep, int32_t *__restrict__ hinfo,
+                        int N, int64_t batch) {
+    using L = Lay<n, m>;
+    constexpr int NT = L::NT, UT = L::UT, w = L::w, LA = L::LA, THREADS = L::THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    double *As = sm + L::pA, *Qs = sm + L::pQ, *pan = sm + L::pPan, *pis = sm + L::pPi, *colb = sm + L::pCol,
+           *Ris = sm + L::pRi, *vq = sm + L::pV, *vhg = vq + w, *vd = vhg + w, *vtmp = vd + w;
+    __shared__ int flag;
+    const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int64_t inst = blockIdx.x / N;
+    const int k = (int)(blockIdx.x % N);
+    const bool first = k == 0, last = k == N - 1;
+    const int mk = last ? 0 : m, wk = n + mk;
+    const double *kp = data + inst * L::data_rows(N) + L::knot_off(k);
+    double *out = prep + inst * L::prep_rows(N) + (int64_t)k * L::HS;
+    constexpr int LR = m + 4;
+    if (tid == 0) flag = 0;
+
+    // ---- stage X = A_k (or C_N), B_k column-major with padded leading dimension; g, d; R
+    const double *Xg = last ? kp + L::oCl : kp + L::oD1;
+    for (int e = tid; e < n * wk; e += THREADS) As[(e / n) * LA + (e % n)] = Xg[e];
+    for (int e = tid; e < wk; e += THREADS) vq[e] = kp[(last ? tri(n) : L::og) + e];
+    for (int e = tid; e < n; e += THREADS) vd[e] = last ? kp[L::oCl + n * n + e] : kp[L::od + e];
+    // ---- Q strip (C fragments) -> Qi
+    double S[NT][2];
+    SM_UNROLL
+    for (int ct = 0; ct < NT; ++ct)
+        SM_UNROLL
+        for (int e = 0; e < 2; ++e) {
+            const int r = 8 * wp + g, c = 8 * ct + 2 * q + e;
+            S[ct][e] = kp[r <= c ? c * (c + 1) / 2 + r : r * (r + 1) / 2 + c];
+        }
+    __syncthreads();
+    int bad = block_gj_inverse<NT>(S, pan, pis, colb, &flag, wp, lane);
+    // Qi -> shared (operand) and global (slot, or the extra block for the first knot)
+    {
+        double *qo = first ? prep + inst * L::prep_rows(N) + (int64_t)N * L::HS : out + L::hQi;
+        SM_UNROLL
+        for (int ct = 0; ct < NT; ++ct) {
+            const int r = 8 * wp + g, c = 8 * ct + 2 * q;
+            *reinterpret_cast<double2 *>(Qs + r * LA + c) = make_double2(S[ct][0], S[ct][1]);
+            *reinterpret_cast<double2 *>(qo + r * n + c) = make_double2(S[ct][0], S[ct][1]);
+        }
+    }
+    // ---- Ri = R^-1 (warp 0, one lane per column)
+    if (!last && wp == 0) {
+        double a[m];
+        const int j = lane < m ? lane : 0;
+        SM_UNROLL
+        for (int i = 0; i < m; ++i) a[i] = kp[L::oR + (i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j)];
+        const int b2 = khw::gj_inverse<m>(a, colb, lane < m ? lane : 31);
+        if (lane < m) {
+            SM_UNROLL
+            for (int i = 0; i < m; ++i) {
+                Ris[i * LR + lane] = a[i];
+                out[L::hRi + i * m + lane] = a[i];
+            }
+        }
+        if (b2 != 0 && bad == 0 && lane == 0) flag = n + b2;
+    }
+    __syncthreads();
+    bad = flag;
+    if (bad != 0 && tid == 0) atomicMin(hinfo + inst, (k + 1) * 1000 + bad);
+    // ---- hg = Hi g
+    if (tid < n) {
+        double s0 = 0.0, s1 = 0.0;
+        SM_UNROLL
+        for (int l = 0; l < n; l += 2) {
+            s0 = fma(Qs[l * LA + tid], vq[l], s0);
+            s1 = fma(Qs[(l + 1) * LA + tid], vq[l + 1], s1);
+        }
+        vhg[tid] = s0 + s1;
+    } else if (tid < wk) {
+        double s = 0.0;
+        for (int l = 0; l < m; ++l) s = fma(Ris[l * LR + tid - n], vq[n + l], s);
+        vhg[tid] = s;
+    }
+    __syncthreads();
+    if (!first) {
+        for (int e = tid; e < wk; e += THREADS) out[L::hHg + e] = vhg[e];
+    }
+    // ---- rho = X hg_x + B hg_u - d
+    if (tid < n) {
+        double s0 = -vd[tid], s1 = 0.0;
+        SM_UNROLL
+        for (int l = 0; l < n; l += 2) {
+            s0 = fma(As[l * LA + tid], vhg[l], s0);
+            s1 = fma(As[(l + 1) * LA + tid], vhg[l + 1], s1);
+        }
+        for (int l = 0; l < mk; ++l) s0 = fma(As[(n + l) * LA + tid], vhg[n + l], s0);
+        out[L::hRho + tid] = s0 + s1;
+    }
+    // ---- T strip = X[rows] Qi   (A operand: X[8wp+g][4s+q], B operand: Qi[4s+q][8ct+g], k-major loads)
+    double T[NT][2];
+    SM_UNROLL
+    for (int ct = 0; ct < NT; ++ct) T[ct][0] = T[ct][1] = 0.0;
+    {
+        const double *xa = As + q * LA + 8 * wp + g;
+        const double *qb = Qs + q * LA + g;
+#pragma unroll 4
+        for (int s = 0; s < n / 4; ++s) {
+            const double a = xa[4 * s * LA];
+            SM_UNROLL
+            for (int ct = 0; ct < NT; ++ct) mma884(T[ct][0], T[ct][1], a, qb[4 * s * LA + 8 * ct]);
+        }
+    }
+    // ---- G strip = T X' + (B Ri) B'   (A operand: the T accumulators; B operand: X[8ct+g][8cp+2q+e])
+    double G[NT][2];
+    SM_UNROLL
+    for (int ct = 0; ct < NT; ++ct) G[ct][0] = G[ct][1] = 0.0;
+    SM_UNROLL
+    for (int cp = 0; cp < NT; ++cp) {
+        const double *xb = As + (8 * cp + 2 * q) * LA + g;
+        SM_UNROLL
+        for (int ct = 0; ct < NT; ++ct) {
+            mma884(G[ct][0], G[ct][1], T[cp][0], xb[8 * ct]);
+            mma884(G[ct][0], G[ct][1], T[cp][1], xb[LA + 8 * ct]);
+        }
+    }
+    if (!last) {
+        double V[UT][2];
+        SM_UNROLL
+        for (int ut = 0; ut < UT; ++ut) V[ut][0] = V[ut][1] = 0.0;
+        SM_UNROLL
+        for (int s = 0; s < m / 4; ++s) {
+            const double a = As[(n + 4 * s + q) * LA + 8 * wp + g];
+            SM_UNROLL
+            for (int ut = 0; ut < UT; ++ut) mma884(V[ut][0], V[ut][1], a, Ris[(4 * s + q) * LR + 8 * ut + g]);
+        }
+        SM_UNROLL
+        for (int ut = 0; ut < UT; ++ut) {
+            const double *bb = As + (n + 8 * ut + 2 * q) * LA + g;
+            SM_UNROLL
+            for (int ct = 0; ct < NT; ++ct) {
+                mma884(G[ct][0], G[ct][1], V[ut][0], bb[8 * ct]);
+                mma884(G[ct][0], G[ct][1], V[ut][1], bb[LA + 8 * ct]);
+            }
+        }
+    }
+    SM_UNROLL
+    for (int ct = 0; ct < NT; ++ct) {
+        const int r = 8 * wp + g, c = 8 * ct + 2 * q;
+        *reinterpret_cast<double2 *>(out + L::hG + r * n + c) = make_double2(G[ct][0], G[ct][1]);
+        if (!first) *reinterpret_cast<double2 *>(out + L::hT + r * n + c) = make_double2(T[ct][0], T[ct][1]);
+    }
+    if (!first) return;
+
+    // ---- first knot: slots Qi := B0 = C Hi C', T := -E0' = -D1 Hi C', hg := -(C hg - c)   (generic code)
+    // W0 = Hi C' (w x n) in shared memory over Qs|pan.. is too large; stream it: for each row i of C
+    const double *C0 = kp + L::oC0;  // n x w column-major
+    double *qo = out + L::hQi, *to = out + L::hT;
+    __syncthreads();
+    // vtmp reuse: per-CTA row buffer of Hi C[i,:]'  (w doubles)
+    for (int i = 0; i < n; ++i) {
+        // hc = Hi C[i,:]'
+        if (tid < n) {
+            double s = 0.0;
+            for (int l = 0; l < n; ++l) s = fma(Qs[l * LA + tid], C0[i + n * l], s);
+            vtmp[tid] = s;
+        } else if (tid < w) {
+            double s = 0.0;
+            for (int l = 0; l < m; ++l) s = fma(Ris[l * LR + tid - n], C0[i + n * (n + l)], s);
+            vtmp[tid] = s;
+        }
+        __syncthreads();
+        // B0[:, i] = C hc ; (-E0')[:, i] ... E0[i][b] = sum_j hc[j] D1[b][j]  ->  T slot row b, column i = -E0[i][b]
+        if (tid < n) {
+            double s = 0.0;
+            for (int j = 0; j < w; ++j) s = fma(C0[tid + n * j], vtmp[j], s);
+            qo[tid * n + i] = s;  // B0[tid][i] (symmetric)
+        } else if (tid < 2 * n) {
+            const int b = tid - n;
+            double s = 0.0;
+            for (int j = 0; j < w; ++j) s = fma(As[j * LA + b], vtmp[j], s);
+            to[b * n + i] = -s;
+        }
+        __syncthreads();
+    }
+    if (tid < n) {
+        double s = -C0[n * w + tid];
+        for (int j = 0; j < w; ++j) s = fma(C0[tid + n * j], vhg[j], s);
+        out[L::hHg + tid] = -s;  // y0 = dp - slot with dp = 0
+    } else if (tid < w) {
+        out[L::hHg + tid] = vhg[tid];
+    }
+}
+
+// ------------------------------------------------------------------ main kernel -----------------------
+template <int n, int m>
+__global__ void __launch_bounds__(Lay<n, m>::THREADS, 2)
+    kkt_cta_kernel(const double *__restrict__ data, const double *__restrict__ prep, const int32_t *__restrict__ hinfo,
+                   double *__restrict__ recs, double *__restrict__ dz, double *__restrict__ mult,
+                   double *__restrict__ res, int32_t *__restrict__ info, int N, int64_t batch) {
+    using L = Lay<n, m>;
+    constexpr int NT = L::NT, w = L::w, LB = L::LB, THREADS = L::THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sm = reinterpret_cast<double *>(smem_raw);
+    double *Ts = sm + L::mT, *Ss = sm + L::mS, *pan = sm + L::mPan, *pis = sm + L::mPi, *colb = sm + L::mCol,
+           *ys = sm + L::mV, *vs = ys + n, *dps = vs + n, *red = dps + n /* 4n */, *xs = red + 4 * n, *rsv = xs + w,
+           *xps = rsv + w;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(sm + L::mBar);
+    __shared__ int flag;
+    const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
+    const int64_t inst = blockIdx.x;
+    const double *db = data + inst * L::data_rows(N);
+    const double *pb = prep + inst * L::prep_rows(N);
+    double *rb = recs + inst * (int64_t)N * L::REC;
+    double *zb = dz + inst * L::z_rows(N);
+    double *mb = mult + inst * L::mult_rows(N);
+    double *resb = res ? res + inst * L::z_rows(N) : nullptr;
+    const int r0 = 8 * wp + g;  // the row of this lane's accumulator entries
+
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        flag = 0;
+    }
+    if (tid < n) dps[tid] = 0.0;
+    __syncthreads();
+    uint32_t ph = 0;
+    // T_k (n x n row-major in the slot) -> Ts with padded rows, one 512-byte bulk copy per row
+    auto issue_T = [&](int k) {
+        if (wp == 0) {
+            const double *src = pb + (int64_t)k * L::HS + L::hT;
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n * n * 8));
+            __syncwarp();
+            for (int r = lane; r < n; r += 32) bulk_g2s(Ts + r * LB, src + r * n, n * 8, bar);
+        }
+    };
+    issue_T(0);
+
+    int st_all = 0;
+    double Cp[NT][2];
+    SM_UNROLL
+    for (int ct = 0; ct < NT; ++ct) Cp[ct][0] = Cp[ct][1] = 0.0;
+
+    // one elimination step: (Cp, dps) of the previous row + slot k  ->  record k, new (Cp, dps)
+    for (int k = 0; k < N; ++k) {
+        const double *slot = pb + (int64_t)k * L::HS;
+        // Sigma strip = Cp + Qi (slot), G strip (prefetched)
+        double S[NT][2], G[NT][2];
+        SM_UNROLL
+        for (int ct = 0; ct < NT; ++ct) {
+            const double2 qv = *reinterpret_cast<const double2 *>(slot + L::hQi + r0 * n + 8 * ct + 2 * q);
+            const double2 gv = *reinterpret_cast<const double2 *>(slot + L::hG + r0 * n + 8 * ct + 2 * q);
+            S[ct][0] = Cp[ct][0] + qv.x;
+            S[ct][1] = Cp[ct][1] + qv.y;
+            G[ct][0] = gv.x;
+            G[ct][1] = gv.y;
+        }
+        if (tid < n) ys[tid] = dps[tid] - slot[L::hHg + tid];  // y = dp - hg_x  (d += next.r_[1])
+        const double rho = tid < n ? slot[L::hRho + tid] : 0.0;
+        if (tid == 0) flag = 0;
+        __syncthreads();
+        {
+            const int bad = block_gj_inverse<NT>(S, pan, pis, colb, &flag, wp, lane);
+            if (bad != 0 && st_all == 0) st_all = k == 0 ? 1000 + 100 + bad : k * 1000 + 200 + bad;
+        }
+        SM_UNROLL
+        for (int ct = 0; ct < NT; ++ct)
+            *reinterpret_cast<double2 *>(Ss + r0 * LB + 8 * ct + 2 * q) = make_double2(S[ct][0], S[ct][1]);
+        __syncthreads();
+        // v = Si y : 4 partial sums per row (Si symmetric: read down the column)
+        {
+            const int i = tid & (n - 1), part = tid / n;
+            double s = 0.0;
+            SM_UNROLL
+            for (int l = 0; l < n / 4; ++l) s = fma(Ss[(part * (n / 4) + l) * LB + i], ys[part * (n / 4) + l], s);
+            red[part * n + i] = s;
+        }
+        mbar_wait(bar, ph);  // T_k has landed
+        ph ^= 1;
+        __syncthreads();
+        if (tid < n) {
+            const double v = (red[tid] + red[n + tid]) + (red[2 * n + tid] + red[3 * n + tid]);
+            vs[tid] = v;
+            rb[(int64_t)k * L::REC + n * n + tid] = v;
+        }
+        // Z strip = T[rows] Si   (A operand: T[8wp+g][8cp+2q+e], B operand: Si[8cp+2q+e][8ct+g] = Si[8ct+g][..])
+        double Z[NT][2];
+        SM_UNROLL
+        for (int ct = 0; ct < NT; ++ct) Z[ct][0] = Z[ct][1] = 0.0;
+        {
+            const double *ta = Ts + r0 * LB + 2 * q;
+            const double *sb = Ss + g * LB + 2 * q;
+            SM_UNROLL
+            for (int cp = 0; cp < NT; ++cp) {
+                const double2 a = *reinterpret_cast<const double2 *>(ta + 8 * cp);
+                SM_UNROLL
+                for (int ct = 0; ct < NT; ++ct) {
+                    const double2 b = *reinterpret_cast<const double2 *>(sb + 8 * ct * LB + 8 * cp);
+                    mma884(Z[ct][0], Z[ct][1], a.x, b.x);
+                    mma884(Z[ct][0], Z[ct][1], a.y, b.y);
+                }
+            }
+        }
+        {
+            double *rk = rb + (int64_t)k * L::REC;
+            SM_UNROLL
+            for (int ct = 0; ct < NT; ++ct)
+                *reinterpret_cast<double2 *>(rk + r0 * n + 8 * ct + 2 * q) = make_double2(Z[ct][0], Z[ct][1]);
+        }
+        __syncthreads();  // vs is published
+        // Cp' strip = G - Z T'   (A operand: the Z accumulators, B operand: T[8ct+g][8cp+2q+e])
+        {
+            const double *tb = Ts + g * LB + 2 * q;
+            SM_UNROLL
+            for (int cp = 0; cp < NT; ++cp) {
+                const double na0 = -Z[cp][0], na1 = -Z[cp][1];
+                SM_UNROLL
+                for (int ct = 0; ct < NT; ++ct) {
+                    const double2 b = *reinterpret_cast<const double2 *>(tb + 8 * ct * LB + 8 * cp);
+                    mma884(G[ct][0], G[ct][1], na0, b.x);
+                    mma884(G[ct][0], G[ct][1], na1, b.y);
+                }
+            }
+        }
+        // dp' = rho + T v : warp wp sums rows 8wp..8wp+7 (lanes over the columns, shuffle reduction)
+        {
+            const double v0 = vs[lane], v1 = vs[lane + 32];
+            double mine = 0.0;
+            SM_UNROLL
+            for (int rr = 0; rr < 8; ++rr) {
+                const double *row = Ts + (8 * wp + rr) * LB;
+                double s = fma(row[lane], v0, row[lane + 32] * v1);
+                SM_UNROLL
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == rr) mine = s;
+            }
+            if (lane < 8) red[8 * wp + lane] = mine;
+        }
+        __syncthreads();  // every warp is done with Ts and Ss
+        if (k + 1 < N) issue_T(k + 1);
+        if (tid < n) dps[tid] = rho + red[tid];
+        // exact symmetrisation of Cp' through Ss
+        SM_UNROLL
+        for (int ct = 0; ct < NT; ++ct)
+            *reinterpret_cast<double2 *>(Ss + r0 * LB + 8 * ct + 2 * q) = make_double2(G[ct][0], G[ct][1]);
+        __syncthreads();
+        SM_UNROLL
+        for (int ct = 0; ct < NT; ++ct)
+            SM_UNROLL
+            for (int e = 0; e < 2; ++e) Cp[ct][e] = 0.5 * (G[ct][e] + Ss[(8 * ct + 2 * q + e) * LB + r0]);
+        __syncthreads();
+    }
+    // ---- last block: mu_N' = Bl'^-1 y_mu   (Cp, dps hold Bl' and y_mu)
+    {
+        if (tid == 0) flag = 0;
+        if (tid < n) ys[tid] = dps[tid];
+        __syncthreads();
+        const int bad = block_gj_inverse<NT>(Cp, pan, pis, colb, &flag, wp, lane);
+        if (bad != 0 && st_all == 0) st_all = N * 1000 + 100 + bad;
+        SM_UNROLL
+        for (int ct = 0; ct < NT; ++ct)
+            *reinterpret_cast<double2 *>(Ss + r0 * LB + 8 * ct + 2 * q) = make_double2(Cp[ct][0], Cp[ct][1]);
+        __syncthreads();
+        if (tid < n) {
+            double s0 = 0.0, s1 = 0.0;
+            SM_UNROLL
+            for (int l = 0; l < n; l += 2) {
+                s0 = fma(Ss[l * LB + tid], ys[l], s0);
+                s1 = fma(Ss[(l + 1) * LB + tid], ys[l + 1], s1);
+            }
+            xs[tid] = s0 + s1;
+            __stcs(mb + L::mult_rows(N) - n + tid, -(s0 + s1));  // mu_N
+        }
+        if (info && tid == 0) {
+            const int hcode = hinfo[inst];
+            info[inst] = hcode != 0x7f7f7f7f ? hcode : st_all;
+        }
+        __syncthreads();
+    }
+
+    // ---------------- backward sweep: x_{k-1} = v_k + Z_k' x_k,  Lambda = -x  (all operands from global / L2)
+    for (int k = N - 1; k >= 0; --k) {
+        const bool first = k == 0, last = k == N - 1;
+        const int mk = last ? 0 : m, wk = n + mk;
+        const double *rk = rb + (int64_t)k * L::REC;
+        const double *slot = pb + (int64_t)k * L::HS;
+        const double *kp = db + L::knot_off(k);
+        const double *D1g = last ? kp + L::oCl : kp + L::oD1;  // [A B] or C_N, column-major n x wk
+        // x_prev = v + Z' x : 4 partial sums per entry
+        {
+            const int i = tid & (n - 1), part = tid / n;
+            double s = 0.0;
+#pragma unroll 4
+            for (int l = 0; l < n / 4; ++l) {
+                const int r = part * (n / 4) + l;
+                s = fma(rk[r * n + i], xs[r], s);
+            }
+            red[part * n + i] = s;
+        }
+        __syncthreads();
+        if (tid < n) xps[tid] = rk[n * n + tid] + (red[tid] + red[n + tid]) + (red[2 * n + tid] + red[3 * n + tid]);
+        __syncthreads();
+        // res_j = g_j - sum_i D1[i][j] x_i (+ x_prev_j) (- sum_i C_1[i][j] mu1'_i at the first knot)
+        for (int j = wp; j < wk; j += L::WARPS) {
+            double s = D1g[lane + n * j] * xs[lane] + D1g[lane + 32 + n * j] * xs[lane + 32];
+            if (first) {
+                const double *C0 = kp + L::oC0;
+                s = fma(C0[lane + n * j], xps[lane], s);
+                s = fma(C0[lane + 32 + n * j], xps[lane + 32], s);
+            }
+            SM_UNROLL
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) {
+                double r = kp[(last ? tri(n) : L::og) + j] - s;
+                if (!first && j < n) r += xps[j];
+                rsv[j] = r;
+            }
+        }
+        __syncthreads();
+        // dz = -Hi res
+        {
+            const double *Qi = first ? pb + (int64_t)N * L::HS : slot + L::hQi;
+            const int i = tid & (n - 1), part = tid / n;
+            double s = 0.0;
+#pragma unroll 4
+            for (int l = 0; l < n / 4; ++l) {
+                const int r = part * (n / 4) + l;
+                s = fma(Qi[r * n + i], rsv[r], s);
+            }
+            red[part * n + i] = s;
+        }
+        __syncthreads();
+        if (tid < n) {
+            const double z = -((red[tid] + red[n + tid]) + (red[2 * n + tid] + red[3 * n + tid]));
+            __stcs(zb + (int64_t)k * w + tid, z);
+            if (resb) __stcs(resb + (int64_t)k * w + tid, rsv[tid]);
+            __stcs(mb + (int64_t)k * n + tid, -xps[tid]);  // lam_{k-1} (k >= 1) or mu_1
+        } else if (tid < wk) {
+            const double *Ri = slot + L::hRi;
+            double s = 0.0;
+            for (int l = 0; l < m; ++l) s = fma(Ri[l * m + tid - n], rsv[n + l], s);
+            __stcs(zb + (int64_t)k * w + tid, -s);
+            if (resb) __stcs(resb + (int64_t)k * w + tid, rsv[tid]);
+        }
+        __syncthreads();
+        if (tid < n) xs[tid] = xps[tid];
+        __syncthreads();
+    }
+}
+
+}  // namespace kcta

@@ -128,9 +128,41 @@ def test_irregular_stage_pattern(handle, oracle_mod):
 
 
 def test_large_dense_schur_variant(handle, oracle_mod):
-    """config 5b shape (n=64, m=16) at a short horizon."""
+    """config 5b shape (n=64, m=16) at a short horizon (cond ~1e6: held to 1e-9)."""
     prob = problems.random_lqr_kkt(64, 16, 6, 2, seed=4)
     _check(prob, handle, oracle_mod, tol=1e-9, res_tol=1e-9)
+    assert handle.last_kernel.startswith("kkt_cta_dmma<64,16")
+
+
+@pytest.mark.parametrize("N,batch", [(12, 3), (101, 2), (30, 5)])
+def test_cta_dmma_kernel(handle, oracle_mod, N, batch):
+    """config 5b-K: CTA-per-instance FP64 tensor-core kernel + parallel pre-pass."""
+    prob = problems.random_lqr_kkt(64, 16, N, batch, seed=N, mid_p=0, hess_mode=1)
+    _check(prob, handle, oracle_mod, truth_instances=(0,))
+    assert handle.last_kernel.startswith("kkt_cta_dmma<64,16")
+
+
+def test_cta_dmma_matches_cooperative_kernel(handle):
+    prob = problems.random_lqr_kkt(64, 16, 20, 3, seed=6, mid_p=0, hess_mode=1)
+    dz1, lam1, i1, r1 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
+    assert handle.last_kernel.startswith("kkt_cta_dmma")
+    handle.set_option("kkt_variant", 2)
+    try:
+        dz2, lam2, i2, r2 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
+        assert handle.last_kernel.startswith("kkt_coop")
+    finally:
+        handle.set_option("kkt_variant", 0)
+    assert (i1 == 0).all() and (i2 == 0).all()
+    assert _rel(dz1, dz2) <= 1e-10 and _rel(lam1, lam2) <= 1e-10
+    assert np.abs(r1 - r2).max() <= 1e-9 * max(1.0, np.abs(r2).max())
+
+
+def test_cta_dmma_info_flags(handle):
+    prob = problems.random_lqr_kkt(64, 16, 10, 3, seed=9, mid_p=0, hess_mode=1)
+    prob["Q"][1, 4] = -np.eye(64)
+    _, _, info = ops.kkt_solve_problem(prob, handle=handle)
+    assert handle.last_kernel.startswith("kkt_cta_dmma")
+    assert info[1] == 5 * 1000 + 1 and (np.delete(info, 1) == 0).all()
 
 
 def test_info_flags_bad_hessian(handle):
