@@ -56,6 +56,34 @@ struct Lay {
                          mV = mCol + 16, mBar = mV + 8 * n + 4 * w, MAIN_TOTAL = mBar + 2;
 };
 
+// ------------------------------------------------------------------ 8 x 8 pivot block ------------------
+// Inverse of an SPD 8 x 8 tile by one warp, Gauss-Jordan without pivoting.  Lane (h = lane >> 3, c = lane & 7)
+// holds rows 2h, 2h+1 of column c; the pivot column, the pivot and the lane's own row-kk entry come by
+// shuffle, so a pivot step costs 7 FP64 instructions (they queue behind the other CTA's DMMAs) and no
+// shared-memory round trip.  Returns the 1-based index of the first non-positive pivot or 0.
+__device__ __forceinline__ int gj8_warp(double &a0, double &a1, int lane) {
+    const int h = lane >> 3, c = lane & 7;
+    int bad = 0;
+    SM_UNROLL
+    for (int kk = 0; kk < 8; ++kk) {
+        const double mine = (kk & 1) ? a1 : a0;  // row kk lives in register kk & 1 of the lanes with h = kk / 2
+        const double ck0 = __shfl_sync(0xffffffffu, a0, (h << 3) | kk);
+        const double ck1 = __shfl_sync(0xffffffffu, a1, (h << 3) | kk);
+        const double piv = __shfl_sync(0xffffffffu, mine, ((kk >> 1) << 3) | kk);
+        const double akk = __shfl_sync(0xffffffffu, mine, ((kk >> 1) << 3) | c);
+        if (!(piv > 0.0) && bad == 0) bad = kk + 1;
+        const double p = rdmma::fast_rcp(piv);
+        const bool pc = c == kk;
+        const double f = pc ? -p : akk * p;
+        const double u0 = pc ? ck0 * f : fma(-ck0, f, a0);
+        const double u1 = pc ? ck1 * f : fma(-ck1, f, a1);
+        const bool prow = h == (kk >> 1);
+        a0 = (prow && !(kk & 1)) ? (pc ? p : f) : u0;
+        a1 = (prow && (kk & 1)) ? (pc ? p : f) : u1;
+    }
+    return bad;
+}
+
 // ------------------------------------------------------------------ block Gauss-Jordan ----------------
 // In place: S[ct][e] = tile (wp, ct) of an SPD n x n matrix in C-fragment layout -> the same tiles of its
 // inverse.  pan: NT*64 doubles (8 x 8 tiles, row-major), pis: 64 doubles, colb: 16 doubles.  Returns the
@@ -69,16 +97,12 @@ __device__ __forceinline__ int block_gj_inverse(double (&S)[NT][2], double *pan,
         *reinterpret_cast<double2 *>(pan + wp * 64 + g * 8 + 2 * q) = make_double2(S[kb][0], S[kb][1]);
         __syncthreads();
         if (wp == kb) {
-            // invert the 8 x 8 pivot block: lane j < 8 owns column j (symmetric: column = row)
-            double a[8];
-            const int j = lane < 8 ? lane : 0;
-            SM_UNROLL
-            for (int i = 0; i < 8; ++i) a[i] = pan[kb * 64 + i * 8 + j];
-            const int bad = khw::gj_inverse<8>(a, colb, lane < 8 ? lane : 31);
-            if (lane < 8) {
-                SM_UNROLL
-                for (int i = 0; i < 8; ++i) pis[i * 8 + lane] = a[i];
-            }
+            // invert the 8 x 8 pivot block (all 32 lanes, two entries each)
+            const int hh = lane >> 3, cc = lane & 7;
+            double a0 = pan[kb * 64 + (2 * hh) * 8 + cc], a1 = pan[kb * 64 + (2 * hh + 1) * 8 + cc];
+            const int bad = gj8_warp(a0, a1, lane);
+            pis[(2 * hh) * 8 + cc] = a0;
+            pis[(2 * hh + 1) * 8 + cc] = a1;
             if (bad != 0 && lane == 0 && *flag == 0) *flag = 8 * kb + bad;
         }
         __syncthreads();
