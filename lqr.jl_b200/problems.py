@@ -287,3 +287,27 @@ def dubins_kkt_batch(batch=262144, seed=1, N=201, dt=0.015, mid_p=0):
                                   0.1 * rng.standard_normal((batch, n)), mid_C, mid_c)
     return dict(n=n, m=m, N=N, p=p, hess_mode=HESS_BLOCKDIAG, Q=Q, R=R, Hux=None, q=q, r=r, A=A,
                 B=B, d=d, D2=None, C=Cs, c=cs)
+
+
+def dubins_turn90(batch, N=11, tf=3.0, seed=2):
+    """Config 4: x0 = 0, xf ~ [1.5, 1.5, pi/2] + N(0, 0.1^2), initial guess = the u = 0.1 rollout
+    (closed-form RK3 of the Dubins car).  Returns Z0 (batch, NN) in Primals order, x0, xf and the options."""
+    n, m = 3, 2
+    rng = np.random.default_rng(seed)
+    dt = tf / (N - 1)
+    o = dict(N=N, iters=10, dt=dt, q_diag=1e-2, r_diag=1e-2, qf_diag=100.0, eps_p=1e-5, eps_d=1e-5, line_search=1)
+    x0 = np.zeros((batch, n))
+    xf = np.array([1.5, 1.5, np.pi / 2]) + 0.1 * rng.standard_normal((batch, n))
+    U = np.full((batch, N - 1, m), 0.1)
+    X = np.zeros((batch, N, n))
+    for k in range(N - 1):
+        th, v, om = X[:, k, 2], U[:, k, 0], U[:, k, 1]
+        th2, th3 = th + 0.5 * dt * om, th + dt * om
+        cb = (np.cos(th) + 4 * np.cos(th2) + np.cos(th3)) / 6
+        sb = (np.sin(th) + 4 * np.sin(th2) + np.sin(th3)) / 6
+        X[:, k + 1] = np.stack([X[:, k, 0] + dt * v * cb, X[:, k, 1] + dt * v * sb, th + dt * om], -1)
+    Z = np.zeros((batch, N * n + (N - 1) * m))
+    body = Z[:, :(N - 1) * (n + m)].reshape(batch, N - 1, n + m)
+    body[:, :, :n], body[:, :, n:] = X[:, :-1], U
+    Z[:, (N - 1) * (n + m):] = X[:, -1]
+    return Z, x0, xf, o

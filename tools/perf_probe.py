@@ -79,9 +79,35 @@ def probe_kkt(h, stream, n, m, N, batch, base, steps, warmup, peak_gbs, dubins=F
                 alg_GBs=by * batch / ms / 1e6, hbm_frac=by * batch / ms / 1e6 / peak_gbs, bytes_per_solve=by)
 
 
+def probe_sqp(h, stream, batch, N, steps, warmup, line_search):
+    """config 4: batched Dubins SQP, 10 outer iterations, device-resident iterates; metric = KKT solves/s."""
+    Z0, x0, xf, o = problems.dubins_turn90(256, N=N)
+    reps = batch // 256
+    x0d = torch.from_numpy(np.tile(x0, (reps, 1))).cuda()
+    xfd = torch.from_numpy(np.tile(xf, (reps, 1))).cuda()
+    Z0d = torch.from_numpy(np.tile(np.broadcast_to(Z0, (256, Z0.shape[-1])), (reps, 1))).cuda()
+    Zd = Z0d.clone()
+    fp = torch.zeros(batch, dtype=torch.float64, device="cuda")
+    fd = torch.zeros(batch, dtype=torch.float64, device="cuda")
+    it = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    o = dict(o, iters=10, line_search=int(line_search))
+    solves = [0]
+
+    def run():
+        Zd.copy_(Z0d)
+        solves[0] = ops.sqp_dubins(h, batch, o, x0d, xfd, Zd, fp, fd, it)
+
+    ms = time_it(run, steps, warmup, stream)
+    by = 64384 if N == 201 else None
+    return dict(kind="sqp", n=3, m=2, N=N, batch=batch, kernel=h.last_kernel, ms=ms, kkt_solves=solves[0],
+                solves_per_s=solves[0] / ms * 1e3, line_search=int(line_search),
+                converged=float(((fp < 1e-5) & (fd < 2e-5)).double().mean()),
+                hbm_frac=(by * solves[0] / ms / 1e6 / json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]) if by else None)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--which", default="c2,c3,5aR,5aK,5bR,5bK")
+    ap.add_argument("--which", default="c2,c3,c4,5aR,5aK,5bR,5bK")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--scale", type=float, default=1.0, help="scale the batches (debug)")
@@ -105,6 +131,10 @@ def main():
             r = probe_kkt(h, stream, 3, 2, 201, int(262144 * S), 256, args.steps, args.warmup, peak, dubins=True, mid_p=1)
         elif w == "c1b":
             r = probe_kkt(h, stream, 4, 1, 101, int(65536 * S), 256, args.steps, args.warmup, peak)
+        elif w == "c4":
+            r = probe_sqp(h, stream, int(65536 * S), 201, args.steps, args.warmup, True)
+        elif w == "c4fs":
+            r = probe_sqp(h, stream, int(65536 * S), 201, args.steps, args.warmup, False)
         elif w == "5aR":
             r = probe_riccati(h, stream, 12, 4, 1001, int(16384 * S), 32, args.steps, args.warmup, peak)
         elif w == "5aK":
