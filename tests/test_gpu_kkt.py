@@ -186,3 +186,39 @@ def test_idempotent_full_width_batch(handle):
     assert np.abs(dyn).max() <= 1e-10
     assert np.abs(X[:, 0] + prob["c"][0]).max() <= 1e-10
     assert np.abs(X[:, -1] + prob["c"][-1]).max() <= 1e-10
+
+
+def _kkt_residuals_all(prob, dz, lam):
+    """Stationarity and primal residuals of every instance (init + dynamics + goal pattern), host einsum."""
+    n, m, N = prob["n"], prob["m"], prob["N"]
+    X, U = ops.split_primals(dz, n, m, N)
+    p = prob["p"]
+    assert p[0] == n and p[-1] == n and all(v == 0 for v in p[1:-1])
+    mu0, mu_last = lam[:, :n], lam[:, -n:]
+    L = lam[:, n:-n].reshape(lam.shape[0], N - 1, n)          # lam_0 .. lam_{N-2}
+    A, B, Q, R = prob["A"], prob["B"], prob["Q"], prob["R"]
+    dyn = np.einsum("bkij,bkj->bki", A, X[:, :-1]) + np.einsum("bkij,bkj->bki", B, U) - X[:, 1:] + prob["d"]
+    C0, CN = prob["C"][0], prob["C"][-1]
+    z0 = np.concatenate([X[:, 0], U[:, 0]], axis=1)
+    prim = max(np.abs(dyn).max(), np.abs(np.einsum("bij,bj->bi", C0, z0) + prob["c"][0]).max(),
+               np.abs(np.einsum("bij,bj->bi", CN, X[:, -1]) + prob["c"][-1]).max())
+    sx = np.einsum("bkij,bkj->bki", Q, X) + prob["q"]
+    sx[:, :-1] += np.einsum("bkji,bkj->bki", A, L)
+    sx[:, 1:] -= L
+    sx[:, 0] += np.einsum("bji,bj->bi", C0[:, :, :n], mu0)
+    sx[:, -1] += np.einsum("bji,bj->bi", CN, mu_last)
+    su = np.einsum("bkij,bkj->bki", R, U) + prob["r"] + np.einsum("bkji,bkj->bki", B, L)
+    su[:, 0] += np.einsum("bji,bj->bi", C0[:, :, n:], mu0)
+    scale = max(1.0, np.abs(prob["q"]).max(), np.abs(lam).max())
+    return max(np.abs(sx).max(), np.abs(su).max()) / scale, prim
+
+
+@pytest.mark.parametrize("n,m,N,batch,kern", [(12, 4, 101, 2049, "kkt_hw<"), (64, 16, 41, 300, "kkt_cta_dmma<")])
+def test_tuned_kernels_kkt_conditions_at_scale(handle, n, m, N, batch, kern):
+    """Size-independent property on a batch that spans many CTAs (and an odd tail): the returned step and
+    multipliers satisfy the KKT conditions  H dz + g + D'lam = 0,  D dz + d = 0  for EVERY instance."""
+    prob = problems.random_lqr_kkt(n, m, N, batch, seed=11, mid_p=0, hess_mode=1)
+    dz, lam, info = ops.kkt_solve_problem(prob, handle=handle)
+    assert handle.last_kernel.startswith(kern) and (info == 0).all()
+    stat, prim = _kkt_residuals_all(prob, dz, lam)
+    assert stat <= 1e-10 and prim <= 1e-10, (stat, prim)

@@ -188,3 +188,24 @@ def test_rollout_entry_point(handle, oracle_mod):
     Xr = np.zeros((50, 101, 4))
     ops.rollout(handle, 4, 1, 101, 50, 0, f["A"], f["B"], f["x0"], np.ascontiguousarray(U), Xr)
     assert _rel(Xr, X) <= 1e-12
+
+
+@pytest.mark.parametrize("n,m,N,batch,kern", [(12, 4, 201, 1027, "riccati_dmma"), (64, 16, 31, 301, "riccati_cta_dmma")])
+def test_tuned_kernels_closed_loop_at_scale(handle, n, m, N, batch, kern):
+    """Size-independent properties on a batch that spans many CTAs (odd tail included): the returned trajectory
+    satisfies the dynamics with the returned gains (u = -K x - kff, x+ = A x + B u) for EVERY instance, and
+    doubling (x0, q, r, qf) doubles the solution."""
+    prob = problems.random_lqr_riccati(n, m, N, batch, seed=21)
+    X, U, K, kff, info = ops.riccati_solve_problem(prob, handle=handle)
+    assert handle.last_kernel.startswith(kern) and (info == 0).all()
+    u_cl = -np.einsum("bkij,bkj->bki", K, X[:, :-1]) - kff
+    x_next = np.einsum("bkij,bkj->bki", prob["A"], X[:, :-1]) + np.einsum("bkij,bkj->bki", prob["B"], U)
+    s = max(1.0, np.abs(X).max())
+    assert np.abs(U - u_cl).max() <= 1e-10 * max(1.0, np.abs(U).max())
+    assert np.abs(X[:, 1:] - x_next).max() <= 1e-10 * s
+    assert np.abs(X[:, 0] - prob["x0"]).max() == 0.0
+    p2 = dict(prob)
+    for key in ("x0", "q", "r", "qf"):
+        p2[key] = 2.0 * prob[key]
+    X2, U2, _, _, _ = ops.riccati_solve_problem(p2, want_gains=False, handle=handle)
+    assert np.abs(X2 - 2 * X).max() <= 1e-9 * s and np.abs(U2 - 2 * U).max() <= 1e-9 * max(1.0, np.abs(U).max())
