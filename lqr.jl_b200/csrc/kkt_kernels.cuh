@@ -22,6 +22,20 @@
 #pragma once
 #include "smallmat.cuh"
 
+// Knot rows are read either from the packed tile (stride KS = 32 doubles between rows, read-only global
+// memory) or from a thread-local array the caller has just filled (KS = 1: the fused SQP kernel linearises
+// the knot on the fly instead of streaming it from HBM).
+template <int KS>
+__device__ __forceinline__ double ldk_keep(const double *p) {
+    if constexpr (KS == 32) return ld_keep(p);
+    else return *p;
+}
+template <int KS>
+__device__ __forceinline__ double ldk_stream(const double *p) {
+    if constexpr (KS == 32) return ld_stream(p);
+    else return *p;
+}
+
 // ------------------------------------------------------------------ per-knot row layout -------
 
 // rows of one knot in the packed data array (see lqrb200.h): H | g | D1 | d | [D2] | C | c
@@ -41,16 +55,17 @@ struct HFactor {
     double u[NU];
     double dinv[w];
 
+    template <int KS = 32>
     __device__ __forceinline__ int load_factor(const double *hp) {
         if constexpr (SOC) {
             return 0;
         } else if constexpr (HESS == LQRB_HESS_DIAG) {  // stores the inverse (:82-91)
             SM_UNROLL
-            for (int i = 0; i < w; ++i) dinv[i] = 1.0 / ld_keep(hp + i * 32);
+            for (int i = 0; i < w; ++i) dinv[i] = 1.0 / ldk_keep<KS>(hp + i * KS);
             return 0;
         } else if constexpr (HESS == LQRB_HESS_BLOCKDIAG) {  // two potrf (:69-77)
             SM_UNROLL
-            for (int e = 0; e < NU; ++e) u[e] = ld_keep(hp + e * 32);
+            for (int e = 0; e < NU; ++e) u[e] = ldk_keep<KS>(hp + e * KS);
             int st = chol_packed<n>(u, dinv);
             if constexpr (mk > 0) {
                 const int st2 = chol_packed<mk>(u + tri(n), dinv + n);
@@ -59,7 +74,7 @@ struct HFactor {
             return st;
         } else {  // whole-matrix potrf (:55-66)
             SM_UNROLL
-            for (int e = 0; e < NU; ++e) u[e] = ld_keep(hp + e * 32);
+            for (int e = 0; e < NU; ++e) u[e] = ldk_keep<KS>(hp + e * KS);
             return chol_packed<w>(u, dinv);
         }
     }
@@ -123,6 +138,7 @@ struct RowFactor {
     double Bh[tri(ps) + 1], Bhinv[ps + 1], Dh[p1 * ps + 1], Eh[ps * p2 + 1], mut[ps + 1];
     double G22[FWD ? tri(p2) + 1 : 1], rho2[FWD ? p2 + 1 : 1];
 
+    template <int KS = 32>
     __device__ __forceinline__ int compute(const double *__restrict__ kp, const HFactor<n, mk, HESS, SOC> &H,
                                            const double *hg, const double *Ah, const double *Ahinv,
                                            const double *lamp) {
@@ -132,7 +148,7 @@ struct RowFactor {
         if constexpr (p2 > 0) {
             double D1[p2 * w];
             SM_UNROLL
-            for (int e = 0; e < p2 * w; ++e) D1[e] = ld_keep(kp + (KR::oD1 + e) * 32);
+            for (int e = 0; e < p2 * w; ++e) D1[e] = ldk_keep<KS>(kp + (KR::oD1 + e) * KS);
             SM_UNROLL
             for (int j = 0; j < p2; ++j) {
                 SM_UNROLL
@@ -151,7 +167,7 @@ struct RowFactor {
                     }
                 SM_UNROLL
                 for (int i = 0; i < p2; ++i) {
-                    double s = -ld_stream(kp + (KR::od + i) * 32);  // d = r_[3] - d  (copy_shur! :285)
+                    double s = -ldk_stream<KS>(kp + (KR::od + i) * KS);  // d = r_[3] - d  (copy_shur! :285)
                     SM_UNROLL
                     for (int l = 0; l < w; ++l) s = fma(D1[i + l * p2], hg[l], s);
                     rho2[i] = s;
@@ -169,7 +185,7 @@ struct RowFactor {
         if constexpr (ps > 0) {
             double Cc[ps * w], WC[w * ps];
             SM_UNROLL
-            for (int e = 0; e < ps * w; ++e) Cc[e] = ld_keep(kp + (KR::oC + e) * 32);
+            for (int e = 0; e < ps * w; ++e) Cc[e] = ldk_keep<KS>(kp + (KR::oC + e) * KS);
             SM_UNROLL
             for (int j = 0; j < ps; ++j) {
                 SM_UNROLL
@@ -187,7 +203,7 @@ struct RowFactor {
                 }
             SM_UNROLL
             for (int i = 0; i < ps; ++i) {
-                double s = -ld_stream(kp + (KR::oc + i) * 32);  // c = r_[2] - c  (:284)
+                double s = -ldk_stream<KS>(kp + (KR::oc + i) * KS);  // c = r_[2] - c  (:284)
                 SM_UNROLL
                 for (int l = 0; l < w; ++l) s = fma(Cc[i + l * ps], hg[l], s);
                 mut[i] = s;
@@ -257,7 +273,7 @@ struct RecRows2 {
 };
 
 // ------------------------------------------------------------------ forward knot --------------
-template <int n, int mk, int p1, int ps, int p2, int HESS, bool SOC>
+template <int n, int mk, int p1, int ps, int p2, int HESS, bool SOC, int KS = 32>
 __device__ __forceinline__ int kkt_fwd_knot(const double *__restrict__ kp, double *__restrict__ rec,
                                             FwdCarry<n> &cy, int knot) {
     using KR = KnotRows<n, mk, ps, p2, HESS>;
@@ -267,7 +283,7 @@ __device__ __forceinline__ int kkt_fwd_knot(const double *__restrict__ kp, doubl
 
     HFactor<n, mk, HESS, SOC> H;
     {
-        const int st = H.load_factor(kp + KR::oH * 32);
+        const int st = H.template load_factor<KS>(kp + KR::oH * KS);
         if (st) info = (knot + 1) * 1000 + st;
     }
     double hg[w];  // H^-1 g  (shur!: r = Y H^-1 g, src/jacobian_blocks.jl:236)
@@ -276,7 +292,7 @@ __device__ __forceinline__ int kkt_fwd_knot(const double *__restrict__ kp, doubl
         for (int i = 0; i < w; ++i) hg[i] = 0.0;
     } else {
         SM_UNROLL
-        for (int i = 0; i < w; ++i) hg[i] = ld_stream(kp + (KR::oG + i) * 32);
+        for (int i = 0; i < w; ++i) hg[i] = ldk_stream<KS>(kp + (KR::oG + i) * KS);
         H.solve(hg);
     }
 
@@ -303,7 +319,7 @@ __device__ __forceinline__ int kkt_fwd_knot(const double *__restrict__ kp, doubl
 
     RowFactor<n, mk, p1, ps, p2, HESS, SOC, true> R;
     {
-        const int st = R.compute(kp, H, hg, Ah, Ahinv, lamp);
+        const int st = R.template compute<KS>(kp, H, hg, Ah, Ahinv, lamp);
         if (st && !info) info = (knot + 1) * 1000 + st;
     }
 
@@ -343,7 +359,7 @@ __device__ __forceinline__ int kkt_fwd_knot(const double *__restrict__ kp, doubl
 
 // ------------------------------------------------------------------ backward knot -------------
 // lam holds lam'_k (un-negated back-substitution value) on entry and lam'_{k-1} on exit.
-template <int n, int mk, int p1, int ps, int p2, int HESS, bool SOC>
+template <int n, int mk, int p1, int ps, int p2, int HESS, bool SOC, int KS = 32>
 __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
                                              const double *__restrict__ rec, double *lam,
                                              double *__restrict__ dz, double *__restrict__ mult_mu,
@@ -354,11 +370,11 @@ __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
     constexpr int w = n + mk;
 
     HFactor<n, mk, HESS, SOC> H;
-    H.load_factor(kp + KR::oH * 32);
+    H.template load_factor<KS>(kp + KR::oH * KS);
     double g[w], hg[w];
     SM_UNROLL
     for (int i = 0; i < w; ++i) {
-        g[i] = SOC ? 0.0 : ld_stream(kp + (KR::oG + i) * 32);
+        g[i] = SOC ? 0.0 : ldk_stream<KS>(kp + (KR::oG + i) * KS);
         hg[i] = g[i];
     }
     if constexpr (ps > 0) H.solve(hg);  // only mu~ needs H^-1 g here
@@ -378,7 +394,7 @@ __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
         for (int i = 0; i < p1; ++i) lamp[i] = rec[(RR::ol + i) * 32];
     }
     RowFactor<n, mk, p1, ps, p2, HESS, SOC, false> R;
-    R.compute(kp, H, hg, Ah, Ahinv, lamp);
+    R.template compute<KS>(kp, H, hg, Ah, Ahinv, lamp);
 
     // mu'_k = B^-1 (mu~ - E^ lam'_k)      (backward_substitution! :130-134)
     double mu[ps + 1];
@@ -426,11 +442,11 @@ __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
         double s = g[j];
         if constexpr (p2 > 0) {
             SM_UNROLL
-            for (int i = 0; i < p2; ++i) s = fma(-ld_keep(kp + (KR::oD1 + i + j * p2) * 32), lam[i], s);
+            for (int i = 0; i < p2; ++i) s = fma(-ldk_keep<KS>(kp + (KR::oD1 + i + j * p2) * KS), lam[i], s);
         }
         if constexpr (ps > 0) {
             SM_UNROLL
-            for (int i = 0; i < ps; ++i) s = fma(-ld_keep(kp + (KR::oC + i + j * ps) * 32), mu[i], s);
+            for (int i = 0; i < ps; ++i) s = fma(-ldk_keep<KS>(kp + (KR::oC + i + j * ps) * KS), mu[i], s);
         }
         if constexpr (p1 > 0) {
             if (j < n) s += lprev[j];  // D2' lam_{k-1} = -(-lam'_{k-1})

@@ -19,6 +19,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "kkt_kernels.cuh"
 
 namespace {
 
@@ -61,6 +62,7 @@ struct Stats {  // per-instance scalars, stored as rows of a [S_COUNT][32]-tiled
 // linearise at Z: writes the packed KKT data and per-instance f, ||c||_1, ||c||_inf, feas_d.
 // feas_d = || (||g_k + D1_k'lam_k + C_k'mu_k + D2_k'lam_{k-1}||)_k ||  with the previous multipliers
 // (residual(solver, recalculate=false), src/cholesky_solver.jl:130,238-252).
+template <bool WRITE>
 __global__ void __launch_bounds__(64) dubins_linearize_kernel(const double *__restrict__ Z, const double *__restrict__ x0,
                                                               const double *__restrict__ xf, const double *__restrict__ mult,
                                                               double *__restrict__ data, double *__restrict__ stats,
@@ -74,7 +76,7 @@ __global__ void __launch_bounds__(64) dubins_linearize_kernel(const double *__re
     const int64_t NN = (int64_t)N * n + (int64_t)(N - 1) * m, P = (int64_t)(N - 1) * n + 2 * n;
     const double *zb = Z + tile * NN * 32 + lane;
     const double *mb = mult + tile * P * 32 + lane;
-    double *db = data + tile * data_rows(N) * 32 + lane;
+    double *db = WRITE ? data + tile * data_rows(N) * 32 + lane : nullptr;  // WRITE = false: statistics only
     double *sb = stats + tile * Stats::S_COUNT * 32 + lane;
     const double *x0b = x0 + tile * n * 32 + lane, *xfb = xf + tile * n * 32 + lane;
     double xg[n];
@@ -91,19 +93,21 @@ __global__ void __launch_bounds__(64) dubins_linearize_kernel(const double *__re
         // cost expansion (diagonal): H = diag(Q dt, R dt), g = [Q (x - xf) dt; R u dt]
         for (int i = 0; i < n; ++i) {
             const double e = x[i] - xg[i];
-            kp[i * 32] = qs;
+            if (WRITE) kp[i * 32] = qs;
             g[i] = qs * e;
             f += 0.5 * qs * e * e;
         }
         if (last) {
-            for (int i = 0; i < n; ++i) kp[(n + i) * 32] = g[i];
             double *Cp = kp + 2 * n * 32;  // C = I, c = x_N - xf
-            for (int j = 0; j < n; ++j)
-                for (int i = 0; i < n; ++i) Cp[(i + j * n) * 32] = (i == j) ? 1.0 : 0.0;
+            if (WRITE) {
+                for (int i = 0; i < n; ++i) kp[(n + i) * 32] = g[i];
+                for (int j = 0; j < n; ++j)
+                    for (int i = 0; i < n; ++i) Cp[(i + j * n) * 32] = (i == j) ? 1.0 : 0.0;
+            }
             const double *mu = mb + mult_row(k) * 32;
             for (int i = 0; i < n; ++i) {
                 const double c = x[i] - xg[i];
-                Cp[(n * n + i) * 32] = c;
+                if (WRITE) Cp[(n * n + i) * 32] = c;
                 c1 += fabs(c);
                 cinf = fmax(cinf, fabs(c));
                 res[i] = g[i] + mu[i * 32] - lam_prev[i];
@@ -114,11 +118,12 @@ __global__ void __launch_bounds__(64) dubins_linearize_kernel(const double *__re
         double u[m];
         for (int i = 0; i < m; ++i) {
             u[i] = zb[((int64_t)k * w + n + i) * 32];
-            kp[(n + i) * 32] = rs;
+            if (WRITE) kp[(n + i) * 32] = rs;
             g[n + i] = rs * u[i];
             f += 0.5 * rs * u[i] * u[i];
         }
-        for (int i = 0; i < w; ++i) kp[(w + i) * 32] = g[i];
+        if (WRITE)
+            for (int i = 0; i < w; ++i) kp[(w + i) * 32] = g[i];
         // dynamics: RK3 map, Jacobians A (3x3), B (3x2); D1 = [A B] column-major 3 x 5
         double cb, sbar, dcb, dsb;
         dubins_avg(x[2], u[1], o.dt, cb, sbar, dcb, dsb);
@@ -134,14 +139,15 @@ __global__ void __launch_bounds__(64) dubins_linearize_kernel(const double *__re
         D1[1 + 4 * n] = o.dt * v * dsb;
         D1[2 + 4 * n] = o.dt;
         double *D1p = kp + 2 * w * 32;
-        for (int e = 0; e < n * w; ++e) D1p[e * 32] = D1[e];
+        if (WRITE)
+            for (int e = 0; e < n * w; ++e) D1p[e * 32] = D1[e];
         for (int i = 0; i < n; ++i) xn[i] = zb[((int64_t)(k + 1) * w + i) * 32];
         const double fx[n] = {x[0] + o.dt * v * cb, x[1] + o.dt * v * sbar, x[2] + o.dt * u[1]};
         const double *lam = mb + (mult_row(k) + (k == 0 ? n : 0)) * 32;
         double lk[n];
         for (int i = 0; i < n; ++i) {
             const double d = fx[i] - xn[i];  // d_k = f(z_k) - x_{k+1}   (test/cartpole.jl:34-42)
-            D1p[(n * w + i) * 32] = d;
+            if (WRITE) D1p[(n * w + i) * 32] = d;
             c1 += fabs(d);
             cinf = fmax(cinf, fabs(d));
             lk[i] = lam[i * 32];
@@ -155,11 +161,12 @@ __global__ void __launch_bounds__(64) dubins_linearize_kernel(const double *__re
         if (k == 0) {  // C = [I 0], c = x_1 - x0
             double *Cp = D1p + (n * w + n) * 32;
             const double *mu = mb;
-            for (int j = 0; j < w; ++j)
-                for (int i = 0; i < n; ++i) Cp[(i + j * n) * 32] = (i == j) ? 1.0 : 0.0;
+            if (WRITE)
+                for (int j = 0; j < w; ++j)
+                    for (int i = 0; i < n; ++i) Cp[(i + j * n) * 32] = (i == j) ? 1.0 : 0.0;
             for (int i = 0; i < n; ++i) {
                 const double c = x[i] - x0b[i * 32];
-                Cp[(n * w + i) * 32] = c;
+                if (WRITE) Cp[(n * w + i) * 32] = c;
                 c1 += fabs(c);
                 cinf = fmax(cinf, fabs(c));
                 res[i] += mu[i * 32];
@@ -180,7 +187,9 @@ __global__ void __launch_bounds__(64) dubins_linearize_kernel(const double *__re
 }
 
 // cost and constraint 1-norm / values at a trial point Zt = Z + alpha*dz (+ dzh)
-template <bool WRITE_C>
+// WRITE_C: 0 nothing; 1 into the c/d rows of the packed KKT data; 2 into a compact array with the row order of
+// the multipliers [c_1; d_1; ...; d_{N-1}; c_N] (fused path: the SOC solve rebuilds everything else from Z)
+template <int WRITE_C>
 __device__ __forceinline__ void dubins_eval(const double *zb, const double *dzb, const double *dhb, double alpha,
                                             const double *x0b, const double *xg, const Opts &o, double *db,
                                             double &f, double &c1) {
@@ -197,7 +206,8 @@ __device__ __forceinline__ void dubins_eval(const double *zb, const double *dzb,
     for (int i = 0; i < n; ++i) {
         const double c = x[i] - x0b[i * 32];
         c1 += fabs(c);
-        if (WRITE_C) db[(2 * w + n * w + n + n * w + i) * 32] = c;
+        if (WRITE_C == 1) db[(2 * w + n * w + n + n * w + i) * 32] = c;
+        if (WRITE_C == 2) db[i * 32] = c;
     }
     for (int k = 0; k < N - 1; ++k) {
         double u[m];
@@ -214,7 +224,8 @@ __device__ __forceinline__ void dubins_eval(const double *zb, const double *dzb,
         for (int i = 0; i < n; ++i) {
             const double d = fx[i] - xn[i];
             c1 += fabs(d);
-            if (WRITE_C) db[(knot_row(k, N) + 2 * w + n * w + i) * 32] = d;
+            if (WRITE_C == 1) db[(knot_row(k, N) + 2 * w + n * w + i) * 32] = d;
+            if (WRITE_C == 2) db[(mult_row(k) + (k == 0 ? n : 0) + i) * 32] = d;
             x[i] = xn[i];
         }
     }
@@ -222,8 +233,147 @@ __device__ __forceinline__ void dubins_eval(const double *zb, const double *dzb,
         const double e = x[i] - xg[i];
         f += 0.5 * o.qfd * e * e;
         c1 += fabs(e);
-        if (WRITE_C) db[(knot_row(N - 1, N) + 2 * n + n * n + i) * 32] = e;
+        if (WRITE_C == 1) db[(knot_row(N - 1, N) + 2 * n + n * n + i) * 32] = e;
+        if (WRITE_C == 2) db[(mult_row(N - 1) + i) * 32] = e;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused linearisation + KKT solve: the thread-per-instance KKT sweeps of kkt_kernels.cuh, fed from a
+// thread-local knot that is linearised on the fly from the iterate (update!, src/cholesky_solver.jl:155-164)
+// instead of being written to HBM by one kernel and streamed back twice by the next.  SOC: H = I, g = 0 and
+// the constraint values are c(x + dx) from `cvals` (second_order_correction!, :254-273).
+template <int KIND, bool SOC>  // KIND 0 first, 1 middle, 2 last knot
+__device__ __forceinline__ void dubins_build_knot(double *kn, const double *x, const double *u, const double *xn,
+                                                  const double *x0v, const double *xg, const Opts &o,
+                                                  const double *cd, const double *cc) {
+    if (KIND == 2) {  // H (3) | g (3) | C = I (9) | c (3)
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) {
+            kn[i] = o.qfd;
+            kn[n + i] = o.qfd * (x[i] - xg[i]);
+            SM_UNROLL
+            for (int j = 0; j < n; ++j) kn[2 * n + i + j * n] = (i == j) ? 1.0 : 0.0;
+            kn[2 * n + n * n + i] = SOC ? cc[i * 32] : x[i] - xg[i];
+        }
+        return;
+    }
+    const double qs = o.qd * o.dt, rs = o.rd * o.dt;
+    SM_UNROLL
+    for (int i = 0; i < n; ++i) {
+        kn[i] = qs;
+        kn[w + i] = qs * (x[i] - xg[i]);
+    }
+    SM_UNROLL
+    for (int i = 0; i < m; ++i) {
+        kn[n + i] = rs;
+        kn[w + n + i] = rs * u[i];
+    }
+    double cb, sbar, dcb, dsb;
+    dubins_avg(x[2], u[1], o.dt, cb, sbar, dcb, dsb);
+    const double v = u[0];
+    double *D1 = kn + 2 * w;
+    SM_UNROLL
+    for (int e = 0; e < n * w; ++e) D1[e] = 0.0;
+    D1[0 + 0 * n] = 1.0; D1[1 + 1 * n] = 1.0; D1[2 + 2 * n] = 1.0;
+    D1[0 + 2 * n] = -o.dt * v * sbar;
+    D1[1 + 2 * n] = o.dt * v * cb;
+    D1[0 + 3 * n] = o.dt * cb;
+    D1[1 + 3 * n] = o.dt * sbar;
+    D1[0 + 4 * n] = o.dt * v * dcb;
+    D1[1 + 4 * n] = o.dt * v * dsb;
+    D1[2 + 4 * n] = o.dt;
+    const double fx[n] = {x[0] + o.dt * v * cb, x[1] + o.dt * v * sbar, x[2] + o.dt * u[1]};
+    SM_UNROLL
+    for (int i = 0; i < n; ++i) D1[n * w + i] = SOC ? cd[i * 32] : fx[i] - xn[i];
+    if (KIND == 0) {  // C = [I 0], c = x_1 - x0
+        double *Cp = D1 + n * w + n;
+        SM_UNROLL
+        for (int j = 0; j < w; ++j)
+            SM_UNROLL
+            for (int i = 0; i < n; ++i) Cp[i + j * n] = (i == j) ? 1.0 : 0.0;
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) Cp[n * w + i] = SOC ? cc[i * 32] : x[i] - x0v[i];
+    }
+}
+
+template <bool SOC>
+__global__ void __launch_bounds__(64, 8)
+    dubins_kkt_fused_kernel(const double *__restrict__ Z, const double *__restrict__ x0, const double *__restrict__ xf,
+                            const double *__restrict__ cvals, double *__restrict__ scratch, double *__restrict__ dz,
+                            double *__restrict__ mult, int32_t *__restrict__ info, Opts o, int64_t batch) {
+    using L = KktLayout<n, m, n, 0, n, LQRB_HESS_DIAG>;
+    constexpr int HD = LQRB_HESS_DIAG;
+    const int64_t inst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= batch) return;
+    const int64_t tile = inst >> 5;
+    const int lane = (int)(inst & 31);
+    const int N = o.N;
+    const int64_t NN = (int64_t)N * n + (int64_t)(N - 1) * m, P = (int64_t)(N - 1) * n + 2 * n;
+    const double *zb = Z + tile * NN * 32 + lane;
+    const double *cvb = SOC ? cvals + tile * P * 32 + lane : nullptr;
+    double *sb = scratch + tile * L::rec_rows(N) * 32 + lane;
+    double *dzb = dz + tile * NN * 32 + lane;
+    double *mb = mult + tile * P * 32 + lane;
+    double xg[n], x0v[n];
+    SM_UNROLL
+    for (int i = 0; i < n; ++i) {
+        xg[i] = xf[tile * n * 32 + lane + i * 32];
+        x0v[i] = x0[tile * n * 32 + lane + i * 32];
+    }
+    auto ldz = [&](int64_t row) { return zb[row * 32]; };
+    double kn[ROWS_FIRST], x[n], u[m], xn[n];
+
+    // ---------------- forward sweep
+    FwdCarry<n> cy;
+    SM_UNROLL
+    for (int i = 0; i < n; ++i) { x[i] = ldz(i); xn[i] = ldz(w + i); }
+    SM_UNROLL
+    for (int i = 0; i < m; ++i) u[i] = ldz(n + i);
+    dubins_build_knot<0, SOC>(kn, x, u, xn, x0v, xg, o, SOC ? cvb + n * 32 : nullptr, cvb);
+    int st = kkt_fwd_knot<n, m, 0, n, n, HD, SOC, 1>(kn, sb, cy, 0);
+    for (int k = 1; k < N - 1; ++k) {
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) { x[i] = xn[i]; xn[i] = ldz((int64_t)(k + 1) * w + i); }
+        SM_UNROLL
+        for (int i = 0; i < m; ++i) u[i] = ldz((int64_t)k * w + n + i);
+        dubins_build_knot<1, SOC>(kn, x, u, xn, x0v, xg, o, SOC ? cvb + mult_row(k) * 32 : nullptr, nullptr);
+        const int s2 = kkt_fwd_knot<n, m, n, 0, n, HD, SOC, 1>(
+            kn, sb + ((int64_t)L::RF::ROWS + (int64_t)(k - 1) * L::RM::ROWS) * 32, cy, k);
+        if (!st) st = s2;
+    }
+    const int64_t rlast = (int64_t)L::RF::ROWS + (int64_t)(N - 2) * L::RM::ROWS;
+    {
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) x[i] = xn[i];
+        dubins_build_knot<2, SOC>(kn, x, u, xn, x0v, xg, o, nullptr, SOC ? cvb + mult_row(N - 1) * 32 : nullptr);
+        const int s2 = kkt_fwd_knot<n, 0, n, n, 0, HD, SOC, 1>(kn, sb + rlast * 32, cy, N - 1);
+        if (!st) st = s2;
+    }
+    if (info) info[inst] = st;
+
+    // ---------------- backward sweep (the knot is linearised again: cheaper than a round trip through HBM)
+    double lam[n];
+    const int64_t mlast = (int64_t)n + n + (int64_t)(N - 2) * n;
+    const int64_t zlast = (int64_t)(N - 1) * w;
+    kkt_bwd_knot<n, 0, n, n, 0, HD, SOC, 1>(kn, sb + rlast * 32, lam, dzb + zlast * 32, mb + mlast * 32,
+                                            mb + (mlast - n) * 32, nullptr);
+    for (int k = N - 2; k >= 1; --k) {
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) { xn[i] = x[i]; x[i] = ldz((int64_t)k * w + i); }
+        SM_UNROLL
+        for (int i = 0; i < m; ++i) u[i] = ldz((int64_t)k * w + n + i);
+        dubins_build_knot<1, SOC>(kn, x, u, xn, x0v, xg, o, SOC ? cvb + mult_row(k) * 32 : nullptr, nullptr);
+        const int64_t mo = (int64_t)n + n + (int64_t)(k - 1) * n;
+        kkt_bwd_knot<n, m, n, 0, n, HD, SOC, 1>(kn, sb + ((int64_t)L::RF::ROWS + (int64_t)(k - 1) * L::RM::ROWS) * 32, lam,
+                                                dzb + (int64_t)k * w * 32, mb + mo * 32, mb + (mo - n) * 32, nullptr);
+    }
+    SM_UNROLL
+    for (int i = 0; i < n; ++i) { xn[i] = x[i]; x[i] = ldz(i); }
+    SM_UNROLL
+    for (int i = 0; i < m; ++i) u[i] = ldz(n + i);
+    dubins_build_knot<0, SOC>(kn, x, u, xn, x0v, xg, o, SOC ? cvb + n * 32 : nullptr, cvb);
+    kkt_bwd_knot<n, m, 0, n, n, HD, SOC, 1>(kn, sb, lam, dzb, mb, mb, nullptr);
 }
 
 // Line search stages (src/sqp.jl:72-94).
@@ -232,6 +382,7 @@ __device__ __forceinline__ void dubins_eval(const double *zb, const double *dzb,
 //   stage 1: second-order-correction trial x + dx + dx^; on failure alpha = rho.
 //   stage 2: trial at the current alpha; on failure alpha *= rho.
 // full_step != 0 skips the tests and takes alpha = 1 (line_search = 0).
+template <bool FUSED>
 __global__ void __launch_bounds__(64) dubins_linesearch_kernel(double *__restrict__ Z, const double *__restrict__ dz,
                                                                const double *__restrict__ dzh, const double *__restrict__ mult,
                                                                double *__restrict__ mult_kept,
@@ -248,7 +399,7 @@ __global__ void __launch_bounds__(64) dubins_linesearch_kernel(double *__restric
     double *zb = Z + tile * NN * 32 + lane;
     const double *dzb = dz + tile * NN * 32 + lane;
     const double *dhb = dzh ? dzh + tile * NN * 32 + lane : nullptr;
-    double *db = data + tile * data_rows(N) * 32 + lane;
+    double *db = data + tile * (FUSED ? P : data_rows(N)) * 32 + lane;  // FUSED: compact constraint values
     double *sb = stats + tile * Stats::S_COUNT * 32 + lane;
     const double *x0b = x0 + tile * n * 32 + lane, *xfb = xf + tile * n * 32 + lane;
     if (sb[Stats::CONV * 32] != 0.0) return;  // converged instances are frozen (:135-137)
@@ -289,15 +440,24 @@ __global__ void __launch_bounds__(64) dubins_linesearch_kernel(double *__restric
         double gdx = 0.0;
         for (int k = 0; k < N; ++k) {
             const int wk = k < N - 1 ? w : n;
-            const double *gp = db + (knot_row(k, N) + wk) * 32;
-            for (int j = 0; j < wk; ++j) gdx = fma(gp[j * 32], dzb[((int64_t)k * w + j) * 32], gdx);
+            if (FUSED) {  // g = [Q (x - xf) dt; R u dt] (terminal: Qf), the same numbers the linearisation forms
+                const double qs = k < N - 1 ? o.qd * o.dt : o.qfd, rs = o.rd * o.dt;
+                for (int j = 0; j < wk; ++j) {
+                    const double zj = zb[((int64_t)k * w + j) * 32];
+                    const double gj = j < n ? qs * (zj - xg[j]) : rs * zj;
+                    gdx = fma(gj, dzb[((int64_t)k * w + j) * 32], gdx);
+                }
+            } else {
+                const double *gp = db + (knot_row(k, N) + wk) * 32;
+                for (int j = 0; j < wk; ++j) gdx = fma(gp[j * 32], dzb[((int64_t)k * w + j) * 32], gdx);
+            }
         }
         const double phi0 = sb[Stats::F0 * 32] + mu * sb[Stats::C1 * 32];
         const double dphi0 = gdx - mu * sb[Stats::C1 * 32];
         sb[Stats::PHI0 * 32] = phi0;
         sb[Stats::DPHI0 * 32] = dphi0;
         double f, c1;
-        dubins_eval<true>(zb, dzb, nullptr, 1.0, x0b, xg, o, db, f, c1);
+        dubins_eval<FUSED ? 2 : 1>(zb, dzb, nullptr, 1.0, x0b, xg, o, db, f, c1);
         if (f + mu * c1 <= phi0 + eta * dphi0) {
             accept(1.0, false);
         } else {
@@ -309,7 +469,7 @@ __global__ void __launch_bounds__(64) dubins_linesearch_kernel(double *__restric
     const double mu = sb[Stats::MU * 32], phi0 = sb[Stats::PHI0 * 32], dphi0 = sb[Stats::DPHI0 * 32];
     double f, c1;
     if (stage == 1) {
-        dubins_eval<false>(zb, dzb, dhb, 1.0, x0b, xg, o, db, f, c1);
+        dubins_eval<0>(zb, dzb, dhb, 1.0, x0b, xg, o, db, f, c1);
         if (f + mu * c1 < phi0 + eta * dphi0) {
             accept(1.0, true);
         } else {
@@ -319,7 +479,7 @@ __global__ void __launch_bounds__(64) dubins_linesearch_kernel(double *__restric
         return;
     }
     const double alpha = sb[Stats::ALPHA * 32];
-    dubins_eval<false>(zb, dzb, nullptr, alpha, x0b, xg, o, db, f, c1);
+    dubins_eval<0>(zb, dzb, nullptr, alpha, x0b, xg, o, db, f, c1);
     if (f + mu * c1 <= phi0 + eta * alpha * dphi0) {
         accept(alpha, false);
     } else {
@@ -369,10 +529,16 @@ extern "C" int32_t lqrb_sqp_dubins_f64(lqrb_handle_t h, int64_t batch, const lqr
     const bool dev = lqrb_is_device_ptr(Z);
     cudaStream_t s = h->stream;
 
-    // device buffers: [Zp | dz | dzh | mult | multh | x0p | xfp | stats] in SQP0, data in SQP1
+    // fused (default): the KKT kernel linearises each knot on the fly; sqp_fused = 0 keeps the three-kernel
+    // path (linearise -> packed data -> generic KKT solve) that it is tested against
+    const bool fused = h->opt("sqp_fused", 1) != 0;
+    // device buffers: [Zp | dz | dzh | mult | multh | x0p | xfp | stats] in SQP0, data (or c values) in SQP1
     const size_t nd = (size_t)ldb * (3 * NN + 3 * P + 2 * n + Stats::S_COUNT);
     double *buf = (double *)lqrb_scratch(h, SCR_SQP0, nd * 8);
-    double *data = (double *)lqrb_scratch(h, SCR_SQP1, (size_t)ldb * drows * 8);
+    double *data = (double *)lqrb_scratch(h, SCR_SQP1, (size_t)ldb * (fused ? P : drows) * 8);
+    using FL = KktLayout<n, m, n, 0, n, LQRB_HESS_DIAG>;
+    double *frec = fused ? (double *)lqrb_scratch(h, SCR_FACT, (size_t)ldb * FL::rec_rows(N) * 8) : nullptr;
+    if (fused && !frec) return 1000 + (int)cudaErrorMemoryAllocation;
     int *counters = (int *)lqrb_scratch(h, SCR_SQP2, 64);
     int32_t *dinfo = (int32_t *)lqrb_scratch(h, SCR_SQP3, (size_t)ldb * 4);
     if (!buf || !data || !counters || !dinfo) return 1000 + (int)cudaErrorMemoryAllocation;
@@ -417,31 +583,53 @@ extern "C" int32_t lqrb_sqp_dubins_f64(lqrb_handle_t h, int64_t batch, const lqr
     int hc[2];
     for (int it = 0; it < opts->iters; ++it) {
         // update! + convergence check (:126-137)
-        dubins_linearize_kernel<<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, data, stats, o, batch, 1, opts->eps_p, opts->eps_d);
-        LQRB_LAUNCH_CHECK(h, "dubins_linearize_kernel");
-        // _solve! (:143)
-        rc = lqrb_kkt_solve_packed_f64(h, n, m, N, batch, p.data(), LQRB_HESS_DIAG, 0, 0, data, dz, mult, nullptr, dinfo);
-        if (rc) return rc;
+        if (fused) {
+            dubins_linearize_kernel<false><<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, nullptr, stats, o, batch, 1, opts->eps_p, opts->eps_d);
+            LQRB_LAUNCH_CHECK(h, "dubins_linearize_kernel");
+            // _solve! (:143) on knots linearised in registers
+            dubins_kkt_fused_kernel<false><<<grid, 64, 0, s>>>(Zp, x0p, xfp, nullptr, frec, dz, mult, dinfo, o, batch);
+            h->kernel_name = "dubins_kkt_fused<3,2,p=3/0/3,hess=2>";
+            LQRB_LAUNCH_CHECK(h, "dubins_kkt_fused_kernel");
+        } else {
+            dubins_linearize_kernel<true><<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, data, stats, o, batch, 1, opts->eps_p, opts->eps_d);
+            LQRB_LAUNCH_CHECK(h, "dubins_linearize_kernel");
+            // _solve! (:143)
+            rc = lqrb_kkt_solve_packed_f64(h, n, m, N, batch, p.data(), LQRB_HESS_DIAG, 0, 0, data, dz, mult, nullptr, dinfo);
+            if (rc) return rc;
+        }
         solves += batch;
         // line search (:146; spec src/sqp.jl:72-94)
         LQRB_CUDA(h, cudaMemsetAsync(counters, 0, 8, s));
-        dubins_linesearch_kernel<<<grid, 64, 0, s>>>(Zp, dz, nullptr, mult, multk, x0p, xfp, data, stats, o, batch, 0,
-                                                     opts->line_search ? 0 : 1, counters);
+        if (fused)
+            dubins_linesearch_kernel<true><<<grid, 64, 0, s>>>(Zp, dz, nullptr, mult, multk, x0p, xfp, data, stats, o, batch, 0,
+                                                               opts->line_search ? 0 : 1, counters);
+        else
+            dubins_linesearch_kernel<false><<<grid, 64, 0, s>>>(Zp, dz, nullptr, mult, multk, x0p, xfp, data, stats, o, batch, 0,
+                                                                opts->line_search ? 0 : 1, counters);
         LQRB_LAUNCH_CHECK(h, "dubins_linesearch_kernel");
         if (!opts->line_search) continue;
         LQRB_CUDA(h, cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, s));
         LQRB_CUDA(h, cudaStreamSynchronize(s));
         if (hc[0] == 0) continue;
         // second-order correction: same chain with Ginv=false on c(x+dx) (:254-273)
-        rc = lqrb_kkt_solve_packed_f64(h, n, m, N, batch, p.data(), LQRB_HESS_DIAG, 0, LQRB_FLAG_SOC, data, dzh, multh,
-                                       nullptr, dinfo);
-        if (rc) return rc;
+        if (fused) {
+            dubins_kkt_fused_kernel<true><<<grid, 64, 0, s>>>(Zp, x0p, xfp, data, frec, dzh, multh, dinfo, o, batch);
+            LQRB_LAUNCH_CHECK(h, "dubins_kkt_fused_kernel");
+        } else {
+            rc = lqrb_kkt_solve_packed_f64(h, n, m, N, batch, p.data(), LQRB_HESS_DIAG, 0, LQRB_FLAG_SOC, data, dzh, multh,
+                                           nullptr, dinfo);
+            if (rc) return rc;
+        }
         solves += batch;
         int pending = hc[0];
         for (int trial = 1; trial < 10 && pending > 0; ++trial) {
             LQRB_CUDA(h, cudaMemsetAsync(counters, 0, 8, s));
-            dubins_linesearch_kernel<<<grid, 64, 0, s>>>(Zp, dz, dzh, mult, multk, x0p, xfp, data, stats, o, batch,
-                                                         trial == 1 ? 1 : 2, 0, counters);
+            if (fused)
+                dubins_linesearch_kernel<true><<<grid, 64, 0, s>>>(Zp, dz, dzh, mult, multk, x0p, xfp, data, stats, o, batch,
+                                                                   trial == 1 ? 1 : 2, 0, counters);
+            else
+                dubins_linesearch_kernel<false><<<grid, 64, 0, s>>>(Zp, dz, dzh, mult, multk, x0p, xfp, data, stats, o, batch,
+                                                                    trial == 1 ? 1 : 2, 0, counters);
             LQRB_LAUNCH_CHECK(h, "dubins_linesearch_kernel");
             LQRB_CUDA(h, cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, s));
             LQRB_CUDA(h, cudaStreamSynchronize(s));
@@ -449,7 +637,7 @@ extern "C" int32_t lqrb_sqp_dubins_f64(lqrb_handle_t h, int64_t batch, const lqr
         }
     }
     // final feasibility numbers at the returned iterate
-    dubins_linearize_kernel<<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, data, stats, o, batch, 0, opts->eps_p, opts->eps_d);
+    dubins_linearize_kernel<false><<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, nullptr, stats, o, batch, 0, opts->eps_p, opts->eps_d);
     LQRB_LAUNCH_CHECK(h, "dubins_linearize_kernel");
 
     // export

@@ -54,3 +54,24 @@ def test_hard_start_exercises_backtracking(handle, oracle_mod):
     phi0 = S.cost(Z0, xf, o | {"N": 21, "dt": 3.0 / 20}) + mu * S.c_norm1(Z0, x0, xf, o | {"N": 21, "dt": 3.0 / 20})
     phi1 = S.cost(Z, xf, o | {"N": 21, "dt": 3.0 / 20}) + mu * S.c_norm1(Z, x0, xf, o | {"N": 21, "dt": 3.0 / 20})
     assert (phi1 <= phi0 + 1e-9).mean() > 0.9
+
+
+def test_fused_path_matches_three_kernel_path(handle):
+    """The fused linearise+KKT kernel (default) and the linearise -> packed data -> generic KKT path walk the same
+    iterates: same per-instance iteration counts, same solve count, solutions equal to rounding."""
+    from lqr_b200 import problems
+    Z0, x0, xf, o = problems.dubins_turn90(200, N=41)
+    rng = np.random.default_rng(1)
+    Z0 = Z0 + 0.2 * rng.standard_normal(Z0.shape)      # forces SOC / backtracking on part of the batch
+    s1 = DubinsSQP(x0, xf, N=41, tf=3.0, iters=10, handle=handle)
+    Z1 = s1.solve_(Z0)
+    assert handle.last_kernel.startswith("dubins_kkt_fused")
+    handle.set_option("sqp_fused", 0)
+    try:
+        s2 = DubinsSQP(x0, xf, N=41, tf=3.0, iters=10, handle=handle)
+        Z2 = s2.solve_(Z0)
+        assert handle.last_kernel.startswith("kkt_tpi<3,2")
+    finally:
+        handle.set_option("sqp_fused", 1)
+    assert s1.kkt_solves == s2.kkt_solves and np.array_equal(s1.iters, s2.iters)
+    assert _rel(Z1, Z2) <= 1e-9
