@@ -53,6 +53,40 @@ struct Lay {
     static_assert(2 * n * n >= n * w, "first knot stages C Hi (n x w) in MA|MB");
 };
 
+// In-place inverse of an SPD matrix from its packed upper Cholesky factor (LAPACK potri = trtri + lauum):
+// u holds U (A = U'U) with dinv[j] = 1/U(j,j) on entry and the upper triangle of A^-1 on exit.
+template <int k>
+__device__ __forceinline__ void potri_packed(double *u, const double *dinv) {
+    SM_UNROLL
+    for (int j = 0; j < k; ++j) {  // V = U^-1, column by column
+        double x[k];
+        SM_UNROLL
+        for (int i = 0; i < j; ++i) {
+            double s = 0.0;
+            SM_UNROLL
+            for (int l = i; l < j; ++l) s = fma(u[tri_idx(i, l)], u[tri_idx(l, j)], s);
+            x[i] = s;
+        }
+        SM_UNROLL
+        for (int i = 0; i < j; ++i) u[tri_idx(i, j)] = -dinv[j] * x[i];
+        u[tri_idx(j, j)] = dinv[j];
+    }
+    SM_UNROLL
+    for (int c = 0; c < k; ++c) {  // A^-1 = V V', column by column (columns > c are still V)
+        SM_UNROLL
+        for (int r = 0; r < c; ++r) {
+            double s = u[tri_idx(r, c)] * u[tri_idx(c, c)];
+            SM_UNROLL
+            for (int l = c + 1; l < k; ++l) s = fma(u[tri_idx(r, l)], u[tri_idx(c, l)], s);
+            u[tri_idx(r, c)] = s;
+        }
+        double d = 0.0;
+        SM_UNROLL
+        for (int l = c; l < k; ++l) d = fma(u[tri_idx(c, l)], u[tri_idx(c, l)], d);
+        u[tri_idx(c, c)] = d;
+    }
+}
+
 // ------------------------------------------------------------------ pre-pass: H_k^-1 for every knot ---
 // BlockCholesky block-diagonal mode (src/block_cholesky.jl:69-77, ldiv! :93-96) applied to the identity.
 template <int n, int m>
@@ -70,33 +104,35 @@ __global__ void __launch_bounds__(128)
     {
         double u[tri(n)], dinv[n];
         SM_UNROLL
-        for (int e = 0; e < tri(n); ++e) u[e] = kp[e];
-        st = chol_packed<n>(u, dinv);
-        SM_UNROLL
-        for (int j = 0; j < n; ++j) {
-            double e[n];
-            SM_UNROLL
-            for (int i = 0; i < n; ++i) e[i] = i == j ? 1.0 : 0.0;
-            solve_chol<n>(u, dinv, e);
-            SM_UNROLL
-            for (int i = 0; i < n; i += 2) *reinterpret_cast<double2 *>(out + n * j + i) = make_double2(e[i], e[i + 1]);
+        for (int e = 0; e < tri(n); e += 2) {  // 16-byte loads: the record is read once, straight through
+            const double2 v = __ldcs(reinterpret_cast<const double2 *>(kp + e));
+            u[e] = v.x;
+            u[e + 1] = v.y;
         }
+        st = chol_packed<n>(u, dinv);
+        potri_packed<n>(u, dinv);
+        SM_UNROLL
+        for (int j = 0; j < n; ++j)
+            SM_UNROLL
+            for (int i = 0; i < n; i += 2)
+                __stcs(reinterpret_cast<double2 *>(out + n * j + i), make_double2(u[sym_idx(i, j)], u[sym_idx(i + 1, j)]));
     }
     if (k < N - 1) {
         double u[tri(m)], dinv[m];
         SM_UNROLL
-        for (int e = 0; e < tri(m); ++e) u[e] = kp[tri(n) + e];
+        for (int e = 0; e < tri(m); e += 2) {
+            const double2 v = __ldcs(reinterpret_cast<const double2 *>(kp + tri(n) + e));
+            u[e] = v.x;
+            u[e + 1] = v.y;
+        }
         const int s2 = chol_packed<m>(u, dinv);
         if (st == 0 && s2 != 0) st = n + s2;
+        potri_packed<m>(u, dinv);
         SM_UNROLL
-        for (int j = 0; j < m; ++j) {
-            double e[m];
+        for (int j = 0; j < m; ++j)
             SM_UNROLL
-            for (int i = 0; i < m; ++i) e[i] = i == j ? 1.0 : 0.0;
-            solve_chol<m>(u, dinv, e);
-            SM_UNROLL
-            for (int i = 0; i < m; i += 2) *reinterpret_cast<double2 *>(out + n * n + m * j + i) = make_double2(e[i], e[i + 1]);
-        }
+            for (int i = 0; i < m; i += 2)
+                __stcs(reinterpret_cast<double2 *>(out + n * n + m * j + i), make_double2(u[sym_idx(i, j)], u[sym_idx(i + 1, j)]));
     }
     if (st != 0) atomicMin(hinfo + inst, (k + 1) * 1000 + st);
 }
