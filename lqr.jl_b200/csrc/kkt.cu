@@ -42,7 +42,8 @@ static bool kkt_has_tpi(const KktShape &s) {
 
 static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
     if (h->opt("kkt_variant", 0) == 2) return false;
-    if (!s.uniform || s.d2x || s.hess != LQRB_HESS_BLOCKDIAG || (flags & LQRB_FLAG_SOC)) return false;
+    (void)flags;
+    if (!s.uniform || s.d2x || s.hess == LQRB_HESS_DENSE) return false;
     if (s.N < 3 || s.P1 != s.n || s.PM != 0 || s.PN != s.n) return false;
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_) return true;
@@ -56,7 +57,8 @@ static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
 
 static bool kkt_has_cta(const lqrb_context *h, const KktShape &s, int flags) {
     if (h->opt("kkt_variant", 0) == 2) return false;
-    if (!s.uniform || s.d2x || s.hess != LQRB_HESS_BLOCKDIAG || (flags & LQRB_FLAG_SOC)) return false;
+    (void)flags;
+    if (!s.uniform || s.d2x || s.hess == LQRB_HESS_DENSE) return false;
     if (s.N < 3 || s.P1 != s.n || s.PM != 0 || s.PN != s.n) return false;
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_) return true;
@@ -223,11 +225,11 @@ static int32_t launch_kkt_tpi(lqrb_context *h, const KktShape &s, int64_t batch,
     return 0;
 }
 
-template <int n, int m>
-static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, const double *data,
+template <int n, int m, int HESS>
+static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, int soc, const double *data,
                              double *scratch, double *dz, double *mult, double *res, int32_t *info,
                              cudaStream_t st) {
-    using L = khw::Lay<n, m>;
+    using L = khw::Lay<n, m, HESS>;
     constexpr int WARPS = 4, MINB = 3;
     const int N = s.N;
     // scratch: [records: batch x N x REC] [Hi: batch x N x HI] [hinfo: batch]
@@ -236,25 +238,25 @@ static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, 
     int32_t *hinfo = reinterpret_cast<int32_t *>(hinv + (size_t)batch * N * L::HI);
     LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)batch * sizeof(int32_t), st));
     const int64_t total = batch * N;
-    khw::kkt_hinv_kernel<n, m><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(data, hinv, hinfo, N, batch);
+    khw::kkt_hinv_kernel<n, m, HESS><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(data, hinv, hinfo, N, batch, soc);
     LQRB_LAUNCH_CHECK(h, "kkt_hinv_kernel");
     const size_t smem = (size_t)WARPS * (2 * L::INST + 4) * sizeof(double);
-    auto kern = khw::kkt_hw_kernel<n, m, WARPS, MINB>;
+    auto kern = khw::kkt_hw_kernel<n, m, HESS, WARPS, MINB>;
     LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t pairs = (batch + 1) / 2;
-    kern<<<(unsigned)((pairs + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(data, hinv, hinfo, recs, dz, mult, res, info, N, batch);
+    kern<<<(unsigned)((pairs + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(data, hinv, hinfo, recs, dz, mult, res, info, N, batch, soc);
     char nm[96];
-    snprintf(nm, sizeof nm, "kkt_hw<%d,%d,p=%d/0/%d,hess=1>", n, m, n, n);
+    snprintf(nm, sizeof nm, "kkt_hw<%d,%d,p=%d/0/%d,hess=%d%s>", n, m, n, n, HESS, soc ? ",soc" : "");
     h->kernel_name = nm;
     LQRB_LAUNCH_CHECK(h, "kkt_hw_kernel");
     return 0;
 }
 
-template <int n, int m>
-static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch, const double *data,
+template <int n, int m, int HESS>
+static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch, int soc, const double *data,
                               double *scratch, double *dz, double *mult, double *res, int32_t *info,
                               cudaStream_t st) {
-    using L = kcta::Lay<n, m>;
+    using L = kcta::Lay<n, m, HESS>;
     const int N = s.N;
     // scratch: [records: batch x N x REC] [pre-pass slots: batch x prep_rows] [hinfo: batch]
     double *recs = scratch;
@@ -262,15 +264,15 @@ static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch,
     int32_t *hinfo = reinterpret_cast<int32_t *>(prep + (size_t)batch * L::prep_rows(N));
     LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)batch * sizeof(int32_t), st));
     const size_t psm = (size_t)L::PREP_TOTAL * sizeof(double), msm = (size_t)L::MAIN_TOTAL * sizeof(double);
-    auto pk = kcta::kkt_cta_prep_kernel<n, m>;
-    auto mk = kcta::kkt_cta_kernel<n, m>;
+    auto pk = kcta::kkt_cta_prep_kernel<n, m, HESS>;
+    auto mk = kcta::kkt_cta_kernel<n, m, HESS>;
     LQRB_CUDA(h, cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
     LQRB_CUDA(h, cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
-    pk<<<(unsigned)(batch * N), L::THREADS, psm, st>>>(data, prep, hinfo, N, batch);
+    pk<<<(unsigned)(batch * N), L::THREADS, psm, st>>>(data, prep, hinfo, N, batch, soc);
     LQRB_LAUNCH_CHECK(h, "kkt_cta_prep_kernel");
-    mk<<<(unsigned)batch, L::THREADS, msm, st>>>(data, prep, hinfo, recs, dz, mult, res, info, N, batch);
+    mk<<<(unsigned)batch, L::THREADS, msm, st>>>(data, prep, hinfo, recs, dz, mult, res, info, N, batch, soc);
     char nm[96];
-    snprintf(nm, sizeof nm, "kkt_cta_dmma<%d,%d,p=%d/0/%d,hess=1>", n, m, n, n);
+    snprintf(nm, sizeof nm, "kkt_cta_dmma<%d,%d,p=%d/0/%d,hess=%d%s>", n, m, n, n, HESS, soc ? ",soc" : "");
     h->kernel_name = nm;
     LQRB_LAUNCH_CHECK(h, "kkt_cta_kernel");
     return 0;
@@ -295,14 +297,22 @@ static int32_t kkt_solve_on(lqrb_context *h, const KktShape &s, int64_t batch, i
                             int32_t *info, cudaStream_t st) {
     if (batch == 0) return 0;
     if (kkt_has_cta(h, s, flags) && ((uintptr_t)data & 15) == 0 && ((uintptr_t)scratch & 15) == 0) {
-#define X(N_, M_) \
-    if (s.n == N_ && s.m == M_) return launch_kkt_cta<N_, M_>(h, s, batch, data, scratch, dz, mult, res, info, st);
+        const int soc = (flags & LQRB_FLAG_SOC) ? 1 : 0;
+#define X(N_, M_)                                                                                               \
+    if (s.n == N_ && s.m == M_)                                                                                 \
+        return s.hess == LQRB_HESS_DIAG                                                                         \
+                   ? launch_kkt_cta<N_, M_, LQRB_HESS_DIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st)      \
+                   : launch_kkt_cta<N_, M_, LQRB_HESS_BLOCKDIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st);
         KKT_CTA_SIZES(X)
 #undef X
     }
     if (kkt_has_hw(h, s, flags) && ((uintptr_t)data & 15) == 0) {
-#define X(N_, M_) \
-    if (s.n == N_ && s.m == M_) return launch_kkt_hw<N_, M_>(h, s, batch, data, scratch, dz, mult, res, info, st);
+        const int soc = (flags & LQRB_FLAG_SOC) ? 1 : 0;
+#define X(N_, M_)                                                                                              \
+    if (s.n == N_ && s.m == M_)                                                                                \
+        return s.hess == LQRB_HESS_DIAG                                                                        \
+                   ? launch_kkt_hw<N_, M_, LQRB_HESS_DIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st)      \
+                   : launch_kkt_hw<N_, M_, LQRB_HESS_BLOCKDIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st);
         KKT_HW_SIZES(X)
 #undef X
     }

@@ -27,14 +27,16 @@ using rdmma::mbar_init;
 using rdmma::mbar_wait;
 using rdmma::mma884;
 
-template <int n, int m>
+template <int n, int m, int HESS = LQRB_HESS_BLOCKDIAG>
 struct Lay {
     static_assert(n % 8 == 0 && m % 8 == 0 && n == 64 && m <= 16, "written for n = 64, m = 8, 16");
+    static_assert(HESS == LQRB_HESS_BLOCKDIAG || HESS == LQRB_HESS_DIAG, "block-diagonal or diagonal cost Hessian");
     static constexpr int NT = n / 8, UT = m / 8, w = n + m, WARPS = NT, THREADS = WARPS * 32;
+    static constexpr int HQ = HESS == LQRB_HESS_DIAG ? n : tri(n), HR = HESS == LQRB_HESS_DIAG ? m : tri(m);
     // packed knot records (tile width 1), identical to kkt_hw_kernels.cuh
-    static constexpr int oQ = 0, oR = tri(n), og = oR + tri(m), oD1 = og + w, od = oD1 + n * w, CORE = od + n;
+    static constexpr int oQ = 0, oR = HQ, og = oR + HR, oD1 = og + w, od = oD1 + n * w, CORE = od + n;
     static constexpr int oC0 = CORE, FIRST = CORE + n * w + n, MID = CORE;
-    static constexpr int oCl = tri(n) + n, LAST = oCl + n * n + n;
+    static constexpr int oCl = HQ + n, LAST = oCl + n * n + n;
     __host__ __device__ static constexpr int64_t data_rows(int N) { return FIRST + (int64_t)(N - 2) * MID + LAST; }
     __host__ __device__ static constexpr int64_t knot_off(int k) { return k == 0 ? 0 : FIRST + (int64_t)(k - 1) * MID; }
     __host__ __device__ static constexpr int64_t mult_rows(int N) { return 2 * n + (int64_t)(N - 1) * n; }
@@ -148,11 +150,11 @@ __device__ __forceinline__ int block_gj_inverse(double (&S)[NT][2], double *pan,
 
 // ------------------------------------------------------------------ pre-pass --------------------------
 // grid = batch * N CTAs of THREADS threads.  knot 0: generic scalar code for the C_1 blocks (once per instance).
-template <int n, int m>
-__global__ void __launch_bounds__(Lay<n, m>::THREADS, 2)
+template <int n, int m, int HESS>
+__global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     kkt_cta_prep_kernel(const double *__restrict__ data, double *__restrict__ prep, int32_t *__restrict__ hinfo,
-                        int N, int64_t batch) {
-    using L = Lay<n, m>;
+                        int N, int64_t batch, int soc) {
+    using L = Lay<n, m, HESS>;
     constexpr int NT = L::NT, UT = L::UT, w = L::w, LA = L::LA, THREADS = L::THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sm = reinterpret_cast<double *>(smem_raw);
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(Lay<n, m>::THREADS, 2)
     // ---- stage X = A_k (or C_N), B_k column-major with padded leading dimension; g, d; R
     const double *Xg = last ? kp + L::oCl : kp + L::oD1;
     for (int e = tid; e < n * wk; e += THREADS) As[(e / n) * LA + (e % n)] = Xg[e];
-    for (int e = tid; e < wk; e += THREADS) vq[e] = kp[(last ? tri(n) : L::og) + e];
+    for (int e = tid; e < wk; e += THREADS) vq[e] = soc ? 0.0 : kp[(last ? L::HQ : L::og) + e];  // SOC: g = 0
     for (int e = tid; e < n; e += THREADS) vd[e] = last ? kp[L::oCl + n * n + e] : kp[L::od + e];
     // ---- Q strip (C fragments) -> Qi
     double S[NT][2];
@@ -181,7 +183,9 @@ __global__ void __launch_bounds__(Lay<n, m>::THREADS, 2)
         SM_UNROLL
         for (int e = 0; e < 2; ++e) {
             const int r = 8 * wp + g, c = 8 * ct + 2 * q + e;
-            S[ct][e] = kp[r <= c ? c * (c + 1) / 2 + r : r * (r + 1) / 2 + c];
+            if (soc) S[ct][e] = r == c ? 1.0 : 0.0;  // second_order_correction!: H = I
+            else if (HESS == LQRB_HESS_DIAG) S[ct][e] = r == c ? kp[r] : 0.0;
+            else S[ct][e] = kp[r <= c ? c * (c + 1) / 2 + r : r * (r + 1) / 2 + c];
         }
     __syncthreads();
     int bad = block_gj_inverse<NT>(S, pan, pis, colb, &flag, wp, lane);
@@ -200,7 +204,11 @@ __global__ void __launch_bounds__(Lay<n, m>::THREADS, 2)
         double a[m];
         const int j = lane < m ? lane : 0;
         SM_UNROLL
-        for (int i = 0; i < m; ++i) a[i] = kp[L::oR + (i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j)];
+        for (int i = 0; i < m; ++i) {
+            if (soc) a[i] = i == j ? 1.0 : 0.0;
+            else if (HESS == LQRB_HESS_DIAG) a[i] = i == j ? kp[L::oR + j] : 0.0;
+            else a[i] = kp[L::oR + (i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j)];
+        }
         const int b2 = khw::gj_inverse<m>(a, colb, lane < m ? lane : 31);
         if (lane < m) {
             SM_UNROLL
@@ -339,12 +347,12 @@ __global__ void __launch_bounds__(Lay<n, m>::THREADS, 2)
 }
 
 // ------------------------------------------------------------------ main kernel -----------------------
-template <int n, int m>
-__global__ void __launch_bounds__(Lay<n, m>::THREADS, 2)
+template <int n, int m, int HESS>
+__global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     kkt_cta_kernel(const double *__restrict__ data, const double *__restrict__ prep, const int32_t *__restrict__ hinfo,
                    double *__restrict__ recs, double *__restrict__ dz, double *__restrict__ mult,
-                   double *__restrict__ res, int32_t *__restrict__ info, int N, int64_t batch) {
-    using L = Lay<n, m>;
+                   double *__restrict__ res, int32_t *__restrict__ info, int N, int64_t batch, int soc) {
+    using L = Lay<n, m, HESS>;
     constexpr int NT = L::NT, w = L::w, LB = L::LB, THREADS = L::THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sm = reinterpret_cast<double *>(smem_raw);
@@ -557,7 +565,7 @@ __global__ void __launch_bounds__(Lay<n, m>::THREADS, 2)
             SM_UNROLL
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             if (lane == 0) {
-                double r = kp[(last ? tri(n) : L::og) + j] - s;
+                double r = (soc ? 0.0 : kp[(last ? L::HQ : L::og) + j]) - s;
                 if (!first && j < n) r += xps[j];
                 rsv[j] = r;
             }

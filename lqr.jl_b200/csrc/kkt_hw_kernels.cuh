@@ -31,18 +31,20 @@ using rdmma::mbar_expect_tx;
 using rdmma::mbar_init;
 using rdmma::mbar_wait;
 
-template <int n, int m>
+template <int n, int m, int HESS = LQRB_HESS_BLOCKDIAG>
 struct Lay {
     static constexpr int w = n + m;
     static_assert(w <= 16 && n % 2 == 0 && m % 2 == 0, "half-warp layout: n + m <= 16, even sizes");
+    static_assert(HESS == LQRB_HESS_BLOCKDIAG || HESS == LQRB_HESS_DIAG, "block-diagonal or diagonal cost Hessian");
+    static constexpr int HQ = HESS == LQRB_HESS_DIAG ? n : tri(n), HR = HESS == LQRB_HESS_DIAG ? m : tri(m);
     // core of a knot record (same place in every knot with controls): H | g | D1 = [A B] | d
-    static constexpr int oQ = 0, oR = tri(n), og = oR + tri(m), oD1 = og + w, od = oD1 + n * w, CORE = od + n;
+    static constexpr int oQ = 0, oR = HQ, og = oR + HR, oD1 = og + w, od = oD1 + n * w, CORE = od + n;
     static constexpr int oC0 = CORE, FIRST = CORE + n * w + n;  // first knot: + C_1 (n x w) | c_1
     static constexpr int MID = CORE;
-    static constexpr int oCl = tri(n) + n, LAST = oCl + n * n + n;  // last knot: Q | g | C_N (n x n) | c_N
+    static constexpr int oCl = HQ + n, LAST = oCl + n * n + n;  // last knot: Q | g | C_N (n x n) | c_N
     static constexpr int HI = n * n + m * m;                        // Qi (full) | Ri (full)
     static constexpr int REC = n * n + n;                           // U (column-major) | v
-    static_assert(tri(n) % 2 == 0 && tri(m) % 2 == 0 && CORE % 2 == 0 && FIRST % 2 == 0 && LAST % 2 == 0 && HI % 2 == 0,
+    static_assert(HQ % 2 == 0 && HR % 2 == 0 && CORE % 2 == 0 && FIRST % 2 == 0 && LAST % 2 == 0 && HI % 2 == 0,
                   "bulk copies need 16-byte pieces");
     __host__ __device__ static constexpr int64_t data_rows(int N) { return FIRST + (int64_t)(N - 2) * MID + LAST; }
     __host__ __device__ static constexpr int64_t knot_off(int k) { return k == 0 ? 0 : FIRST + (int64_t)(k - 1) * MID; }
@@ -89,11 +91,12 @@ __device__ __forceinline__ void potri_packed(double *u, const double *dinv) {
 
 // ------------------------------------------------------------------ pre-pass: H_k^-1 for every knot ---
 // BlockCholesky block-diagonal mode (src/block_cholesky.jl:69-77, ldiv! :93-96) applied to the identity.
-template <int n, int m>
+// soc != 0: H = I (second_order_correction!, src/cholesky_solver.jl:254-273).
+template <int n, int m, int HESS>
 __global__ void __launch_bounds__(128)
     kkt_hinv_kernel(const double *__restrict__ data, double *__restrict__ hinv, int32_t *__restrict__ hinfo,
-                    int N, int64_t batch) {
-    using L = Lay<n, m>;
+                    int N, int64_t batch, int soc) {
+    using L = Lay<n, m, HESS>;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= batch * N) return;
     const int64_t inst = idx / N;
@@ -101,6 +104,28 @@ __global__ void __launch_bounds__(128)
     const double *kp = data + inst * L::data_rows(N) + L::knot_off(k);
     double *out = hinv + idx * L::HI;
     int st = 0;
+    if (HESS == LQRB_HESS_DIAG || soc) {  // stores the inverse (src/block_cholesky.jl:82-91), or the identity
+        SM_UNROLL
+        for (int j = 0; j < n; ++j) {
+            const double q = soc ? 1.0 : kp[j];
+            if (!(q > 0.0) && st == 0) st = j + 1;
+            SM_UNROLL
+            for (int i = 0; i < n; i += 2)
+                __stcs(reinterpret_cast<double2 *>(out + n * j + i), make_double2(i == j ? 1.0 / q : 0.0, i + 1 == j ? 1.0 / q : 0.0));
+        }
+        if (k < N - 1) {
+            SM_UNROLL
+            for (int j = 0; j < m; ++j) {
+                const double r = soc ? 1.0 : kp[L::oR + j];
+                if (!(r > 0.0) && st == 0) st = n + j + 1;
+                SM_UNROLL
+                for (int i = 0; i < m; i += 2)
+                    __stcs(reinterpret_cast<double2 *>(out + n * n + m * j + i), make_double2(i == j ? 1.0 / r : 0.0, i + 1 == j ? 1.0 / r : 0.0));
+            }
+        }
+        if (st != 0) atomicMin(hinfo + inst, (k + 1) * 1000 + st);
+        return;
+    }
     {
         double u[tri(n)], dinv[n];
         SM_UNROLL
@@ -206,12 +231,13 @@ __device__ __forceinline__ int gj_inverse(double (&a)[n], double *colb, int hl) 
 }
 
 // ------------------------------------------------------------------ main kernel -----------------------
-template <int n, int m, int WARPS, int MINB>
+template <int n, int m, int HESS, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     kkt_hw_kernel(const double *__restrict__ data, const double *__restrict__ hinv, const int32_t *__restrict__ hinfo,
                   double *__restrict__ recs, double *__restrict__ dz, double *__restrict__ mult,
-                  double *__restrict__ res, int32_t *__restrict__ info, int N, int64_t batch) {
-    using L = Lay<n, m>;
+                  double *__restrict__ res, int32_t *__restrict__ info, int N, int64_t batch, int soc) {
+    using L = Lay<n, m, HESS>;
+    const double gsc = soc ? 0.0 : 1.0;  // second-order correction: g = 0
     constexpr int w = L::w;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hh = lane >> 4, hl = lane & 15;
@@ -242,15 +268,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 
     // one lane per half-warp streams its instance's knot; both halves complete on the warp's barriers
     auto issue_core = [&](int k) {
-        if (lane == 0) mbar_expect_tx(bars, 2u * (uint32_t)((k < N - 1 ? L::CORE : tri(n) + n + n * n + n) * 8));
+        if (lane == 0) mbar_expect_tx(bars, 2u * (uint32_t)((k < N - 1 ? L::CORE : L::HQ + n + n * n + n) * 8));
         __syncwarp();
         if (hl == 0) {
             const double *src = db + L::knot_off(k);
             if (k < N - 1) {
                 bulk_g2s(core, src, L::CORE * 8, bars);
             } else {  // last knot: Q | g | C_N | c_N land where Q | g(x) | A | d live
-                bulk_g2s(core + L::oQ, src, tri(n) * 8, bars);
-                bulk_g2s(core + L::og, src + tri(n), n * 8, bars);
+                bulk_g2s(core + L::oQ, src, L::HQ * 8, bars);
+                bulk_g2s(core + L::og, src + L::HQ, n * 8, bars);
                 bulk_g2s(core + L::oD1, src + L::oCl, n * n * 8, bars);
                 bulk_g2s(core + L::od, src + L::oCl + n * n, n * 8, bars);
             }
@@ -286,13 +312,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             SM_UNROLL
             for (int l = 0; l < n; l += 2) {
                 const double2 v = *reinterpret_cast<const double2 *>(core + L::og + l);
-                gq[l] = v.x;
-                gq[l + 1] = v.y;
+                gq[l] = gsc * v.x;
+                gq[l + 1] = gsc * v.y;
             }
             hgj = dot_col<n>(hi + n * hl, gq);
         } else if (hl < n + mk) {
             SM_UNROLL
-            for (int s = 0; s < m; ++s) hgj = fma(hi[n * n + m * (hl - n) + s], core[L::og + n + s], hgj);
+            for (int s = 0; s < m; ++s) hgj = fma(hi[n * n + m * (hl - n) + s], gsc * core[L::og + n + s], hgj);
         }
         hgs[hl] = hgj;
 
@@ -464,7 +490,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         // res_k = D1' lam_k + C' mu_k + D2' lam_{k-1} + g_k  with Lambda = -x   (calc_residual! :201-236)
         double r = 0.0;
         if (hl < wk) {
-            r = core[L::og + hl];
+            r = gsc * core[L::og + hl];
             if (!last) {  // D1' lam_k : column hl of [A B] dotted with lam_k = -x_k
                 double xv[n];
                 SM_UNROLL

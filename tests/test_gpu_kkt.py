@@ -90,6 +90,17 @@ def test_half_warp_kernel(handle, oracle_mod, n, m, N, batch):
     assert handle.last_kernel.startswith("kkt_hw<")
 
 
+@pytest.mark.parametrize("hess", [1, 2])
+@pytest.mark.parametrize("soc", [False, True])
+@pytest.mark.parametrize("n,m,N,batch,kern", [(12, 4, 40, 6, "kkt_hw<"), (8, 4, 21, 5, "kkt_hw<"), (64, 16, 12, 2, "kkt_cta_dmma<")])
+def test_tuned_kernels_hessian_modes_and_soc(handle, oracle_mod, n, m, N, batch, kern, hess, soc):
+    """Diagonal / block-diagonal BlockCholesky modes (src/block_cholesky.jl:69-91) and the Ginv=false chain of
+    second_order_correction! (src/cholesky_solver.jl:254-273) on the tuned large-size kernels."""
+    prob = problems.random_lqr_kkt(n, m, N, batch, seed=3 * n + hess, mid_p=0, hess_mode=hess)
+    _check(prob, handle, oracle_mod, soc=soc, tol=1e-9 if soc else TOL, res_tol=1e-9 if soc else TOL)
+    assert handle.last_kernel.startswith(kern) and (",soc" in handle.last_kernel) == soc
+
+
 def test_half_warp_matches_cooperative_kernel(handle):
     prob = problems.random_lqr_kkt(12, 4, 120, 11, seed=5, mid_p=0, hess_mode=1)
     dz1, lam1, i1, r1 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
