@@ -7,7 +7,7 @@
 // written as one symmetric form:   F = [A B]  (n x w, w = n + m)
 //   T = F' * P^            (w x 16)      P^ = [P p; p' 0] embedded in a 16 x 16 "physical" tile space
 //   M = T * F + blkdiag(Q, R)            (w x w)   = [Qxx Qxu; Qux Quu]
-//   P^_ = Mxx^ - W'W,  W = L^-1 [Mux | gu],  Quu = L L'   (Schur complement of the control block)
+//   K = Quu^-1 [Qux | gu],  P^_ = Mxx^ - [Qxu | gu]' K     (Schur complement of the control block)
 // One warp owns one instance for the whole horizon.  P^ lives in mma.sync m8n8k4 accumulator
 // registers across all knots:
 //   * P^ is symmetric, so its accumulator (C) fragment IS a valid B fragment of the next T = F'P^
@@ -108,12 +108,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return fma(r, e, r);
 }
 
-// Inverse of the SPD m x m control block a (full storage, upper triangle read) by 2 x 2 block
-// elimination: two dependent reciprocals instead of four dependent rsqrt.  The potrf-style info is
-// the index of the first non-positive Cholesky pivot (pivots: a00, detA/a00, s00, detS/s00).
-// Row 0 of the inverse of the SPD m x m block a (upper triangle read), same 2 x 2 block elimination.
-// Each quad lane q calls this on the block cyclically permuted by q, so "row 0" is its own row q and
-// nothing has to be selected afterwards.  info as above (meaningful for the unpermuted lane q = 0).
+// Row 0 of the inverse of the SPD m x m control block a (upper triangle read) by 2 x 2 block elimination:
+// two dependent reciprocals instead of four dependent rsqrt.  Each quad lane q calls this on the block
+// cyclically permuted by q, so "row 0" is its own row q and nothing has to be selected afterwards.
+// info: index of the first non-positive Cholesky pivot (pivots: a00, detA/a00, s00, detS/s00), potrf
+// semantics; meaningful for the unpermuted lane q = 0.
 template <int m>
 __device__ __forceinline__ int spd_inv_row0(const double (&a)[4][4], double (&mi)[4]) {
     int info = 0;
@@ -167,72 +166,6 @@ __device__ __forceinline__ int spd_inv_row0(const double (&a)[4][4], double (&mi
         }
     }
     return info;
-}
-
-template <int m>
-__device__ __forceinline__ int spd_inv_small(const double (&a)[4][4], double (&Mi)[4][4]) {
-    int info = 0;
-    if constexpr (m == 1) {
-        if (!(a[0][0] > 0.0)) info = 1;
-        Mi[0][0] = fast_rcp(a[0][0]);
-        return info;
-    } else {
-        const double detA = fma(a[0][0], a[1][1], -a[0][1] * a[0][1]);
-        if (!(a[0][0] > 0.0)) info = 1;
-        else if (!(detA > 0.0)) info = 2;
-        const double rA = fast_rcp(detA);
-        const double i00 = a[1][1] * rA, i01 = -a[0][1] * rA, i11 = a[0][0] * rA;
-        if constexpr (m == 2) {
-            Mi[0][0] = i00; Mi[0][1] = Mi[1][0] = i01; Mi[1][1] = i11;
-            return info;
-        } else {
-            constexpr int r = m - 2;  // trailing block size: 1 or 2
-            double X[2][2], S[2][2];  // X = A^-1 B, S = D - B'X
-            SM_UNROLL
-            for (int j = 0; j < r; ++j) {
-                X[0][j] = fma(i00, a[0][2 + j], i01 * a[1][2 + j]);
-                X[1][j] = fma(i01, a[0][2 + j], i11 * a[1][2 + j]);
-            }
-            SM_UNROLL
-            for (int i = 0; i < r; ++i)
-                SM_UNROLL
-                for (int j = i; j < r; ++j)
-                    S[i][j] = a[2 + i][2 + j] - fma(a[0][2 + i], X[0][j], a[1][2 + i] * X[1][j]);
-            double s00, s01 = 0.0, s11 = 0.0;
-            if constexpr (r == 1) {
-                if (info == 0 && !(S[0][0] > 0.0)) info = 3;
-                s00 = fast_rcp(S[0][0]);
-            } else {
-                const double detS = fma(S[0][0], S[1][1], -S[0][1] * S[0][1]);
-                if (info == 0 && !(S[0][0] > 0.0)) info = 3;
-                else if (info == 0 && !(detS > 0.0)) info = 4;
-                const double rS = fast_rcp(detS);
-                s00 = S[1][1] * rS; s01 = -S[0][1] * rS; s11 = S[0][0] * rS;
-            }
-            // Minv12 = -X S^-1 ; Minv11 = A^-1 - Minv12 X'
-            double Y[2][2];
-            SM_UNROLL
-            for (int i = 0; i < 2; ++i) {
-                Y[i][0] = -fma(X[i][0], s00, r == 2 ? X[i][1] * s01 : 0.0);
-                if (r == 2) Y[i][1] = -fma(X[i][0], s01, X[i][1] * s11);
-            }
-            double m00 = i00, m01 = i01, m11 = i11;
-            SM_UNROLL
-            for (int j = 0; j < r; ++j) {
-                m00 = fma(-Y[0][j], X[0][j], m00);
-                m01 = fma(-Y[0][j], X[1][j], m01);
-                m11 = fma(-Y[1][j], X[1][j], m11);
-            }
-            Mi[0][0] = m00; Mi[0][1] = Mi[1][0] = m01; Mi[1][1] = m11;
-            SM_UNROLL
-            for (int i = 0; i < 2; ++i)
-                SM_UNROLL
-                for (int j = 0; j < r; ++j) Mi[i][2 + j] = Mi[2 + j][i] = Y[i][j];
-            Mi[2][2] = s00;
-            if (r == 2) { Mi[2][3] = Mi[3][2] = s01; Mi[3][3] = s11; }
-            return info;
-        }
-    }
 }
 
 template <int n, int m, int STAGES, int WARPS, int MINB>
