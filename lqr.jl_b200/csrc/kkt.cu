@@ -174,6 +174,7 @@ static int32_t check_kkt(lqrb_context *h, int n, int m, int N, int64_t batch, co
 }
 
 static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch);
+static int64_t kkt_tuned_chunk(const lqrb_context *h, const KktShape &s);
 
 struct KktSizes {
     int64_t NN, P, data_rows, rec_rows;
@@ -192,8 +193,6 @@ static KktSizes kkt_sizes(const KktShape &s) {
         if (k > 0) z.sD2 += (int64_t)s.n * w;
     }
     z.rec_rows = kkt_coop_rec_rows(s.n, s.m, s.N, s.p);  // an upper bound that also fits the TPI records
-    // the half-warp kernel keeps (U, v) records, H^-1 of every knot and a status word per instance
-    z.rec_rows = std::max<int64_t>(z.rec_rows, (int64_t)(kkt_hw_scratch_doubles(s, 2) + 1) / 2);
     return z;
 }
 
@@ -232,23 +231,30 @@ static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, 
     using L = khw::Lay<n, m, HESS>;
     constexpr int WARPS = 4, MINB = 3;
     const int N = s.N;
-    // scratch: [records: batch x N x REC] [Hi: batch x N x HI] [hinfo: batch]
-    double *recs = scratch;
-    double *hinv = recs + (size_t)batch * N * L::REC;
-    int32_t *hinfo = reinterpret_cast<int32_t *>(hinv + (size_t)batch * N * L::HI);
-    LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)batch * sizeof(int32_t), st));
-    const int64_t total = batch * N;
-    khw::kkt_hinv_kernel<n, m, HESS><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(data, hinv, hinfo, N, batch, soc);
-    LQRB_LAUNCH_CHECK(h, "kkt_hinv_kernel");
     const size_t smem = (size_t)WARPS * (2 * L::INST + 4) * sizeof(double);
     auto kern = khw::kkt_hw_kernel<n, m, HESS, WARPS, MINB>;
     LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t pairs = (batch + 1) / 2;
-    kern<<<(unsigned)((pairs + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(data, hinv, hinfo, recs, dz, mult, res, info, N, batch, soc);
+    const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
+    for (int64_t first = 0; first < batch; first += chunk) {
+        const int64_t cb = std::min(chunk, batch - first);
+        // scratch (reused by every chunk): [records: cb x N x REC] [Hi: cb x N x HI] [hinfo: cb]
+        double *recs = scratch;
+        double *hinv = recs + (size_t)cb * N * L::REC;
+        int32_t *hinfo = reinterpret_cast<int32_t *>(hinv + (size_t)cb * N * L::HI);
+        const double *dc = data + first * L::data_rows(N);
+        LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)cb * sizeof(int32_t), st));
+        const int64_t total = cb * N;
+        khw::kkt_hinv_kernel<n, m, HESS><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(dc, hinv, hinfo, N, cb, soc);
+        LQRB_LAUNCH_CHECK(h, "kkt_hinv_kernel");
+        const int64_t pairs = (cb + 1) / 2;
+        kern<<<(unsigned)((pairs + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(
+            dc, hinv, hinfo, recs, dz + first * L::z_rows(N), mult + first * L::mult_rows(N),
+            res ? res + first * L::z_rows(N) : nullptr, info ? info + first : nullptr, N, cb, soc);
+        LQRB_LAUNCH_CHECK(h, "kkt_hw_kernel");
+    }
     char nm[96];
     snprintf(nm, sizeof nm, "kkt_hw<%d,%d,p=%d/0/%d,hess=%d%s>", n, m, n, n, HESS, soc ? ",soc" : "");
     h->kernel_name = nm;
-    LQRB_LAUNCH_CHECK(h, "kkt_hw_kernel");
     return 0;
 }
 
@@ -258,38 +264,68 @@ static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch,
                               cudaStream_t st) {
     using L = kcta::Lay<n, m, HESS>;
     const int N = s.N;
-    // scratch: [records: batch x N x REC] [pre-pass slots: batch x prep_rows] [hinfo: batch]
-    double *recs = scratch;
-    double *prep = recs + (size_t)batch * N * L::REC;
-    int32_t *hinfo = reinterpret_cast<int32_t *>(prep + (size_t)batch * L::prep_rows(N));
-    LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)batch * sizeof(int32_t), st));
     const size_t psm = (size_t)L::PREP_TOTAL * sizeof(double), msm = (size_t)L::MAIN_TOTAL * sizeof(double);
     auto pk = kcta::kkt_cta_prep_kernel<n, m, HESS>;
     auto mk = kcta::kkt_cta_kernel<n, m, HESS>;
     LQRB_CUDA(h, cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
     LQRB_CUDA(h, cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
-    pk<<<(unsigned)(batch * N), L::THREADS, psm, st>>>(data, prep, hinfo, N, batch, soc);
-    LQRB_LAUNCH_CHECK(h, "kkt_cta_prep_kernel");
-    mk<<<(unsigned)batch, L::THREADS, msm, st>>>(data, prep, hinfo, recs, dz, mult, res, info, N, batch, soc);
+    const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
+    for (int64_t first = 0; first < batch; first += chunk) {
+        const int64_t cb = std::min(chunk, batch - first);
+        // scratch (reused by every chunk): [records: cb x N x REC] [pre-pass slots: cb x prep_rows] [hinfo: cb]
+        double *recs = scratch;
+        double *prep = recs + (size_t)cb * N * L::REC;
+        int32_t *hinfo = reinterpret_cast<int32_t *>(prep + (size_t)cb * L::prep_rows(N));
+        const double *dc = data + first * L::data_rows(N);
+        LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)cb * sizeof(int32_t), st));
+        pk<<<(unsigned)(cb * N), L::THREADS, psm, st>>>(dc, prep, hinfo, N, cb, soc);
+        LQRB_LAUNCH_CHECK(h, "kkt_cta_prep_kernel");
+        mk<<<(unsigned)cb, L::THREADS, msm, st>>>(dc, prep, hinfo, recs, dz + first * L::z_rows(N),
+                                                  mult + first * L::mult_rows(N),
+                                                  res ? res + first * L::z_rows(N) : nullptr,
+                                                  info ? info + first : nullptr, N, cb, soc);
+        LQRB_LAUNCH_CHECK(h, "kkt_cta_kernel");
+    }
     char nm[96];
     snprintf(nm, sizeof nm, "kkt_cta_dmma<%d,%d,p=%d/0/%d,hess=%d%s>", n, m, n, n, HESS, soc ? ",soc" : "");
     h->kernel_name = nm;
-    LQRB_LAUNCH_CHECK(h, "kkt_cta_kernel");
     return 0;
 }
 
 static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch) {
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_)   \
-        return (size_t)batch * ((size_t)s.N * kcta::Lay<N_, M_>::REC + kcta::Lay<N_, M_>::prep_rows(s.N)) + (size_t)(batch + 1) / 2 + 2;
+        return (size_t)batch * ((size_t)s.N * kcta::Lay<N_, M_>::REC + kcta::Lay<N_, M_>::prep_rows(s.N) + 1) + 2;
     KKT_CTA_SIZES(X)
 #undef X
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_)   \
-        return (size_t)batch * s.N * (khw::Lay<N_, M_>::REC + khw::Lay<N_, M_>::HI) + (size_t)(batch + 1) / 2 + 2;
+        return (size_t)batch * ((size_t)s.N * (khw::Lay<N_, M_>::REC + khw::Lay<N_, M_>::HI) + 1) + 2;
     KKT_HW_SIZES(X)
 #undef X
     return 0;
+}
+
+// The tuned large-size kernels keep records and pre-pass results in scratch (2.5 MB per instance for n=12,
+// N=1001; 13.7 MB for n=64, N=101).  Batches are processed in chunks so that the scratch stays under
+// `scratch_budget_mb` (default 48 GB of the 180 GB) whatever the batch size.  A chunk is a whole number of
+// resident waves of the sequential kernel (its CTAs live for the whole horizon, so a partial wave is a tail).
+static int64_t kkt_tuned_chunk(const lqrb_context *h, const KktShape &s) {
+    const size_t per = kkt_hw_scratch_doubles(s, 1);
+    if (per == 0) return 0;
+    const size_t budget = (size_t)h->opt("scratch_budget_mb", 49152) << 20;
+    int64_t c = (int64_t)(budget / (per * 8));
+    // kkt_hw: 3 CTAs x 8 instances per SM; kkt_cta: 2 CTAs x 1 instance per SM
+    const int64_t wave = (int64_t)h->sm_count * (s.n + s.m <= 16 ? 24 : 2);
+    c = std::max<int64_t>(wave, c / wave * wave);
+    return c;
+}
+
+static size_t kkt_scratch_bytes(const lqrb_context *h, const KktShape &s, const KktSizes &z, int64_t batch) {
+    size_t bytes = (size_t)lqrb_padded_batch(batch) * z.rec_rows * 8;
+    const int64_t chunk = kkt_tuned_chunk(h, s);
+    if (chunk > 0) bytes = std::max(bytes, kkt_hw_scratch_doubles(s, std::min(batch, chunk)) * 8 + 64);
+    return bytes;
 }
 
 static int32_t kkt_solve_on(lqrb_context *h, const KktShape &s, int64_t batch, int flags,
@@ -339,7 +375,7 @@ extern "C" int32_t lqrb_kkt_solve_packed_f64(lqrb_handle_t h, int32_t n, int32_t
     LQRB_CUDA(h, cudaSetDevice(h->device));
     const KktShape s = make_shape(n, m, N, p, hess_mode, explicit_d2);
     const KktSizes z = kkt_sizes(s);
-    double *scratch = (double *)lqrb_scratch(h, SCR_FACT, (size_t)lqrb_padded_batch(batch) * z.rec_rows * 8);
+    double *scratch = (double *)lqrb_scratch(h, SCR_FACT, kkt_scratch_bytes(h, s, z, batch));
     if (!scratch) return 1000 + (int)cudaErrorMemoryAllocation;
     return kkt_solve_on(h, s, batch, flags, data, scratch, dz, mult, res, info, h->stream);
 }
@@ -430,7 +466,7 @@ extern "C" int32_t lqrb_kkt_solve_f64(lqrb_handle_t h, int32_t n, int32_t m, int
         double *dzp = (double *)lqrb_scratch(h, SCR_PACK_OUT, (size_t)ldb * z.NN * 8);
         double *mp = (double *)lqrb_scratch(h, SCR_PACK_OUT2, (size_t)ldb * z.P * 8);
         double *rp = res ? (double *)lqrb_scratch(h, SCR_PACK_OUT3, (size_t)ldb * z.NN * 8) : nullptr;
-        double *scr = (double *)lqrb_scratch(h, SCR_FACT, (size_t)ldb * z.rec_rows * 8);
+        double *scr = (double *)lqrb_scratch(h, SCR_FACT, kkt_scratch_bytes(h, s, z, batch));
         if (!data || !dzp || !mp || !scr || (res && !rp)) return 1000 + (int)cudaErrorMemoryAllocation;
         rc = kkt_pack_on(h, s, z, batch, src, data, h->stream);
         if (rc) return rc;
@@ -449,7 +485,7 @@ extern "C" int32_t lqrb_kkt_solve_f64(lqrb_handle_t h, int32_t n, int32_t m, int
     const size_t in_bytes = (size_t)chunk * in_per * 8, out_bytes = (size_t)chunk * out_per * 8;
     const size_t pk_bytes = (size_t)chunk * z.data_rows * 8;
     const size_t po_bytes = (size_t)chunk * (2 * z.NN + z.P) * 8;
-    const size_t sc_bytes = (size_t)chunk * z.rec_rows * 8;
+    const size_t sc_bytes = (kkt_scratch_bytes(h, s, z, chunk) + 255) / 256 * 256;
     char *stage_in = (char *)lqrb_scratch(h, SCR_STAGE_A, 2 * in_bytes);
     char *stage_out = (char *)lqrb_scratch(h, SCR_STAGE_B, 2 * out_bytes);
     char *pk = (char *)lqrb_scratch(h, SCR_PACK_IN, 2 * pk_bytes);

@@ -233,3 +233,24 @@ def test_tuned_kernels_kkt_conditions_at_scale(handle, n, m, N, batch, kern):
     assert handle.last_kernel.startswith(kern) and (info == 0).all()
     stat, prim = _kkt_residuals_all(prob, dz, lam)
     assert stat <= 1e-10 and prim <= 1e-10, (stat, prim)
+
+
+@pytest.mark.parametrize("n,m,N,batch", [(12, 4, 30, 9000), (64, 16, 8, 700)])
+def test_tuned_kernels_chunked_scratch(handle, n, m, N, batch):
+    """The tuned kernels process the batch in chunks when their scratch would exceed `scratch_budget_mb`;
+    a tiny budget forces several chunks (one resident wave each) and must reproduce the one-chunk result."""
+    prob = problems.random_lqr_kkt(n, m, N, 64, seed=5, mid_p=0, hess_mode=1)
+    rep = (batch + 63) // 64
+    big = {k: (np.tile(v, (rep,) + (1,) * (v.ndim - 1))[:batch] if isinstance(v, np.ndarray) and v.ndim > 1 else v)
+           for k, v in prob.items()}
+    big["C"] = [np.tile(c, (rep, 1, 1))[:batch] for c in prob["C"]]
+    big["c"] = [np.tile(c, (rep, 1))[:batch] for c in prob["c"]]
+    dz1, lam1, i1 = ops.kkt_solve_problem(big, handle=handle)
+    handle.set_option("scratch_budget_mb", 1)
+    try:
+        dz2, lam2, i2 = ops.kkt_solve_problem(big, handle=handle)
+    finally:
+        handle.set_option("scratch_budget_mb", 49152)
+    assert (i1 == 0).all() and (i2 == 0).all()
+    assert np.array_equal(dz1, dz2) and np.array_equal(lam1, lam2)
+    assert np.array_equal(dz1[:64], dz1[64:128])      # replicated instances give replicated answers
