@@ -364,7 +364,8 @@ __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
                                              const double *__restrict__ rec, double *lam,
                                              double *__restrict__ dz, double *__restrict__ mult_mu,
                                              double *__restrict__ mult_lprev,
-                                             double *__restrict__ res_out) {
+                                             double *__restrict__ res_out, double *dz_reg = nullptr,
+                                             double *mult_inf = nullptr) {
     using KR = KnotRows<n, mk, ps, p2, HESS>;
     using RR = RecRows2<p1>;
     constexpr int w = n + mk;
@@ -433,6 +434,12 @@ __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
     for (int i = 0; i < ps; ++i) __stcs(mult_mu + i * 32, -mu[i]);
     SM_UNROLL
     for (int i = 0; i < p1; ++i) __stcs(mult_lprev + i * 32, -lprev[i]);
+    if (mult_inf) {  // running ||Lambda||_inf for the caller's merit penalty
+        SM_UNROLL
+        for (int i = 0; i < ps; ++i) *mult_inf = fmax(*mult_inf, fabs(mu[i]));
+        SM_UNROLL
+        for (int i = 0; i < p1; ++i) *mult_inf = fmax(*mult_inf, fabs(lprev[i]));
+    }
 
     // res_k = D1'lam_k + C'mu_k + D2'lam_{k-1} + g_k  (calc_residual! :201-236), with the final
     // (negated) multipliers; D2 = [-I 0].
@@ -461,6 +468,10 @@ __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
     H.solve(z);
     SM_UNROLL
     for (int j = 0; j < w; ++j) __stcs(dz + j * 32, -z[j]);
+    if (dz_reg) {
+        SM_UNROLL
+        for (int j = 0; j < w; ++j) dz_reg[j] = -z[j];
+    }
     if constexpr (p1 > 0) {
         SM_UNROLL
         for (int i = 0; i < p1; ++i) lam[i] = lprev[i];

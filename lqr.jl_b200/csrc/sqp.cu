@@ -376,6 +376,215 @@ __global__ void __launch_bounds__(64, 8)
     kkt_bwd_knot<n, m, 0, n, n, HD, SOC, 1>(kn, sb, lam, dzb, mb, mb, nullptr);
 }
 
+// ---------------------------------------------------------------------------------------------
+// One whole SQP iteration per launch (full fusion): forward sweep = linearise + statistics (f, ||c||_1,
+// feas_p, feas_d with the kept multipliers, convergence freeze, :126-137) + KKT forward elimination;
+// backward sweep = back-substitution + primal step + the alpha = 1 trial of the line search accumulated on
+// the fly (grad f'dx, ||Lambda||_inf, f(x+dx), ||c(x+dx)||_1, c(x+dx) stored for a possible SOC solve);
+// epilogue = stage 0 of dubins_linesearch_kernel (penalty, phi0, phi'0, Armijo test, accept or flag for SOC).
+__global__ void __launch_bounds__(64, 8)  // 65,536 instances = 1,024 CTAs must fit in one wave (148 x 8)
+    dubins_sqp_step_kernel(double *__restrict__ Z, const double *__restrict__ x0, const double *__restrict__ xf,
+                           double *__restrict__ mult_kept, double *__restrict__ cvals, double *__restrict__ scratch,
+                           double *__restrict__ dz, int32_t *__restrict__ info, double *__restrict__ stats, Opts o,
+                           int64_t batch, double eps_p, double eps_d, int full_step, int *__restrict__ counters) {
+    using L = KktLayout<n, m, n, 0, n, LQRB_HESS_DIAG>;
+    constexpr int HD = LQRB_HESS_DIAG;
+    const int64_t inst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= batch) return;
+    const int64_t tile = inst >> 5;
+    const int lane = (int)(inst & 31);
+    const int N = o.N;
+    const int64_t NN = (int64_t)N * n + (int64_t)(N - 1) * m, P = (int64_t)(N - 1) * n + 2 * n;
+    double *st = stats + tile * Stats::S_COUNT * 32 + lane;
+    if (st[Stats::CONV * 32] != 0.0) return;  // converged instances are frozen (:135-137)
+    double *zb = Z + tile * NN * 32 + lane;
+    double *cvb = cvals + tile * P * 32 + lane;
+    double *sb = scratch + tile * L::rec_rows(N) * 32 + lane;
+    double *dzb = dz + tile * NN * 32 + lane;
+    double *mb = mult_kept + tile * P * 32 + lane;
+    double xg[n], x0v[n];
+    SM_UNROLL
+    for (int i = 0; i < n; ++i) {
+        xg[i] = xf[tile * n * 32 + lane + i * 32];
+        x0v[i] = x0[tile * n * 32 + lane + i * 32];
+    }
+    auto ldz = [&](int64_t row) { return zb[row * 32]; };
+    const double qs = o.qd * o.dt, rs = o.rd * o.dt;
+    double kn[ROWS_FIRST], x[n], u[m], xn[n];
+
+    // ---------------- forward sweep: statistics at Z + elimination
+    double f = 0.0, c1 = 0.0, cinf = 0.0, fd2 = 0.0, lam_prev[n] = {0.0, 0.0, 0.0};
+    // knot with controls: g at kn[w..], D1 at kn[2w..], d after D1 (and C | c of the first knot after that)
+    auto knot_stats = [&](int k) {
+        const double *D1 = kn + 2 * w;
+        double lk[n];
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) {
+            const double e = x[i] - xg[i];
+            f += 0.5 * qs * e * e;
+            const double d = D1[n * w + i];
+            c1 += fabs(d);
+            cinf = fmax(cinf, fabs(d));
+            lk[i] = mb[(mult_row(k) + (k == 0 ? n : 0) + i) * 32];
+        }
+        SM_UNROLL
+        for (int i = 0; i < m; ++i) f += 0.5 * rs * u[i] * u[i];
+        SM_UNROLL
+        for (int j = 0; j < w; ++j) {
+            double s = kn[w + j];
+            SM_UNROLL
+            for (int i = 0; i < n; ++i) s = fma(D1[i + j * n], lk[i], s);
+            if (j < n) {
+                if (k > 0) s -= lam_prev[j];
+                else {
+                    const double c = D1[n * w + n + n * w + j];  // c = x_1 - x0
+                    c1 += fabs(c);
+                    cinf = fmax(cinf, fabs(c));
+                    s += mb[j * 32];
+                }
+            }
+            fd2 += s * s;
+        }
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) lam_prev[i] = lk[i];
+    };
+    FwdCarry<n> cy;
+    SM_UNROLL
+    for (int i = 0; i < n; ++i) { x[i] = ldz(i); xn[i] = ldz(w + i); }
+    SM_UNROLL
+    for (int i = 0; i < m; ++i) u[i] = ldz(n + i);
+    dubins_build_knot<0, false>(kn, x, u, xn, x0v, xg, o, nullptr, nullptr);
+    knot_stats(0);
+    int s1 = kkt_fwd_knot<n, m, 0, n, n, HD, false, 1>(kn, sb, cy, 0);
+    for (int k = 1; k < N - 1; ++k) {
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) { x[i] = xn[i]; xn[i] = ldz((int64_t)(k + 1) * w + i); }
+        SM_UNROLL
+        for (int i = 0; i < m; ++i) u[i] = ldz((int64_t)k * w + n + i);
+        dubins_build_knot<1, false>(kn, x, u, xn, x0v, xg, o, nullptr, nullptr);
+        knot_stats(k);
+        const int s2 = kkt_fwd_knot<n, m, n, 0, n, HD, false, 1>(
+            kn, sb + ((int64_t)L::RF::ROWS + (int64_t)(k - 1) * L::RM::ROWS) * 32, cy, k);
+        if (!s1) s1 = s2;
+    }
+    const int64_t rlast = (int64_t)L::RF::ROWS + (int64_t)(N - 2) * L::RM::ROWS;
+    {
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) x[i] = xn[i];
+        dubins_build_knot<2, false>(kn, x, u, xn, x0v, xg, o, nullptr, nullptr);
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) {  // terminal knot: g = Qf (x - xf), c = x_N - xf
+            const double e = x[i] - xg[i];
+            f += 0.5 * o.qfd * e * e;
+            c1 += fabs(e);
+            cinf = fmax(cinf, fabs(e));
+            const double r = kn[n + i] + mb[(mult_row(N - 1) + i) * 32] - lam_prev[i];
+            fd2 += r * r;
+        }
+        const int s2 = kkt_fwd_knot<n, 0, n, n, 0, HD, false, 1>(kn, sb + rlast * 32, cy, N - 1);
+        if (!s1) s1 = s2;
+    }
+    if (info) info[inst] = s1;
+    const double feasd = sqrt(fd2);
+    st[Stats::F0 * 32] = f;
+    st[Stats::C1 * 32] = c1;
+    st[Stats::CINF * 32] = cinf;
+    st[Stats::FEASD * 32] = feasd;
+    if (cinf < eps_p && feasd < eps_d) {
+        st[Stats::CONV * 32] = 1.0;
+        return;
+    }
+
+    // ---------------- backward sweep: step, multipliers (kept for the next feas_d) and the alpha = 1 trial
+    double lam[n], dzr[w], xtn[n];
+    double gdx = 0.0, linf = 0.0, ft = 0.0, c1t = 0.0;
+    const int64_t mlast = (int64_t)n + n + (int64_t)(N - 2) * n;
+    const int64_t zlast = (int64_t)(N - 1) * w;
+    kkt_bwd_knot<n, 0, n, n, 0, HD, false, 1>(kn, sb + rlast * 32, lam, dzb + zlast * 32, mb + mlast * 32,
+                                              mb + (mlast - n) * 32, nullptr, dzr, &linf);
+    SM_UNROLL
+    for (int i = 0; i < n; ++i) {
+        gdx = fma(kn[n + i], dzr[i], gdx);
+        xtn[i] = x[i] + dzr[i];
+        const double e = xtn[i] - xg[i];
+        ft += 0.5 * o.qfd * e * e;
+        c1t += fabs(e);
+        cvb[(mult_row(N - 1) + i) * 32] = e;
+    }
+    auto knot_trial = [&](int k) {
+        double xt[n], ut[m];
+        SM_UNROLL
+        for (int j = 0; j < w; ++j) gdx = fma(kn[w + j], dzr[j], gdx);
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) {
+            xt[i] = x[i] + dzr[i];
+            const double e = xt[i] - xg[i];
+            ft += 0.5 * qs * e * e;
+        }
+        SM_UNROLL
+        for (int i = 0; i < m; ++i) {
+            ut[i] = u[i] + dzr[n + i];
+            ft += 0.5 * rs * ut[i] * ut[i];
+        }
+        double cb, sbar, dcb, dsb;
+        dubins_avg(xt[2], ut[1], o.dt, cb, sbar, dcb, dsb);
+        const double fx[n] = {xt[0] + o.dt * ut[0] * cb, xt[1] + o.dt * ut[0] * sbar, xt[2] + o.dt * ut[1]};
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) {
+            const double d = fx[i] - xtn[i];
+            c1t += fabs(d);
+            cvb[(mult_row(k) + (k == 0 ? n : 0) + i) * 32] = d;
+            xtn[i] = xt[i];
+        }
+    };
+    for (int k = N - 2; k >= 1; --k) {
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) { xn[i] = x[i]; x[i] = ldz((int64_t)k * w + i); }
+        SM_UNROLL
+        for (int i = 0; i < m; ++i) u[i] = ldz((int64_t)k * w + n + i);
+        dubins_build_knot<1, false>(kn, x, u, xn, x0v, xg, o, nullptr, nullptr);
+        const int64_t mo = (int64_t)n + n + (int64_t)(k - 1) * n;
+        kkt_bwd_knot<n, m, n, 0, n, HD, false, 1>(kn, sb + ((int64_t)L::RF::ROWS + (int64_t)(k - 1) * L::RM::ROWS) * 32, lam,
+                                                  dzb + (int64_t)k * w * 32, mb + mo * 32, mb + (mo - n) * 32, nullptr,
+                                                  dzr, &linf);
+        knot_trial(k);
+    }
+    SM_UNROLL
+    for (int i = 0; i < n; ++i) { xn[i] = x[i]; x[i] = ldz(i); }
+    SM_UNROLL
+    for (int i = 0; i < m; ++i) u[i] = ldz(n + i);
+    dubins_build_knot<0, false>(kn, x, u, xn, x0v, xg, o, nullptr, nullptr);
+    kkt_bwd_knot<n, m, 0, n, n, HD, false, 1>(kn, sb, lam, dzb, mb, mb, nullptr, dzr, &linf);
+    knot_trial(0);
+    SM_UNROLL
+    for (int i = 0; i < n; ++i) {  // c_1(x + dx) = x_1 + dx_1 - x0
+        const double c = xtn[i] - x0v[i];
+        c1t += fabs(c);
+        cvb[i * 32] = c;
+    }
+
+    // ---------------- stage 0 of the line search (src/sqp.jl:72-94)
+    st[Stats::ITERS * 32] += 1.0;
+    bool take = full_step != 0;
+    if (!take) {
+        const double eta = 1e-4;
+        const double mu = fmax(st[Stats::MU * 32], 1.1 * linf);  // mu <- max(mu, 1.1 ||lambda||_inf)
+        st[Stats::MU * 32] = mu;
+        const double phi0 = f + mu * c1, dphi0 = gdx - mu * c1;
+        st[Stats::PHI0 * 32] = phi0;
+        st[Stats::DPHI0 * 32] = dphi0;
+        take = ft + mu * c1t <= phi0 + eta * dphi0;
+    }
+    st[Stats::ALPHA * 32] = 1.0;
+    if (take) {
+        for (int64_t r = 0; r < NN; ++r) zb[r * 32] += dzb[r * 32];
+        st[Stats::DONE * 32] = 1.0;
+    } else {
+        st[Stats::DONE * 32] = 0.0;
+        atomicAdd(&counters[0], 1);  // needs the second-order correction solve
+    }
+}
+
 // Line search stages (src/sqp.jl:72-94).
 //   stage 0: penalty update, phi0, phi'0; trial alpha = 1; on failure write c(x+dx) into the data rows
 //            for the second-order correction solve and set need_soc.
@@ -584,12 +793,12 @@ extern "C" int32_t lqrb_sqp_dubins_f64(lqrb_handle_t h, int64_t batch, const lqr
     for (int it = 0; it < opts->iters; ++it) {
         // update! + convergence check (:126-137)
         if (fused) {
-            dubins_linearize_kernel<false><<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, nullptr, stats, o, batch, 1, opts->eps_p, opts->eps_d);
-            LQRB_LAUNCH_CHECK(h, "dubins_linearize_kernel");
-            // _solve! (:143) on knots linearised in registers
-            dubins_kkt_fused_kernel<false><<<grid, 64, 0, s>>>(Zp, x0p, xfp, nullptr, frec, dz, mult, dinfo, o, batch);
-            h->kernel_name = "dubins_kkt_fused<3,2,p=3/0/3,hess=2>";
-            LQRB_LAUNCH_CHECK(h, "dubins_kkt_fused_kernel");
+            // update! + convergence check + _solve! + line-search stage 0 in one kernel
+            LQRB_CUDA(h, cudaMemsetAsync(counters, 0, 8, s));
+            dubins_sqp_step_kernel<<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, data, frec, dz, dinfo, stats, o, batch,
+                                                       opts->eps_p, opts->eps_d, opts->line_search ? 0 : 1, counters);
+            h->kernel_name = "dubins_sqp_step<3,2,p=3/0/3,hess=2>";
+            LQRB_LAUNCH_CHECK(h, "dubins_sqp_step_kernel");
         } else {
             dubins_linearize_kernel<true><<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, data, stats, o, batch, 1, opts->eps_p, opts->eps_d);
             LQRB_LAUNCH_CHECK(h, "dubins_linearize_kernel");
@@ -599,14 +808,12 @@ extern "C" int32_t lqrb_sqp_dubins_f64(lqrb_handle_t h, int64_t batch, const lqr
         }
         solves += batch;
         // line search (:146; spec src/sqp.jl:72-94)
-        LQRB_CUDA(h, cudaMemsetAsync(counters, 0, 8, s));
-        if (fused)
-            dubins_linesearch_kernel<true><<<grid, 64, 0, s>>>(Zp, dz, nullptr, mult, multk, x0p, xfp, data, stats, o, batch, 0,
-                                                               opts->line_search ? 0 : 1, counters);
-        else
+        if (!fused) {
+            LQRB_CUDA(h, cudaMemsetAsync(counters, 0, 8, s));
             dubins_linesearch_kernel<false><<<grid, 64, 0, s>>>(Zp, dz, nullptr, mult, multk, x0p, xfp, data, stats, o, batch, 0,
                                                                 opts->line_search ? 0 : 1, counters);
-        LQRB_LAUNCH_CHECK(h, "dubins_linesearch_kernel");
+            LQRB_LAUNCH_CHECK(h, "dubins_linesearch_kernel");
+        }
         if (!opts->line_search) continue;
         LQRB_CUDA(h, cudaMemcpyAsync(hc, counters, 8, cudaMemcpyDeviceToHost, s));
         LQRB_CUDA(h, cudaStreamSynchronize(s));
