@@ -231,8 +231,10 @@ static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, 
     using L = khw::Lay<n, m, HESS>;
     constexpr int WARPS = 4, MINB = 3;
     const int N = s.N;
-    const size_t smem = (size_t)WARPS * (2 * L::INST + 4) * sizeof(double);
-    auto kern = khw::kkt_hw_kernel<n, m, HESS, WARPS, MINB>;
+    // default: the block-layout kernel (4 x 4 lane grid per instance); kkt_variant = 3 keeps the column-per-lane one
+    const bool blocks = h->opt("kkt_variant", 0) != 3;
+    const size_t smem = (size_t)WARPS * (2 * (blocks ? L::INST2 : L::INST) + 4) * sizeof(double);
+    auto kern = blocks ? khw::kkt_hw2_kernel<n, m, HESS, WARPS, MINB> : khw::kkt_hw_kernel<n, m, HESS, WARPS, MINB>;
     LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
     for (int64_t first = 0; first < batch; first += chunk) {
@@ -253,7 +255,7 @@ static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, 
         LQRB_LAUNCH_CHECK(h, "kkt_hw_kernel");
     }
     char nm[96];
-    snprintf(nm, sizeof nm, "kkt_hw<%d,%d,p=%d/0/%d,hess=%d%s>", n, m, n, n, HESS, soc ? ",soc" : "");
+    snprintf(nm, sizeof nm, "kkt_hw<%d,%d,p=%d/0/%d,hess=%d%s%s>", n, m, n, n, HESS, soc ? ",soc" : "", blocks ? "" : ",cols");
     h->kernel_name = nm;
     return 0;
 }

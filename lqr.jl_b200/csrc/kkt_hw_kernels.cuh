@@ -52,6 +52,8 @@ struct Lay {
     __host__ __device__ static constexpr int64_t z_rows(int N) { return (int64_t)N * n + (int64_t)(N - 1) * m; }
     // shared memory per instance (doubles): core | hi | MA | MB | vectors
     static constexpr int sHi = CORE, sMA = sHi + HI, sMB = sMA + n * n, sVec = sMB + n * n, INST = sVec + 128;
+    // block-layout kernel (kkt_hw2_kernel): three n x n operand buffers
+    static constexpr int sMC = sMB + n * n, sVec2 = sMC + n * n, INST2 = sVec2 + 128;
     static_assert(2 * n * n >= n * w, "first knot stages C Hi (n x w) in MA|MB");
 };
 
@@ -556,5 +558,473 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         xcur = xprev;
     }
 }
+
+
+// ------------------------------------------------------------------ block-layout variant --------------
+// Same algorithm and records as kkt_hw_kernel, but every n x n block is spread over the 16 lanes of the
+// half-warp as a 4 x 4 grid of (n/4) x (n/4) register blocks instead of one column per lane.  A product
+// C = X Y' then needs only the lane's n/4 rows of X and n/4 rows of Y from shared memory (2 n^2 / 4 doubles per
+// lane instead of n^2 broadcast to every lane), which halves the shared-memory wavefronts the column
+// version is bound by; Gauss-Jordan exchanges the pivot row / column with 7 shuffles per pivot and the exact
+// symmetrisation is a block transpose by shuffle.  Vectors stay one entry per lane.
+template <int n, int bs>
+__device__ __forceinline__ void gemm_rr(double (&acc)[bs][bs], const double *X, const double *Y, double sign) {
+    // acc[r][c] += sign * sum_l X[r*n + l] * Y[c*n + l]
+    SM_UNROLL
+    for (int l = 0; l < n; l += 2) {
+        double2 xv[bs], yv[bs];
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r) xv[r] = *reinterpret_cast<const double2 *>(X + r * n + l);
+        SM_UNROLL
+        for (int c = 0; c < bs; ++c) yv[c] = *reinterpret_cast<const double2 *>(Y + c * n + l);
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r)
+            SM_UNROLL
+            for (int c = 0; c < bs; ++c) {
+                acc[r][c] = fma(sign * xv[r].x, yv[c].x, acc[r][c]);
+                acc[r][c] = fma(sign * xv[r].y, yv[c].y, acc[r][c]);
+            }
+    }
+}
+
+// In-place Gauss-Jordan inverse of the SPD matrix held as register blocks: lane (bi, bj) of the half-warp
+// owns rows bs*bi.., columns bs*bj...  Returns the 1-based index of the first non-positive pivot or 0.
+template <int n, int bs>
+__device__ __forceinline__ int gj_block(double (&a)[bs][bs], int bi, int bj) {
+    int bad = 0;
+    SM_UNROLL
+    for (int k = 0; k < n; ++k) {
+        const int kb = k / bs, kr = k % bs;
+        double prow[bs], pcol[bs];
+        SM_UNROLL
+        for (int c = 0; c < bs; ++c) prow[c] = __shfl_sync(0xffffffffu, a[kr][c], (kb << 2) | bj, 16);  // A[k][cols]
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r) pcol[r] = __shfl_sync(0xffffffffu, a[r][kr], (bi << 2) | kb, 16);  // A[rows][k]
+        const double piv = __shfl_sync(0xffffffffu, a[kr][kr], (kb << 2) | kb, 16);
+        if (!(piv > 0.0) && bad == 0) bad = k + 1;
+        const double p = fast_rcp(piv);
+        const bool rowk = bi == kb, colk = bj == kb;
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r) {
+            const double f = pcol[r] * p;
+            SM_UNROLL
+            for (int c = 0; c < bs; ++c) {
+                const bool pr = rowk && r == kr, pc = colk && c == kr;
+                const double upd = fma(-f, prow[c], a[r][c]);
+                a[r][c] = pr ? (pc ? p : prow[c] * p) : (pc ? -f : upd);
+            }
+        }
+    }
+    return bad;
+}
+
+template <int n, int m, int HESS, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+    kkt_hw2_kernel(const double *__restrict__ data, const double *__restrict__ hinv, const int32_t *__restrict__ hinfo,
+                   double *__restrict__ recs, double *__restrict__ dz, double *__restrict__ mult,
+                   double *__restrict__ res, int32_t *__restrict__ info, int N, int64_t batch, int soc) {
+    using L = Lay<n, m, HESS>;
+    static_assert(n % 4 == 0, "4 x 4 lane grid");
+    constexpr int bs = n / 4;
+    const double gsc = soc ? 0.0 : 1.0;  // second-order correction: g = 0
+    constexpr int w = L::w;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, hh = lane >> 4, hl = lane & 15;
+    const int bi = hl >> 2, bj = hl & 3, r0 = bs * bi, c0 = bs * bj;
+    const int64_t inst_raw = ((int64_t)blockIdx.x * WARPS + warp) * 2 + hh;
+    if (((int64_t)blockIdx.x * WARPS + warp) * 2 >= batch) return;  // whole warp leaves
+    const bool active = inst_raw < batch;
+    const int64_t inst = active ? inst_raw : batch - 1;  // an odd tail shadows the last instance (no stores)
+
+    double *wb = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (2 * L::INST2 + 4);
+    double *S = wb + hh * L::INST2;
+    // AT: X row-major (A_k or C_N), later U column-major; WC: W (or E0) column-major; SI: Sigma^-1
+    double *core = S, *hi = S + L::sHi, *AT = S + L::sMA, *WC = S + L::sMB, *SI = S + L::sMC, *vec = S + L::sVec2;
+    double *UC = AT;
+    double *ys = vec, *vs = vec + 16, *hgs = vec + 32, *xs = vec + 48, *rs_ = vec + 64, *colb = vec + 80;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wb + 2 * L::INST2);  // [0] core, [1] Hi
+    if (lane == 0) {
+        mbar_init(bars, 1);
+        mbar_init(bars + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phC = 0, phH = 0;
+
+    const double *db = data + inst * L::data_rows(N);
+    const double *hb = hinv + inst * (int64_t)N * L::HI;
+    double *rb = recs + inst * (int64_t)N * L::REC;
+    double *zb = dz + inst * L::z_rows(N);
+    double *mb = mult + inst * L::mult_rows(N);
+    double *resb = res ? res + inst * L::z_rows(N) : nullptr;
+
+    auto issue_core = [&](int k) {
+        if (lane == 0) mbar_expect_tx(bars, 2u * (uint32_t)((k < N - 1 ? L::CORE : L::HQ + n + n * n + n) * 8));
+        __syncwarp();
+        if (hl == 0) {
+            const double *src = db + L::knot_off(k);
+            if (k < N - 1) {
+                bulk_g2s(core, src, L::CORE * 8, bars);
+            } else {
+                bulk_g2s(core + L::oQ, src, L::HQ * 8, bars);
+                bulk_g2s(core + L::og, src + L::HQ, n * 8, bars);
+                bulk_g2s(core + L::oD1, src + L::oCl, n * n * 8, bars);
+                bulk_g2s(core + L::od, src + L::oCl + n * n, n * 8, bars);
+            }
+        }
+    };
+    auto issue_hi = [&](int k) {
+        if (lane == 0) mbar_expect_tx(bars + 1, 2u * (uint32_t)(L::HI * 8));
+        __syncwarp();
+        if (hl == 0) bulk_g2s(hi, hb + (int64_t)k * L::HI, L::HI * 8, bars + 1);
+    };
+    issue_hi(0);
+    issue_core(0);
+
+    int st_all = 0;
+    double Cp[bs][bs], dp = 0.0;  // pending Schur complement (this lane's block) and right-hand side (entry hl)
+    SM_UNROLL
+    for (int r = 0; r < bs; ++r)
+        SM_UNROLL
+        for (int c = 0; c < bs; ++c) Cp[r][c] = 0.0;
+
+    // ---------------- forward sweep: k = 0 .. N-1
+    for (int k = 0; k < N; ++k) {
+        const bool first = k == 0, last = k == N - 1;
+        const int mk = last ? 0 : m;
+        mbar_wait(bars + 1, phH);
+        phH ^= 1;
+        mbar_wait(bars, phC);
+        phC ^= 1;
+        const double *Xs = core + L::oD1;          // A_k, or C_N at the last knot (n x n, column-major)
+        const double *Bs = core + L::oD1 + n * n;  // B_k
+        // hg = Hi g  (one entry per lane)
+        double hgj = 0.0;
+        if (hl < n) {
+            double gq[n];
+            SM_UNROLL
+            for (int l = 0; l < n; l += 2) {
+                const double2 v = *reinterpret_cast<const double2 *>(core + L::og + l);
+                gq[l] = gsc * v.x;
+                gq[l + 1] = gsc * v.y;
+            }
+            hgj = dot_col<n>(hi + n * hl, gq);
+        } else if (hl < n + mk) {
+            SM_UNROLL
+            for (int s = 0; s < m; ++s) hgj = fma(hi[n * n + m * (hl - n) + s], gsc * core[L::og + n + s], hgj);
+        }
+        hgs[hl] = hgj;
+        // X row hl -> AT (row-major copy of the column-major knot block)
+        double xrow[n];
+        SM_UNROLL
+        for (int l = 0; l < n; ++l) xrow[l] = hl < n ? Xs[hl + n * l] : 0.0;
+        if (hl < n) store_col<n>(AT + n * hl, xrow);
+        __syncwarp();
+        // rho = X hg_x + B hg_u - d
+        double rho = 0.0;
+        if (hl < n) {
+            rho = -core[L::od + hl];
+            SM_UNROLL
+            for (int l = 0; l < n; ++l) rho = fma(xrow[l], hgs[l], rho);
+            if (!last) {
+                SM_UNROLL
+                for (int t = 0; t < m; ++t) rho = fma(Bs[hl + n * t], hgs[n + t], rho);
+            }
+        }
+        // W = Qi X'  (block), published column-major
+        double Wb[bs][bs];
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r)
+            SM_UNROLL
+            for (int c = 0; c < bs; ++c) Wb[r][c] = 0.0;
+        gemm_rr<n, bs>(Wb, hi + n * r0, AT + n * c0, 1.0);
+        SM_UNROLL
+        for (int c = 0; c < bs; ++c)
+            SM_UNROLL
+            for (int r = 0; r < bs; ++r) WC[(c0 + c) * n + r0 + r] = Wb[r][c];
+        // Sigma block (middle / last knots) and right-hand side
+        double Sb[bs][bs], y = dp - hgj;  // d += next.r_[1]
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r)
+            SM_UNROLL
+            for (int c = 0; c < bs; ++c) Sb[r][c] = Cp[r][c] + hi[(r0 + r) * n + c0 + c];  // res.A .+= YYt[ip1,ip1]
+        // V = Ri B[cols]' for the B Ri B' part of G22
+        double Vb[m][bs];
+        if (!last) {
+            SM_UNROLL
+            for (int c = 0; c < bs; ++c) {
+                double brow[m];
+                SM_UNROLL
+                for (int s = 0; s < m; ++s) brow[s] = Bs[c0 + c + n * s];
+                SM_UNROLL
+                for (int t = 0; t < m; ++t) {
+                    double v = 0.0;
+                    SM_UNROLL
+                    for (int s = 0; s < m; ++s) v = fma(hi[n * n + t + m * s], brow[s], v);
+                    Vb[t][c] = v;
+                }
+            }
+        }
+        __syncwarp();  // WC is published
+        // G22 = X W + B V
+        double Gb[bs][bs];
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r)
+            SM_UNROLL
+            for (int c = 0; c < bs; ++c) Gb[r][c] = 0.0;
+        gemm_rr<n, bs>(Gb, AT + n * r0, WC + n * c0, 1.0);
+        if (!last) {
+            SM_UNROLL
+            for (int r = 0; r < bs; ++r)
+                SM_UNROLL
+                for (int t = 0; t < m; ++t) {
+                    const double b = Bs[r0 + r + n * t];
+                    SM_UNROLL
+                    for (int c = 0; c < bs; ++c) Gb[r][c] = fma(b, Vb[t][c], Gb[r][c]);
+                }
+        }
+        double sF = -1.0;  // F = sF * (matrix in WC): middle knots F = -W
+        if (first) {
+            // first knot: T0 = C Hi (n x w) staged in WC|SI, then B0 = T0 C', E0 = T0 D1', y0 = C hg - c
+            __syncwarp();  // every lane is done reading W from WC
+            const double *C0 = db + L::oC0;
+            double t0[n];
+            SM_UNROLL
+            for (int i = 0; i < n; ++i) t0[i] = 0.0;
+            if (hl < n) {
+                SM_UNROLL
+                for (int l = 0; l < n; ++l) {
+                    const double c = hi[n * hl + l];
+                    SM_UNROLL
+                    for (int i = 0; i < n; ++i) t0[i] = fma(C0[i + n * l], c, t0[i]);
+                }
+            } else if (hl < w) {
+                SM_UNROLL
+                for (int s = 0; s < m; ++s) {
+                    const double c = hi[n * n + m * (hl - n) + s];
+                    SM_UNROLL
+                    for (int i = 0; i < n; ++i) t0[i] = fma(C0[i + n * (n + s)], c, t0[i]);
+                }
+            }
+            if (hl < w) store_col<n>(WC + n * hl, t0);
+            __syncwarp();
+            double a[n], Fc[n];
+            SM_UNROLL
+            for (int i = 0; i < n; ++i) a[i] = Fc[i] = 0.0;
+            double yy = 0.0;
+            if (hl < n) {
+                double crow[w], drow[w];
+                SM_UNROLL
+                for (int j = 0; j < w; ++j) {
+                    crow[j] = C0[hl + n * j];
+                    drow[j] = core[L::oD1 + hl + n * j];
+                    yy = fma(crow[j], hgs[j], yy);
+                }
+                acc_cols<n, w>(a, WC, crow, 1.0);
+                acc_cols<n, w>(Fc, WC, drow, 1.0);
+                yy -= C0[n * w + hl];
+            }
+            y = yy;
+            __syncwarp();  // T0 is consumed
+            if (hl < n) {
+                store_col<n>(WC + n * hl, Fc);  // E0, column-major
+                store_col<n>(SI + n * hl, a);   // B0 (symmetric)
+            }
+            __syncwarp();
+            SM_UNROLL
+            for (int r = 0; r < bs; ++r)
+                SM_UNROLL
+                for (int c = 0; c < bs; ++c) Sb[r][c] = SI[(r0 + r) * n + c0 + c];
+            sF = 1.0;
+        }
+        __syncwarp();  // knot data, Hi and AT are no longer read
+        if (k + 1 < N) {
+            issue_hi(k + 1);
+            issue_core(k + 1);
+        }
+        {
+            const int bad = gj_block<n, bs>(Sb, bi, bj);
+            if (bad != 0 && st_all == 0) st_all = first ? 1000 + 100 + bad : k * 1000 + 200 + bad;
+        }
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r)
+            SM_UNROLL
+            for (int c = 0; c < bs; ++c) SI[(r0 + r) * n + c0 + c] = Sb[r][c];
+        ys[hl] = y;
+        __syncwarp();
+        // v = Si y
+        double v = 0.0;
+        if (hl < n) {
+            double yv[n];
+            SM_UNROLL
+            for (int l = 0; l < n; l += 2) {
+                const double2 t = *reinterpret_cast<const double2 *>(ys + l);
+                yv[l] = t.x;
+                yv[l + 1] = t.y;
+            }
+            v = dot_col<n>(SI + n * hl, yv);
+        }
+        vs[hl] = v;
+        // U = Si F  (block), published column-major in the AT buffer
+        double Ub[bs][bs];
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r)
+            SM_UNROLL
+            for (int c = 0; c < bs; ++c) Ub[r][c] = 0.0;
+        gemm_rr<n, bs>(Ub, SI + n * r0, WC + n * c0, sF);
+        SM_UNROLL
+        for (int c = 0; c < bs; ++c)
+            SM_UNROLL
+            for (int r = 0; r < bs; ++r) UC[(c0 + c) * n + r0 + r] = Ub[r][c];
+        __syncwarp();
+        if (active && hl < n) {  // record (U column-major, v)
+            double *rk = rb + (int64_t)k * L::REC;
+            SM_UNROLL
+            for (int i = 0; i < n; i += 2)
+                *reinterpret_cast<double2 *>(rk + n * hl + i) = *reinterpret_cast<const double2 *>(UC + n * hl + i);
+            rk[n * n + hl] = v;
+        }
+        // Cp' = G22 - F'U ; dp' = rho - F'v
+        gemm_rr<n, bs>(Gb, WC + n * r0, UC + n * c0, -sF);
+        if (hl < n) {
+            double vv[n];
+            SM_UNROLL
+            for (int l = 0; l < n; l += 2) {
+                const double2 t = *reinterpret_cast<const double2 *>(vs + l);
+                vv[l] = t.x;
+                vv[l + 1] = t.y;
+            }
+            dp = rho - sF * dot_col<n>(WC + n * hl, vv);
+        } else {
+            dp = 0.0;
+        }
+        // exact symmetrisation: block transpose by shuffle (an antisymmetric residue is amplified by |A|^2 per knot)
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r)
+            SM_UNROLL
+            for (int c = 0; c < bs; ++c) {
+                const double t = __shfl_sync(0xffffffffu, Gb[c][r], (bj << 2) | bi, 16);
+                Cp[r][c] = 0.5 * (Gb[r][c] + t);
+            }
+        __syncwarp();
+    }
+    // ---------------- last block: mu_N' = Bl'^-1 y_mu  (Cp, dp hold Bl' and y_mu)
+    double xcur = 0.0;
+    {
+        const int bad = gj_block<n, bs>(Cp, bi, bj);
+        if (bad != 0 && st_all == 0) st_all = N * 1000 + 100 + bad;
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r)
+            SM_UNROLL
+            for (int c = 0; c < bs; ++c) SI[(r0 + r) * n + c0 + c] = Cp[r][c];
+        ys[hl] = dp;
+        __syncwarp();
+        if (hl < n) {
+            double yv[n];
+            SM_UNROLL
+            for (int l = 0; l < n; l += 2) {
+                const double2 t = *reinterpret_cast<const double2 *>(ys + l);
+                yv[l] = t.x;
+                yv[l + 1] = t.y;
+            }
+            xcur = dot_col<n>(SI + n * hl, yv);
+        }
+        __syncwarp();
+    }
+    if (info && active && hl == 0) {
+        const int hcode = hinfo[inst];
+        info[inst] = hcode != 0x7f7f7f7f ? hcode : st_all;
+    }
+    if (active && hl < n) __stcs(mb + L::mult_rows(N) - n + hl, -xcur);  // mu_N
+
+    // ---------------- backward sweep: k = N-1 .. 0     x_{k-1} = v_k - U_k x_k,  Lambda = -x
+    issue_hi(N - 1);
+    issue_core(N - 1);
+    for (int k = N - 1; k >= 0; --k) {
+        const bool first = k == 0, last = k == N - 1;
+        const int mk = last ? 0 : m, wk = n + mk;
+        const double *rk = rb + (int64_t)k * L::REC;
+        // record loads (written by this half-warp in the forward sweep)
+        double ucol[n];  // row hl of U_k: U[hl][j] = rk[n*j + hl]
+        SM_UNROLL
+        for (int j = 0; j < n; ++j) ucol[j] = hl < n ? rk[n * j + hl] : 0.0;
+        const double vk = hl < n ? rk[n * n + hl] : 0.0;
+        xs[hl] = xcur;  // x of the block after this record: mu_N' (k = N-1) or lam_k'
+        __syncwarp();
+        double xprev = vk - dot_vec<n>(ucol, xs);  // k >= 1: lam_{k-1}' ; k = 0: mu_1'
+        mbar_wait(bars + 1, phH);
+        phH ^= 1;
+        mbar_wait(bars, phC);
+        phC ^= 1;
+        // res_k = D1' lam_k + C' mu_k + D2' lam_{k-1} + g_k  with Lambda = -x   (calc_residual! :201-236)
+        double r = 0.0;
+        if (hl < wk) {
+            r = gsc * core[L::og + hl];
+            if (!last) {  // D1' lam_k : column hl of [A B] dotted with lam_k = -x_k
+                double xv[n];
+                SM_UNROLL
+                for (int l = 0; l < n; l += 2) {
+                    const double2 t = *reinterpret_cast<const double2 *>(xs + l);
+                    xv[l] = t.x;
+                    xv[l + 1] = t.y;
+                }
+                r -= dot_col<n>(core + L::oD1 + n * hl, xv);
+            } else {  // C_N' mu_N
+                double xv[n];
+                SM_UNROLL
+                for (int l = 0; l < n; l += 2) {
+                    const double2 t = *reinterpret_cast<const double2 *>(xs + l);
+                    xv[l] = t.x;
+                    xv[l + 1] = t.y;
+                }
+                r -= dot_col<n>(core + L::oD1 + n * hl, xv);
+            }
+            if (!first && hl < n) r += xprev;  // D2' lam_{k-1} = -lam_{k-1} = +x_{k-1}
+        }
+        if (first) {  // C_1' mu_1 with mu_1 = -xprev
+            ys[hl] = xprev;
+            __syncwarp();
+            if (hl < wk) {
+                const double *C0 = db + L::oC0;
+                double s = 0.0;
+                SM_UNROLL
+                for (int i = 0; i < n; ++i) s = fma(C0[i + n * hl], ys[i], s);
+                r -= s;
+            }
+        }
+        rs_[hl] = r;
+        __syncwarp();
+        // dz_k = -Hi res_k   (calc_primals! :195-199)
+        double z = 0.0;
+        if (hl < n) {
+            double rv[n];
+            SM_UNROLL
+            for (int l = 0; l < n; l += 2) {
+                const double2 t = *reinterpret_cast<const double2 *>(rs_ + l);
+                rv[l] = t.x;
+                rv[l + 1] = t.y;
+            }
+            z = -dot_col<n>(hi + n * hl, rv);
+        } else if (hl < wk) {
+            SM_UNROLL
+            for (int s = 0; s < m; ++s) z = fma(-hi[n * n + m * (hl - n) + s], rs_[n + s], z);
+        }
+        if (active && hl < wk) {
+            __stcs(zb + (int64_t)k * w + hl, z);
+            if (resb) __stcs(resb + (int64_t)k * w + hl, r);
+        }
+        if (active && hl < n) {
+            // multipliers: [mu_1 (n); lam_1 (n); ...; lam_{N-1}; mu_N]; this knot produces lam_{k-1} (k>=1) or mu_1
+            __stcs(mb + (int64_t)k * n + hl, -xprev);
+        }
+        __syncwarp();  // knot data, Hi, xs, ys, rs_ are free
+        if (k > 0) {
+            issue_hi(k - 1);
+            issue_core(k - 1);
+        }
+        xcur = xprev;
+    }
+}
+
 
 }  // namespace khw
