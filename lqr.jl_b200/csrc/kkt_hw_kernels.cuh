@@ -53,7 +53,10 @@ struct Lay {
     // shared memory per instance (doubles): core | hi | MA | MB | vectors
     static constexpr int sHi = CORE, sMA = sHi + HI, sMB = sMA + n * n, sVec = sMB + n * n, INST = sVec + 128;
     // block-layout kernel (kkt_hw2_kernel): three n x n operand buffers
-    static constexpr int sMC = sMB + n * n, sVec2 = sMC + n * n, INST2 = sVec2 + 128;
+    // the two instances of a warp sit 2 (mod 16) doubles apart: their 16-byte row loads then fall into disjoint
+    // bank groups (rows of one instance are 3n doubles apart: even 16-byte slots; the other instance: odd slots)
+    static constexpr int sMC = sMB + n * n, sVec2 = sMC + n * n, INST2raw = sVec2 + 128,
+                         INST2 = INST2raw + ((2 - INST2raw % 16) + 16) % 16;
     static_assert(2 * n * n >= n * w, "first knot stages C Hi (n x w) in MA|MB");
 };
 
