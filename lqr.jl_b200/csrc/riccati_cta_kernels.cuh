@@ -32,7 +32,7 @@ using rdmma::mma884;
 
 template <int n, int m>
 struct Cfg {
-    static_assert(n % 8 == 0 && m % 8 == 0 && m <= 16 && n >= 32 && n <= 64, "tile map: n = 32..64, m = 8, 16");
+    static_assert(n % 8 == 0 && m % 8 == 0 && m <= 16 && m <= n && n >= 16 && n <= 64, "tile map: n = 16..64 (multiples of 8), m = 8, 16");
     static constexpr int NT = n / 8, UT = m / 8, WARPS = NT, THREADS = WARPS * 32, w = n + m;
     static constexpr int JT = NT / 2 + 1;  // owned column tiles of M per warp (see own_ct)
     // every fragment is read as one 16-byte load at [row g][8*blk + 2q]: leading dimensions = 8 (mod 16)
@@ -58,6 +58,7 @@ struct Cfg {
 // warps that share an SM sub-partition (wp, wp + NT/2) carry NT/2 + NT/2 + 1 tiles together.
 template <int NT>
 __device__ __forceinline__ bool owns_j(int wp, int j) {
+    if (NT % 2) return j <= NT / 2;  // odd NT: (NT-1)/2 ring tiles each, no antipodal tile
     return j < NT / 2 || (j == NT / 2 && wp < NT / 2);
 }
 template <int NT>
@@ -249,11 +250,11 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
             SM_UNROLL
             for (int i = 0; i < HR; ++i) {
                 const double *sp = slot + (HR * hh + i) * m + j;
-                double s0 = sp[0], s1 = sp[m * m];
+                double s0 = sp[0], s1 = sp[m * m];  // WARPS >= 2
                 SM_UNROLL
-                for (int sl = 2; sl < WARPS; sl += 2) {
-                    s0 += sp[sl * m * m];
-                    s1 += sp[(sl + 1) * m * m];
+                for (int sl = 2; sl < WARPS; ++sl) {
+                    if (sl & 1) s1 += sp[sl * m * m];
+                    else s0 += sp[sl * m * m];
                 }
                 a[i] = s0 + s1;
             }

@@ -53,7 +53,7 @@ def test_tpi_sizes(handle, oracle_mod, n, m, N, lti):
     assert handle.last_kernel.startswith("riccati_tpi")
 
 
-@pytest.mark.parametrize("n,m,N,batch", [(5, 2, 20, 9), (12, 3, 101, 10), (7, 7, 15, 5), (32, 7, 12, 3), (40, 16, 11, 2)])
+@pytest.mark.parametrize("n,m,N,batch", [(5, 2, 20, 9), (12, 3, 101, 10), (7, 7, 15, 5), (32, 7, 12, 3), (40, 12, 11, 2)])
 def test_cooperative_sizes(handle, oracle_mod, n, m, N, batch):
     prob = problems.random_lqr_riccati(n, m, N, batch, seed=n)
     _check(prob, handle, oracle_mod)
@@ -70,7 +70,8 @@ def test_dmma_sizes(handle, oracle_mod, n, m, N, batch, lti):
     assert handle.last_kernel.startswith("riccati_dmma")
 
 
-@pytest.mark.parametrize("n,m,N,batch", [(32, 8, 12, 3), (64, 16, 11, 2), (64, 16, 2, 3), (64, 16, 101, 5), (32, 8, 300, 7)])
+@pytest.mark.parametrize("n,m,N,batch", [(32, 8, 12, 3), (64, 16, 11, 2), (64, 16, 2, 3), (64, 16, 101, 5), (32, 8, 300, 7),
+                                         (16, 8, 40, 5), (24, 8, 30, 4), (48, 16, 25, 3)])
 @pytest.mark.parametrize("lti", [False, True])
 def test_cta_dmma_sizes(handle, oracle_mod, n, m, N, batch, lti):
     """CTA-per-instance FP64 tensor-core kernel (config 5b shape and its smaller sibling)."""
