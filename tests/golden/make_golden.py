@@ -20,6 +20,15 @@ KKT_CASES = {
     "cartpole_kkt": lambda: problems.cartpole_fixture(),
     "double_integrator_kkt": lambda: problems.double_integrator_fixture(),
     "dubins_kkt": lambda: problems.dubins_kkt_batch(2, seed=1, N=201),
+    # config 5 shapes at short horizons (the tuned large-size kernels)
+    "quad_kkt": lambda: problems.random_lqr_kkt(12, 4, 41, 2, seed=31, mid_p=0, hess_mode=1),
+    "large_kkt": lambda: problems.random_lqr_kkt(64, 16, 8, 2, seed=32, mid_p=0, hess_mode=1),
+}
+
+RICCATI_CASES = {
+    "cartpole_riccati": lambda: problems.riccati_cartpole_batch(4, seed=0),
+    "quad_riccati": lambda: problems.random_lqr_riccati(12, 4, 41, 2, seed=33),
+    "large_riccati": lambda: problems.random_lqr_riccati(64, 16, 8, 2, seed=34),
 }
 
 
@@ -30,16 +39,17 @@ def main():
         prob = make()
         dz, lam = dense_kkt.kkt_truth(prob, 0)
         np.savez_compressed(os.path.join(here, name + ".npz"), dz=dz, mult=lam)
-    prob = problems.riccati_cartpole_batch(4, seed=0)
-    kp = dense_kkt.riccati_as_kkt(prob)
-    n, m, N = 4, 1, 101
-    X = np.zeros((4, N, n))
-    U = np.zeros((4, N - 1, m))
-    for i in range(4):
-        zt, _ = dense_kkt.kkt_truth(kp, i)
-        body = zt[:(N - 1) * (n + m)].reshape(N - 1, n + m)
-        X[i, :-1], U[i], X[i, -1] = body[:, :n], body[:, n:], zt[(N - 1) * (n + m):]
-    np.savez_compressed(os.path.join(here, "cartpole_riccati.npz"), X=X, U=U, batch=4, seed=0)
+    for name, make in RICCATI_CASES.items():
+        prob = make()
+        kp = dense_kkt.riccati_as_kkt(prob)
+        n, m, N, b = prob["n"], prob["m"], prob["N"], prob["x0"].shape[0]
+        X = np.zeros((b, N, n))
+        U = np.zeros((b, N - 1, m))
+        for i in range(b):
+            zt, _ = dense_kkt.kkt_truth(kp, i)
+            body = zt[:(N - 1) * (n + m)].reshape(N - 1, n + m)
+            X[i, :-1], U[i], X[i, -1] = body[:, :n], body[:, n:], zt[(N - 1) * (n + m):]
+        np.savez_compressed(os.path.join(here, name + ".npz"), X=X, U=U, batch=b, seed=0)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,39 @@
+"""GPU parity against the committed golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py:
+refined-truth outputs of the global KKT solve on seeded inputs).  Every kernel family is covered: thread per
+instance (cartpole, double integrator, Dubins), warp / half-warp per instance (n=12), CTA per instance (n=64)."""
+import os
+
+import numpy as np
+import pytest
+
+from lqr_b200 import ops
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-10
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("name,kernel", [("cartpole_kkt", "kkt_tpi<4,1"), ("double_integrator_kkt", "kkt_tpi<6,3"),
+                                         ("dubins_kkt", "kkt_tpi<3,2"), ("quad_kkt", "kkt_hw<12,4"),
+                                         ("large_kkt", "kkt_cta_dmma<64,16")])
+def test_kkt_golden(handle, name, kernel):
+    from tests.golden.make_golden import KKT_CASES
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    dz, lam, info = ops.kkt_solve_problem(KKT_CASES[name](), handle=handle)
+    assert handle.last_kernel.startswith(kernel) and (info == 0).all()
+    tol = 1e-9 if name == "large_kkt" else TOL   # n=64 at N=8: cond ~1e6 (same allowance as test_gpu_kkt.py)
+    assert _rel(dz[0], z["dz"]) <= tol and _rel(lam[0], z["mult"]) <= tol
+
+
+@pytest.mark.parametrize("name,kernel", [("cartpole_riccati", "riccati_tpi<4,1"), ("quad_riccati", "riccati_dmma<12,4"),
+                                         ("large_riccati", "riccati_cta_dmma<64,16")])
+def test_riccati_golden(handle, name, kernel):
+    from tests.golden.make_golden import RICCATI_CASES
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    X, U, _, _, info = ops.riccati_solve_problem(RICCATI_CASES[name](), want_gains=False, handle=handle)
+    assert handle.last_kernel.startswith(kernel) and (info == 0).all()
+    assert _rel(X[: z["X"].shape[0]], z["X"]) <= TOL and _rel(U[: z["U"].shape[0]], z["U"]) <= TOL
