@@ -94,6 +94,14 @@ __device__ __forceinline__ void potri_packed(double *u, const double *dinv) {
     }
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.256), streaming; addresses must be 32-byte aligned
+__device__ __forceinline__ void ld256_cs(const double *p, double &a, double &b, double &c, double &d) {
+    asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void st256_cs(double *p, double a, double b, double c, double d) {
+    asm volatile("st.global.cs.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 // ------------------------------------------------------------------ pre-pass: H_k^-1 for every knot ---
 // BlockCholesky block-diagonal mode (src/block_cholesky.jl:69-77, ldiv! :93-96) applied to the identity.
 // soc != 0: H = I (second_order_correction!, src/cholesky_solver.jl:254-273).
@@ -131,38 +139,65 @@ __global__ void __launch_bounds__(128)
         if (st != 0) atomicMin(hinfo + inst, (k + 1) * 1000 + st);
         return;
     }
+    // The H part of a record (HQ + HR doubles, 16-byte aligned) is read straight through with 256-bit loads
+    // (a 16-byte head when the record starts on an odd 16-byte slot); the inverse goes out with 256-bit
+    // stores, one full 32-byte sector per request (16-byte pieces from 32 different knots per request cost a
+    // whole L2 sector transaction each).
+    constexpr int HH = L::HQ + L::HR;
+    double h[HH];
+    auto ld128 = [&](int e) {
+        const double2 v = __ldcs(reinterpret_cast<const double2 *>(kp + e));
+        h[e] = v.x;
+        h[e + 1] = v.y;
+    };
+    if ((reinterpret_cast<uintptr_t>(kp) & 31) == 0) {
+        SM_UNROLL
+        for (int e = 0; e + 4 <= HH; e += 4) ld256_cs(kp + e, h[e], h[e + 1], h[e + 2], h[e + 3]);
+        if constexpr (HH % 4 == 2) ld128(HH - 2);
+    } else {
+        ld128(0);
+        SM_UNROLL
+        for (int e = 2; e + 4 <= HH; e += 4) ld256_cs(kp + e, h[e], h[e + 1], h[e + 2], h[e + 3]);
+        if constexpr (HH % 4 == 0) ld128(HH - 2);
+    }
     {
         double u[tri(n)], dinv[n];
         SM_UNROLL
-        for (int e = 0; e < tri(n); e += 2) {  // 16-byte loads: the record is read once, straight through
-            const double2 v = __ldcs(reinterpret_cast<const double2 *>(kp + e));
-            u[e] = v.x;
-            u[e + 1] = v.y;
-        }
+        for (int e = 0; e < tri(n); ++e) u[e] = h[e];
         st = chol_packed<n>(u, dinv);
         potri_packed<n>(u, dinv);
         SM_UNROLL
-        for (int j = 0; j < n; ++j)
-            SM_UNROLL
-            for (int i = 0; i < n; i += 2)
-                __stcs(reinterpret_cast<double2 *>(out + n * j + i), make_double2(u[sym_idx(i, j)], u[sym_idx(i + 1, j)]));
+        for (int j = 0; j < n; ++j) {
+            if constexpr (n % 4 == 0) {
+                SM_UNROLL
+                for (int i = 0; i < n; i += 4)
+                    st256_cs(out + n * j + i, u[sym_idx(i, j)], u[sym_idx(i + 1, j)], u[sym_idx(i + 2, j)], u[sym_idx(i + 3, j)]);
+            } else {
+                SM_UNROLL
+                for (int i = 0; i < n; i += 2)
+                    __stcs(reinterpret_cast<double2 *>(out + n * j + i), make_double2(u[sym_idx(i, j)], u[sym_idx(i + 1, j)]));
+            }
+        }
     }
     if (k < N - 1) {
         double u[tri(m)], dinv[m];
         SM_UNROLL
-        for (int e = 0; e < tri(m); e += 2) {
-            const double2 v = __ldcs(reinterpret_cast<const double2 *>(kp + tri(n) + e));
-            u[e] = v.x;
-            u[e + 1] = v.y;
-        }
+        for (int e = 0; e < tri(m); ++e) u[e] = h[tri(n) + e];
         const int s2 = chol_packed<m>(u, dinv);
         if (st == 0 && s2 != 0) st = n + s2;
         potri_packed<m>(u, dinv);
         SM_UNROLL
-        for (int j = 0; j < m; ++j)
-            SM_UNROLL
-            for (int i = 0; i < m; i += 2)
-                __stcs(reinterpret_cast<double2 *>(out + n * n + m * j + i), make_double2(u[sym_idx(i, j)], u[sym_idx(i + 1, j)]));
+        for (int j = 0; j < m; ++j) {
+            if constexpr (n % 4 == 0 && m % 4 == 0) {
+                SM_UNROLL
+                for (int i = 0; i < m; i += 4)
+                    st256_cs(out + n * n + m * j + i, u[sym_idx(i, j)], u[sym_idx(i + 1, j)], u[sym_idx(i + 2, j)], u[sym_idx(i + 3, j)]);
+            } else {
+                SM_UNROLL
+                for (int i = 0; i < m; i += 2)
+                    __stcs(reinterpret_cast<double2 *>(out + n * n + m * j + i), make_double2(u[sym_idx(i, j)], u[sym_idx(i + 1, j)]));
+            }
+        }
     }
     if (st != 0) atomicMin(hinfo + inst, (k + 1) * 1000 + st);
 }
@@ -273,14 +308,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 
     // one lane per half-warp streams its instance's knot; both halves complete on the warp's barriers
     auto issue_core = [&](int k) {
-        if (lane == 0) mbar_expect_tx(bars, 2u * (uint32_t)((k < N - 1 ? L::CORE : L::HQ + n + n * n + n) * 8));
+        // only g | D1 | d of a record is read here (H went through the pre-pass)
+        if (lane == 0) mbar_expect_tx(bars, 2u * (uint32_t)((k < N - 1 ? L::CORE - L::og : n + n * n + n) * 8));
         __syncwarp();
         if (hl == 0) {
             const double *src = db + L::knot_off(k);
             if (k < N - 1) {
-                bulk_g2s(core, src, L::CORE * 8, bars);
+                bulk_g2s(core + L::og, src + L::og, (L::CORE - L::og) * 8, bars);
             } else {  // last knot: Q | g | C_N | c_N land where Q | g(x) | A | d live
-                bulk_g2s(core + L::oQ, src, L::HQ * 8, bars);
                 bulk_g2s(core + L::og, src + L::HQ, n * 8, bars);
                 bulk_g2s(core + L::oD1, src + L::oCl, n * n * 8, bars);
                 bulk_g2s(core + L::od, src + L::oCl + n * n, n * 8, bars);
@@ -662,14 +697,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     double *resb = res ? res + inst * L::z_rows(N) : nullptr;
 
     auto issue_core = [&](int k) {
-        if (lane == 0) mbar_expect_tx(bars, 2u * (uint32_t)((k < N - 1 ? L::CORE : L::HQ + n + n * n + n) * 8));
+        // only g | D1 | d of a record is read here (H went through the pre-pass)
+        if (lane == 0) mbar_expect_tx(bars, 2u * (uint32_t)((k < N - 1 ? L::CORE - L::og : n + n * n + n) * 8));
         __syncwarp();
         if (hl == 0) {
             const double *src = db + L::knot_off(k);
             if (k < N - 1) {
-                bulk_g2s(core, src, L::CORE * 8, bars);
+                bulk_g2s(core + L::og, src + L::og, (L::CORE - L::og) * 8, bars);
             } else {
-                bulk_g2s(core + L::oQ, src, L::HQ * 8, bars);
                 bulk_g2s(core + L::og, src + L::HQ, n * 8, bars);
                 bulk_g2s(core + L::oD1, src + L::oCl, n * n * 8, bars);
                 bulk_g2s(core + L::od, src + L::oCl + n * n, n * 8, bars);
