@@ -180,6 +180,18 @@ int32_t lqrb_kkt_solve_packed_f64(lqrb_handle_t handle, int32_t n, int32_t m, in
                                   int32_t explicit_d2, int32_t flags, const double *data,
                                   double *dz, double *mult, double *res, int32_t *info);
 
+/* Replaces residual(solver; recalculate=true) : src/cholesky_solver.jl:238-252 — calc_residual! (:201-236)
+ * with the KEPT multipliers of an earlier solve and freshly evaluated Jacobians / gradients (what step!
+ * reports as feas_d, :126-134):
+ *   res_k = D1_k' lam_k + C_k' mu_k + D2_k' lam_{k-1} + g_k,   norms[i] = || (||res_k||)_k || = ||res||_2.
+ * Arrays as in lqrb_kkt_solve_f64 (instance-major, host or device); mult[P,batch] in the reference's
+ * multiplier order.  LQRB_FLAG_SOC drops g (Ginv = false, :229-231; q, r may then be NULL).
+ * res[NN,batch] | NULL, norms[batch] | NULL (not both NULL).                                            */
+int32_t lqrb_kkt_residual_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                              const int32_t *p, int32_t flags, const double *q, const double *r,
+                              const double *A, const double *B, const double *D2, const double *C,
+                              const double *mult, double *res, double *norms);
+
 /* ---------------------------------------------------------------- Dubins SQP ---------------- */
 /* Fixed-count SQP outer loop (solve!/step!, src/cholesky_solver.jl:109-153, globalised as the
  * in-repo spec src/sqp.jl:72-94: L1 merit, eta=1e-4, rho=0.5, <=10 trials, SOC tried at alpha=1)

@@ -461,9 +461,17 @@ def step_(solver: CholeskySolver):
 
 
 def residual(solver: CholeskySolver, recalculate=False):
-    """residual(solver) (src/cholesky_solver.jl:238-252): norm over knots of ||res_k||, res_k = D1'lam_k +
-    C'mu_k + D2'lam_{k-1} + g_k, per instance."""
+    """residual(solver; recalculate) (src/cholesky_solver.jl:238-252): norm over knots of ||res_k||, res_k =
+    D1'lam_k + C'mu_k + D2'lam_{k-1} + g_k, per instance.  recalculate=True evaluates it on the device from the
+    solver's CURRENT blocks (after update_) and the multipliers kept from the last solve — the reference
+    re-linearises first (:240-246), here the caller has already pushed the new blocks with update_()."""
     n, m, N = solver.n, solver.m, solver.N
+    if recalculate:
+        f = solver.flat
+        norms = np.zeros(solver.batch)
+        ops.kkt_residual(solver.handle, n, m, N, solver.batch, f["p"], 0 if solver._Ginv else _lib.FLAG_SOC,
+                         f["q"], f["r"], f["A"], f["B"], f["D2"], f["C"], solver.lam, solver.res, norms)
+        return norms
     r = solver.res
     body = r[:, :(N - 1) * (n + m)].reshape(solver.batch, N - 1, n + m)
     per_knot = np.concatenate([np.linalg.norm(body, axis=2), np.linalg.norm(r[:, (N - 1) * (n + m):], axis=1)[:, None]], axis=1)

@@ -78,6 +78,7 @@ _SIGS = {
     "lqrb_kkt_pack_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32] + [c_dp] * 12),
     "lqrb_kkt_solve_packed_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32, c_i32, c_i32]
                                   + [c_dp] * 4 + [c_vp]),
+    "lqrb_kkt_residual_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32] + [c_dp] * 9),
     "lqrb_sqp_dubins_f64": (c_i32, [c_vp, c_i64, C.POINTER(SqpOptions)] + [c_dp] * 5 + [c_vp, C.POINTER(c_i64)]),
 }
 

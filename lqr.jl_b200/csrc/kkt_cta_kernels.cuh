@@ -29,7 +29,7 @@ using rdmma::mma884;
 
 template <int n, int m, int HESS = LQRB_HESS_BLOCKDIAG>
 struct Lay {
-    static_assert(n % 8 == 0 && m % 8 == 0 && n == 64 && m <= 16, "written for n = 64, m = 8, 16");
+    static_assert(n % 8 == 0 && m % 8 == 0 && n >= 16 && n <= 64 && m <= 16 && m <= n, "n = 16..64 (multiples of 8), m = 8, 16");
     static_assert(HESS == LQRB_HESS_BLOCKDIAG || HESS == LQRB_HESS_DIAG, "block-diagonal or diagonal cost Hessian");
     static constexpr int NT = n / 8, UT = m / 8, w = n + m, WARPS = NT, THREADS = WARPS * 32;
     static constexpr int HQ = HESS == LQRB_HESS_DIAG ? n : tri(n), HR = HESS == LQRB_HESS_DIAG ? m : tri(m);
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         __syncthreads();
         // v = Si y : 4 partial sums per row (Si symmetric: read down the column)
         {
-            const int i = tid & (n - 1), part = tid / n;
+            const int i = tid % n, part = tid / n;  // THREADS = 4 n
             double s = 0.0;
             SM_UNROLL
             for (int l = 0; l < n / 4; ++l) s = fma(Ss[(part * (n / 4) + l) * LB + i], ys[part * (n / 4) + l], s);
@@ -478,12 +478,18 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         }
         // dp' = rho + T v : warp wp sums rows 8wp..8wp+7 (lanes over the columns, shuffle reduction)
         {
-            const double v0 = vs[lane], v1 = vs[lane + 32];
+            constexpr int NC = (n + 31) / 32;  // column chunks of a row per lane
+            double vv[NC];
+            SM_UNROLL
+            for (int c = 0; c < NC; ++c) vv[c] = lane + 32 * c < n ? vs[lane + 32 * c] : 0.0;
             double mine = 0.0;
             SM_UNROLL
             for (int rr = 0; rr < 8; ++rr) {
                 const double *row = Ts + (8 * wp + rr) * LB;
-                double s = fma(row[lane], v0, row[lane + 32] * v1);
+                double s = 0.0;
+                SM_UNROLL
+                for (int c = 0; c < NC; ++c)
+                    if (lane + 32 * c < n) s = fma(row[lane + 32 * c], vv[c], s);
                 SM_UNROLL
                 for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
                 if (lane == rr) mine = s;
@@ -542,7 +548,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         const double *D1g = last ? kp + L::oCl : kp + L::oD1;  // [A B] or C_N, column-major n x wk
         // x_prev = v + Z' x : 4 partial sums per entry
         {
-            const int i = tid & (n - 1), part = tid / n;
+            const int i = tid % n, part = tid / n;  // THREADS = 4 n
             double s = 0.0;
 #pragma unroll 4
             for (int l = 0; l < n / 4; ++l) {
@@ -556,11 +562,11 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         __syncthreads();
         // res_j = g_j - sum_i D1[i][j] x_i (+ x_prev_j) (- sum_i C_1[i][j] mu1'_i at the first knot)
         for (int j = wp; j < wk; j += L::WARPS) {
-            double s = D1g[lane + n * j] * xs[lane] + D1g[lane + 32 + n * j] * xs[lane + 32];
+            double s = 0.0;
+            for (int i = lane; i < n; i += 32) s = fma(D1g[i + n * j], xs[i], s);
             if (first) {
                 const double *C0 = kp + L::oC0;
-                s = fma(C0[lane + n * j], xps[lane], s);
-                s = fma(C0[lane + 32 + n * j], xps[lane + 32], s);
+                for (int i = lane; i < n; i += 32) s = fma(C0[i + n * j], xps[i], s);
             }
             SM_UNROLL
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -574,7 +580,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         // dz = -Hi res
         {
             const double *Qi = first ? pb + (int64_t)N * L::HS : slot + L::hQi;
-            const int i = tid & (n - 1), part = tid / n;
+            const int i = tid % n, part = tid / n;  // THREADS = 4 n
             double s = 0.0;
 #pragma unroll 4
             for (int l = 0; l < n / 4; ++l) {

@@ -176,9 +176,23 @@ end
 _solve!(s::BatchedCholeskySolver) = _call_kkt!(s, Int32(0))
 "second_order_correction!: src/cholesky_solver.jl:254-273 (the Ginv=false chain)"
 second_order_correction!(s::BatchedCholeskySolver) = _call_kkt!(s, FLAG_SOC)
-"residual(solver): src/cholesky_solver.jl:238-252"
-function residual(s::BatchedCholeskySolver)
+"residual(solver; recalculate): src/cholesky_solver.jl:238-252.  recalculate=true evaluates res on the device
+from the solver's current blocks and the multipliers kept from the last solve (calc_residual!, :201-236)."
+function residual(s::BatchedCholeskySolver; recalculate::Bool=false)
     n, m, N = size(s)
+    if recalculate
+        norms = zeros(size(s.res, 2))
+        GC.@preserve s norms begin
+            rc = ccall((:lqrb_kkt_residual_f64, lib), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Int32, Int64, Ptr{Int32}, Int32,
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                 Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                s.handle.ptr, s.n, s.m, s.N, size(s.res, 2), s.p, Int32(0),
+                s.q, s.r, s.A, s.B, ptr_or_null(s.D2), s.C, s.λ, s.res, norms)
+        end
+        check(s.handle, rc)
+        return norms
+    end
     map(1:size(s.res, 2)) do i
         r = view(s.res, :, i)
         norm([norm(view(r, (k - 1) * (n + m) .+ (1:(k < N ? n + m : n)))) for k = 1:N])

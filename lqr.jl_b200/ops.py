@@ -82,6 +82,13 @@ def kkt_solve_packed(h: Handle, n, m, N, batch, p, hess_mode, explicit_d2, flags
            ptr(data), ptr(dz), ptr(mult), ptr(res), ptr(info))
 
 
+def kkt_residual(h: Handle, n, m, N, batch, p, flags, q, r, A, B, D2, C, mult, res=None, norms=None):
+    """res_k = D1'lam_k + C'mu_k + D2'lam_{k-1} + g_k for given multipliers (residual, src/cholesky_solver.jl:238-252)."""
+    p = _p32(p)
+    h.call("lqrb_kkt_residual_f64", n, m, N, batch, p.ctypes.data, flags, ptr(q), ptr(r), ptr(A), ptr(B), ptr(D2),
+           ptr(C), ptr(mult), ptr(res), ptr(norms))
+
+
 # ------------------------------------------------------------------ layout helpers (host, numpy)
 def cm(a):
     """math-order (..., rows, cols) -> column-major contiguous float64 buffer (Julia order)."""

@@ -2,6 +2,7 @@
 scripts, checked with the identities those scripts state."""
 import numpy as np
 import pytest
+import torch
 
 import lqr_b200 as LQR
 from lqr_b200 import problems
@@ -122,3 +123,60 @@ def test_cholesky_solver_step_sequence_like_reference_script(handle):
     # second_order_correction!: dz^ = -D'(DD')^-1 d (:254-273); cond(DD') ~ 1e7 here
     dzh = LQR.second_order_correction_(solver)[0]
     assert _rel(dzh, -D.T @ np.linalg.solve(D @ D.T, d)) < 1e-6 or np.linalg.norm(d) == 0
+
+
+@pytest.mark.parametrize("mid_p,explicit_D2", [(0, False), (1, False), (1, True)])
+def test_residual_recalculate_matches_dense(handle, mid_p, explicit_D2):
+    """residual(solver; recalculate=true) (src/cholesky_solver.jl:238-252): calc_residual! with the KEPT
+    multipliers on re-evaluated blocks.  Checked against the dense g + D'lam of the get_* extractors
+    (test/cholesky_comp.jl:45) — relative 1e-12: it is one dot product per entry."""
+    prob = problems.random_lqr_kkt(4, 2, 9, 5, seed=11, mid_p=mid_p, explicit_D2=explicit_D2)
+    solver = LQR.CholeskySolver(prob, handle=handle)._solve_()
+    res_solve = solver.res.copy()
+    # same blocks: the recalculated residual is the one the solve reported
+    nrm = LQR.residual(solver, recalculate=True)
+    assert _rel(solver.res, res_solve) < 1e-12
+    assert _rel(nrm, np.linalg.norm(res_solve, axis=1)) < 1e-12
+    assert _rel(nrm, LQR.residual(solver)) < 1e-12
+    # new blocks, kept multipliers (what step! evaluates after the line search, :126-134)
+    rng = np.random.default_rng(5)
+    lam = solver.lam.copy()
+    solver.update_(A=prob["A"] + 0.01 * rng.standard_normal(prob["A"].shape),
+                   q=prob["q"] + 0.1 * rng.standard_normal(prob["q"].shape))
+    solver.lam[...] = lam
+    nrm = LQR.residual(solver, recalculate=True)
+    for i in (0, 4):
+        D, _ = LQR.get_linearized_constraints(solver, i)
+        _, g = LQR.get_cost_expansion(solver, i)
+        want = g + D.T @ lam[i]
+        assert _rel(solver.res[i], want) < 1e-12
+        assert abs(nrm[i] - np.linalg.norm(want)) < 1e-12 * np.linalg.norm(want)
+
+
+def test_residual_entry_device_pointers_and_soc(handle):
+    """lqrb_kkt_residual_f64 on device-resident arrays; LQRB_FLAG_SOC drops the gradient (Ginv = false,
+    src/cholesky_solver.jl:229-231) and accepts NULL q, r; argument errors are LAPACK-style."""
+    from lqr_b200 import _lib, ops
+    prob = problems.random_lqr_kkt(3, 2, 12, 40, seed=4, mid_p=1)
+    f = ops.kkt_flatten(prob)
+    n, m, N, b = 3, 2, 12, 40
+    NN, P = _lib.num_vars(n, m, N), _lib.num_cons(n, N, f["p"])
+    rng = np.random.default_rng(0)
+    lam = rng.standard_normal((b, P))
+    host_res, host_nrm = np.zeros((b, NN)), np.zeros(b)
+    ops.kkt_residual(handle, n, m, N, b, f["p"], 0, f["q"], f["r"], f["A"], f["B"], f["D2"], f["C"], lam, host_res, host_nrm)
+    dev = {k: torch.from_numpy(np.ascontiguousarray(f[k])).cuda() for k in ("q", "r", "A", "B", "C")}
+    dlam = torch.from_numpy(lam).cuda()
+    dres, dnrm = torch.zeros((b, NN), dtype=torch.float64, device="cuda"), torch.zeros(b, dtype=torch.float64, device="cuda")
+    ops.kkt_residual(handle, n, m, N, b, f["p"], 0, dev["q"], dev["r"], dev["A"], dev["B"], None, dev["C"], dlam, dres, dnrm)
+    handle.synchronize()
+    assert np.array_equal(dres.cpu().numpy(), host_res) and np.array_equal(dnrm.cpu().numpy(), host_nrm)
+    # SOC: no gradient
+    soc_res = np.zeros((b, NN))
+    ops.kkt_residual(handle, n, m, N, b, f["p"], _lib.FLAG_SOC, None, None, f["A"], f["B"], f["D2"], f["C"], lam, soc_res, None)
+    g = np.concatenate([np.concatenate([prob["q"][:, :N - 1], prob["r"]], axis=2).reshape(b, -1), prob["q"][:, N - 1]], axis=1)
+    assert _rel(host_res - soc_res, g) < 1e-12
+    with pytest.raises(LQR.LqrbError):
+        ops.kkt_residual(handle, n, m, N, b, f["p"], 0, None, None, f["A"], f["B"], None, f["C"], lam, soc_res, None)
+    with pytest.raises(LQR.LqrbError):
+        ops.kkt_residual(handle, n, m, N, b, f["p"], 0, f["q"], f["r"], f["A"], f["B"], None, f["C"], lam, None, None)

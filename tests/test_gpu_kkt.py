@@ -153,6 +153,25 @@ def test_cta_dmma_kernel(handle, oracle_mod, N, batch):
     assert handle.last_kernel.startswith("kkt_cta_dmma<64,16")
 
 
+@pytest.mark.parametrize("hess,soc", [(1, False), (2, False), (1, True)])
+@pytest.mark.parametrize("n,m,N,batch", [(16, 8, 24, 5), (32, 8, 30, 4), (48, 16, 16, 3)])
+def test_cta_dmma_other_sizes(handle, oracle_mod, n, m, N, batch, hess, soc):
+    """The CTA-per-instance tensor-core KKT kernel at the other sizes of the Riccati CTA family
+    (n = 16, 32, 48: 2, 4, 6 warps), against the oracle and against the cooperative kernel."""
+    prob = problems.random_lqr_kkt(n, m, N, batch, seed=7 * n + hess, mid_p=0, hess_mode=hess)
+    _check(prob, handle, oracle_mod, soc=soc, tol=1e-9 if soc else TOL, res_tol=1e-9 if soc else TOL)
+    assert handle.last_kernel.startswith(f"kkt_cta_dmma<{n},{m}") and (",soc" in handle.last_kernel) == soc
+    dz1, lam1, i1 = ops.kkt_solve_problem(prob, soc=soc, handle=handle)
+    handle.set_option("kkt_variant", 2)
+    try:
+        dz2, lam2, i2 = ops.kkt_solve_problem(prob, soc=soc, handle=handle)
+        assert handle.last_kernel.startswith("kkt_coop")
+    finally:
+        handle.set_option("kkt_variant", 0)
+    assert (i1 == 0).all() and (i2 == 0).all()
+    assert _rel(dz1, dz2) <= 1e-9 and _rel(lam1, lam2) <= 1e-9
+
+
 def test_cta_dmma_matches_cooperative_kernel(handle):
     prob = problems.random_lqr_kkt(64, 16, 20, 3, seed=6, mid_p=0, hess_mode=1)
     dz1, lam1, i1, r1 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
