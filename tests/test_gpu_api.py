@@ -125,12 +125,12 @@ def test_cholesky_solver_step_sequence_like_reference_script(handle):
     assert _rel(dzh, -D.T @ np.linalg.solve(D @ D.T, d)) < 1e-6 or np.linalg.norm(d) == 0
 
 
-@pytest.mark.parametrize("mid_p,explicit_D2", [(0, False), (1, False), (1, True)])
-def test_residual_recalculate_matches_dense(handle, mid_p, explicit_D2):
+@pytest.mark.parametrize("m,mid_p,explicit_D2", [(2, 0, False), (3, 2, False), (2, 1, True)])
+def test_residual_recalculate_matches_dense(handle, m, mid_p, explicit_D2):
     """residual(solver; recalculate=true) (src/cholesky_solver.jl:238-252): calc_residual! with the KEPT
     multipliers on re-evaluated blocks.  Checked against the dense g + D'lam of the get_* extractors
     (test/cholesky_comp.jl:45) — relative 1e-12: it is one dot product per entry."""
-    prob = problems.random_lqr_kkt(4, 2, 9, 5, seed=11, mid_p=mid_p, explicit_D2=explicit_D2)
+    prob = problems.random_lqr_kkt(4, m, 9, 5, seed=11, mid_p=mid_p, explicit_D2=explicit_D2)
     solver = LQR.CholeskySolver(prob, handle=handle)._solve_()
     res_solve = solver.res.copy()
     # same blocks: the recalculated residual is the one the solve reported
