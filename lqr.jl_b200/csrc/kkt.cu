@@ -53,7 +53,7 @@ static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
 }
 
 // CTA-per-instance FP64 tensor-core instantiations (same stage pattern)
-#define KKT_CTA_SIZES(X) X(64, 16) X(48, 16) X(32, 8) X(16, 8)
+#define KKT_CTA_SIZES(X) X(64, 16) X(48, 16) X(32, 8) X(24, 8) X(16, 8)
 
 static bool kkt_has_cta(const lqrb_context *h, const KktShape &s, int flags) {
     if (h->opt("kkt_variant", 0) == 2) return false;

@@ -562,11 +562,16 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         __syncthreads();
         // res_j = g_j - sum_i D1[i][j] x_i (+ x_prev_j) (- sum_i C_1[i][j] mu1'_i at the first knot)
         for (int j = wp; j < wk; j += L::WARPS) {
+            constexpr int NC = (n + 31) / 32;
             double s = 0.0;
-            for (int i = lane; i < n; i += 32) s = fma(D1g[i + n * j], xs[i], s);
+            SM_UNROLL
+            for (int c = 0; c < NC; ++c)
+                if (lane + 32 * c < n) s = fma(D1g[lane + 32 * c + n * j], xs[lane + 32 * c], s);
             if (first) {
                 const double *C0 = kp + L::oC0;
-                for (int i = lane; i < n; i += 32) s = fma(C0[i + n * j], xps[i], s);
+                SM_UNROLL
+                for (int c = 0; c < NC; ++c)
+                    if (lane + 32 * c < n) s = fma(C0[lane + 32 * c + n * j], xps[lane + 32 * c], s);
             }
             SM_UNROLL
             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);

@@ -154,10 +154,10 @@ def test_cta_dmma_kernel(handle, oracle_mod, N, batch):
 
 
 @pytest.mark.parametrize("hess,soc", [(1, False), (2, False), (1, True)])
-@pytest.mark.parametrize("n,m,N,batch", [(16, 8, 24, 5), (32, 8, 30, 4), (48, 16, 16, 3)])
+@pytest.mark.parametrize("n,m,N,batch", [(16, 8, 24, 5), (24, 8, 18, 3), (32, 8, 30, 4), (48, 16, 16, 3)])
 def test_cta_dmma_other_sizes(handle, oracle_mod, n, m, N, batch, hess, soc):
     """The CTA-per-instance tensor-core KKT kernel at the other sizes of the Riccati CTA family
-    (n = 16, 32, 48: 2, 4, 6 warps), against the oracle and against the cooperative kernel."""
+    (n = 16, 24, 32, 48: 2, 3, 4, 6 warps), against the oracle and against the cooperative kernel."""
     prob = problems.random_lqr_kkt(n, m, N, batch, seed=7 * n + hess, mid_p=0, hess_mode=hess)
     _check(prob, handle, oracle_mod, soc=soc, tol=1e-9 if soc else TOL, res_tol=1e-9 if soc else TOL)
     assert handle.last_kernel.startswith(f"kkt_cta_dmma<{n},{m}") and (",soc" in handle.last_kernel) == soc
