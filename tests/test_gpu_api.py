@@ -180,3 +180,56 @@ def test_residual_entry_device_pointers_and_soc(handle):
         ops.kkt_residual(handle, n, m, N, b, f["p"], 0, None, None, f["A"], f["B"], None, f["C"], lam, soc_res, None)
     with pytest.raises(LQR.LqrbError):
         ops.kkt_residual(handle, n, m, N, b, f["p"], 0, f["q"], f["r"], f["A"], f["B"], None, f["C"], lam, None, None)
+
+
+def test_edge_cases_empty_batch_shortest_horizon_and_argument_errors(handle, oracle_mod):
+    """Empty batch is a no-op; N = 2 is the shortest horizon (one control knot + the terminal knot); argument
+    errors come back as negative LAPACK-style codes (never a crash, never a silent fallback)."""
+    from lqr_b200 import _lib, ops
+    # ---- batch = 0: every entry returns 0 and touches nothing
+    prob = problems.random_lqr_kkt(4, 2, 6, 1, seed=1)
+    f = ops.kkt_flatten(prob)
+    e = np.zeros((0, 1))
+    ops.kkt_solve(handle, 4, 2, 6, 0, f["p"], f["hess_mode"], 0, e, e, None, e, e, e, e, e, None, e, e, e, e, None, None)
+    ops.kkt_residual(handle, 4, 2, 6, 0, f["p"], 0, e, e, e, e, None, e, e, e, None)
+    rp = problems.random_lqr_riccati(4, 2, 6, 1, seed=1)
+    g = ops.riccati_flatten(rp)
+    ops.riccati(handle, 4, 2, 6, 0, 0, e, e, e, e, e, e, e, e, e, e, None, None, None)
+    # ---- shortest horizons: N = 2 needs m >= n to be feasible with init + goal rows (cooperative kernel);
+    # the thread-per-instance and tuned families at their shortest feasible N
+    for n, m, N in [(2, 2, 2), (3, 3, 2), (3, 2, 3), (4, 1, 5), (12, 4, 4)]:
+        p2 = problems.random_lqr_kkt(n, m, N, 3, seed=n)
+        dz, lam, info = ops.kkt_solve_problem(p2, handle=handle)
+        dzo, lamo, infoo = oracle_mod.kkt_solve(p2)
+        assert (info == 0).all() and (infoo == 0).all(), (n, m, N, handle.last_kernel, info)
+        assert _rel(dz, dzo) < 1e-9 and _rel(lam, lamo) < 1e-9, (n, m, N, handle.last_kernel)
+    for n, m in [(2, 2), (4, 1), (12, 4)]:
+        r2 = problems.random_lqr_riccati(n, m, 2, 3, seed=n)
+        X, U, K, kff, info = ops.riccati_solve_problem(r2, handle=handle)
+        Xo, Uo, Ko, kffo, _ = oracle_mod.riccati(r2)
+        assert (info == 0).all() and _rel(X, Xo) < 1e-10 and _rel(U, Uo) < 1e-10 and _rel(K, Ko) < 1e-10
+    # an over-determined problem (N = 2, m < n: 12 rows on 9 unknowns) is REPORTED, by the kernel and by the oracle
+    bad = problems.random_lqr_kkt(4, 1, 2, 3, seed=4)
+    _, _, info = ops.kkt_solve_problem(bad, handle=handle)
+    _, _, infoo = oracle_mod.kkt_solve(bad)
+    assert (info != 0).all() and (infoo != 0).all()
+    # ---- argument errors
+    dz, lam = np.zeros((1, _lib.num_vars(4, 2, 6))), np.zeros((1, _lib.num_cons(4, 6, f["p"])))
+    def code(call):
+        with pytest.raises(LQR.LqrbError) as ei:
+            call()
+        return str(ei.value)
+    assert "code -4" in code(lambda: ops.kkt_solve(handle, 4, 2, 1, 1, f["p"], 1, 0, f["Q"], f["R"], None, f["q"], f["r"],
+                                                   f["A"], f["B"], f["d"], None, f["C"], f["c"], dz, lam))
+    assert "code -3" in code(lambda: ops.kkt_solve(handle, 4, 5, 6, 1, f["p"], 1, 0, f["Q"], f["R"], None, f["q"], f["r"],
+                                                   f["A"], f["B"], f["d"], None, f["C"], f["c"], dz, lam))
+    assert "code -7" in code(lambda: ops.kkt_solve(handle, 4, 2, 6, 1, f["p"], 7, 0, f["Q"], f["R"], None, f["q"], f["r"],
+                                                   f["A"], f["B"], f["d"], None, f["C"], f["c"], dz, lam))
+    bad_p = f["p"].copy(); bad_p[2] = 99
+    assert "code -6" in code(lambda: ops.kkt_solve(handle, 4, 2, 6, 1, bad_p, 1, 0, f["Q"], f["R"], None, f["q"], f["r"],
+                                                   f["A"], f["B"], f["d"], None, f["C"], f["c"], dz, lam))
+    assert "code -20" in code(lambda: ops.kkt_solve(handle, 4, 2, 6, 1, f["p"], 1, 0, f["Q"], f["R"], None, f["q"], f["r"],
+                                                    f["A"], f["B"], f["d"], None, f["C"], f["c"], None, lam))
+    # the handle is still usable after the errors
+    dz2, lam2, info2 = ops.kkt_solve_problem(prob, handle=handle)
+    assert (info2 == 0).all()
