@@ -382,6 +382,13 @@ __global__ void __launch_bounds__(64, 8)
 // backward sweep = back-substitution + primal step + the alpha = 1 trial of the line search accumulated on
 // the fly (grad f'dx, ||Lambda||_inf, f(x+dx), ||c(x+dx)||_1, c(x+dx) stored for a possible SOC solve);
 // epilogue = stage 0 of dubins_linesearch_kernel (penalty, phi0, phi'0, Armijo test, accept or flag for SOC).
+// L2 prefetch of one 256-byte row of a packed tile (one request per 32-byte sector): the kernel runs ~3.5 warps
+// per scheduler, so the loads at the top of every knot are latency the other warps cannot cover; prefetching the
+// next knot's rows costs no registers.
+__device__ __forceinline__ void prefetch_row_l2(const double *p, int lane) {
+    if ((lane & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __global__ void __launch_bounds__(64, 8)  // 65,536 instances = 1,024 CTAs must fit in one wave (148 x 8)
     dubins_sqp_step_kernel(double *__restrict__ Z, const double *__restrict__ x0, const double *__restrict__ xf,
                            double *__restrict__ mult_kept, double *__restrict__ cvals, double *__restrict__ scratch,
@@ -457,6 +464,12 @@ __global__ void __launch_bounds__(64, 8)  // 65,536 instances = 1,024 CTAs must 
     knot_stats(0);
     int s1 = kkt_fwd_knot<n, m, 0, n, n, HD, false, 1>(kn, sb, cy, 0);
     for (int k = 1; k < N - 1; ++k) {
+        if (k + 2 < N) {  // next knot: u_{k+1}, x_{k+2}, kept lam_{k+1}
+            SM_UNROLL
+            for (int i = 0; i < w; ++i) prefetch_row_l2(zb + ((int64_t)(k + 1) * w + n + i) * 32, lane);
+            SM_UNROLL
+            for (int i = 0; i < n; ++i) prefetch_row_l2(mb + (mult_row(k + 1) + i) * 32, lane);
+        }
         SM_UNROLL
         for (int i = 0; i < n; ++i) { x[i] = xn[i]; xn[i] = ldz((int64_t)(k + 1) * w + i); }
         SM_UNROLL
@@ -538,6 +551,13 @@ __global__ void __launch_bounds__(64, 8)  // 65,536 instances = 1,024 CTAs must 
         }
     };
     for (int k = N - 2; k >= 1; --k) {
+        if (k >= 2) {  // previous knot: z_{k-1} and its record
+            SM_UNROLL
+            for (int i = 0; i < w; ++i) prefetch_row_l2(zb + ((int64_t)(k - 1) * w + i) * 32, lane);
+            const double *rp = sb + ((int64_t)L::RF::ROWS + (int64_t)(k - 2) * L::RM::ROWS) * 32;
+            SM_UNROLL
+            for (int i = 0; i < L::RM::ROWS; ++i) prefetch_row_l2(rp + i * 32, lane);
+        }
         SM_UNROLL
         for (int i = 0; i < n; ++i) { xn[i] = x[i]; x[i] = ldz((int64_t)k * w + i); }
         SM_UNROLL
