@@ -625,6 +625,31 @@ __device__ __forceinline__ void gemm_rr(double (&acc)[bs][bs], const double *X, 
     }
 }
 
+// Two products that share the Y operand: acc1 += s1 * X1 Y', acc2 += s2 * X2 Y' (the Y rows are loaded once).
+template <int n, int bs>
+__device__ __forceinline__ void gemm_rr2(double (&acc1)[bs][bs], double (&acc2)[bs][bs], const double *X1, const double *X2,
+                                         const double *Y, double s1, double s2) {
+    SM_UNROLL
+    for (int l = 0; l < n; l += 2) {
+        double2 x1[bs], x2[bs], yv[bs];
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r) x1[r] = *reinterpret_cast<const double2 *>(X1 + r * n + l);
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r) x2[r] = *reinterpret_cast<const double2 *>(X2 + r * n + l);
+        SM_UNROLL
+        for (int c = 0; c < bs; ++c) yv[c] = *reinterpret_cast<const double2 *>(Y + c * n + l);
+        SM_UNROLL
+        for (int r = 0; r < bs; ++r)
+            SM_UNROLL
+            for (int c = 0; c < bs; ++c) {
+                acc1[r][c] = fma(s1 * x1[r].x, yv[c].x, acc1[r][c]);
+                acc1[r][c] = fma(s1 * x1[r].y, yv[c].y, acc1[r][c]);
+                acc2[r][c] = fma(s2 * x2[r].x, yv[c].x, acc2[r][c]);
+                acc2[r][c] = fma(s2 * x2[r].y, yv[c].y, acc2[r][c]);
+            }
+    }
+}
+
 // In-place Gauss-Jordan inverse of the SPD matrix held as register blocks: lane (bi, bj) of the half-warp
 // owns rows bs*bi.., columns bs*bj...  Returns the 1-based index of the first non-positive pivot or 0.
 template <int n, int bs>
@@ -810,7 +835,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         for (int r = 0; r < bs; ++r)
             SM_UNROLL
             for (int c = 0; c < bs; ++c) Gb[r][c] = 0.0;
-        gemm_rr<n, bs>(Gb, AT + n * r0, WC + n * c0, 1.0);
+        if (first) gemm_rr<n, bs>(Gb, AT + n * r0, WC + n * c0, 1.0);  // k >= 1: with U below (same W operand)
         if (!last) {
             SM_UNROLL
             for (int r = 0; r < bs; ++r)
@@ -909,7 +934,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         for (int r = 0; r < bs; ++r)
             SM_UNROLL
             for (int c = 0; c < bs; ++c) Ub[r][c] = 0.0;
-        gemm_rr<n, bs>(Ub, SI + n * r0, WC + n * c0, sF);
+        if (first) {
+            gemm_rr<n, bs>(Ub, SI + n * r0, WC + n * c0, sF);
+        } else {
+            gemm_rr2<n, bs>(Gb, Ub, AT + n * r0, SI + n * r0, WC + n * c0, 1.0, sF);
+            __syncwarp();  // AT (the X rows) is consumed: U goes into the same buffer
+        }
         SM_UNROLL
         for (int c = 0; c < bs; ++c)
             SM_UNROLL
