@@ -164,6 +164,28 @@ def cpu_leg(n, m, N, f, target_seconds=12.0, steps=1, warmup=0):
     return cnt / t, cores, f"{cnt} of {total} instances per step, {len(times)} step(s)", 1e3 * t
 
 
+def sparse_leg(n, m, N, seed, seconds=3.0, max_inst=256):
+    """The reference's other solver on the same instances: SparseSolver assembles the global KKT pieces and calls
+    a sparse factorisation (src/sparse_solver.jl:267-292).  Analogue here: scipy's sparse LU of [H D'; D 0] per
+    instance (assembly excluded), one core, bounded sample.  Reported next to the block-recursion port."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    from lqr_b200 import problems
+    from oracle import dense_kkt
+    prob = dense_kkt.riccati_as_kkt(problems.riccati_cartpole_batch(max_inst, seed=seed, N=N))
+    t_solve, cnt = 0.0, 0
+    while cnt < max_inst and t_solve < seconds:
+        H, g, D, d = dense_kkt.assemble(prob, cnt)
+        K = sp.bmat([[H, D.T], [D, None]], format="csc")
+        rhs = -np.concatenate([g, d])
+        t0 = time.perf_counter()
+        spla.splu(K).solve(rhs)
+        t_solve += time.perf_counter() - t0
+        cnt += 1
+    return {"value": cnt / t_solve, "unit": UNIT, "cores": 1, "sample": f"{cnt} instances",
+            "what": "scipy sparse LU of the assembled KKT system (analogue of src/sparse_solver.jl:267-292)"}
+
+
 # ------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -328,7 +350,8 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             v, cores, sample, _ = cpu_leg(n, m, N, f, target_seconds=12.0)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                                    "sparse_kkt": sparse_leg(n, m, N, seed=0)}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
