@@ -23,12 +23,19 @@ KKT_CASES = {
     # config 5 shapes at short horizons (the tuned large-size kernels)
     "quad_kkt": lambda: problems.random_lqr_kkt(12, 4, 41, 2, seed=31, mid_p=0, hess_mode=1),
     "large_kkt": lambda: problems.random_lqr_kkt(64, 16, 8, 2, seed=32, mid_p=0, hess_mode=1),
+    # the other CTA sizes, a stage-constrained Dubins problem, a diagonal-Hessian problem, an explicit-D2 problem
+    "mid32_kkt": lambda: problems.random_lqr_kkt(32, 8, 14, 2, seed=35, mid_p=0, hess_mode=1),
+    "mid24_kkt": lambda: problems.random_lqr_kkt(24, 8, 12, 2, seed=36, mid_p=0, hess_mode=2),
+    "dubins_stage_kkt": lambda: problems.dubins_kkt_batch(2, seed=5, N=61, mid_p=1),
+    "explicit_d2_kkt": lambda: problems.random_lqr_kkt(5, 2, 12, 2, seed=37, mid_p=1, hess_mode=0, explicit_D2=True),
 }
 
 RICCATI_CASES = {
     "cartpole_riccati": lambda: problems.riccati_cartpole_batch(4, seed=0),
     "quad_riccati": lambda: problems.random_lqr_riccati(12, 4, 41, 2, seed=33),
     "large_riccati": lambda: problems.random_lqr_riccati(64, 16, 8, 2, seed=34),
+    "mid24_riccati": lambda: problems.random_lqr_riccati(24, 8, 30, 2, seed=38),
+    "lti_riccati": lambda: problems.random_lqr_riccati(8, 4, 60, 2, seed=39, lti=True),
 }
 
 

@@ -19,18 +19,21 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("name,kernel", [("cartpole_kkt", "kkt_tpi<4,1"), ("double_integrator_kkt", "kkt_tpi<6,3"),
                                          ("dubins_kkt", "kkt_tpi<3,2"), ("quad_kkt", "kkt_hw<12,4"),
-                                         ("large_kkt", "kkt_cta_dmma<64,16")])
+                                         ("large_kkt", "kkt_cta_dmma<64,16"), ("mid32_kkt", "kkt_cta_dmma<32,8"),
+                                         ("mid24_kkt", "kkt_cta_dmma<24,8"), ("dubins_stage_kkt", "kkt_tpi<3,2,p=3/1/3"),
+                                         ("explicit_d2_kkt", "kkt_coop")])
 def test_kkt_golden(handle, name, kernel):
     from tests.golden.make_golden import KKT_CASES
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     dz, lam, info = ops.kkt_solve_problem(KKT_CASES[name](), handle=handle)
     assert handle.last_kernel.startswith(kernel) and (info == 0).all()
-    tol = 1e-9 if name == "large_kkt" else TOL   # n=64 at N=8: cond ~1e6 (same allowance as test_gpu_kkt.py)
+    tol = 1e-9 if name in ("large_kkt", "mid32_kkt", "mid24_kkt") else TOL   # n=64 at N=8: cond ~1e6 (same allowance as test_gpu_kkt.py)
     assert _rel(dz[0], z["dz"]) <= tol and _rel(lam[0], z["mult"]) <= tol
 
 
 @pytest.mark.parametrize("name,kernel", [("cartpole_riccati", "riccati_tpi<4,1"), ("quad_riccati", "riccati_dmma<12,4"),
-                                         ("large_riccati", "riccati_cta_dmma<64,16")])
+                                         ("large_riccati", "riccati_cta_dmma<64,16"), ("mid24_riccati", "riccati_cta_dmma<24,8"),
+                                         ("lti_riccati", "riccati_dmma<8,4")])
 def test_riccati_golden(handle, name, kernel):
     from tests.golden.make_golden import RICCATI_CASES
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
