@@ -169,13 +169,26 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     const double *kp = data + inst * L::data_rows(N) + L::knot_off(k);
     double *out = prep + inst * L::prep_rows(N) + (int64_t)k * L::HS;
     constexpr int LR = m + 4;
-    if (tid == 0) flag = 0;
+    __shared__ __align__(8) uint64_t xbar;
+    if (tid == 0) {
+        flag = 0;
+        mbar_init(&xbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
-    // ---- stage X = A_k (or C_N), B_k column-major with padded leading dimension; g, d; R
+    // ---- stage X = A_k (or C_N), B_k column-major with padded leading dimension: one bulk copy per column,
+    // in flight while Q is inverted (plain loads here put the whole HBM latency in front of the first barrier);
+    // g, d wait in registers
     const double *Xg = last ? kp + L::oCl : kp + L::oD1;
-    for (int e = tid; e < n * wk; e += THREADS) As[(e / n) * LA + (e % n)] = Xg[e];
-    for (int e = tid; e < wk; e += THREADS) vq[e] = soc ? 0.0 : kp[(last ? L::HQ : L::og) + e];  // SOC: g = 0
-    for (int e = tid; e < n; e += THREADS) vd[e] = last ? kp[L::oCl + n * n + e] : kp[L::od + e];
+    if (wp == 0) {
+        if (lane == 0) mbar_expect_tx(&xbar, (uint32_t)(n * wk * 8));
+        __syncwarp();
+        for (int j = lane; j < wk; j += 32) bulk_g2s(As + j * LA, Xg + (int64_t)j * n, n * 8, &xbar);
+    }
+    static_assert(THREADS >= w, "one thread per entry of g");
+    const double gq_reg = (tid < wk && !soc) ? kp[(last ? L::HQ : L::og) + tid] : 0.0;  // SOC: g = 0
+    const double vd_reg = tid < n ? (last ? kp[L::oCl + n * n + tid] : kp[L::od + tid]) : 0.0;
     // ---- Q strip (C fragments) -> Qi
     double S[NT][2];
     SM_UNROLL
@@ -189,6 +202,9 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         }
     __syncthreads();
     int bad = block_gj_inverse<NT>(S, pan, pis, colb, &flag, wp, lane);
+    if (tid < wk) vq[tid] = gq_reg;
+    if (tid < n) vd[tid] = vd_reg;
+    mbar_wait(&xbar, 0);  // X has landed (every thread observes the barrier: the bulk writes are then visible)
     // Qi -> shared (operand) and global (slot, or the extra block for the first knot)
     {
         double *qo = first ? prep + inst * L::prep_rows(N) + (int64_t)N * L::HS : out + L::hQi;
@@ -546,6 +562,17 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         const double *slot = pb + (int64_t)k * L::HS;
         const double *kp = db + L::knot_off(k);
         const double *D1g = last ? kp + L::oCl : kp + L::oD1;  // [A B] or C_N, column-major n x wk
+        // the three operands of the NEXT step (record, [g | A B], Hi slot) go to L2 now: the mat-vecs below read
+        // straight from global memory and every step is three dependent load phases
+        if (k > 0 && tid == 0) {
+            const double *rn = rb + (int64_t)(k - 1) * L::REC;
+            const double *sn = pb + (int64_t)(k - 1) * L::HS;
+            const double *kn = db + L::knot_off(k - 1);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rn), "r"(L::REC * 8) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kn + L::og), "r"((L::CORE - L::og) * 8) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sn + L::hQi), "r"(n * n * 8) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sn + L::hRi), "r"(m * m * 8) : "memory");
+        }
         // x_prev = v + Z' x : 4 partial sums per entry
         {
             const int i = tid % n, part = tid / n;  // THREADS = 4 n
