@@ -50,11 +50,11 @@ struct Lay {
     static constexpr int REC = n * n + n;  // Z (row-major) | v
     // shared memory of the pre-pass (doubles)
     static constexpr int LA = n + 4;  // k-major operand loads: leading dimension = 4 (mod 16)
-    static constexpr int pA = 0, pQ = pA + w * LA, pPan = pQ + n * LA, pPi = pPan + NT * 64, pCol = pPi + 64,
+    static constexpr int pA = 0, pQ = pA + w * LA, pPan = pQ + n * LA, pPi = pPan + 2 * NT * 64, pCol = pPi + 128,
                          pRi = pCol + 2 * m, pV = pRi + m * (m + 4), PREP_TOTAL = pV + 4 * w + 64;
     // shared memory of the main kernel (doubles)
     static constexpr int LB = n + 8;  // paired (16-byte) operand loads: leading dimension = 8 (mod 16)
-    static constexpr int mT = 0, mS = mT + n * LB, mPan = mS + n * LB, mPi = mPan + NT * 64, mCol = mPi + 64,
+    static constexpr int mT = 0, mS = mT + n * LB, mPan = mS + n * LB, mPi = mPan + 2 * NT * 64, mCol = mPi + 128,
                          mV = mCol + 16, mBar = mV + 8 * n + 4 * w, MAIN_TOTAL = mBar + 2;
 };
 
@@ -88,43 +88,58 @@ __device__ __forceinline__ int gj8_warp(double &a0, double &a1, int lane) {
 
 // ------------------------------------------------------------------ block Gauss-Jordan ----------------
 // In place: S[ct][e] = tile (wp, ct) of an SPD n x n matrix in C-fragment layout -> the same tiles of its
-// inverse.  pan: NT*64 doubles (8 x 8 tiles, row-major), pis: 64 doubles, colb: 16 doubles.  Returns the
-// 1-based index of the first non-positive pivot (potrf semantics) or 0; identical in every thread.
+// inverse.  pan: 2 x NT*64 doubles (8 x 8 tiles, row-major, double-buffered column panels), pis: 2 x 64 doubles
+// (double-buffered pivot inverses).  Returns the 1-based index of the first non-positive pivot (potrf
+// semantics) or 0; identical in every thread.
+//
+// One CTA barrier per block step: the warp that owns the NEXT pivot updates that tile first, inverts it with
+// shuffles (gj8_warp) while the other warps are still in their rank-8 updates, and every warp publishes its
+// tile of the next column panel before the barrier (look-ahead).  In-place Gauss-Jordan leaves
+// A_kj = A_jk' for the columns still to be eliminated (j > kb) and A_kj = -A_jk' for the ones already done
+// (A_ik <- -A_ik Pi but A_kj <- +Pi A_kj), so the pivot row is taken from the column panel with that sign.
 template <int NT>
 __device__ __forceinline__ int block_gj_inverse(double (&S)[NT][2], double *pan, double *pis, double *colb,
                                                 int *flag, int wp, int lane) {
+    (void)colb;
     const int g = lane >> 2, q = lane & 3;
+    const int hh = lane >> 3, cc = lane & 7;
+    // invert the tile this warp has just written to p64 (row-major) and leave the inverse in po
+    auto pivot = [&](const double *p64, double *po, int kb) {
+        __syncwarp();
+        double a0 = p64[(2 * hh) * 8 + cc], a1 = p64[(2 * hh + 1) * 8 + cc];
+        const int bad = gj8_warp(a0, a1, lane);
+        po[(2 * hh) * 8 + cc] = a0;
+        po[(2 * hh + 1) * 8 + cc] = a1;
+        if (bad != 0 && lane == 0 && *flag == 0) *flag = 8 * kb + bad;
+    };
+    // prologue: column panel 0 and its pivot
+    *reinterpret_cast<double2 *>(pan + wp * 64 + g * 8 + 2 * q) = make_double2(S[0][0], S[0][1]);
+    if (wp == 0) pivot(pan, pis, 0);
+    __syncthreads();
     SM_UNROLL
     for (int kb = 0; kb < NT; ++kb) {
-        *reinterpret_cast<double2 *>(pan + wp * 64 + g * 8 + 2 * q) = make_double2(S[kb][0], S[kb][1]);
-        __syncthreads();
-        if (wp == kb) {
-            // invert the 8 x 8 pivot block (all 32 lanes, two entries each)
-            const int hh = lane >> 3, cc = lane & 7;
-            double a0 = pan[kb * 64 + (2 * hh) * 8 + cc], a1 = pan[kb * 64 + (2 * hh + 1) * 8 + cc];
-            const int bad = gj8_warp(a0, a1, lane);
-            pis[(2 * hh) * 8 + cc] = a0;
-            pis[(2 * hh + 1) * 8 + cc] = a1;
-            if (bad != 0 && lane == 0 && *flag == 0) *flag = 8 * kb + bad;
-        }
-        __syncthreads();
-        const double2 pv = *reinterpret_cast<const double2 *>(pis + g * 8 + 2 * q);  // Pi[g][2q..2q+1] (symmetric)
+        const double *pc = pan + (kb & 1) * NT * 64;
+        double *pn = pan + ((kb + 1) & 1) * NT * 64;
+        const double2 pv = *reinterpret_cast<const double2 *>(pis + (kb & 1) * 64 + g * 8 + 2 * q);  // Pi[g][2q..2q+1]
         if (wp != kb) {
-            // T = A_wk Pi ; A_wj -= T A_kj ; A_wk = -T.  The pivot row A_kj is taken from the column panel:
-            // in-place Gauss-Jordan leaves A_kj = A_jk' for the columns still to be eliminated (j > kb) and
-            // A_kj = -A_jk' for the ones already done (A_ik <- -A_ik Pi but A_kj <- +Pi A_kj).
+            // T = A_wk Pi ; A_wj -= T A_kj ; A_wk = -T
             double t0 = 0.0, t1 = 0.0;
             mma884(t0, t1, S[kb][0], pv.x);
             mma884(t0, t1, S[kb][1], pv.y);
             const double n0 = -t0, n1 = -t1;
-            SM_UNROLL
-            for (int j = 0; j < NT; ++j) {
-                if (j != kb) {
-                    const double2 b = *reinterpret_cast<const double2 *>(pan + j * 64 + g * 8 + 2 * q);
-                    mma884(S[j][0], S[j][1], j < kb ? t0 : n0, b.x);
-                    mma884(S[j][0], S[j][1], j < kb ? t1 : n1, b.y);
-                }
+            auto update = [&](int j) {
+                const double2 b = *reinterpret_cast<const double2 *>(pc + j * 64 + g * 8 + 2 * q);
+                mma884(S[j][0], S[j][1], j < kb ? t0 : n0, b.x);
+                mma884(S[j][0], S[j][1], j < kb ? t1 : n1, b.y);
+            };
+            if (kb + 1 < NT) {
+                update(kb + 1);  // the next panel tile first
+                *reinterpret_cast<double2 *>(pn + wp * 64 + g * 8 + 2 * q) = make_double2(S[kb + 1][0], S[kb + 1][1]);
+                if (wp == kb + 1) pivot(pn + wp * 64, pis + ((kb + 1) & 1) * 64, kb + 1);
             }
+            SM_UNROLL
+            for (int j = 0; j < NT; ++j)
+                if (j != kb && j != kb + 1) update(j);
             S[kb][0] = n0;
             S[kb][1] = n1;
         } else {
@@ -132,12 +147,14 @@ __device__ __forceinline__ int block_gj_inverse(double (&S)[NT][2], double *pan,
             SM_UNROLL
             for (int j = 0; j < NT; ++j) {
                 if (j != kb) {
-                    const double2 b = *reinterpret_cast<const double2 *>(pan + j * 64 + g * 8 + 2 * q);
+                    const double2 b = *reinterpret_cast<const double2 *>(pc + j * 64 + g * 8 + 2 * q);
                     double s0 = 0.0, s1 = 0.0;
                     mma884(s0, s1, pv.x, b.x);
                     mma884(s0, s1, pv.y, b.y);
                     S[j][0] = j < kb ? -s0 : s0;
                     S[j][1] = j < kb ? -s1 : s1;
+                    if (j == kb + 1)
+                        *reinterpret_cast<double2 *>(pn + wp * 64 + g * 8 + 2 * q) = make_double2(S[j][0], S[j][1]);
                 }
             }
             S[kb][0] = pv.x;
