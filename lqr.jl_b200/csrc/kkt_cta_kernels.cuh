@@ -593,36 +593,50 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         // x_prev = v + Z' x : 4 partial sums per entry
         {
             const int i = tid % n, part = tid / n;  // THREADS = 4 n
+            // all n/4 loads in flight at once (they come from L2: one latency per phase, not one per batch of 4)
+            double zv[n / 4];
+            SM_UNROLL
+            for (int l = 0; l < n / 4; ++l) zv[l] = rk[(part * (n / 4) + l) * n + i];
             double s = 0.0;
-#pragma unroll 4
-            for (int l = 0; l < n / 4; ++l) {
-                const int r = part * (n / 4) + l;
-                s = fma(rk[r * n + i], xs[r], s);
-            }
+            SM_UNROLL
+            for (int l = 0; l < n / 4; ++l) s = fma(zv[l], xs[part * (n / 4) + l], s);
             red[part * n + i] = s;
         }
         __syncthreads();
         if (tid < n) xps[tid] = rk[n * n + tid] + (red[tid] + red[n + tid]) + (red[2 * n + tid] + red[3 * n + tid]);
         __syncthreads();
         // res_j = g_j - sum_i D1[i][j] x_i (+ x_prev_j) (- sum_i C_1[i][j] mu1'_i at the first knot)
-        for (int j = wp; j < wk; j += L::WARPS) {
-            constexpr int NC = (n + 31) / 32;
-            double s = 0.0;
+        {
+            constexpr int NC = (n + 31) / 32, JW = (w + L::WARPS - 1) / L::WARPS;  // columns per warp
+            double dv[JW][NC], gj[JW];
             SM_UNROLL
-            for (int c = 0; c < NC; ++c)
-                if (lane + 32 * c < n) s = fma(D1g[lane + 32 * c + n * j], xs[lane + 32 * c], s);
-            if (first) {
-                const double *C0 = kp + L::oC0;
+            for (int jj = 0; jj < JW; ++jj) {  // every load of the phase first
+                const int j = wp + jj * L::WARPS;
                 SM_UNROLL
-                for (int c = 0; c < NC; ++c)
-                    if (lane + 32 * c < n) s = fma(C0[lane + 32 * c + n * j], xps[lane + 32 * c], s);
+                for (int c = 0; c < NC; ++c) dv[jj][c] = (j < wk && lane + 32 * c < n) ? D1g[lane + 32 * c + n * j] : 0.0;
+                gj[jj] = (j < wk && lane == 0 && !soc) ? kp[(last ? L::HQ : L::og) + j] : 0.0;
             }
             SM_UNROLL
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) {
-                double r = (soc ? 0.0 : kp[(last ? L::HQ : L::og) + j]) - s;
-                if (!first && j < n) r += xps[j];
-                rsv[j] = r;
+            for (int jj = 0; jj < JW; ++jj) {
+                const int j = wp + jj * L::WARPS;
+                if (j >= wk) break;  // warp-uniform
+                double s = 0.0;
+                SM_UNROLL
+                for (int c = 0; c < NC; ++c)
+                    if (lane + 32 * c < n) s = fma(dv[jj][c], xs[lane + 32 * c], s);
+                if (first) {
+                    const double *C0 = kp + L::oC0;
+                    SM_UNROLL
+                    for (int c = 0; c < NC; ++c)
+                        if (lane + 32 * c < n) s = fma(C0[lane + 32 * c + n * j], xps[lane + 32 * c], s);
+                }
+                SM_UNROLL
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) {
+                    double r = gj[jj] - s;
+                    if (!first && j < n) r += xps[j];
+                    rsv[j] = r;
+                }
             }
         }
         __syncthreads();
@@ -630,12 +644,12 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         {
             const double *Qi = first ? pb + (int64_t)N * L::HS : slot + L::hQi;
             const int i = tid % n, part = tid / n;  // THREADS = 4 n
+            double qv[n / 4];
+            SM_UNROLL
+            for (int l = 0; l < n / 4; ++l) qv[l] = Qi[(part * (n / 4) + l) * n + i];
             double s = 0.0;
-#pragma unroll 4
-            for (int l = 0; l < n / 4; ++l) {
-                const int r = part * (n / 4) + l;
-                s = fma(Qi[r * n + i], rsv[r], s);
-            }
+            SM_UNROLL
+            for (int l = 0; l < n / 4; ++l) s = fma(qv[l], rsv[part * (n / 4) + l], s);
             red[part * n + i] = s;
         }
         __syncthreads();
