@@ -111,6 +111,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--scale", type=float, default=1.0, help="scale the batches (debug)")
+    ap.add_argument("--opt", action="append", default=[], help="name=value passed to lqrb_set_option (kernel A/B)")
     args = ap.parse_args()
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -120,6 +121,9 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     h.set_stream(stream.cuda_stream)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        h.set_option(name, int(val))
     S = args.scale
     out = []
     for w in args.which.split(","):
