@@ -130,6 +130,26 @@ def test_no_affine_terms_reference_form(handle, oracle_mod):
     _check(prob, handle, oracle_mod)
 
 
+@pytest.mark.parametrize("D,N,kern", [(2, 21, "riccati_tpi<4,2"), (3, 31, "riccati_tpi<6,3"), (4, 26, "riccati_dmma<8,4")])
+def test_condensed_least_squares_identity(handle, D, N, kern):
+    """test/least_squares.jl:38: the controls of the Riccati pass make the gradient of the reference's condensed
+    least-squares form vanish (an identity that does not go through the oracle).  DoubleIntegrator(D) numbers."""
+    from tests.conftest import condensed_least_squares_gradient
+    n, m, dt = 2 * D, D, 2.0 / (N - 1)
+    A = np.eye(n); A[:D, D:] = dt * np.eye(D)
+    B = np.vstack([0.5 * dt * dt * np.eye(D), dt * np.eye(D)])
+    Q = np.diag(np.concatenate([10.0 * np.ones(D), np.ones(D)])); R = 0.1 * np.eye(m); Qf = 10 * Q
+    rng = np.random.default_rng(D)
+    x0 = np.concatenate([np.ones((3, D)), np.zeros((3, D))], axis=1) + 0.1 * rng.standard_normal((3, n))
+    prob = dict(n=n, m=m, N=N, lti=True, A=A[None].repeat(3, 0), B=B[None].repeat(3, 0), Q=Q[None].repeat(3, 0),
+                R=R[None].repeat(3, 0), q=None, r=None, Qf=Qf[None].repeat(3, 0), qf=None, x0=x0)
+    X, U, K, kff, info = ops.riccati_solve_problem(prob, handle=handle)
+    assert handle.last_kernel.startswith(kern) and (info == 0).all()
+    for i in range(3):
+        grad, scale = condensed_least_squares_gradient(A, B, Q, R, Qf, x0[i], U[i])
+        assert np.abs(grad).max() < 1e-11 * max(1.0, scale)
+
+
 def test_device_resident_path_matches_host_path(handle):
     import torch
     prob = problems.riccati_cartpole_batch(100, seed=3)
