@@ -280,6 +280,8 @@ static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch,
         int32_t *hinfo = reinterpret_cast<int32_t *>(prep + (size_t)cb * L::prep_rows(N));
         const double *dc = data + first * L::data_rows(N);
         LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)cb * sizeof(int32_t), st));
+        kcta::kkt_cta_ri_kernel<n, m, HESS><<<(unsigned)((cb * (N - 1) + 7) / 8), 128, 0, st>>>(dc, prep, hinfo, N, cb, soc);
+        LQRB_LAUNCH_CHECK(h, "kkt_cta_ri_kernel");
         pk<<<(unsigned)(cb * N), L::THREADS, psm, st>>>(dc, prep, hinfo, N, cb, soc);
         LQRB_LAUNCH_CHECK(h, "kkt_cta_prep_kernel");
         mk<<<(unsigned)cb, L::THREADS, msm, st>>>(dc, prep, hinfo, recs, dz + first * L::z_rows(N),

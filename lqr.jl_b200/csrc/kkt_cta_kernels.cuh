@@ -165,6 +165,43 @@ __device__ __forceinline__ int block_gj_inverse(double (&S)[NT][2], double *pan,
     return *flag;
 }
 
+// ------------------------------------------------------------------ R^-1 for every knot ---------------
+// One half-warp per knot with controls, lane j holds column j (Gauss-Jordan through shared memory, m serial
+// pivots).  Inside the pre-pass this chain kept seven of the eight warps of the CTA at a barrier for a fifth of
+// its time; here it is a fully parallel launch and the pre-pass reads the m x m result from its slot.
+template <int n, int m, int HESS>
+__global__ void __launch_bounds__(128)
+    kkt_cta_ri_kernel(const double *__restrict__ data, double *__restrict__ prep, int32_t *__restrict__ hinfo, int N,
+                      int64_t batch, int soc) {
+    using L = Lay<n, m, HESS>;
+    static_assert(m <= 16, "one half-warp per R");
+    __shared__ __align__(16) double colb_all[8][2 * m];
+    const int wp = threadIdx.x >> 5, lane = threadIdx.x & 31, hh = lane >> 4, hl = lane & 15;
+    const int64_t total = batch * (N - 1);
+    const int64_t pair = ((int64_t)blockIdx.x * 4 + wp) * 2;
+    if (pair >= total) return;  // whole warp leaves
+    const bool active = pair + hh < total;
+    const int64_t idx = active ? pair + hh : total - 1;
+    const int64_t inst = idx / (N - 1);
+    const int k = (int)(idx % (N - 1));
+    const double *kp = data + inst * L::data_rows(N) + L::knot_off(k);
+    double *out = prep + inst * L::prep_rows(N) + (int64_t)k * L::HS + L::hRi;
+    double a[m];
+    const int j = hl < m ? hl : 0;
+    SM_UNROLL
+    for (int i = 0; i < m; ++i) {
+        if (soc) a[i] = i == j ? 1.0 : 0.0;  // second_order_correction!: H = I
+        else if (HESS == LQRB_HESS_DIAG) a[i] = i == j ? kp[L::oR + j] : 0.0;
+        else a[i] = kp[L::oR + (i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j)];
+    }
+    const int bad = khw::gj_inverse<m>(a, colb_all[2 * wp + hh], hl < m ? hl : 31);
+    if (active && hl < m) {
+        SM_UNROLL
+        for (int i = 0; i < m; ++i) out[i * m + hl] = a[i];
+    }
+    if (active && bad != 0 && hl == 0) atomicMin(hinfo + inst, (k + 1) * 1000 + n + bad);
+}
+
 // ------------------------------------------------------------------ pre-pass --------------------------
 // grid = batch * N CTAs of THREADS threads.  knot 0: generic scalar code for the C_1 blocks (once per instance).
 template <int n, int m, int HESS>
@@ -206,6 +243,10 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     static_assert(THREADS >= w, "one thread per entry of g");
     const double gq_reg = (tid < wk && !soc) ? kp[(last ? L::HQ : L::og) + tid] : 0.0;  // SOC: g = 0
     const double vd_reg = tid < n ? (last ? kp[L::oCl + n * n + tid] : kp[L::od + tid]) : 0.0;
+    constexpr int RI_PER = (m * m + THREADS - 1) / THREADS;  // Ri (kkt_cta_ri_kernel) also waits in registers
+    double ri_reg[RI_PER];
+    SM_UNROLL
+    for (int e = 0; e < RI_PER; ++e) ri_reg[e] = (!last && tid + e * THREADS < m * m) ? out[L::hRi + tid + e * THREADS] : 0.0;
     // ---- Q strip (C fragments) -> Qi
     double S[NT][2];
     SM_UNROLL
@@ -232,25 +273,11 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
             *reinterpret_cast<double2 *>(qo + r * n + c) = make_double2(S[ct][0], S[ct][1]);
         }
     }
-    // ---- Ri = R^-1 (warp 0, one lane per column)
-    if (!last && wp == 0) {
-        double a[m];
-        const int j = lane < m ? lane : 0;
-        SM_UNROLL
-        for (int i = 0; i < m; ++i) {
-            if (soc) a[i] = i == j ? 1.0 : 0.0;
-            else if (HESS == LQRB_HESS_DIAG) a[i] = i == j ? kp[L::oR + j] : 0.0;
-            else a[i] = kp[L::oR + (i <= j ? j * (j + 1) / 2 + i : i * (i + 1) / 2 + j)];
-        }
-        const int b2 = khw::gj_inverse<m>(a, colb, lane < m ? lane : 31);
-        if (lane < m) {
-            SM_UNROLL
-            for (int i = 0; i < m; ++i) {
-                Ris[i * LR + lane] = a[i];
-                out[L::hRi + i * m + lane] = a[i];
-            }
-        }
-        if (b2 != 0 && bad == 0 && lane == 0) flag = n + b2;
+    // ---- Ri from its slot (kkt_cta_ri_kernel)
+    SM_UNROLL
+    for (int e = 0; e < RI_PER; ++e) {
+        const int t = tid + e * THREADS;
+        if (!last && t < m * m) Ris[(t / m) * LR + (t % m)] = ri_reg[e];
     }
     __syncthreads();
     bad = flag;
