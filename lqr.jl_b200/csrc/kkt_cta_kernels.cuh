@@ -74,7 +74,7 @@ __device__ __forceinline__ int gj8_warp(double &a0, double &a1, int lane) {
         const double piv = __shfl_sync(0xffffffffu, mine, ((kk >> 1) << 3) | kk);
         const double akk = __shfl_sync(0xffffffffu, mine, ((kk >> 1) << 3) | c);
         if (!(piv > 0.0) && bad == 0) bad = kk + 1;
-        const double p = rdmma::fast_rcp(piv);
+        const double p = rdmma::fast_rcp3(piv);
         const bool pc = c == kk;
         const double f = pc ? -p : akk * p;
         const double u0 = pc ? ck0 * f : fma(-ck0, f, a0);

@@ -108,6 +108,18 @@ __device__ __forceinline__ double fast_rcp(double x) {
     return fma(r, e, r);
 }
 
+// The same seed (20 bits, measured: tools/ubench/rcp_test.cu) with ONE third-order step r (1 + e + e^2),
+// e = 1 - x r: three dependent FMAs instead of four, within one ulp of the correctly rounded quotient.  For the
+// serial 8 x 8 pivot chains of the CTA kernels, where the reciprocal is on the critical path of the whole CTA
+// (5b-K: -2 %; no gain, or a small loss, in the warp-level kernels, which keep fast_rcp).
+__device__ __forceinline__ double fast_rcp3(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+}
+
 // Row 0 of the inverse of the SPD m x m control block a (upper triangle read) by 2 x 2 block elimination:
 // two dependent reciprocals instead of four dependent rsqrt.  Each quad lane q calls this on the block
 // cyclically permuted by q, so "row 0" is its own row q and nothing has to be selected afterwards.
