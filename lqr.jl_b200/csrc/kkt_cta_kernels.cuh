@@ -137,11 +137,15 @@ __device__ __forceinline__ int block_gj_inverse(double (&S)[NT][2], double *pan,
                 *reinterpret_cast<double2 *>(pn + wp * 64 + g * 8 + 2 * q) = make_double2(S[kb + 1][0], S[kb + 1][1]);
                 if (wp == kb + 1) pivot(pn + wp * 64, pis + ((kb + 1) & 1) * 64, kb + 1);
             }
-            SM_UNROLL
-            for (int j = 0; j < NT; ++j)
-                if (j != kb && j != kb + 1) update(j);
-            S[kb][0] = n0;
-            S[kb][1] = n1;
+            // The warp that owns the next pivot row stops here: in the next step its whole strip is rebuilt from
+            // the column panel (A_kj = +-Pi A_jk'), so its other tiles are dead — and it is the critical path.
+            if (wp != kb + 1 || kb + 1 >= NT) {
+                SM_UNROLL
+                for (int j = 0; j < NT; ++j)
+                    if (j != kb && j != kb + 1) update(j);
+                S[kb][0] = n0;
+                S[kb][1] = n1;
+            }
         } else {
             // the pivot row: A_kj = Pi A_kj, A_kk = Pi
             SM_UNROLL
