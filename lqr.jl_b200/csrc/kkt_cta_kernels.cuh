@@ -572,7 +572,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         for (int ct = 0; ct < NT; ++ct)
             SM_UNROLL
             for (int e = 0; e < 2; ++e) Cp[ct][e] = 0.5 * (G[ct][e] + Ss[(8 * ct + 2 * q + e) * LB + r0]);
-        __syncthreads();
+        // no barrier here: Ss is next written after the barriers of the following Gauss-Jordan
     }
     // ---- last block: mu_N' = Bl'^-1 y_mu   (Cp, dps hold Bl' and y_mu)
     {
