@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
                 }
                 const double ckk = cb[kk];
                 if (!(ckk > 0.0) && bad == 0) bad = kk + 1;
-                const double p = rdmma::fast_rcp(ckk);
+                const double p = rdmma::fast_rcp3(ckk);
                 const bool piv = (lane & 15) == kk;
                 const double f = piv ? -p : akk * p;
                 SM_UNROLL
