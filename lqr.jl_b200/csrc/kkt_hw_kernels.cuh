@@ -52,11 +52,12 @@ struct Lay {
     __host__ __device__ static constexpr int64_t z_rows(int N) { return (int64_t)N * n + (int64_t)(N - 1) * m; }
     // shared memory per instance (doubles): core | hi | MA | MB | vectors
     static constexpr int sHi = CORE, sMA = sHi + HI, sMB = sMA + n * n, sVec = sMB + n * n, INST = sVec + 128;
-    // block-layout kernel (kkt_hw2_kernel): three n x n operand buffers
-    // the two instances of a warp sit 2 (mod 16) doubles apart: their 16-byte row loads then fall into disjoint
-    // bank groups (rows of one instance are 3n doubles apart: even 16-byte slots; the other instance: odd slots)
-    static constexpr int sMC = sMB + n * n, sVec2 = sMC + n * n, INST2raw = sVec2 + 128,
-                         INST2 = INST2raw + ((2 - INST2raw % 16) + 16) % 16;
+    // block-layout kernel (kkt_hw2_kernel): g | D1 | d of the knot (H is only read by the pre-pass), Hi, three
+    // n x n operand buffers, 64 doubles of vectors.  7,008 bytes per instance for n = 12, m = 4: eight 2-warp
+    // CTAs = 16 warps per SM (the kernel is bound by the latency of its serial chains: warps are throughput).
+    static constexpr int sCore2 = CORE - og, sHi2 = sCore2, s2A = sHi2 + HI, s2B = s2A + n * n, s2C = s2B + n * n,
+                         sVec2 = s2C + n * n, INST2 = sVec2 + 64;
+    static_assert(INST2 % 2 == 0 && og % 2 == 0, "16-byte alignment of the per-instance buffers");
     static_assert(2 * n * n >= n * w, "first knot stages C Hi (n x w) in MA|MB");
 };
 
@@ -702,9 +703,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     double *wb = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (2 * L::INST2 + 4);
     double *S = wb + hh * L::INST2;
     // AT: X row-major (A_k or C_N), later U column-major; WC: W (or E0) column-major; SI: Sigma^-1
-    double *core = S, *hi = S + L::sHi, *AT = S + L::sMA, *WC = S + L::sMB, *SI = S + L::sMC, *vec = S + L::sVec2;
+    // `core` keeps the offsets of a knot record; its H part (offsets < og) is not backed by shared memory
+    double *core = S - L::og, *hi = S + L::sHi2, *AT = S + L::s2A, *WC = S + L::s2B, *SI = S + L::s2C, *vec = S + L::sVec2;
     double *UC = AT;
-    double *ys = vec, *vs = vec + 16, *hgs = vec + 32, *xs = vec + 48, *rs_ = vec + 64, *colb = vec + 80;
+    double *ys = vec, *vs = vec + 16, *hgs = vec + 32, *xs = vec + 32 /* backward sweep only */, *rs_ = vec + 48;
     uint64_t *bars = reinterpret_cast<uint64_t *>(wb + 2 * L::INST2);  // [0] core, [1] Hi
     if (lane == 0) {
         mbar_init(bars, 1);
