@@ -230,13 +230,13 @@ static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, 
                              cudaStream_t st) {
     using L = khw::Lay<n, m, HESS>;
     const int N = s.N;
-    // default: the block-layout kernel (4 x 4 lane grid per instance), eight 2-warp CTAs per SM (128 registers,
-    // 28 KB of shared memory per CTA: 16 warps per SM hide the serial chains of one another);
-    // kkt_variant = 3 keeps the column-per-lane kernel (three 4-warp CTAs)
+    // default: the block-layout kernel (4 x 4 lane grid per instance); kkt_variant = 3 keeps the column-per-lane one.
+    // Three 4-warp CTAs per SM at 168 registers: eight 2-warp CTAs at 128 registers (16 warps, a few spills) were
+    // 3.5 % slower in an A/B on one box (48.95 vs 47.2 ms) — the kernel is not latency-bound.
+    constexpr int WARPS = 4, MINB = 3;
     const bool blocks = h->opt("kkt_variant", 0) != 3;
-    const int WARPS = blocks ? 2 : 4;
     const size_t smem = (size_t)WARPS * (2 * (blocks ? L::INST2 : L::INST) + 4) * sizeof(double);
-    auto kern = blocks ? khw::kkt_hw2_kernel<n, m, HESS, 2, 8> : khw::kkt_hw_kernel<n, m, HESS, 4, 3>;
+    auto kern = blocks ? khw::kkt_hw2_kernel<n, m, HESS, WARPS, MINB> : khw::kkt_hw_kernel<n, m, HESS, WARPS, MINB>;
     LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
     for (int64_t first = 0; first < batch; first += chunk) {
@@ -321,8 +321,8 @@ static int64_t kkt_tuned_chunk(const lqrb_context *h, const KktShape &s) {
     if (per == 0) return 0;
     const size_t budget = (size_t)h->opt("scratch_budget_mb", 49152) << 20;
     int64_t c = (int64_t)(budget / (per * 8));
-    // kkt_hw: 8 CTAs x 4 instances per SM; kkt_cta: 2 CTAs x 1 instance per SM
-    const int64_t wave = (int64_t)h->sm_count * (s.n + s.m <= 16 ? 32 : 2);
+    // kkt_hw: 3 CTAs x 8 instances per SM; kkt_cta: 2 CTAs x 1 instance per SM
+    const int64_t wave = (int64_t)h->sm_count * (s.n + s.m <= 16 ? 24 : 2);
     c = std::max<int64_t>(wave, c / wave * wave);
     return c;
 }
