@@ -262,6 +262,11 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
             SM_UNROLL
             for (int kk = 0; kk < m; ++kk) {
                 double *cb = colb + (kk & 1) * m;  // double-buffered: one warp barrier per pivot
+                // the pivot itself comes by shuffle, so that its reciprocal (the longest link of the chain) runs
+                // while the pivot column makes its round trip through shared memory
+                const double ckk = __shfl_sync(0xffffffffu, a[kk % HR], ((kk / HR) << 4) | kk);
+                if (!(ckk > 0.0) && bad == 0) bad = kk + 1;
+                const double p = rdmma::fast_rcp3(ckk);
                 if ((lane & 15) == kk) {
                     SM_UNROLL
                     for (int i = 0; i < HR; i += 2) *reinterpret_cast<double2 *>(cb + HR * hh + i) = make_double2(a[i], a[i + 1]);
@@ -276,9 +281,6 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
                     c[i] = v.x;
                     c[i + 1] = v.y;
                 }
-                const double ckk = cb[kk];
-                if (!(ckk > 0.0) && bad == 0) bad = kk + 1;
-                const double p = rdmma::fast_rcp3(ckk);
                 const bool piv = (lane & 15) == kk;
                 const double f = piv ? -p : akk * p;
                 SM_UNROLL
