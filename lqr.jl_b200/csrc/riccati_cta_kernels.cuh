@@ -295,12 +295,17 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
             }
             if (bad != 0 && st_all == 0) st_all = (k + 1) * 1000 + bad;
             {
-                double kf = 0.0;
+                double kf0 = 0.0, kf1 = 0.0;  // two chains: this warp is the critical path of the CTA
                 SM_UNROLL
-                for (int i = 0; i < HR; ++i) {
-                    if ((lane & 15) < m) Mi[(HR * hh + i) * LM + j] = a[i];
-                    kf = fma(a[i], gh[n + HR * hh + i], kf);  // Muu^-1 symmetric: column j dotted with g^u
+                for (int i = 0; i < HR; i += 2) {
+                    if ((lane & 15) < m) {
+                        Mi[(HR * hh + i) * LM + j] = a[i];
+                        Mi[(HR * hh + i + 1) * LM + j] = a[i + 1];
+                    }
+                    kf0 = fma(a[i], gh[n + HR * hh + i], kf0);  // Muu^-1 symmetric: column j dotted with g^u
+                    kf1 = fma(a[i + 1], gh[n + HR * hh + i + 1], kf1);
                 }
+                double kf = kf0 + kf1;
                 kf += __shfl_xor_sync(0xffffffffu, kf, 16);
                 if (lane < m) {
                     kffs[lane] = kf;
