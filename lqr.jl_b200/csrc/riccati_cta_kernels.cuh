@@ -382,10 +382,19 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
 
     // ---------------- forward rollout   (src/dynamic_programming.jl:66-70)
     // [A B] of knot `it` alternates between the F region and the (now free) P|K' region
+    // The rollout reads [A B] row by row (thread = row), so the padded leading dimension of the DMMA fragments is
+    // not needed here: ONE 8 n w-byte bulk copy per knot instead of w copies of one column each (the copy engine's
+    // rate for 512-byte pieces, not HBM, was what a forward step waited for).
     double *Fb[2] = {Fs, Ps};
+    auto issue_fwd = [&](int k, double *Fdst, uint64_t *b) {
+        if (lane == 0) {
+            mbar_expect_tx(b, (uint32_t)(w * n * 8));
+            bulk_g2s(Fdst, rec_g + (int64_t)(lti ? 0 : k) * F, w * n * 8, b);
+        }
+    };
     if (wp == 0) {
-        issue_knot(0, Fb[0], false, bar);
-        if (steps > 1) issue_knot(1, Fb[1], false, bar + 1);
+        issue_fwd(0, Fb[0], bar);
+        if (steps > 1) issue_fwd(1, Fb[1], bar + 1);
     }
     if (tid < n) zs[tid] = tb[tri(n) + n + tid];
     __syncthreads();
@@ -439,7 +448,7 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
         SM_UNROLL
         for (int zz = 0; zz < XZ; ++zz) {
             const int zi = XZ * xp_ + zz;
-            xa = fma(Fc[zi * LF + xi_], zc[zi], xa);
+            xa = fma(Fc[zi * n + xi_], zc[zi], xa);
         }
         red[WARPS * m + xp_ * n + xi_] = xa;
         __syncthreads();
@@ -449,7 +458,7 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
             for (int pp = 0; pp < XP; ++pp) s += red[WARPS * m + pp * n + tid];
             zn[tid] = s;
         }
-        if (wp == 0 && it + 2 < steps) issue_knot(it + 2, Fb[it & 1], false, bar + (it & 1));
+        if (wp == 0 && it + 2 < steps) issue_fwd(it + 2, Fb[it & 1], bar + (it & 1));
         __syncthreads();
     }
     if (tid < n) __stcs(zb + (int64_t)steps * w + tid, zs[(steps & 1) * w + tid]);
