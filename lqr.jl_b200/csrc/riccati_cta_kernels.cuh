@@ -160,8 +160,10 @@ __global__ void __launch_bounds__(Cfg<n, m>::THREADS, 2)
                     const double2 au = *reinterpret_cast<const double2 *>(fu + 8 * ut * LF + 8 * cp);
                     mma884(Tu[ut][0], Tu[ut][1], au.x, bw.x);
                     mma884(Tu[ut][0], Tu[ut][1], au.y, bw.y);
-                    gua[ut][0] = fma(au.x, pk.x, gua[ut][0]);
-                    gua[ut][1] = fma(au.y, pk.y, gua[ut][1]);
+                    if (wp == 0) {  // B'p is the same in every warp: only warp 0 publishes it
+                        gua[ut][0] = fma(au.x, pk.x, gua[ut][0]);
+                        gua[ut][1] = fma(au.y, pk.y, gua[ut][1]);
+                    }
                 }
             }
             if (wp == 0) {  // g^u = r + B'p
