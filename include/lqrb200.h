@@ -20,9 +20,15 @@
  * Two data layouts
  *   INSTANCE-MAJOR ("Julia order"): what LQR.jl holds — one instance contiguous, every small matrix
  *     column-major, knot index next, batch index outermost.  E.g. A is Float64[n, n, N-1, batch].
- *   PACKED batch-minor SoA (device resident, the layout the kernels stream): a 2-D array
- *     [rows][ldb] where consecutive instances are consecutive doubles (coalesced, TMA-tileable) and
- *     `ldb = lqrb_padded_batch(batch)`.  Row maps are given by the *_layout functions below.
+ *   PACKED tiled batch-minor SoA (device resident, the layout the kernels stream): [tile][rows][T]
+ *     doubles, a tile = T consecutive instances, element (row, inst) at
+ *         ((inst / T) * rows + row) * T + inst % T,        ldb = lqrb_padded_batch(batch) instances.
+ *     T depends on the size class: T = 32 where one THREAD owns an instance (a warp reads one row of
+ *     its tile as one 256-byte line), T = 1 (plain per-instance records in the same row order) where a
+ *     half-warp, warp or CTA owns an instance and bulk-copies whole knot records.  Query it with
+ *     lqrb_riccati_tile_width / lqrb_kkt_tile_width; the *_pack_f64 / *_unpack_f64 entry points apply
+ *     it themselves.  "[rows][ldb]" in the comments below is shorthand for this tiled layout.  Row
+ *     maps are given by the *_layout functions below.
  */
 #ifndef LQRB200_H
 #define LQRB200_H
@@ -124,10 +130,18 @@ int32_t lqrb_riccati_pack_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_
 int32_t lqrb_riccati_solve_packed_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N,
                                       int64_t batch, int32_t flags, const double *knots,
                                       const double *term, double *Z, double *gains, int32_t *info);
-/* packed [rows][ldb] -> instance-major [rows, batch] (and back); device pointers. */
-int32_t lqrb_unpack_rows_f64(lqrb_handle_t handle, int64_t rows, int64_t batch, const double *packed,
-                             double *instance_major);
-int32_t lqrb_pack_rows_f64(lqrb_handle_t handle, int64_t rows, int64_t batch,
+/* tile width T (1 or 32) of the packed arrays of this size class on this handle (> 0; < 0 = bad argument). */
+int32_t lqrb_riccati_tile_width(lqrb_handle_t handle, int32_t n, int32_t m);
+/* packed outputs of lqrb_riccati_solve_packed_f64 -> instance-major Z[NN,batch], optional
+ * K[m,n,N-1,batch], kff[m,N-1,batch] (gains may be NULL when neither is wanted); device pointers. */
+int32_t lqrb_riccati_unpack_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                                const double *Z_packed, const double *gains_packed, double *Z,
+                                double *K, double *kff);
+/* generic: packed [tile][rows][T] -> instance-major [rows, batch] (and back); device pointers;
+ * `tile` = the T of the size class that produced / will consume the array (1 or 32). */
+int32_t lqrb_unpack_rows_f64(lqrb_handle_t handle, int64_t rows, int64_t batch, int32_t tile,
+                             const double *packed, double *instance_major);
+int32_t lqrb_pack_rows_f64(lqrb_handle_t handle, int64_t rows, int64_t batch, int32_t tile,
                            const double *instance_major, double *packed);
 
 /* forward simulate with given controls: rollout!, src/least_squares.jl:195-202.
@@ -179,6 +193,16 @@ int32_t lqrb_kkt_solve_packed_f64(lqrb_handle_t handle, int32_t n, int32_t m, in
                                   int64_t batch, const int32_t *p, int32_t hess_mode,
                                   int32_t explicit_d2, int32_t flags, const double *data,
                                   double *dz, double *mult, double *res, int32_t *info);
+
+/* tile width T (1 or 32) of `data`, dz, mult, res for this shape on this handle (> 0; < 0 = bad argument). */
+int32_t lqrb_kkt_tile_width(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, const int32_t *p,
+                            int32_t hess_mode, int32_t explicit_d2);
+/* packed outputs of lqrb_kkt_solve_packed_f64 -> instance-major dz[NN,batch], mult[P,batch],
+ * res[NN,batch] | NULL; device pointers. */
+int32_t lqrb_kkt_unpack_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                            const int32_t *p, int32_t hess_mode, int32_t explicit_d2,
+                            const double *dz_packed, const double *mult_packed,
+                            const double *res_packed, double *dz, double *mult, double *res);
 
 /* Replaces residual(solver; recalculate=true) : src/cholesky_solver.jl:238-252 — calc_residual! (:201-236)
  * with the KEPT multipliers of an earlier solve and freshly evaluated Jacobians / gradients (what step!

@@ -69,8 +69,12 @@ _SIGS = {
     "lqrb_riccati_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_i32] + [c_dp] * 12 + [c_vp]),
     "lqrb_riccati_pack_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_i32] + [c_dp] * 11),
     "lqrb_riccati_solve_packed_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_i32] + [c_dp] * 4 + [c_vp]),
-    "lqrb_unpack_rows_f64": (c_i32, [c_vp, c_i64, c_i64, c_dp, c_dp]),
-    "lqrb_pack_rows_f64": (c_i32, [c_vp, c_i64, c_i64, c_dp, c_dp]),
+    "lqrb_riccati_tile_width": (c_i32, [c_vp, c_i32, c_i32]),
+    "lqrb_riccati_unpack_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64] + [c_dp] * 5),
+    "lqrb_unpack_rows_f64": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_dp, c_dp]),
+    "lqrb_pack_rows_f64": (c_i32, [c_vp, c_i64, c_i64, c_i32, c_dp, c_dp]),
+    "lqrb_kkt_tile_width": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_i32, c_i32]),
+    "lqrb_kkt_unpack_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32, c_i32] + [c_dp] * 6),
     "lqrb_rollout_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_i32] + [c_dp] * 5),
     "lqrb_block_cholesky_f64": (c_i32, [c_vp, c_i32, c_i32, c_i64, c_i32] + [c_dp] * 4 + [c_vp]),
     "lqrb_block_ldiv_f64": (c_i32, [c_vp, c_i32, c_i32, c_i64, c_i32, c_dp, c_i32, c_dp]),

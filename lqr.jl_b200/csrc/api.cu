@@ -19,7 +19,7 @@ void *lqrb_scratch(lqrb_context *h, int slot, size_t bytes) {
     if (bytes == 0) bytes = 16;
     if (h->scratch_bytes[slot] >= bytes) return h->scratch[slot];
     if (h->scratch[slot]) {
-        cudaStreamSynchronize(h->stream);
+        cudaDeviceSynchronize();  // the slot may still be in use on the handle's copy streams
         cudaFree(h->scratch[slot]);
         h->scratch[slot] = nullptr;
         h->scratch_bytes[slot] = 0;
@@ -282,14 +282,20 @@ DevMap lqrb_get_map(lqrb_context *h, const std::string &key, const std::vector<R
     d.rows = (int64_t)map.size();
     void *p = nullptr;
     const size_t bytes = map.size() * sizeof(RowMap) + 16;
-    if (cudaMalloc(&p, bytes) != cudaSuccess ||
-        cudaMemcpy(p, map.data(), map.size() * sizeof(RowMap), cudaMemcpyHostToDevice) != cudaSuccess ||
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) {
+        e = cudaMemcpy(p, map.data(), map.size() * sizeof(RowMap), cudaMemcpyHostToDevice);
         // a pageable-source cudaMemcpy may return while the DMA from its staging buffer is still in flight on
         // the legacy stream; the kernels that read the map run on non-blocking streams, so wait for it here
         // (once per map shape)
-        cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) {
-        lqrb_fail(h, 1000 + (int)cudaGetLastError(), "row map upload failed");
-        return DevMap();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
+        if (e != cudaSuccess) cudaFree(p);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        lqrb_cuda_fail(h, e, "row map upload");
+        d.dev = nullptr;  // rows stays > 0: the pack / unpack launchers report the failure instead of skipping
+        return d;
     }
     d.dev = (const RowMap *)p;
     h->maps[key] = d;
@@ -306,8 +312,8 @@ DevMap lqrb_get_map(lqrb_context *h, const std::string &key, std::vector<RowMap>
 int32_t lqrb_gather_pack(lqrb_context *h, const DevMap &map, const ArrayTable &src, int64_t batch,
                          int tile_w, double *packed, cudaStream_t s) {
     const int64_t rows = map.rows;
+    if (rows > 0 && !map.dev) return 1000 + (int)cudaErrorMemoryAllocation;  // failed row-map upload (lqrb_get_map)
     if (rows == 0 || batch == 0) return 0;
-    if (!map.dev) return 1000 + (int)cudaErrorMemoryAllocation;
     dim3 grid((unsigned)((batch + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
     if (tile_w == 32)
         gather_pack_kernel<32><<<grid, block, 0, s>>>(map.dev, src, rows, batch, packed);
@@ -320,8 +326,8 @@ int32_t lqrb_gather_pack(lqrb_context *h, const DevMap &map, const ArrayTable &s
 int32_t lqrb_scatter_unpack(lqrb_context *h, const DevMap &map, const ArrayTableOut &dst,
                             int64_t batch, int tile_w, const double *packed, cudaStream_t s) {
     const int64_t rows = map.rows;
+    if (rows > 0 && !map.dev) return 1000 + (int)cudaErrorMemoryAllocation;  // failed row-map upload (lqrb_get_map)
     if (rows == 0 || batch == 0) return 0;
-    if (!map.dev) return 1000 + (int)cudaErrorMemoryAllocation;
     dim3 grid((unsigned)((batch + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
     if (tile_w == 32)
         scatter_unpack_kernel<32><<<grid, block, 0, s>>>(map.dev, dst, rows, batch, packed);
@@ -338,32 +344,34 @@ static std::vector<RowMap> identity_map(int64_t rows) {
     return m;
 }
 
-extern "C" int32_t lqrb_unpack_rows_f64(lqrb_handle_t h, int64_t rows, int64_t batch,
+extern "C" int32_t lqrb_unpack_rows_f64(lqrb_handle_t h, int64_t rows, int64_t batch, int32_t tile,
                                         const double *packed, double *instance_major) {
     if (!h) return -1;
     if (rows < 0) return -2;
     if (batch < 0) return -3;
-    if (!packed) return -4;
-    if (!instance_major) return -5;
+    if (tile != 1 && tile != LQRB_TILE) return lqrb_fail(h, -4, "tile must be 1 or 32 (lqrb_*_tile_width)");
+    if (!packed) return -5;
+    if (!instance_major) return -6;
     LQRB_CUDA(h, cudaSetDevice(h->device));
     ArrayTableOut t = {};
     t.ptr[0] = instance_major;
     t.stride[0] = rows;
     return lqrb_scatter_unpack(h, lqrb_get_map(h, "id" + std::to_string(rows), identity_map(rows)), t,
-                               batch, (int)h->opt("tile", LQRB_TILE), packed, h->stream);
+                               batch, tile, packed, h->stream);
 }
 
-extern "C" int32_t lqrb_pack_rows_f64(lqrb_handle_t h, int64_t rows, int64_t batch,
+extern "C" int32_t lqrb_pack_rows_f64(lqrb_handle_t h, int64_t rows, int64_t batch, int32_t tile,
                                       const double *instance_major, double *packed) {
     if (!h) return -1;
     if (rows < 0) return -2;
     if (batch < 0) return -3;
-    if (!instance_major) return -4;
-    if (!packed) return -5;
+    if (tile != 1 && tile != LQRB_TILE) return lqrb_fail(h, -4, "tile must be 1 or 32 (lqrb_*_tile_width)");
+    if (!instance_major) return -5;
+    if (!packed) return -6;
     LQRB_CUDA(h, cudaSetDevice(h->device));
     ArrayTable t = {};
     t.ptr[0] = instance_major;
     t.stride[0] = rows;
     return lqrb_gather_pack(h, lqrb_get_map(h, "id" + std::to_string(rows), identity_map(rows)), t,
-                            batch, (int)h->opt("tile", LQRB_TILE), packed, h->stream);
+                            batch, tile, packed, h->stream);
 }

@@ -329,6 +329,9 @@ static int64_t kkt_tuned_chunk(const lqrb_context *h, const KktShape &s) {
 
 static size_t kkt_scratch_bytes(const lqrb_context *h, const KktShape &s, const KktSizes &z, int64_t batch) {
     size_t bytes = (size_t)lqrb_padded_batch(batch) * z.rec_rows * 8;
+    // the tuned kernels' records only when one of them will actually run for this shape (a dense Hessian, an
+    // irregular stage pattern, explicit D2 or kkt_variant = 2 route the same (n, m) to the cooperative kernel)
+    if (!kkt_has_hw(h, s, 0) && !kkt_has_cta(h, s, 0)) return bytes;
     const int64_t chunk = kkt_tuned_chunk(h, s);
     if (chunk > 0) bytes = std::max(bytes, kkt_hw_scratch_doubles(s, std::min(batch, chunk)) * 8 + 64);
     return bytes;
@@ -439,6 +442,28 @@ static int32_t kkt_unpack_on(lqrb_context *h, const KktShape &s, const KktSizes 
     t.stride[0] = z.NN;
     return lqrb_scatter_unpack(h, lqrb_get_map(h, "id" + std::to_string(z.NN), identity_rows(z.NN)), t, batch,
                                tile, resp, st);
+}
+
+extern "C" int32_t lqrb_kkt_tile_width(lqrb_handle_t h, int32_t n, int32_t m, int32_t N, const int32_t *p,
+                                       int32_t hess_mode, int32_t explicit_d2) {
+    int32_t rc = check_kkt(h, n, m, N, 0, p, hess_mode);
+    if (rc) return rc;
+    return lqrb_kkt_tile(h, n, m, N, p, hess_mode, explicit_d2);
+}
+
+extern "C" int32_t lqrb_kkt_unpack_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N, int64_t batch,
+                                       const int32_t *p, int32_t hess_mode, int32_t explicit_d2,
+                                       const double *dzp, const double *multp, const double *resp, double *dz,
+                                       double *mult, double *res) {
+    int32_t rc = check_kkt(h, n, m, N, batch, p, hess_mode);
+    if (rc) return rc;
+    if (!dzp || !multp) return lqrb_fail(h, -9, "packed dz / mult is NULL");
+    if (!dz || !mult) return lqrb_fail(h, -12, "dz / mult is NULL");
+    if (res && !resp) return lqrb_fail(h, -11, "res requested but the packed res is NULL");
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    const KktShape s = make_shape(n, m, N, p, hess_mode, explicit_d2);
+    const KktSizes z = kkt_sizes(s);
+    return kkt_unpack_on(h, s, z, batch, dzp, multp, resp, dz, mult, res, h->stream);
 }
 
 // ------------------------------------------------------------------ full call -----------------

@@ -308,6 +308,25 @@ static int32_t riccati_unpack_on(lqrb_context *h, int n, int m, int N, int64_t b
     return rc;
 }
 
+extern "C" int32_t lqrb_riccati_tile_width(lqrb_handle_t h, int32_t n, int32_t m) {
+    if (!h) return -1;
+    if (n < 1) return -2;
+    if (m < 1) return -3;
+    return lqrb_riccati_tile(h, n, m);
+}
+
+extern "C" int32_t lqrb_riccati_unpack_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N, int64_t batch,
+                                           const double *Zp, const double *gains, double *Z, double *K,
+                                           double *kff) {
+    int32_t rc = check_dims(h, n, m, N, batch);
+    if (rc) return rc;
+    if (!Zp) return lqrb_fail(h, -6, "packed Z is NULL");
+    if ((K || kff) && !gains) return lqrb_fail(h, -7, "K / kff requested but the packed gains are NULL");
+    if (!Z) return lqrb_fail(h, -8, "Z is NULL");
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    return riccati_unpack_on(h, n, m, N, batch, Zp, gains, Z, K, kff, h->stream);
+}
+
 // ------------------------------------------------------------------ full call -----------------
 extern "C" int32_t lqrb_riccati_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N, int64_t batch,
                                     int32_t flags, const double *A, const double *B, const double *Q,

@@ -849,7 +849,9 @@ extern "C" int32_t lqrb_sqp_dubins_f64(lqrb_handle_t h, int64_t batch, const lqr
         }
         solves += batch;
         int pending = hc[0];
-        for (int trial = 1; trial < 10 && pending > 0; ++trial) {
+        // trial 1 = the SOC step; trials 2..10 = the reference's back-tracking iterations i = 2..10 (alpha = rho^1..rho^9,
+        // src/sqp.jl:76-92)
+        for (int trial = 1; trial < 11 && pending > 0; ++trial) {
             LQRB_CUDA(h, cudaMemsetAsync(counters, 0, 8, s));
             if (fused)
                 dubins_linesearch_kernel<true><<<grid, 64, 0, s>>>(Zp, dz, dzh, mult, multk, x0p, xfp, data, stats, o, batch,

@@ -39,12 +39,24 @@ def riccati_solve_packed(h: Handle, n, m, N, batch, flags, knots, term, Z, gains
            ptr(gains), ptr(info))
 
 
-def unpack_rows(h: Handle, rows, batch, packed, out):
-    h.call("lqrb_unpack_rows_f64", rows, batch, ptr(packed), ptr(out))
+def riccati_tile_width(h: Handle, n, m) -> int:
+    t = int(_lib.lib().lqrb_riccati_tile_width(h._h, n, m))
+    if t <= 0:
+        raise _lib.LqrbError(f"lqrb_riccati_tile_width: bad argument {-t}")
+    return t
 
 
-def pack_rows(h: Handle, rows, batch, src, packed):
-    h.call("lqrb_pack_rows_f64", rows, batch, ptr(src), ptr(packed))
+def riccati_unpack(h: Handle, n, m, N, batch, Zp, gains, Z, K=None, kff=None):
+    """Packed outputs of riccati_solve_packed -> instance-major (applies the size class's tile width)."""
+    h.call("lqrb_riccati_unpack_f64", n, m, N, batch, ptr(Zp), ptr(gains), ptr(Z), ptr(K), ptr(kff))
+
+
+def unpack_rows(h: Handle, rows, batch, tile, packed, out):
+    h.call("lqrb_unpack_rows_f64", rows, batch, tile, ptr(packed), ptr(out))
+
+
+def pack_rows(h: Handle, rows, batch, tile, src, packed):
+    h.call("lqrb_pack_rows_f64", rows, batch, tile, ptr(src), ptr(packed))
 
 
 def rollout(h: Handle, n, m, N, batch, flags, A, B, x0, U, X):
@@ -80,6 +92,21 @@ def kkt_solve_packed(h: Handle, n, m, N, batch, p, hess_mode, explicit_d2, flags
     p = _p32(p)
     h.call("lqrb_kkt_solve_packed_f64", n, m, N, batch, p.ctypes.data, hess_mode, int(explicit_d2), flags,
            ptr(data), ptr(dz), ptr(mult), ptr(res), ptr(info))
+
+
+def kkt_tile_width(h: Handle, n, m, N, p, hess_mode, explicit_d2=False) -> int:
+    p = _p32(p)
+    t = int(_lib.lib().lqrb_kkt_tile_width(h._h, n, m, N, p.ctypes.data, hess_mode, int(explicit_d2)))
+    if t <= 0:
+        raise _lib.LqrbError(f"lqrb_kkt_tile_width: bad argument {-t}")
+    return t
+
+
+def kkt_unpack(h: Handle, n, m, N, batch, p, hess_mode, explicit_d2, dzp, multp, resp, dz, mult, res=None):
+    """Packed outputs of kkt_solve_packed -> instance-major (applies the shape's tile width)."""
+    p = _p32(p)
+    h.call("lqrb_kkt_unpack_f64", n, m, N, batch, p.ctypes.data, hess_mode, int(explicit_d2), ptr(dzp), ptr(multp),
+           ptr(resp), ptr(dz), ptr(mult), ptr(res))
 
 
 def kkt_residual(h: Handle, n, m, N, batch, p, flags, q, r, A, B, D2, C, mult, res=None, norms=None):

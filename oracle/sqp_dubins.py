@@ -122,7 +122,7 @@ def solve(Z0, x0, xf, o):
             Z[ok] += dz[ok] + dzh[ok]
             done |= ok
             alpha[~done] = rho
-            for _trial in range(2, 10):
+            for _trial in range(2, 11):  # the reference's i = 2..10 (src/sqp.jl:76-92): alpha = rho^1..rho^9
                 if done.all():
                     break
                 ok = (phi(Z + alpha[:, None] * dz) <= phi0 + eta * alpha * dphi0) & ~done

@@ -167,7 +167,7 @@ def test_device_resident_path_matches_host_path(handle):
         ops.riccati_pack(handle, n, m, N, b, 0, dev["A"], dev["B"], dev["Q"], dev["R"], dev["q"], dev["r"],
                          dev["Qf"], dev["qf"], dev["x0"], knots, term)
         ops.riccati_solve_packed(handle, n, m, N, b, 0, knots, term, Zp)
-        ops.unpack_rows(handle, L.z_rows, b, Zp, Z)
+        ops.unpack_rows(handle, L.z_rows, b, ops.riccati_tile_width(handle, n, m), Zp, Z)
         torch.cuda.synchronize()
     finally:
         handle.set_stream(None)
