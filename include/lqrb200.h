@@ -70,6 +70,11 @@ const char *lqrb_last_kernel_name(lqrb_handle_t handle);
 /* tuning knob: 0 = default choice, otherwise force a variant. */
 int32_t lqrb_set_option(lqrb_handle_t handle, const char *name, int64_t value);
 
+/* Diagnostic: best FP64 throughput (TFLOP/s) of this device over `seconds` of back-to-back launches of a
+ * register-only kernel; kind 0 = DFMA (vector pipe), 1 = DMMA (mma.sync.m8n8k4.f64, tensor pipe).  These are the
+ * peaks the FP64-bound rooflines in DESIGN.md / bench.py are quoted against ("to be measured"). */
+int32_t lqrb_fp64_peak_f64(lqrb_handle_t handle, int32_t kind, double seconds, double *tflops);
+
 /* ---------------------------------------------------------------- layouts -------------------- */
 int64_t lqrb_padded_batch(int64_t batch); /* ldb: batch rounded up to a multiple of 32 */
 
@@ -203,6 +208,37 @@ int32_t lqrb_kkt_unpack_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t 
                             const int32_t *p, int32_t hess_mode, int32_t explicit_d2,
                             const double *dz_packed, const double *mult_packed,
                             const double *res_packed, double *dz, double *mult, double *res);
+
+/* ---- the five steps of _solve! one by one, with the factor kept for further right-hand sides ----
+ * The reference keeps `shur_blocks` / `chol_blocks` (Vector{BlockUpperTriangular3}, src/jacobian_blocks.jl:95-169) in
+ * the solver and re-uses them (test/cholesky_solve.jl:14-35).  Here the HANDLE keeps one factorisation on the device:
+ *
+ * lqrb_kkt_factor_f64  = calculate_shur_factors! (matrix part, src/jacobian_blocks.jl:220-286) + cholesky!(U, F)
+ *   (src/cholesky_solve.jl:28-67): S = D H^-1 D' factored block row by block row as U'U; LQRB_FLAG_SOC: S = D D'.
+ *   Arrays as in lqrb_kkt_solve_f64 (instance-major, host or device).  info[batch] | NULL.
+ * lqrb_kkt_solve_factored_f64 = the right-hand-side part of calculate_shur_factors! (h = D H^-1 g - d) +
+ *   forward_substitution! (:93-117) + backward_substitution! (:119-143) + calculate_primals!
+ *   (src/cholesky_solver.jl:185-236) with the kept U — no O(n^3) work.  q, r, d, c: the new right-hand side
+ *   (the second-order correction's constraint values, a refinement residual, ...); shape, batch and flags must
+ *   be those of the kept factorisation (else -1).  Runs on the general (any size / stage pattern) kernel.     */
+int32_t lqrb_kkt_factor_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                            const int32_t *p, int32_t hess_mode, int32_t flags, const double *Q,
+                            const double *R, const double *Hux, const double *A, const double *B,
+                            const double *D2, const double *C, int32_t *info);
+int32_t lqrb_kkt_solve_factored_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                                    const int32_t *p, int32_t hess_mode, int32_t explicit_d2, int32_t flags,
+                                    const double *q, const double *r, const double *d, const double *c,
+                                    double *dz, double *mult, double *res, int32_t *info);
+/* Replaces get_shur_factors (src/cholesky_solver.jl:333-341) and get_cholesky (:352-359), i.e. copy_shur_factors!
+ * (src/jacobian_blocks.jl:173-211) on the device's block rows: dense column-major S[P,P,batch] (symmetric, both
+ * triangles filled), h[P,batch] = D H^-1 g - d, U[P,P,batch] (upper triangular, U'U = S), in the multiplier order
+ * [mu_1; lam_1; ...; mu_N].  Any of S, h, U may be NULL.  Debug / parity path: P^2 doubles per instance.      */
+int32_t lqrb_kkt_get_shur_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                              const int32_t *p, int32_t hess_mode, int32_t flags, const double *Q,
+                              const double *R, const double *Hux, const double *q, const double *r,
+                              const double *A, const double *B, const double *d, const double *D2,
+                              const double *C, const double *c, double *S, double *h, double *U,
+                              int32_t *info);
 
 /* Replaces residual(solver; recalculate=true) : src/cholesky_solver.jl:238-252 — calc_residual! (:201-236)
  * with the KEPT multipliers of an earlier solve and freshly evaluated Jacobians / gradients (what step!

@@ -38,6 +38,7 @@ __all__ = [
     "CholeskySolver", "build_shur_factors", "calculate_shur_factors_", "forward_substitution_",
     "backward_substitution_", "calculate_primals_", "residual", "second_order_correction_", "get_step",
     "get_multipliers", "get_residual", "get_linearized_constraints", "get_cost_expansion", "step_",
+    "get_shur_factors", "get_cholesky", "copy_shur_factors_",
     "Handle", "LqrbError", "HESS_DENSE", "HESS_BLOCKDIAG", "HESS_DIAG",
 ]
 
@@ -222,7 +223,7 @@ def cholesky_(chol, A, B=None, C=None):
     """cholesky!(chol, A, B[, C]) (src/block_cholesky.jl:55-91); or cholesky!(U, F) on Schur blocks
     (src/cholesky_solve.jl:28-33) when called with a CholeskySolver's block lists."""
     if isinstance(chol, _ShurBlocks):
-        return chol.solver._stage("cholesky")
+        return chol.solver._stage("cholesky")      # lqrb_kkt_factor_f64
     n, m, b = chol.n, chol.m, chol.batch
     A = np.broadcast_to(_b(A, 2), (b, n, n))
     B = np.zeros((b, m, m)) if B is None else np.broadcast_to(_b(B, 2), (b, m, m))
@@ -339,19 +340,26 @@ def copy_blocks_(D, d, blocks, i=0):
 
 # ===================================================================== CholeskySolver
 class _ShurBlocks:
-    """Stand-in for the Vector{BlockUpperTriangular3} the reference passes between the five steps
-    (src/jacobian_blocks.jl:95-169).  On the device the block rows live in registers and a scratch
-    record, so this object only carries the solver it belongs to."""
+    """The Vector{BlockUpperTriangular3} the reference passes between the five steps
+    (src/jacobian_blocks.jl:95-169).  On the device the block rows are records kept by the handle
+    (lqrb_kkt_factor_f64); this object names them for the step functions and gives dense read-back:
+    ``kind`` = "shur" (the unfactored S blocks + h) or "chol" (the block rows of U)."""
 
-    def __init__(self, solver):
+    def __init__(self, solver, kind):
         self.solver = solver
+        self.kind = kind
+
+    def dense(self):
+        """(M, h): dense S (kind "shur") or U (kind "chol") of every instance, read back from the device."""
+        S, h, U = self.solver._dense_factors()
+        return (S, h) if self.kind == "shur" else (U, h)
 
 
 def build_shur_factors(conSet_or_solver, uplo="U"):
     """build_shur_factors(conSet, :U) (src/jacobian_blocks.jl:155-169)."""
     if uplo not in ("U", ":U"):
         raise ValueError("only the upper variant has substitution methods (src/cholesky_solve.jl:145-168)")
-    return _ShurBlocks(conSet_or_solver)
+    return _ShurBlocks(conSet_or_solver, "shur")
 
 
 class CholeskySolver:
@@ -361,10 +369,12 @@ class CholeskySolver:
     mirror takes the linearised data directly: `Jinv`-side cost blocks (Q, R, Hux, q, r with a
     hess_mode = BlockCholesky mode) and `conSet.blocks`-side constraint blocks (A, B, d, C, c, p[, D2]).
 
-    _solve_() runs the whole chain of src/cholesky_solver.jl:166-182 in ONE fused kernel launch; the five
-    step functions (calculate_shur_factors_, cholesky_, forward_substitution_, backward_substitution_,
-    calculate_primals_) are kept for call-site compatibility: the first stages the inputs, the launch
-    happens on the first of the factor/substitution steps, the last publishes dZ.
+    _solve_() runs the whole chain of src/cholesky_solver.jl:166-182 in ONE fused kernel launch.  The five step
+    functions of the reference's script (test/cholesky_solve.jl:14-35) are real device steps too, in two launches
+    on the general kernel: calculate_shur_factors_ + cholesky_ = lqrb_kkt_factor_f64 (the handle keeps U; the
+    unfactored S and U can be read back with get_shur_factors / get_cholesky), forward_substitution_ +
+    backward_substitution_ + calculate_primals_ = lqrb_kkt_solve_factored_f64 (any number of right-hand sides
+    against the kept factor, see solve_factored_).
     """
 
     def __init__(self, prob: dict, handle: Handle | None = None, device: int = 0):
@@ -374,8 +384,8 @@ class CholeskySolver:
         self.n, self.m, self.N = prob["n"], prob["m"], prob["N"]
         self.batch = self.flat["batch"]
         self.p = np.asarray(prob["p"], dtype=np.int32)
-        self.shur_blocks = _ShurBlocks(self)
-        self.chol_blocks = _ShurBlocks(self)
+        self.shur_blocks = _ShurBlocks(self, "shur")
+        self.chol_blocks = _ShurBlocks(self, "chol")
         NN, P = _lib.num_vars(self.n, self.m, self.N), _lib.num_cons(self.n, self.N, self.p)
         self.dZ = np.zeros((self.batch, NN))
         self.lam = np.zeros((self.batch, P))
@@ -405,12 +415,53 @@ class CholeskySolver:
         self._run(False)
         return self
 
+    # ---- the reference's five steps as two device launches
+    def _flags(self):
+        return 0 if self._Ginv else _lib.FLAG_SOC
+
+    def factor_(self):
+        """calculate_shur_factors! + cholesky!(chol_blocks, shur_blocks): the handle keeps the block rows of U."""
+        f = self.flat
+        ops.kkt_factor(self.handle, self.n, self.m, self.N, self.batch, f["p"], f["hess_mode"], self._flags(),
+                       f["Q"], f["R"], f["Hux"], f["A"], f["B"], f["D2"], f["C"], self.info)
+        self._state = "factored"
+        return self
+
+    def solve_factored_(self, q=None, r=None, d=None, c=None):
+        """forward_substitution! + backward_substitution! + calculate_primals! with the kept factor.  Without
+        arguments the right-hand side is the solver's own (q, r, d, c); pass new ones to re-use the factor
+        (src/cholesky_solver.jl:246,259-263).  c is the list over knots of (batch, p_k) arrays."""
+        if self._state not in ("factored", "solved_factored"):
+            self.factor_()
+        f = self.flat
+        cflat = f["c"] if c is None else np.ascontiguousarray(
+            np.concatenate([np.asarray(ck, dtype=np.float64).reshape(self.batch, -1) for ck in c], axis=1))
+        ops.kkt_solve_factored(self.handle, self.n, self.m, self.N, self.batch, f["p"], f["hess_mode"],
+                               f["D2"] is not None, self._flags(), ops.f64(f["q"] if q is None else q),
+                               ops.f64(f["r"] if r is None else r), ops.f64(f["d"] if d is None else d), cflat,
+                               self.dZ, self.lam, self.res, None)
+        self._state = "solved_factored"
+        return self
+
     def _stage(self, step):
         if step == "shur":
             self._state = "staged"
-        elif self._state != "solved":
-            self._run(not self._Ginv)
+        elif step == "cholesky":
+            self.factor_()
+        elif self._state != "solved_factored":
+            self.solve_factored_()
         return self
+
+    def _dense_factors(self):
+        """Dense (S, h, U) of every instance computed by the DEVICE path (lqrb_kkt_get_shur_f64), math order."""
+        f = self.flat
+        P = self.lam.shape[1]
+        S, U = np.zeros((self.batch, P, P)), np.zeros((self.batch, P, P))
+        h = np.zeros((self.batch, P))
+        ops.kkt_get_shur(self.handle, self.n, self.m, self.N, self.batch, f["p"], f["hess_mode"], self._flags(),
+                         f["Q"], f["R"], f["Hux"], f["q"], f["r"], f["A"], f["B"], f["d"], f["D2"], f["C"], f["c"],
+                         S, h, U, None)
+        return S, h, np.swapaxes(U, -1, -2).copy()     # S is symmetric; U comes back column-major
 
     def second_order_correction_(self, d=None, c=None):
         """second_order_correction! (src/cholesky_solver.jl:254-273): the same chain with Ginv=false,
@@ -432,18 +483,20 @@ class CholeskySolver:
 
 
 def calculate_shur_factors_(shur, Jinv=None, blocks=None, Ginv=True):
-    """calculate_shur_factors!(F, Jinv, blocks[, Ginv]) (src/jacobian_blocks.jl:220-229)."""
+    """calculate_shur_factors!(F, Jinv, blocks[, Ginv]) (src/jacobian_blocks.jl:220-229).  On the device S is
+    formed block row by block row inside the factor launch (cholesky_ below); this call fixes Ginv and marks the
+    data as staged.  get_shur_factors(solver) returns the S and h the device forms."""
     shur.solver._Ginv = bool(Ginv)
     return shur.solver._stage("shur")
 
 
 def forward_substitution_(chol):
-    """forward_substitution!(chol) (src/cholesky_solve.jl:93-117)."""
+    """forward_substitution!(chol) (src/cholesky_solve.jl:93-117) — first half of lqrb_kkt_solve_factored_f64."""
     return chol.solver._stage("forward")
 
 
 def backward_substitution_(chol):
-    """backward_substitution!(chol) (src/cholesky_solve.jl:119-143)."""
+    """backward_substitution!(chol) (src/cholesky_solve.jl:119-143) — second half of the same launch."""
     return chol.solver._stage("backward")
 
 
@@ -452,6 +505,28 @@ def calculate_primals_(dZ, Jinv=None, chol=None, blocks=None):
     chol.solver._stage("primals")
     dZ[...] = chol.solver.dZ
     return dZ
+
+
+def get_shur_factors(solver: CholeskySolver):
+    """get_shur_factors (src/cholesky_solver.jl:333-341): dense (S, h, lam) per instance, S and h as the DEVICE forms
+    them (copy_shur_factors!, src/jacobian_blocks.jl:173-211), lam = the multipliers of the last solve."""
+    S, h, _ = solver._dense_factors()
+    return S, h, solver.lam
+
+
+def get_cholesky(solver: CholeskySolver):
+    """get_cholesky (src/cholesky_solver.jl:352-359): dense upper-triangular U with U'U = S, from the device."""
+    return solver._dense_factors()[2]
+
+
+def copy_shur_factors_(S, h, lam, blocks: _ShurBlocks):
+    """copy_shur_factors!(S, h, lam, F) (src/jacobian_blocks.jl:173-180): dense image of the block rows `blocks`
+    (solver.shur_blocks -> S, solver.chol_blocks -> U) of every instance; lam gets the kept multipliers."""
+    M, hv = blocks.dense()
+    S[...] = M
+    h[...] = hv
+    lam[...] = blocks.solver.lam
+    return S, h, lam
 
 
 def step_(solver: CholeskySolver):

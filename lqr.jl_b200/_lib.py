@@ -60,6 +60,7 @@ _SIGS = {
     "lqrb_launch_count": (c_i64, [c_vp]),
     "lqrb_last_kernel_name": (C.c_char_p, [c_vp]),
     "lqrb_set_option": (c_i32, [c_vp, C.c_char_p, c_i64]),
+    "lqrb_fp64_peak_f64": (c_i32, [c_vp, c_i32, C.c_double, C.POINTER(C.c_double)]),
     "lqrb_padded_batch": (c_i64, [c_i64]),
     "lqrb_num_vars": (c_i64, [c_i32, c_i32, c_i32]),
     "lqrb_num_cons": (c_i64, [c_i32, c_i32, c_vp]),
@@ -82,6 +83,10 @@ _SIGS = {
     "lqrb_kkt_pack_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32] + [c_dp] * 12),
     "lqrb_kkt_solve_packed_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32, c_i32, c_i32]
                                   + [c_dp] * 4 + [c_vp]),
+    "lqrb_kkt_factor_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32, c_i32] + [c_dp] * 7 + [c_vp]),
+    "lqrb_kkt_solve_factored_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32, c_i32, c_i32] + [c_dp] * 7
+                                    + [c_vp]),
+    "lqrb_kkt_get_shur_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32, c_i32] + [c_dp] * 14 + [c_vp]),
     "lqrb_kkt_residual_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32] + [c_dp] * 9),
     "lqrb_sqp_dubins_f64": (c_i32, [c_vp, c_i64, C.POINTER(SqpOptions)] + [c_dp] * 5 + [c_vp, C.POINTER(c_i64)]),
 }

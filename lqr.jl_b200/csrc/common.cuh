@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -50,6 +51,8 @@ enum ScratchSlot {
     SCR_SQP1,
     SCR_SQP2,
     SCR_SQP3,
+    SCR_KEEP_DATA,  // lqrb_kkt_factor_f64: packed matrices of the kept factorisation
+    SCR_KEEP_REC,   //                      block rows of U (BlockUpperTriangular3 records)
     SCR_COUNT
 };
 
@@ -76,6 +79,8 @@ struct lqrb_context {
     std::map<std::string, int64_t> options;
     std::map<std::string, struct DevMap> maps;  // cached device copies of row maps
     std::map<std::string, void *> blobs;        // cached device tables (cooperative KKT offsets)
+    std::string kept_key;                       // shape + flags of the factorisation kept by lqrb_kkt_factor_f64
+    int64_t kept_batch = 0;
 
     int64_t opt(const char *name, int64_t dflt) const {
         auto it = options.find(name);

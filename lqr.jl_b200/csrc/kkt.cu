@@ -565,3 +565,271 @@ extern "C" int32_t lqrb_kkt_solve_f64(lqrb_handle_t h, int32_t n, int32_t m, int
     for (int i = 0; i < 2; ++i) LQRB_CUDA(h, cudaStreamSynchronize(h->copy_stream[i]));
     return 0;
 }
+
+
+// ------------------------------------------------------------------ factor / solve split, dense extractors ----
+// The reference keeps the Schur blocks (`shur_blocks`) and their Cholesky factor (`chol_blocks`) in the solver and
+// runs the five steps of _solve! one by one (test/cholesky_solve.jl:14-35), re-using the factor for further
+// right-hand sides.  Here the handle owns ONE kept factorisation (packed matrices + the block rows of U in the
+// cooperative kernel's record layout, tile width 1); the fused kernels of lqrb_kkt_solve_f64 never touch it.
+
+// stage instance-major arrays on the device when they are host pointers; returns device pointers
+static int32_t stage_inputs(lqrb_context *h, int slot, int cnt, const double *const *src, const int64_t *per,
+                            int64_t batch, const double **dev, cudaStream_t st) {
+    bool host = false;
+    size_t total = 0;
+    for (int i = 0; i < cnt; ++i)
+        if (src[i] && per[i] > 0) {
+            if (!lqrb_is_device_ptr(src[i])) host = true;
+            total += (size_t)per[i] * batch;
+        }
+    if (!host) {
+        for (int i = 0; i < cnt; ++i) dev[i] = (src[i] && per[i] > 0) ? src[i] : nullptr;
+        return 0;
+    }
+    double *cur = (double *)lqrb_scratch(h, slot, total * 8);
+    if (!cur) return 1000 + (int)cudaErrorMemoryAllocation;
+    for (int i = 0; i < cnt; ++i) {
+        if (!src[i] || per[i] == 0) {
+            dev[i] = nullptr;
+            continue;
+        }
+        LQRB_CUDA(h, cudaMemcpyAsync(cur, src[i], (size_t)per[i] * batch * 8, cudaMemcpyDefault, st));
+        dev[i] = cur;
+        cur += per[i] * batch;
+    }
+    return 0;
+}
+
+static void kkt_per_instance(const KktShape &s, const KktSizes &z, bool has_hux, bool has_d2, int64_t per[11]) {
+    const int64_t n = s.n, m = s.m, N = s.N, K1 = N - 1;
+    const int64_t v[11] = {n * n * N, m * m * K1, has_hux ? m * n * K1 : 0, n * N,  m * K1, n * n * K1,
+                           n * m * K1, n * K1,     has_d2 ? z.sD2 : 0,     z.sC,   z.sc};
+    for (int i = 0; i < 11; ++i) per[i] = v[i];
+}
+
+// row map of the right-hand-side array of phase 2: per knot g (w) | d (p2) | c (ps); sources 0 q, 1 r, 2 d, 3 c
+static std::vector<RowMap> kkt_rhs_map(const KktShape &s) {
+    std::vector<RowMap> map;
+    int coff = 0;
+    for (int k = 0; k < s.N; ++k) {
+        const int mk = k < s.N - 1 ? s.m : 0, p2 = k < s.N - 1 ? s.n : 0, ps = s.p[k];
+        for (int i = 0; i < s.n; ++i) map.push_back({0, k * s.n + i, 0.0});
+        for (int i = 0; i < mk; ++i) map.push_back({1, k * s.m + i, 0.0});
+        for (int i = 0; i < p2; ++i) map.push_back({2, k * s.n + i, 0.0});
+        for (int i = 0; i < ps; ++i) map.push_back({3, coff + i, 0.0});
+        coff += ps;
+    }
+    return map;
+}
+
+static std::string kept_key_of(const KktShape &s, int flags) {
+    return shape_key("keep", s) + ((flags & LQRB_FLAG_SOC) ? "soc" : "");
+}
+
+extern "C" int32_t lqrb_kkt_factor_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N, int64_t batch,
+                                       const int32_t *p, int32_t hess_mode, int32_t flags, const double *Q,
+                                       const double *R, const double *Hux, const double *A, const double *B,
+                                       const double *D2, const double *C, int32_t *info) {
+    int32_t rc = check_kkt(h, n, m, N, batch, p, hess_mode);
+    if (rc) return rc;
+    if (!Q || !R || !A || !B) return lqrb_fail(h, -9, "a required input array is NULL");
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    const KktShape s = make_shape(n, m, N, p, hess_mode, D2 != nullptr);
+    const KktSizes z = kkt_sizes(s);
+    if (z.sC > 0 && !C) return lqrb_fail(h, -15, "C is NULL but p has non-zero entries");
+    h->kept_key.clear();
+    h->kept_batch = 0;
+    if (batch == 0) return 0;
+    cudaStream_t st = h->stream;
+    int64_t per[11];
+    kkt_per_instance(s, z, Hux != nullptr, D2 != nullptr, per);
+    // sources in kkt_data_map order: Q R Hux q r A B d D2 C c — the right-hand-side rows are filled with zeros
+    const double *src[11] = {Q, R, Hux, nullptr, nullptr, A, B, nullptr, D2, C, nullptr};
+    const double *dev[11];
+    rc = stage_inputs(h, SCR_STAGE_A, 11, src, per, batch, dev, st);
+    if (rc) return rc;
+    double *data = (double *)lqrb_scratch(h, SCR_KEEP_DATA, (size_t)batch * z.data_rows * 8);
+    double *rec = (double *)lqrb_scratch(h, SCR_KEEP_REC, (size_t)batch * z.rec_rows * 8);
+    int32_t *dinfo = (int32_t *)lqrb_scratch(h, SCR_INFO, (size_t)batch * sizeof(int32_t));
+    if (!data || !rec || !dinfo) return 1000 + (int)cudaErrorMemoryAllocation;
+    ArrayTable t = {};
+    for (int i = 0; i < 11; ++i) {
+        t.ptr[i] = dev[i];
+        t.stride[i] = per[i];
+    }
+    rc = lqrb_gather_pack(h, lqrb_get_map(h, shape_key("kd", s), kkt_data_map(s)), t, batch, 1, data, st);
+    if (rc) return rc;
+    KktCoopExtra ex;
+    ex.phase = 1;
+    const bool info_dev = info && lqrb_is_device_ptr(info);
+    rc = launch_kkt_coop(h, n, m, N, p, hess_mode, s.d2x, flags, batch, data, rec, nullptr, nullptr, nullptr,
+                         info_dev ? info : dinfo, st, &ex);
+    if (rc) return rc;
+    if (info && !info_dev) {
+        LQRB_CUDA(h, cudaMemcpyAsync(info, dinfo, (size_t)batch * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        LQRB_CUDA(h, cudaStreamSynchronize(st));
+    }
+    h->kept_key = kept_key_of(s, flags);
+    h->kept_batch = batch;
+    return 0;
+}
+
+extern "C" int32_t lqrb_kkt_solve_factored_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N, int64_t batch,
+                                               const int32_t *p, int32_t hess_mode, int32_t explicit_d2,
+                                               int32_t flags, const double *q, const double *r, const double *d,
+                                               const double *c, double *dz, double *mult, double *res,
+                                               int32_t *info) {
+    int32_t rc = check_kkt(h, n, m, N, batch, p, hess_mode);
+    if (rc) return rc;
+    const bool soc = (flags & LQRB_FLAG_SOC) != 0;
+    if (!soc && (!q || !r)) return lqrb_fail(h, -10, "q / r is NULL");
+    if (!d) return lqrb_fail(h, -12, "d is NULL");
+    if (!dz) return lqrb_fail(h, -14, "dz is NULL");
+    if (!mult) return lqrb_fail(h, -15, "mult is NULL");
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    const KktShape s = make_shape(n, m, N, p, hess_mode, explicit_d2);
+    const KktSizes z = kkt_sizes(s);
+    if (z.sc > 0 && !c) return lqrb_fail(h, -13, "c is NULL but p has non-zero entries");
+    if (h->kept_key.empty() || h->kept_key != kept_key_of(s, flags) || h->kept_batch != batch)
+        return lqrb_fail(h, -1, "no kept factorisation of this shape / batch / flags: call lqrb_kkt_factor_f64 first");
+    if (batch == 0) return 0;
+    cudaStream_t st = h->stream;
+    const int64_t per[4] = {(int64_t)n * N, (int64_t)m * (N - 1), (int64_t)n * (N - 1), z.sc};
+    const double *src[4] = {q, r, d, c};
+    const double *dev[4];
+    rc = stage_inputs(h, SCR_STAGE_A, 4, src, per, batch, dev, st);
+    if (rc) return rc;
+    const int64_t rhs_rows = z.NN + z.P;
+    double *rhs = (double *)lqrb_scratch(h, SCR_PACK_IN2, (size_t)batch * rhs_rows * 8);
+    if (!rhs) return 1000 + (int)cudaErrorMemoryAllocation;
+    ArrayTable t = {};
+    for (int i = 0; i < 4; ++i) {
+        t.ptr[i] = dev[i];
+        t.stride[i] = per[i];
+    }
+    rc = lqrb_gather_pack(h, lqrb_get_map(h, shape_key("krhs", s), kkt_rhs_map(s)), t, batch, 1, rhs, st);
+    if (rc) return rc;
+    // tile width 1: the packed outputs ARE the instance-major arrays; host outputs go through a staging buffer
+    const bool out_dev = lqrb_is_device_ptr(dz);
+    double *odz = dz, *om = mult, *ores = res;
+    int32_t *oi = info;
+    if (!out_dev) {
+        odz = (double *)lqrb_scratch(h, SCR_STAGE_B, (size_t)batch * (2 * z.NN + z.P) * 8 + (size_t)batch * 4);
+        if (!odz) return 1000 + (int)cudaErrorMemoryAllocation;
+        om = odz + batch * z.NN;
+        ores = om + batch * z.P;
+        oi = reinterpret_cast<int32_t *>(ores + batch * z.NN);
+    }
+    KktCoopExtra ex;
+    ex.phase = 2;
+    ex.rhs = rhs;
+    rc = launch_kkt_coop(h, n, m, N, p, hess_mode, s.d2x, flags, batch, (const double *)h->scratch[SCR_KEEP_DATA],
+                         (double *)h->scratch[SCR_KEEP_REC], odz, om, (res || !out_dev) ? ores : nullptr,
+                         (info || !out_dev) ? oi : nullptr, st, &ex);
+    if (rc) return rc;
+    if (!out_dev) {
+        LQRB_CUDA(h, cudaMemcpyAsync(dz, odz, (size_t)batch * z.NN * 8, cudaMemcpyDeviceToHost, st));
+        LQRB_CUDA(h, cudaMemcpyAsync(mult, om, (size_t)batch * z.P * 8, cudaMemcpyDeviceToHost, st));
+        if (res) LQRB_CUDA(h, cudaMemcpyAsync(res, ores, (size_t)batch * z.NN * 8, cudaMemcpyDeviceToHost, st));
+        if (info) LQRB_CUDA(h, cudaMemcpyAsync(info, oi, (size_t)batch * 4, cudaMemcpyDeviceToHost, st));
+        LQRB_CUDA(h, cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+// dense P x P image of the block rows (copy_shur_factors! / copy_block!, src/jacobian_blocks.jl:173-211):
+// knot k contributes A (lam_{k-1}, aliasing C_{k-1}), B (mu_k), D, E, F; the vector slots give h (c_k, d_{k-1}).
+static void assemble_block_rows(const KktShape &s, const double *rec, int64_t P, bool factor, double *M, double *hv) {
+    const int n = s.n, N = s.N;
+    int64_t off = 0;  // mult offset of mu_k
+    for (int k = 0; k < N; ++k) {
+        const int p1 = k > 0 ? n : 0, ps = s.p[k], p2 = k < N - 1 ? n : 0;
+        const double *rB = rec, *rD = rB + (int64_t)ps * ps, *rE = rD + (int64_t)p1 * ps, *rF = rE + (int64_t)ps * p2,
+                     *rmu = rF + (int64_t)p1 * p2, *rC = rmu + ps, *rl = rC + (int64_t)p1 * p1;
+        const int64_t i1 = off - p1, is = off, i2 = off + ps;
+        auto put = [&](int64_t i, int64_t j, double v) {
+            M[i + j * P] = v;
+            if (!factor) M[j + i * P] = v;  // Symmetric(S, :U)
+        };
+        for (int j = 0; j < p1; ++j)
+            for (int i = 0; i <= j; ++i) put(i1 + i, i1 + j, rC[i + (int64_t)j * p1]);
+        for (int j = 0; j < ps; ++j)
+            for (int i = 0; i <= j; ++i) put(is + i, is + j, rB[i + (int64_t)j * ps]);
+        for (int j = 0; j < ps; ++j)
+            for (int i = 0; i < p1; ++i) put(i1 + i, is + j, rD[i + (int64_t)j * p1]);
+        for (int j = 0; j < p2; ++j)
+            for (int i = 0; i < ps; ++i) put(is + i, i2 + j, rE[i + (int64_t)j * ps]);
+        for (int j = 0; j < p2; ++j)
+            for (int i = 0; i < p1; ++i) put(i1 + i, i2 + j, rF[i + (int64_t)j * p1]);
+        if (hv) {
+            for (int i = 0; i < ps; ++i) hv[is + i] = rmu[i];
+            for (int i = 0; i < p1; ++i) hv[i1 + i] = rl[i];
+        }
+        rec += kkt_coop_rec_knot_rows(p1, ps, p2);
+        off += ps + p2;
+    }
+}
+
+extern "C" int32_t lqrb_kkt_get_shur_f64(lqrb_handle_t h, int32_t n, int32_t m, int32_t N, int64_t batch,
+                                         const int32_t *p, int32_t hess_mode, int32_t flags, const double *Q,
+                                         const double *R, const double *Hux, const double *q, const double *r,
+                                         const double *A, const double *B, const double *d, const double *D2,
+                                         const double *C, const double *c, double *S, double *hvec, double *U,
+                                         int32_t *info) {
+    int32_t rc = check_kkt(h, n, m, N, batch, p, hess_mode);
+    if (rc) return rc;
+    if (!Q || !R || !q || !r || !A || !B || !d) return lqrb_fail(h, -9, "a required input array is NULL");
+    if (!S && !hvec && !U) return lqrb_fail(h, -20, "S, h and U are all NULL");
+    LQRB_CUDA(h, cudaSetDevice(h->device));
+    const KktShape s = make_shape(n, m, N, p, hess_mode, D2 != nullptr);
+    const KktSizes z = kkt_sizes(s);
+    if (z.sC > 0 && (!C || !c)) return lqrb_fail(h, -18, "C/c is NULL but p has non-zero entries");
+    if (batch == 0) return 0;
+    cudaStream_t st = h->stream;
+    int64_t per[11];
+    kkt_per_instance(s, z, Hux != nullptr, D2 != nullptr, per);
+    const double *src[11] = {Q, R, Hux, q, r, A, B, d, D2, C, c};
+    const double *dev[11];
+    rc = stage_inputs(h, SCR_STAGE_A, 11, src, per, batch, dev, st);
+    if (rc) return rc;
+    double *data = (double *)lqrb_scratch(h, SCR_PACK_IN, (size_t)batch * z.data_rows * 8);
+    double *rec = (double *)lqrb_scratch(h, SCR_FACT, (size_t)batch * z.rec_rows * 8);
+    double *sd = (double *)lqrb_scratch(h, SCR_PACK_OUT, (size_t)batch * z.rec_rows * 8);
+    double *out = (double *)lqrb_scratch(h, SCR_PACK_OUT2, (size_t)batch * (z.NN + z.P) * 8);
+    int32_t *dinfo = (int32_t *)lqrb_scratch(h, SCR_INFO, (size_t)batch * sizeof(int32_t));
+    if (!data || !rec || !sd || !out || !dinfo) return 1000 + (int)cudaErrorMemoryAllocation;
+    ArrayTable t = {};
+    for (int i = 0; i < 11; ++i) {
+        t.ptr[i] = dev[i];
+        t.stride[i] = per[i];
+    }
+    rc = lqrb_gather_pack(h, lqrb_get_map(h, shape_key("kd", s), kkt_data_map(s)), t, batch, 1, data, st);
+    if (rc) return rc;
+    LQRB_CUDA(h, cudaMemsetAsync(sd, 0, (size_t)batch * z.rec_rows * 8, st));
+    KktCoopExtra ex;
+    ex.phase = 0;
+    ex.sdump = sd;
+    rc = launch_kkt_coop(h, n, m, N, p, hess_mode, s.d2x, flags, batch, data, rec, out, out + batch * z.NN, nullptr,
+                         dinfo, st, &ex);
+    if (rc) return rc;
+    std::vector<double> hrec((size_t)z.rec_rows), hsd((size_t)z.rec_rows), dense((size_t)z.P * z.P), hv((size_t)z.P);
+    if (info) LQRB_CUDA(h, cudaMemcpyAsync(info, dinfo, (size_t)batch * 4, cudaMemcpyDefault, st));
+    for (int64_t i = 0; i < batch; ++i) {
+        LQRB_CUDA(h, cudaMemcpyAsync(hrec.data(), rec + i * z.rec_rows, (size_t)z.rec_rows * 8, cudaMemcpyDeviceToHost, st));
+        LQRB_CUDA(h, cudaMemcpyAsync(hsd.data(), sd + i * z.rec_rows, (size_t)z.rec_rows * 8, cudaMemcpyDeviceToHost, st));
+        LQRB_CUDA(h, cudaStreamSynchronize(st));
+        if (S || hvec) {
+            std::fill(dense.begin(), dense.end(), 0.0);
+            assemble_block_rows(s, hsd.data(), z.P, false, dense.data(), hv.data());
+            if (S) LQRB_CUDA(h, cudaMemcpy(S + i * z.P * z.P, dense.data(), (size_t)z.P * z.P * 8, cudaMemcpyDefault));
+            if (hvec) LQRB_CUDA(h, cudaMemcpy(hvec + i * z.P, hv.data(), (size_t)z.P * 8, cudaMemcpyDefault));
+        }
+        if (U) {
+            std::fill(dense.begin(), dense.end(), 0.0);
+            assemble_block_rows(s, hrec.data(), z.P, true, dense.data(), nullptr);
+            LQRB_CUDA(h, cudaMemcpy(U + i * z.P * z.P, dense.data(), (size_t)z.P * z.P * 8, cudaMemcpyDefault));
+        }
+    }
+    return 0;
+}

@@ -139,6 +139,9 @@ struct KktCoopArgs {
     const int64_t *rec_off;   // device: record row offset per knot [N+1]
     const int64_t *mult_off;  // device: mult row offset of mu_k per knot [N+1]
     double *gws;              // global workspace (nullptr: shared memory)
+    const double *rhs;        // phase 2: per instance [per knot: g (w) | d (p2) | c (ps)], tile width 1
+    double *sdump;            // optional: raw Schur blocks S (before cholesky!) in the record layout
+    int phase;                // 0 fused, 1 factor only, 2 solve with the kept factor
     int n, m, N, hess, d2x, soc;
     int64_t batch;
     int P;  // max p_k
@@ -173,14 +176,28 @@ __global__ void __launch_bounds__(THREADS) kkt_coop_kernel(KktCoopArgs a) {
         int st_all = 0;
 
         // ======================= forward sweep =======================
+        // phase 0: fused solve; 1: factor only (calculate_shur_factors! + cholesky!(U, F), blocks kept in `scratch`);
+        // 2: solve with the kept factor and a new right-hand side (a.rhs): only the vector part of
+        //    calculate_shur_factors! and forward_substitution! run here, no O(n^3) work.
+        const bool fac = a.phase != 2;
+        const double *rhsb = a.rhs ? a.rhs + ii * (NN + mult_rows) : nullptr;
+        double *sdb = a.sdump ? a.sdump + ii * rec_rows : nullptr;
         for (int k = 0; k < N; ++k) {
             const int mk = k < N - 1 ? m : 0, w = n + mk, p1 = k > 0 ? n : 0, ps = a.p[k],
                       p2 = k < N - 1 ? n : 0;
             const double *kp = db + a.knot_off[k];
             double *rec = sb + a.rec_off[k];
+            double *rB = rec, *rD = rB + (int64_t)ps * ps, *rE = rD + (int64_t)p1 * ps, *rF = rE + (int64_t)ps * p2,
+                   *rmu = rF + (int64_t)p1 * p2, *rC = rmu + ps, *rl = rC + (int64_t)p1 * p1;
+            // raw (unfactored) Schur blocks in the same record layout: B | D | E | F | c | C_{k-1} | d_{k-1}
+            double *sd = sdb ? sdb + a.rec_off[k] : nullptr;
             const int hr = hess_rows(n, mk, a.hess);
-            const double *gp = kp + hr, *D1p = gp + w, *dvp = D1p + p2 * w,
-                         *D2p = dvp + p2, *Cp_in = D2p + ((a.d2x && k > 0) ? n * w : 0), *cp_in = Cp_in + ps * w;
+            const double *D1p = kp + hr + w, *D2p = D1p + p2 * w + p2,
+                         *Cp_in = D2p + ((a.d2x && k > 0) ? n * w : 0);
+            // right-hand-side rows g | d | c: inside the knot record, or (phase 2) in the separate rhs array
+            const double *gp = rhsb ? rhsb + (int64_t)k * (n + m) + a.mult_off[k] : kp + hr;
+            const double *dvp = rhsb ? gp + w : D1p + p2 * w;
+            const double *cp_in = rhsb ? dvp + p2 : Cp_in + ps * w;
             // ---- load H (full storage), g, D1, D2, C
             load_hessian<G>(Hf, dinv, kp, n, mk, a.hess, a.soc, t);
             for (int e = t; e < w; e += G) hg[e] = a.soc ? 0.0 : gp[e];
@@ -196,83 +213,128 @@ __global__ void __launch_bounds__(THREADS) kkt_coop_kernel(KktCoopArgs a) {
             int st = factor_hessian<G>(Hf, dinv, w, a.hess, a.soc, t);
             if (st && !st_all) st_all = (k + 1) * 1000 + st;
             // ---- W = H^-1 Y' (columns of D2', D1', C') and hg = H^-1 g
-            for (int e = t; e < w * p1; e += G) W2[e] = D2[(e / w) + (e % w) * n];
-            for (int e = t; e < w * p2; e += G) WD[e] = D1[(e / w) + (e % w) * p2];
-            for (int e = t; e < w * ps; e += G) WC[e] = Cc[(e / w) + (e % w) * ps];
-            group_sync<G>();
+            if (fac) {
+                for (int e = t; e < w * p1; e += G) W2[e] = D2[(e / w) + (e % w) * n];
+                for (int e = t; e < w * p2; e += G) WD[e] = D1[(e / w) + (e % w) * p2];
+                for (int e = t; e < w * ps; e += G) WC[e] = Cc[(e / w) + (e % w) * ps];
+                group_sync<G>();
+            }
             solve_hessian<G>(Hf, dinv, w, a.hess, a.soc, hg, 1, w, t);
-            solve_hessian<G>(Hf, dinv, w, a.hess, a.soc, W2, p1, w, t);
-            solve_hessian<G>(Hf, dinv, w, a.hess, a.soc, WD, p2, w, t);
-            solve_hessian<G>(Hf, dinv, w, a.hess, a.soc, WC, ps, w, t);
+            if (fac) {
+                solve_hessian<G>(Hf, dinv, w, a.hess, a.soc, W2, p1, w, t);
+                solve_hessian<G>(Hf, dinv, w, a.hess, a.soc, WD, p2, w, t);
+                solve_hessian<G>(Hf, dinv, w, a.hess, a.soc, WC, ps, w, t);
+            }
             // ---- finish block row k-1
             if (p1) {
-                co_gemm<G>(0, 0, n, n, w, 1.0, D2, n, W2, w, 1.0, Cp, n, t);  // C_{k-1} += D2 H^-1 D2'
-                for (int e = t; e < n * n; e += G) Ah[e] = Cp[e];
+                if (fac) {
+                    co_gemm<G>(0, 0, n, n, w, 1.0, D2, n, W2, w, 1.0, Cp, n, t);  // C_{k-1} += D2 H^-1 D2'
+                    for (int e = t; e < n * n; e += G) Ah[e] = Cp[e];
+                } else {
+                    for (int e = t; e < n * n; e += G) Ah[e] = rC[e];  // the kept factor C^_{k-1}
+                }
                 co_gemm<G>(0, 0, n, 1, w, 1.0, D2, n, hg, w, 1.0, dp, n, t);  // d_{k-1} += rho1
                 for (int e = t; e < n; e += G) lamp[e] = dp[e];
                 group_sync<G>();
-                st = co_chol<G>(Ah, n, n, t);
-                if (st && !st_all) st_all = k * 1000 + 200 + st;
+                if (fac) {
+                    if (sd) {
+                        double *sC = sd + (int64_t)ps * ps + (int64_t)p1 * ps + (int64_t)ps * p2 + (int64_t)p1 * p2 + ps;
+                        for (int e = t; e < n * n; e += G) sC[e] = Ah[e];
+                        for (int e = t; e < n; e += G) sC[n * n + e] = dp[e];
+                        group_sync<G>();
+                    }
+                    st = co_chol<G>(Ah, n, n, t);
+                    if (st && !st_all) st_all = k * 1000 + 200 + st;
+                }
                 co_trsm_ut<G>(Ah, n, n, lamp, 1, n, t);
                 if (active) {
-                    double *rC = rec + (int64_t)ps * ps + (int64_t)p1 * ps + (int64_t)ps * p2 + (int64_t)p1 * p2 + ps;
-                    for (int e = t; e < n * n; e += G) rC[e] = Ah[e];
-                    for (int e = t; e < n; e += G) rC[n * n + e] = lamp[e];
+                    if (fac)
+                        for (int e = t; e < n * n; e += G) rC[e] = Ah[e];
+                    for (int e = t; e < n; e += G) rl[e] = lamp[e];
                 }
             }
             if (p1 && p2) {
-                co_gemm<G>(0, 0, n, n, w, 1.0, D2, n, WD, w, 0.0, Fh, n, t);  // F = D2 WD
-                co_trsm_ut<G>(Ah, n, n, Fh, n, n, t);
+                if (fac) {
+                    co_gemm<G>(0, 0, n, n, w, 1.0, D2, n, WD, w, 0.0, Fh, n, t);  // F = D2 WD
+                    if (sd) {
+                        double *sF = sd + (int64_t)ps * ps + (int64_t)p1 * ps + (int64_t)ps * p2;
+                        for (int e = t; e < n * n; e += G) sF[e] = Fh[e];
+                        group_sync<G>();
+                    }
+                    co_trsm_ut<G>(Ah, n, n, Fh, n, n, t);
+                } else {
+                    for (int e = t; e < n * n; e += G) Fh[e] = rF[e];
+                    group_sync<G>();
+                }
             }
             if (ps) {
-                co_gemm<G>(0, 0, ps, ps, w, 1.0, Cc, ps, WC, w, 0.0, Bh, ps, t);  // B = C WC
+                if (fac) {
+                    co_gemm<G>(0, 0, ps, ps, w, 1.0, Cc, ps, WC, w, 0.0, Bh, ps, t);  // B = C WC
+                } else {
+                    for (int e = t; e < ps * ps; e += G) Bh[e] = rB[e];
+                    for (int e = t; e < p1 * ps; e += G) Dh[e] = rD[e];
+                    for (int e = t; e < ps * p2; e += G) Eh[e] = rE[e];
+                }
                 for (int e = t; e < ps; e += G) cvec[e] = -cp_in[e];
                 group_sync<G>();
                 co_gemm<G>(0, 0, ps, 1, w, 1.0, Cc, ps, hg, w, 1.0, cvec, ps, t);  // c = rhos - c
                 for (int e = t; e < ps; e += G) mut[e] = cvec[e];
                 group_sync<G>();
-                if (p2) co_gemm<G>(0, 0, ps, p2, w, 1.0, Cc, ps, WD, w, 0.0, Eh, ps, t);  // E = C WD
-                if (p1) {
-                    co_gemm<G>(0, 0, n, ps, w, 1.0, D2, n, WC, w, 0.0, Dh, n, t);  // D = D2 WC
-                    co_trsm_ut<G>(Ah, n, n, Dh, ps, n, t);
-                    co_gemm<G>(1, 0, ps, ps, n, -1.0, Dh, n, Dh, n, 1.0, Bh, ps, t);
-                    co_gemm<G>(1, 0, ps, 1, n, -1.0, Dh, n, lamp, n, 1.0, mut, ps, t);
-                    if (p2) co_gemm<G>(1, 0, ps, p2, n, -1.0, Dh, n, Fh, n, 1.0, Eh, ps, t);
+                if (fac) {
+                    if (p2) co_gemm<G>(0, 0, ps, p2, w, 1.0, Cc, ps, WD, w, 0.0, Eh, ps, t);  // E = C WD
+                    if (p1) co_gemm<G>(0, 0, n, ps, w, 1.0, D2, n, WC, w, 0.0, Dh, n, t);     // D = D2 WC
+                    if (sd) {
+                        double *s0 = sd;
+                        for (int e = t; e < ps * ps; e += G) s0[e] = Bh[e];
+                        s0 += (int64_t)ps * ps;
+                        for (int e = t; e < p1 * ps; e += G) s0[e] = Dh[e];
+                        s0 += (int64_t)p1 * ps;
+                        for (int e = t; e < ps * p2; e += G) s0[e] = Eh[e];
+                        s0 += (int64_t)ps * p2 + (int64_t)p1 * p2;
+                        for (int e = t; e < ps; e += G) s0[e] = cvec[e];
+                        group_sync<G>();
+                    }
+                    if (p1) {
+                        co_trsm_ut<G>(Ah, n, n, Dh, ps, n, t);
+                        co_gemm<G>(1, 0, ps, ps, n, -1.0, Dh, n, Dh, n, 1.0, Bh, ps, t);
+                        if (p2) co_gemm<G>(1, 0, ps, p2, n, -1.0, Dh, n, Fh, n, 1.0, Eh, ps, t);
+                    }
                 }
-                st = co_chol<G>(Bh, ps, ps, t);
-                if (st && !st_all) st_all = (k + 1) * 1000 + 100 + st;
+                if (p1) co_gemm<G>(1, 0, ps, 1, n, -1.0, Dh, n, lamp, n, 1.0, mut, ps, t);
+                if (fac) {
+                    st = co_chol<G>(Bh, ps, ps, t);
+                    if (st && !st_all) st_all = (k + 1) * 1000 + 100 + st;
+                }
                 co_trsm_ut<G>(Bh, ps, ps, mut, 1, ps, t);
-                if (p2) co_trsm_ut<G>(Bh, ps, ps, Eh, p2, ps, t);
+                if (fac && p2) co_trsm_ut<G>(Bh, ps, ps, Eh, p2, ps, t);
             }
             if (p2) {
-                co_gemm<G>(0, 0, n, n, w, 1.0, D1, n, WD, w, 0.0, Cp, n, t);  // G22
+                if (fac) co_gemm<G>(0, 0, n, n, w, 1.0, D1, n, WD, w, 0.0, Cp, n, t);  // G22
                 for (int e = t; e < n; e += G) dp[e] = -dvp[e];
                 group_sync<G>();
                 co_gemm<G>(0, 0, n, 1, w, 1.0, D1, n, hg, w, 1.0, dp, n, t);  // rho2 - d
                 if (p1) {
-                    co_gemm<G>(1, 0, n, n, n, -1.0, Fh, n, Fh, n, 1.0, Cp, n, t);
+                    if (fac) co_gemm<G>(1, 0, n, n, n, -1.0, Fh, n, Fh, n, 1.0, Cp, n, t);
                     co_gemm<G>(1, 0, n, 1, n, -1.0, Fh, n, lamp, n, 1.0, dp, n, t);
                 }
                 if (ps) {
-                    co_gemm<G>(1, 0, n, n, ps, -1.0, Eh, ps, Eh, ps, 1.0, Cp, n, t);
+                    if (fac) co_gemm<G>(1, 0, n, n, ps, -1.0, Eh, ps, Eh, ps, 1.0, Cp, n, t);
                     co_gemm<G>(1, 0, n, 1, ps, -1.0, Eh, ps, mut, ps, 1.0, dp, n, t);
                 }
             }
             if (active) {
-                double *r0 = rec;
-                for (int e = t; e < ps * ps; e += G) r0[e] = Bh[e];
-                r0 += (int64_t)ps * ps;
-                for (int e = t; e < p1 * ps; e += G) r0[e] = Dh[e];
-                r0 += (int64_t)p1 * ps;
-                for (int e = t; e < ps * p2; e += G) r0[e] = Eh[e];
-                r0 += (int64_t)ps * p2;
-                for (int e = t; e < p1 * p2; e += G) r0[e] = Fh[e];
-                r0 += (int64_t)p1 * p2;
-                for (int e = t; e < ps; e += G) r0[e] = mut[e];
+                if (fac) {
+                    for (int e = t; e < ps * ps; e += G) rB[e] = Bh[e];
+                    for (int e = t; e < p1 * ps; e += G) rD[e] = Dh[e];
+                    for (int e = t; e < ps * p2; e += G) rE[e] = Eh[e];
+                    for (int e = t; e < p1 * p2; e += G) rF[e] = Fh[e];
+                }
+                for (int e = t; e < ps; e += G) rmu[e] = mut[e];
             }
             group_sync<G>();
         }
         if (active && a.info && t == 0) a.info[inst] = st_all;
+        if (a.phase == 1) continue;  // factor only
 
         // ======================= backward sweep =======================
         for (int k = N - 1; k >= 0; --k) {
@@ -281,8 +343,9 @@ __global__ void __launch_bounds__(THREADS) kkt_coop_kernel(KktCoopArgs a) {
             const double *kp = db + a.knot_off[k];
             const double *rec = sb + a.rec_off[k];
             const int hr = hess_rows(n, mk, a.hess);
-            const double *gp = kp + hr, *D1p = gp + w, *dvp = D1p + p2 * w,
-                         *D2p = dvp + p2, *Cp_in = D2p + ((a.d2x && k > 0) ? n * w : 0);
+            const double *D1p = kp + hr + w, *D2p = D1p + p2 * w + p2,
+                         *Cp_in = D2p + ((a.d2x && k > 0) ? n * w : 0);
+            const double *gp = rhsb ? rhsb + (int64_t)k * (n + m) + a.mult_off[k] : kp + hr;
             const double *rB = rec, *rD = rB + (int64_t)ps * ps, *rE = rD + (int64_t)p1 * ps,
                          *rF = rE + (int64_t)ps * p2, *rmu = rF + (int64_t)p1 * p2, *rC = rmu + ps,
                          *rl = rC + (int64_t)p1 * p1;
@@ -409,7 +472,7 @@ static double *coop_global_ws(lqrb_context *h, cudaStream_t st, size_t bytes_per
 
 int32_t launch_kkt_coop(lqrb_context *h, int n, int m, int N, const int32_t *p, int hess, int d2x,
                         int flags, int64_t batch, const double *data, double *scratch, double *dz,
-                        double *mult, double *res, int32_t *info, cudaStream_t st) {
+                        double *mult, double *res, int32_t *info, cudaStream_t st, const KktCoopExtra *extra) {
     CoopTables tb;
     int32_t rc = get_tables(h, n, m, N, p, hess, d2x, &tb);
     if (rc) return rc;
@@ -417,6 +480,9 @@ int32_t launch_kkt_coop(lqrb_context *h, int n, int m, int N, const int32_t *p, 
     a.data = data; a.scratch = scratch; a.dz = dz; a.mult = mult; a.res = res; a.info = info;
     a.p = tb.p; a.knot_off = tb.knot_off; a.rec_off = tb.rec_off; a.mult_off = tb.mult_off;
     a.gws = nullptr;
+    a.rhs = extra ? extra->rhs : nullptr;
+    a.sdump = extra ? extra->sdump : nullptr;
+    a.phase = extra ? extra->phase : 0;
     a.n = n; a.m = m; a.N = N; a.hess = hess; a.d2x = d2x; a.soc = (flags & LQRB_FLAG_SOC) ? 1 : 0;
     a.batch = batch; a.P = tb.P;
     const size_t wsd = kkt_coop_ws_doubles(n, m, tb.P);

@@ -19,6 +19,17 @@ __host__ __device__ inline size_t kkt_coop_ws_doubles(int n, int m, int P) {
            2 * (size_t)n * P + 4 * n + 3 * P + 16;
 }
 
+// phase 0: fused solve (default); 1: factor only — calculate_shur_factors! (src/jacobian_blocks.jl:220-229) +
+// cholesky!(U, F) (src/cholesky_solve.jl:28-33), the block rows of U stay in `scratch`; 2: forward / backward
+// substitution + calculate_primals! with the kept U and the right-hand-side rows `rhs` ([per knot: g | d | c] per
+// instance).  `sdump` (phases 0, 1): the unfactored Schur blocks S and h in the record layout (copy_shur_factors!).
+struct KktCoopExtra {
+    int phase = 0;
+    const double *rhs = nullptr;
+    double *sdump = nullptr;
+};
+
 int32_t launch_kkt_coop(lqrb_context *h, int n, int m, int N, const int32_t *p, int hess, int d2x,
                         int flags, int64_t batch, const double *data, double *scratch, double *dz,
-                        double *mult, double *res, int32_t *info, cudaStream_t st);
+                        double *mult, double *res, int32_t *info, cudaStream_t st,
+                        const KktCoopExtra *extra = nullptr);

@@ -109,6 +109,29 @@ def kkt_unpack(h: Handle, n, m, N, batch, p, hess_mode, explicit_d2, dzp, multp,
            ptr(resp), ptr(dz), ptr(mult), ptr(res))
 
 
+def kkt_factor(h: Handle, n, m, N, batch, p, hess_mode, flags, Q, R, Hux, A, B, D2, C, info=None):
+    """calculate_shur_factors! (matrices) + cholesky!(U, F); the handle keeps the factor."""
+    p = _p32(p)
+    h.call("lqrb_kkt_factor_f64", n, m, N, batch, p.ctypes.data, hess_mode, flags, ptr(Q), ptr(R), ptr(Hux), ptr(A),
+           ptr(B), ptr(D2), ptr(C), ptr(info))
+
+
+def kkt_solve_factored(h: Handle, n, m, N, batch, p, hess_mode, explicit_d2, flags, q, r, d, c, dz, mult, res=None,
+                       info=None):
+    """forward / backward substitution + primals with the kept factor and a new right-hand side."""
+    p = _p32(p)
+    h.call("lqrb_kkt_solve_factored_f64", n, m, N, batch, p.ctypes.data, hess_mode, int(explicit_d2), flags, ptr(q),
+           ptr(r), ptr(d), ptr(c), ptr(dz), ptr(mult), ptr(res), ptr(info))
+
+
+def kkt_get_shur(h: Handle, n, m, N, batch, p, hess_mode, flags, Q, R, Hux, q, r, A, B, d, D2, C, c, S=None, hvec=None,
+                 U=None, info=None):
+    """dense S, h, U of the device's block rows (get_shur_factors / get_cholesky)."""
+    p = _p32(p)
+    h.call("lqrb_kkt_get_shur_f64", n, m, N, batch, p.ctypes.data, hess_mode, flags, ptr(Q), ptr(R), ptr(Hux), ptr(q),
+           ptr(r), ptr(A), ptr(B), ptr(d), ptr(D2), ptr(C), ptr(c), ptr(S), ptr(hvec), ptr(U), ptr(info))
+
+
 def kkt_residual(h: Handle, n, m, N, batch, p, flags, q, r, A, B, D2, C, mult, res=None, norms=None):
     """res_k = D1'lam_k + C'mu_k + D2'lam_{k-1} + g_k for given multipliers (residual, src/cholesky_solver.jl:238-252)."""
     p = _p32(p)

@@ -95,17 +95,28 @@ def test_cholesky_solver_step_sequence_like_reference_script(handle):
     prob = problems.double_integrator_fixture()
     solver = LQR.CholeskySolver(prob, handle=handle)
     LQR.calculate_shur_factors_(solver.shur_blocks, None, None)        # :14
-    LQR.cholesky_(solver.chol_blocks, solver.shur_blocks)               # :22
-    LQR.forward_substitution_(solver.chol_blocks)                       # :28
+    D, d = LQR.get_linearized_constraints(solver)                       # :17
+    H, g = LQR.get_cost_expansion(solver)
+    Sd, rd, _ = LQR.get_shur_factors(solver)                            # :18  S, h as the DEVICE forms them
+    S = D @ np.linalg.solve(H, D.T)
+    r = D @ np.linalg.solve(H, g) - d
+    assert _rel(Sd[0], S) < 1e-12                                       # :19  S ≈ D*(H\D')
+    assert _rel(rd[0], r) < 1e-12                                       # :20  D*(H\g) - d ≈ r
+    LQR.cholesky_(solver.chol_blocks, solver.shur_blocks)               # :22  lqrb_kkt_factor_f64
+    assert handle.last_kernel.startswith("kkt_coop") and (solver.info == 0).all()
+    U = LQR.get_cholesky(solver)[0]                                     # :23  block rows of U from the device
+    assert np.array_equal(U, np.triu(U))
+    assert _rel(U, np.linalg.cholesky(Sd[0]).T) < 1e-9                  # :24  cholesky(S).U ≈ U
+    assert _rel(U.T @ U, Sd[0]) < 1e-12                                 # :25  U'U ≈ S
+    LQR.forward_substitution_(solver.chol_blocks)                       # :28  lqrb_kkt_solve_factored_f64
     LQR.backward_substitution_(solver.chol_blocks)                      # :29
     lam = LQR.get_multipliers(solver)[0]                                # :30
     dZ = np.zeros_like(solver.dZ)
     LQR.calculate_primals_(dZ, None, solver.chol_blocks, None)          # :34
     dZ = LQR.get_step(solver)[0]                                        # :35
-    D, d = LQR.get_linearized_constraints(solver)                       # :17
-    H, g = LQR.get_cost_expansion(solver)
-    S = D @ np.linalg.solve(H, D.T)
-    r = D @ np.linalg.solve(H, g) - d
+    S2, h2, lam2 = np.zeros_like(Sd), np.zeros_like(rd), np.zeros_like(solver.lam)
+    LQR.copy_shur_factors_(S2, h2, lam2, solver.shur_blocks)            # src/jacobian_blocks.jl:173-180
+    assert np.array_equal(S2, Sd) and np.array_equal(lam2, solver.lam)
     assert _rel(lam, -np.linalg.solve(S, r)) < 1e-7                     # :31
     assert _rel(dZ, -np.linalg.solve(H, D.T @ lam + g)) < 1e-10         # :36
     assert np.linalg.norm(D @ dZ + d) < 1e-10                           # :39
@@ -117,9 +128,11 @@ def test_cholesky_solver_step_sequence_like_reference_script(handle):
     res = LQR.residual(solver)[0]
     assert abs(res - np.linalg.norm(g + D.T @ lam)) < 1e-9 * max(1.0, res)
     assert _rel(LQR.get_residual(solver)[0], g + D.T @ lam) < 1e-10
-    # _solve! gives the same thing in one call (:166-182)
+    # _solve! gives the same thing in one fused launch on the tuned kernel (:166-182)
     s2 = LQR.CholeskySolver(prob, handle=handle)._solve_()
-    assert np.array_equal(s2.dZ, solver.dZ) and np.array_equal(s2.lam, solver.lam)
+    assert handle.last_kernel.startswith("kkt_tpi<6,3")
+    assert _rel(s2.dZ, solver.dZ) < 1e-10 and _rel(s2.lam, solver.lam) < 1e-9
+    assert _rel(s2.res, solver.res) < 1e-9
     # second_order_correction!: dz^ = -D'(DD')^-1 d (:254-273); cond(DD') ~ 1e7 here
     dzh = LQR.second_order_correction_(solver)[0]
     assert _rel(dzh, -D.T @ np.linalg.solve(D @ D.T, d)) < 1e-6 or np.linalg.norm(d) == 0
@@ -233,3 +246,60 @@ def test_edge_cases_empty_batch_shortest_horizon_and_argument_errors(handle, ora
     # the handle is still usable after the errors
     dz2, lam2, info2 = ops.kkt_solve_problem(prob, handle=handle)
     assert (info2 == 0).all()
+
+
+@pytest.mark.parametrize("n,m,N,b,mid_p,hess,d2x", [(4, 1, 12, 5, 0, 2, False), (6, 3, 9, 3, 1, 1, False),
+                                                    (5, 2, 8, 4, 2, 0, True), (12, 4, 10, 3, 0, 1, False),
+                                                    (3, 2, 2, 2, 0, 1, False)])
+def test_factor_once_solve_many(handle, oracle_mod, n, m, N, b, mid_p, hess, d2x):
+    """lqrb_kkt_factor_f64 once, lqrb_kkt_solve_factored_f64 for several right-hand sides; each
+    must equal the fused solve of the same data (oracle and the tuned / cooperative kernels)."""
+    prob = problems.random_lqr_kkt(n, m, N, b, seed=17 + n, mid_p=mid_p, hess_mode=hess, explicit_D2=d2x)
+    solver = LQR.CholeskySolver(prob, handle=handle).factor_()
+    assert (solver.info == 0).all()
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        if trial:
+            prob = dict(prob, q=rng.standard_normal(prob["q"].shape), r=rng.standard_normal(prob["r"].shape),
+                        d=rng.standard_normal(prob["d"].shape), c=[rng.standard_normal(ck.shape) for ck in prob["c"]])
+        solver.solve_factored_(q=prob["q"], r=prob["r"], d=prob["d"], c=prob["c"])
+        dzo, lamo, _, reso = oracle_mod.kkt_solve(prob, want_res=True)
+        assert _rel(solver.dZ, dzo) < 1e-10 and _rel(solver.lam, lamo) < 1e-10
+        assert np.abs(solver.res - reso).max() < 1e-10 * max(1.0, np.abs(reso).max())
+    # a solve against a factor of another shape is refused
+    other = LQR.CholeskySolver(problems.random_lqr_kkt(n, m, N + 1, b, seed=1, mid_p=mid_p, hess_mode=hess), handle=handle)
+    other._state = "factored"
+    with pytest.raises(LQR.LqrbError):
+        other.solve_factored_()
+
+
+def test_soc_with_kept_factor(handle, oracle_mod):
+    """second_order_correction!'s chain (Ginv = false) through the factor / solve split: S = D D' is factored once
+    and re-used for two sets of constraint values (src/cholesky_solver.jl:259-263)."""
+    prob = problems.cartpole_fixture()
+    solver = LQR.CholeskySolver(prob, handle=handle)
+    solver._Ginv = False
+    solver.factor_()
+    rng = np.random.default_rng(2)
+    for _ in range(2):
+        d = 1e-3 * rng.standard_normal(prob["d"].shape)
+        c = [1e-3 * rng.standard_normal(ck.shape) for ck in prob["c"]]
+        solver.solve_factored_(d=d, c=c)
+        dzo, lamo, _ = oracle_mod.kkt_solve(dict(prob, d=d, c=c), soc=True)
+        assert _rel(solver.dZ, dzo) < 1e-9 and _rel(solver.lam, lamo) < 1e-9
+
+
+@pytest.mark.parametrize("name", ["cartpole", "dubins_mid"])
+def test_dense_extractors_on_other_shapes(handle, name):
+    """test/constraint_blocks.jl:70-72,122-125 identities (S ≈ D(H\\D'), U'U ≈ S) on the device's block rows."""
+    prob = problems.cartpole_fixture(31) if name == "cartpole" else problems.dubins_kkt_batch(3, seed=4, N=17, mid_p=1)
+    solver = LQR.CholeskySolver(prob, handle=handle)._solve_()
+    S, h, lam = LQR.get_shur_factors(solver)
+    U = LQR.get_cholesky(solver)
+    for i in range(S.shape[0]):
+        D, d = LQR.get_linearized_constraints(solver, i)
+        H, g = LQR.get_cost_expansion(solver, i)
+        assert _rel(S[i], D @ np.linalg.solve(H, D.T)) < 1e-11
+        assert _rel(h[i], D @ np.linalg.solve(H, g) - d) < 1e-11
+        assert _rel(U[i].T @ U[i], S[i]) < 1e-12
+        assert _rel(lam[i], -np.linalg.solve(S[i], h[i])) < 1e-6
