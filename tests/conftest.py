@@ -28,6 +28,22 @@ def handle():
     h.close()
 
 
+@pytest.fixture(scope="session")
+def build_abi_smoke():
+    """Compiles tests/abi_smoke.c (plain C99 caller of the ABI) against include/lqrb200.h and the in-tree library."""
+    import subprocess
+
+    def build(out_dir):
+        from lqr_b200 import _lib
+        exe = os.path.join(out_dir, "abi_smoke")
+        lib_dir = os.path.dirname(_lib.LIB_PATH)
+        subprocess.run(["gcc", "-std=c99", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "abi_smoke.c"), "-o", exe, "-L", lib_dir, "-llqrb200", "-lm",
+                        f"-Wl,-rpath,{lib_dir}"], check=True, capture_output=True, text=True)
+        return exe
+    return build
+
+
 def condensed_least_squares_gradient(A, B, Q, R, Qf, x0, U):
     """The reference's condensed form (src/least_squares.jl: build_toeplitz, buildAb!): x_{2..N} = T u + L x0 with
     T block-Toeplitz (T[i,j] = A^(i-j) B) and L[i] = A^i, cost |Hx (T u + L x0)|^2 + u' Hu u.  Returns the

@@ -165,3 +165,41 @@ def test_two_rank_gloo_timing_protocol(tmp_path):
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0, e[-2000:]
     assert sorted(o.split()[2] for o, _ in outs) == ["0", "512"]
+
+
+def test_header_is_plain_c_and_the_c_caller_links(tmp_path, build_abi_smoke):
+    """include/lqrb200.h is valid C99 (no C++-isms, no torch types) and tests/abi_smoke.c — the non-Python caller
+    of the ABI — compiles against it with -Wall -Wextra -Werror and links the in-tree library (run on the GPU by
+    tests/test_gpu_abi.py)."""
+    exe = build_abi_smoke(str(tmp_path))
+    out = subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    assert "liblqrb200.so" in out and "not found" not in out.split("liblqrb200.so")[1].splitlines()[0]
+
+
+def test_julia_shim_binds_every_header_symbol():
+    """lqr.jl_b200/julia/LQRB200.jl ccalls every exported entry of include/lqrb200.h, with the argument count the
+    header declares (the shim is static — Julia is not installed — so this is the check that it cannot drift)."""
+    hdr = open(os.path.join(ROOT, "include", "lqrb200.h")).read()
+    hdr_nc = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decl = {}
+    for mm in re.finditer(r"\b(lqrb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr_nc, flags=re.S):
+        args = mm.group(2).strip()
+        decl[mm.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    assert set(decl) == set(_lib.EXPORTS)
+    jl = open(os.path.join(ROOT, "lqr.jl_b200", "julia", "LQRB200.jl")).read()
+    bound = {}
+    for mm in re.finditer(r"ccall\(\(:(lqrb_[a-z0-9_]+), lib\),\s*([A-Za-z0-9{}]+),\s*\(([^)]*)\)", jl, flags=re.S):
+        types = [t for t in mm.group(3).replace("\n", " ").split(",") if t.strip()]
+        bound.setdefault(mm.group(1), set()).add(len(types))
+    missing = sorted(set(decl) - set(bound))
+    assert not missing, f"the Julia shim does not bind: {missing}"
+    for name, counts in bound.items():
+        assert name in decl, f"{name} is not in the header"
+        assert counts == {decl[name]}, (name, counts, decl[name])
+    # the reference's own names are exported (SURVEY 8b)
+    for name in ("LQRProblem", "DPSolver", "solve!", "BlockCholesky", "InvertedQuadratic", "update_cholesky!",
+                 "ConstraintBlock", "dims", "build_shur_factors", "calculate_shur_factors!", "forward_substitution!",
+                 "backward_substitution!", "calculate_primals!", "CholeskySolver", "_solve!", "step!", "residual",
+                 "get_step", "get_multipliers", "get_shur_factors", "get_cholesky", "copy_shur_factors!", "rollout!",
+                 "second_order_correction!", "num_vars"):
+        assert re.search(r"\b" + re.escape(name) + r"(?![A-Za-z0-9_])", jl.split("export", 1)[1]), name
