@@ -240,6 +240,14 @@ int32_t lqrb_kkt_get_shur_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_
                               const double *C, const double *c, double *S, double *h, double *U,
                               int32_t *info);
 
+/* Diagnostic of the last lqrb_kkt_solve*_f64 launch on this handle that used one of the tuned large-size kernels
+ * (which carry explicit block inverses): log2 of the worst pivot ratio met in any Schur block of each instance (of the
+ * last chunk when the batch was processed in chunks; -1 = not tracked), and how many instances were found
+ * ill-conditioned (>= 2^kkt_cond_bits, option, default 12) and solved again by the Cholesky-based general kernel, the
+ * reference's own operation order (src/cholesky_solve.jl:47-67).  Either output may be NULL.                    */
+int32_t lqrb_kkt_last_condition(lqrb_handle_t handle, int64_t count, int32_t *log2_pivot_ratio,
+                                int64_t *resolved);
+
 /* Replaces residual(solver; recalculate=true) : src/cholesky_solver.jl:238-252 — calc_residual! (:201-236)
  * with the KEPT multipliers of an earlier solve and freshly evaluated Jacobians / gradients (what step!
  * reports as feas_d, :126-134):

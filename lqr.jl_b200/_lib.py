@@ -87,6 +87,7 @@ _SIGS = {
     "lqrb_kkt_solve_factored_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32, c_i32, c_i32] + [c_dp] * 7
                                     + [c_vp]),
     "lqrb_kkt_get_shur_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32, c_i32] + [c_dp] * 14 + [c_vp]),
+    "lqrb_kkt_last_condition": (c_i32, [c_vp, c_i64, c_vp, C.POINTER(c_i64)]),
     "lqrb_kkt_residual_f64": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_i64, c_vp, c_i32] + [c_dp] * 9),
     "lqrb_sqp_dubins_f64": (c_i32, [c_vp, c_i64, C.POINTER(SqpOptions)] + [c_dp] * 5 + [c_vp, C.POINTER(c_i64)]),
 }
@@ -172,6 +173,13 @@ class Handle:
     @property
     def launches(self) -> int:
         return int(lib().lqrb_launch_count(self._h))
+
+    def kkt_last_condition(self, count: int):
+        """(log2 pivot ratios of the last tuned KKT launch, number of instances re-solved by the Cholesky-based kernel)."""
+        out = np.zeros(count, dtype=np.int32)
+        n = c_i64(0)
+        self.call("lqrb_kkt_last_condition", count, out.ctypes.data, C.byref(n))
+        return out, int(n.value)
 
     @property
     def last_kernel(self) -> str:

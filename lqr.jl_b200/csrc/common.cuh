@@ -53,6 +53,8 @@ enum ScratchSlot {
     SCR_SQP3,
     SCR_KEEP_DATA,  // lqrb_kkt_factor_f64: packed matrices of the kept factorisation
     SCR_KEEP_REC,   //                      block rows of U (BlockUpperTriangular3 records)
+    SCR_REFINE,       // records of the instances re-solved by the Cholesky-based kernel (ill-conditioned blocks)
+    SCR_REFINE_LIST,  // their indices
     SCR_COUNT
 };
 
@@ -79,6 +81,8 @@ struct lqrb_context {
     std::map<std::string, int64_t> options;
     std::map<std::string, struct DevMap> maps;  // cached device copies of row maps
     std::map<std::string, void *> blobs;        // cached device tables (cooperative KKT offsets)
+    std::vector<int32_t> last_cond;             // conditioning estimates of the last tuned KKT launch (log2 pivot ratio)
+    int64_t last_refined = 0;                   // instances of that launch re-solved by the Cholesky-based kernel
     std::string kept_key;                       // shape + flags of the factorisation kept by lqrb_kkt_factor_f64
     int64_t kept_batch = 0;
 

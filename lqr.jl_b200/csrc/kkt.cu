@@ -7,6 +7,10 @@
 #include "kkt_cta_kernels.cuh"
 #include "kkt_kernels.cuh"
 
+// default of the `kkt_cond_bits` option: instances whose worst Schur-block pivot ratio reaches 2^bits are solved again
+// by the Cholesky-based kernel (see kkt_resolve_ill_conditioned; calibrated with tools/stress_scales.py)
+#define LQRB_KKT_COND_BITS 12
+
 // ------------------------------------------------------------------ size classes --------------
 // thread-per-instance instantiations: (n, m, P1, PM, PN) with p = [P1, PM, ..., PM, PN].
 //   cartpole (test/problems.jl:58-88): 4,1 init+goal          dubins: 3,2 init+goal (+1 mid row)
@@ -224,6 +228,51 @@ static int32_t launch_kkt_tpi(lqrb_context *h, const KktShape &s, int64_t batch,
     return 0;
 }
 
+// The tuned large-size kernels (kkt_hw2, kkt_cta) carry the block elimination with explicit SPD inverses (products
+// instead of the reference's sequential triangular solves); their error grows with cond(Sigma_k) where the reference's
+// U'U form (src/cholesky_solve.jl:47-67) does not.  Both kernels report, per instance, log2 of the worst pivot ratio
+// met in any Sigma_k (free: integer compares of the pivots' high words).  Instances above `kkt_cond_bits` are solved
+// again by the Cholesky-based general kernel — the reference's own operation order — which overwrites their outputs.
+// `kkt_refine` = 0 switches this off.  Costs one 4-byte-per-instance read-back and a stream synchronisation.
+static int32_t kkt_resolve_ill_conditioned(lqrb_context *h, const KktShape &s, int64_t cb, int flags, const double *dc,
+                                           const int32_t *cinfo_dev, double *dz, double *mult, double *res, int32_t *info,
+                                           cudaStream_t st) {
+    h->last_refined = 0;
+    if (h->opt("kkt_refine", 1) == 0) return 0;
+    const int slot = st == h->copy_stream[1] ? 1 : 0;
+    int32_t *hc = (int32_t *)lqrb_pinned(h, 2 + slot, (size_t)cb * sizeof(int32_t));
+    if (!hc) return 1000 + (int)cudaErrorMemoryAllocation;
+    LQRB_CUDA(h, cudaMemcpyAsync(hc, cinfo_dev, (size_t)cb * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    LQRB_CUDA(h, cudaStreamSynchronize(st));
+    h->last_cond.assign(hc, hc + cb);
+    const int thr = (int)h->opt("kkt_cond_bits", LQRB_KKT_COND_BITS);
+    std::vector<int32_t> list;
+    for (int64_t i = 0; i < cb; ++i)
+        if (hc[i] >= thr) list.push_back((int32_t)i);
+    if (list.empty()) return 0;
+    const KktSizes z = kkt_sizes(s);
+    // the general kernel keeps full-storage records: process the list in pieces that fit the scratch budget
+    const size_t per = (size_t)z.rec_rows * 8;
+    const int64_t piece = std::max<int64_t>(1, (int64_t)(((size_t)h->opt("scratch_budget_mb", 49152) << 20) / 4 / per));
+    for (size_t first = 0; first < list.size(); first += (size_t)piece) {
+        const int64_t cnt = std::min<int64_t>(piece, (int64_t)(list.size() - first));
+        // separate slices per stream: the host-buffer path has two of these in flight
+        int32_t *dl = (int32_t *)lqrb_scratch(h, SCR_REFINE_LIST, 2 * (size_t)cb * sizeof(int32_t));
+        double *rec = (double *)lqrb_scratch(h, SCR_REFINE, 2 * (size_t)std::min<int64_t>(piece, cb) * per);
+        if (!dl || !rec) return 1000 + (int)cudaErrorMemoryAllocation;
+        dl += slot * cb;
+        rec += (size_t)slot * std::min<int64_t>(piece, cb) * z.rec_rows;
+        LQRB_CUDA(h, cudaMemcpyAsync(dl, list.data() + first, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        KktCoopExtra ex;
+        ex.list = dl;
+        int32_t rc = launch_kkt_coop(h, s.n, s.m, s.N, s.p, s.hess, s.d2x, flags, cnt, dc, rec, dz, mult, res, info, st, &ex);
+        if (rc) return rc;
+        LQRB_CUDA(h, cudaStreamSynchronize(st));  // `list` (pageable) must outlive the copy
+    }
+    h->last_refined = (int64_t)list.size();
+    return 0;
+}
+
 template <int n, int m, int HESS>
 static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, int soc, const double *data,
                              double *scratch, double *dz, double *mult, double *res, int32_t *info,
@@ -239,12 +288,14 @@ static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, 
     auto kern = blocks ? khw::kkt_hw2_kernel<n, m, HESS, WARPS, MINB> : khw::kkt_hw_kernel<n, m, HESS, WARPS, MINB>;
     LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
+    int64_t refined = 0;
     for (int64_t first = 0; first < batch; first += chunk) {
         const int64_t cb = std::min(chunk, batch - first);
-        // scratch (reused by every chunk): [records: cb x N x REC] [Hi: cb x N x HI] [hinfo: cb]
+        // scratch (reused by every chunk): [records: cb x N x REC] [Hi: cb x N x HI] [hinfo: cb] [cinfo: cb]
         double *recs = scratch;
         double *hinv = recs + (size_t)cb * N * L::REC;
         int32_t *hinfo = reinterpret_cast<int32_t *>(hinv + (size_t)cb * N * L::HI);
+        int32_t *cinfo = hinfo + cb;  // conditioning estimates (the "+ 1" double per instance holds both)
         const double *dc = data + first * L::data_rows(N);
         LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)cb * sizeof(int32_t), st));
         const int64_t total = cb * N;
@@ -253,12 +304,19 @@ static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, 
         const int64_t pairs = (cb + 1) / 2;
         kern<<<(unsigned)((pairs + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(
             dc, hinv, hinfo, recs, dz + first * L::z_rows(N), mult + first * L::mult_rows(N),
-            res ? res + first * L::z_rows(N) : nullptr, info ? info + first : nullptr, N, cb, soc);
+            res ? res + first * L::z_rows(N) : nullptr, info ? info + first : nullptr, cinfo, N, cb, soc);
         LQRB_LAUNCH_CHECK(h, "kkt_hw_kernel");
+        int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * L::z_rows(N),
+                                                 mult + first * L::mult_rows(N), res ? res + first * L::z_rows(N) : nullptr,
+                                                 info ? info + first : nullptr, st);
+        if (rc) return rc;
+        refined += h->last_refined;
     }
-    char nm[96];
+    char nm[128];
     snprintf(nm, sizeof nm, "kkt_hw<%d,%d,p=%d/0/%d,hess=%d%s%s>", n, m, n, n, HESS, soc ? ",soc" : "", blocks ? "" : ",cols");
     h->kernel_name = nm;
+    if (refined) h->kernel_name += "+kkt_coop[" + std::to_string(refined) + " ill-conditioned]";
+    h->last_refined = refined;
     return 0;
 }
 
@@ -274,27 +332,37 @@ static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch,
     LQRB_CUDA(h, cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
     LQRB_CUDA(h, cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
     const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
+    int64_t refined = 0;
     for (int64_t first = 0; first < batch; first += chunk) {
         const int64_t cb = std::min(chunk, batch - first);
-        // scratch (reused by every chunk): [records: cb x N x REC] [pre-pass slots: cb x prep_rows] [hinfo: cb]
+        // scratch (reused by every chunk): [records: cb x N x REC] [pre-pass slots: cb x prep_rows] [hinfo: cb] [cinfo: cb]
         double *recs = scratch;
         double *prep = recs + (size_t)cb * N * L::REC;
         int32_t *hinfo = reinterpret_cast<int32_t *>(prep + (size_t)cb * L::prep_rows(N));
+        int32_t *cinfo = hinfo + cb;  // conditioning estimates (the "+ 1" double per instance holds both)
         const double *dc = data + first * L::data_rows(N);
         LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)cb * sizeof(int32_t), st));
+        LQRB_CUDA(h, cudaMemsetAsync(cinfo, 0, (size_t)cb * sizeof(int32_t), st));
         kcta::kkt_cta_ri_kernel<n, m, HESS><<<(unsigned)((cb * (N - 1) + 7) / 8), 128, 0, st>>>(dc, prep, hinfo, N, cb, soc);
         LQRB_LAUNCH_CHECK(h, "kkt_cta_ri_kernel");
-        pk<<<(unsigned)(cb * N), L::THREADS, psm, st>>>(dc, prep, hinfo, N, cb, soc);
+        pk<<<(unsigned)(cb * N), L::THREADS, psm, st>>>(dc, prep, hinfo, cinfo, N, cb, soc);
         LQRB_LAUNCH_CHECK(h, "kkt_cta_prep_kernel");
         mk<<<(unsigned)cb, L::THREADS, msm, st>>>(dc, prep, hinfo, recs, dz + first * L::z_rows(N),
                                                   mult + first * L::mult_rows(N),
                                                   res ? res + first * L::z_rows(N) : nullptr,
-                                                  info ? info + first : nullptr, N, cb, soc);
+                                                  info ? info + first : nullptr, cinfo, N, cb, soc);
         LQRB_LAUNCH_CHECK(h, "kkt_cta_kernel");
+        int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * L::z_rows(N),
+                                                 mult + first * L::mult_rows(N), res ? res + first * L::z_rows(N) : nullptr,
+                                                 info ? info + first : nullptr, st);
+        if (rc) return rc;
+        refined += h->last_refined;
     }
-    char nm[96];
+    char nm[128];
     snprintf(nm, sizeof nm, "kkt_cta_dmma<%d,%d,p=%d/0/%d,hess=%d%s>", n, m, n, n, HESS, soc ? ",soc" : "");
     h->kernel_name = nm;
+    if (refined) h->kernel_name += "+kkt_coop[" + std::to_string(refined) + " ill-conditioned]";
+    h->last_refined = refined;
     return 0;
 }
 
@@ -831,5 +899,17 @@ extern "C" int32_t lqrb_kkt_get_shur_f64(lqrb_handle_t h, int32_t n, int32_t m, 
             LQRB_CUDA(h, cudaMemcpy(U + i * z.P * z.P, dense.data(), (size_t)z.P * z.P * 8, cudaMemcpyDefault));
         }
     }
+    return 0;
+}
+
+
+extern "C" int32_t lqrb_kkt_last_condition(lqrb_handle_t h, int64_t count, int32_t *log2_pivot_ratio, int64_t *resolved) {
+    if (!h) return -1;
+    if (count < 0) return -2;
+    if (log2_pivot_ratio) {
+        for (int64_t i = 0; i < count; ++i)
+            log2_pivot_ratio[i] = i < (int64_t)h->last_cond.size() ? h->last_cond[(size_t)i] : -1;
+    }
+    if (resolved) *resolved = h->last_refined;
     return 0;
 }

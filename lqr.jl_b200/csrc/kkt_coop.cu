@@ -139,6 +139,7 @@ struct KktCoopArgs {
     const int64_t *rec_off;   // device: record row offset per knot [N+1]
     const int64_t *mult_off;  // device: mult row offset of mu_k per knot [N+1]
     double *gws;              // global workspace (nullptr: shared memory)
+    const int32_t *list;      // optional: the instances to process (batch = its length); nullptr = 0..batch-1
     const double *rhs;        // phase 2: per instance [per knot: g (w) | d (p2) | c (ps)], tile width 1
     double *sdump;            // optional: raw Schur blocks S (before cholesky!) in the record layout
     int phase;                // 0 fused, 1 factor only, 2 solve with the kept factor
@@ -166,11 +167,11 @@ __global__ void __launch_bounds__(THREADS) kkt_coop_kernel(KktCoopArgs a) {
     for (int64_t inst = (int64_t)blockIdx.x * IPC + g; inst < a.batch;
          inst += (int64_t)gridDim.x * IPC) {
         const bool active = true;
-        const int64_t ii = inst;
+        const int64_t ii = a.list ? (int64_t)a.list[inst] : inst;  // optional instance list (re-solve of a subset)
         const int64_t data_rows = a.knot_off[N], rec_rows = a.rec_off[N], mult_rows = a.mult_off[N];
         const int64_t NN = (int64_t)N * n + (int64_t)(N - 1) * m;
         const double *db = a.data + ii * data_rows;
-        double *sb = a.scratch + ii * rec_rows;
+        double *sb = a.scratch + inst * rec_rows;  // records by position: a list needs only its own slots
         double *zb = a.dz + ii * NN, *mb = a.mult + ii * mult_rows;
         double *rb = a.res ? a.res + ii * NN : nullptr;
         int st_all = 0;
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(THREADS) kkt_coop_kernel(KktCoopArgs a) {
         //    calculate_shur_factors! and forward_substitution! run here, no O(n^3) work.
         const bool fac = a.phase != 2;
         const double *rhsb = a.rhs ? a.rhs + ii * (NN + mult_rows) : nullptr;
-        double *sdb = a.sdump ? a.sdump + ii * rec_rows : nullptr;
+        double *sdb = a.sdump ? a.sdump + inst * rec_rows : nullptr;
         for (int k = 0; k < N; ++k) {
             const int mk = k < N - 1 ? m : 0, w = n + mk, p1 = k > 0 ? n : 0, ps = a.p[k],
                       p2 = k < N - 1 ? n : 0;
@@ -238,10 +239,10 @@ __global__ void __launch_bounds__(THREADS) kkt_coop_kernel(KktCoopArgs a) {
                 group_sync<G>();
                 if (fac) {
                     if (sd) {
+                        // raw S block C_{k-1} = D1 H^-1 D1' (left here by knot k-1) + D2 H^-1 D2', and d_{k-1} likewise
                         double *sC = sd + (int64_t)ps * ps + (int64_t)p1 * ps + (int64_t)ps * p2 + (int64_t)p1 * p2 + ps;
-                        for (int e = t; e < n * n; e += G) sC[e] = Ah[e];
-                        for (int e = t; e < n; e += G) sC[n * n + e] = dp[e];
-                        group_sync<G>();
+                        co_gemm<G>(0, 0, n, n, w, 1.0, D2, n, W2, w, 1.0, sC, n, t);
+                        co_gemm<G>(0, 0, n, 1, w, 1.0, D2, n, hg, w, 1.0, sC + n * n, n, t);
                     }
                     st = co_chol<G>(Ah, n, n, t);
                     if (st && !st_all) st_all = k * 1000 + 200 + st;
@@ -313,6 +314,15 @@ __global__ void __launch_bounds__(THREADS) kkt_coop_kernel(KktCoopArgs a) {
                 for (int e = t; e < n; e += G) dp[e] = -dvp[e];
                 group_sync<G>();
                 co_gemm<G>(0, 0, n, 1, w, 1.0, D1, n, hg, w, 1.0, dp, n, t);  // rho2 - d
+                if (fac && sdb) {
+                    // the unfactored parts of C_k and d_k go to knot k+1's slot (the A_{k+1} = C_k aliasing)
+                    const int psn = a.p[k + 1], p2n = k + 1 < N - 1 ? n : 0;
+                    double *sCn = sdb + a.rec_off[k + 1] + (int64_t)psn * psn + (int64_t)n * psn + (int64_t)psn * p2n +
+                                  (int64_t)n * p2n + psn;
+                    for (int e = t; e < n * n; e += G) sCn[e] = Cp[e];
+                    for (int e = t; e < n; e += G) sCn[n * n + e] = dp[e];
+                    group_sync<G>();
+                }
                 if (p1) {
                     if (fac) co_gemm<G>(1, 0, n, n, n, -1.0, Fh, n, Fh, n, 1.0, Cp, n, t);
                     co_gemm<G>(1, 0, n, 1, n, -1.0, Fh, n, lamp, n, 1.0, dp, n, t);
@@ -333,7 +343,7 @@ __global__ void __launch_bounds__(THREADS) kkt_coop_kernel(KktCoopArgs a) {
             }
             group_sync<G>();
         }
-        if (active && a.info && t == 0) a.info[inst] = st_all;
+        if (active && a.info && t == 0) a.info[ii] = st_all;
         if (a.phase == 1) continue;  // factor only
 
         // ======================= backward sweep =======================
@@ -480,6 +490,7 @@ int32_t launch_kkt_coop(lqrb_context *h, int n, int m, int N, const int32_t *p, 
     a.data = data; a.scratch = scratch; a.dz = dz; a.mult = mult; a.res = res; a.info = info;
     a.p = tb.p; a.knot_off = tb.knot_off; a.rec_off = tb.rec_off; a.mult_off = tb.mult_off;
     a.gws = nullptr;
+    a.list = extra ? extra->list : nullptr;
     a.rhs = extra ? extra->rhs : nullptr;
     a.sdump = extra ? extra->sdump : nullptr;
     a.phase = extra ? extra->phase : 0;

@@ -27,6 +27,7 @@ struct KktCoopExtra {
     int phase = 0;
     const double *rhs = nullptr;
     double *sdump = nullptr;
+    const int32_t *list = nullptr;  // device list of instance indices to process (batch = its length)
 };
 
 int32_t launch_kkt_coop(lqrb_context *h, int n, int m, int N, const int32_t *p, int hess, int d2x,

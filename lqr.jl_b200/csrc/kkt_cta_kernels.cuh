@@ -63,7 +63,9 @@ struct Lay {
 // holds rows 2h, 2h+1 of column c; the pivot column, the pivot and the lane's own row-kk entry come by
 // shuffle, so a pivot step costs 7 FP64 instructions (they queue behind the other CTA's DMMAs) and no
 // shared-memory round trip.  Returns the 1-based index of the first non-positive pivot or 0.
-__device__ __forceinline__ int gj8_warp(double &a0, double &a1, int lane) {
+// lo / hi: running min / max of the high words of the (positive) pivots — integer compares order positive doubles, so
+// (hi - lo) >> 20 is log2 of the pivot ratio, the conditioning estimate of the block (integer pipe, off the FP64 chain).
+__device__ __forceinline__ int gj8_warp(double &a0, double &a1, int lane, int &lo, int &hi) {
     const int h = lane >> 3, c = lane & 7;
     int bad = 0;
     SM_UNROLL
@@ -74,6 +76,8 @@ __device__ __forceinline__ int gj8_warp(double &a0, double &a1, int lane) {
         const double piv = __shfl_sync(0xffffffffu, mine, ((kk >> 1) << 3) | kk);
         const double akk = __shfl_sync(0xffffffffu, mine, ((kk >> 1) << 3) | c);
         if (!(piv > 0.0) && bad == 0) bad = kk + 1;
+        lo = min(lo, __double2hiint(piv));
+        hi = max(hi, __double2hiint(piv));
         const double p = rdmma::fast_rcp3(piv);
         const bool pc = c == kk;
         const double f = pc ? -p : akk * p;
@@ -86,6 +90,9 @@ __device__ __forceinline__ int gj8_warp(double &a0, double &a1, int lane) {
     return bad;
 }
 
+// log2 of the pivot ratio from the min / max pivot high words (0 when a pivot was not positive: info says so)
+__device__ __forceinline__ int pivot_bits(int lo, int hi) { return (lo > 0 && hi >= lo) ? (hi - lo) >> 20 : 0; }
+
 // ------------------------------------------------------------------ block Gauss-Jordan ----------------
 // In place: S[ct][e] = tile (wp, ct) of an SPD n x n matrix in C-fragment layout -> the same tiles of its
 // inverse.  pan: 2 x NT*64 doubles (8 x 8 tiles, row-major, double-buffered column panels), pis: 2 x 64 doubles
@@ -97,6 +104,7 @@ __device__ __forceinline__ int gj8_warp(double &a0, double &a1, int lane) {
 // tile of the next column panel before the barrier (look-ahead).  In-place Gauss-Jordan leaves
 // A_kj = A_jk' for the columns still to be eliminated (j > kb) and A_kj = -A_jk' for the ones already done
 // (A_ik <- -A_ik Pi but A_kj <- +Pi A_kj), so the pivot row is taken from the column panel with that sign.
+// flag[1], flag[2]: min / max pivot high word over the whole matrix (see gj8_warp), set by the caller to INT_MAX / 0.
 template <int NT>
 __device__ __forceinline__ int block_gj_inverse(double (&S)[NT][2], double *pan, double *pis, double *colb,
                                                 int *flag, int wp, int lane) {
@@ -107,10 +115,15 @@ __device__ __forceinline__ int block_gj_inverse(double (&S)[NT][2], double *pan,
     auto pivot = [&](const double *p64, double *po, int kb) {
         __syncwarp();
         double a0 = p64[(2 * hh) * 8 + cc], a1 = p64[(2 * hh + 1) * 8 + cc];
-        const int bad = gj8_warp(a0, a1, lane);
+        int lo = 0x7fffffff, hi = 0;
+        const int bad = gj8_warp(a0, a1, lane, lo, hi);
         po[(2 * hh) * 8 + cc] = a0;
         po[(2 * hh + 1) * 8 + cc] = a1;
-        if (bad != 0 && lane == 0 && *flag == 0) *flag = 8 * kb + bad;
+        if (lane == 0) {
+            if (bad != 0 && *flag == 0) *flag = 8 * kb + bad;
+            atomicMin(flag + 1, lo);
+            atomicMax(flag + 2, hi);
+        }
     };
     // prologue: column panel 0 and its pivot
     *reinterpret_cast<double2 *>(pan + wp * 64 + g * 8 + 2 * q) = make_double2(S[0][0], S[0][1]);
@@ -211,14 +224,15 @@ __global__ void __launch_bounds__(128)
 template <int n, int m, int HESS>
 __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     kkt_cta_prep_kernel(const double *__restrict__ data, double *__restrict__ prep, int32_t *__restrict__ hinfo,
-                        int N, int64_t batch, int soc) {
+                        int32_t *__restrict__ cinfo, int N, int64_t batch, int soc) {
     using L = Lay<n, m, HESS>;
     constexpr int NT = L::NT, UT = L::UT, w = L::w, LA = L::LA, THREADS = L::THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sm = reinterpret_cast<double *>(smem_raw);
     double *As = sm + L::pA, *Qs = sm + L::pQ, *pan = sm + L::pPan, *pis = sm + L::pPi, *colb = sm + L::pCol,
            *Ris = sm + L::pRi, *vq = sm + L::pV, *vhg = vq + w, *vd = vhg + w, *vtmp = vd + w;
-    __shared__ int flag;
+    __shared__ int flag3[3];
+    int &flag = flag3[0];
     const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int64_t inst = blockIdx.x / N;
     const int k = (int)(blockIdx.x % N);
@@ -230,6 +244,8 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     __shared__ __align__(8) uint64_t xbar;
     if (tid == 0) {
         flag = 0;
+        flag3[1] = 0x7fffffff;
+        flag3[2] = 0;
         mbar_init(&xbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -286,6 +302,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     __syncthreads();
     bad = flag;
     if (bad != 0 && tid == 0) atomicMin(hinfo + inst, (k + 1) * 1000 + bad);
+    if (tid == 0) atomicMax(cinfo + inst, pivot_bits(flag3[1], flag3[2]));  // conditioning estimate of Q_k
     // ---- hg = Hi g
     if (tid < n) {
         double s0 = 0.0, s1 = 0.0;
@@ -415,7 +432,8 @@ template <int n, int m, int HESS>
 __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     kkt_cta_kernel(const double *__restrict__ data, const double *__restrict__ prep, const int32_t *__restrict__ hinfo,
                    double *__restrict__ recs, double *__restrict__ dz, double *__restrict__ mult,
-                   double *__restrict__ res, int32_t *__restrict__ info, int N, int64_t batch, int soc) {
+                   double *__restrict__ res, int32_t *__restrict__ info, int32_t *__restrict__ cinfo, int N,
+                   int64_t batch, int soc) {
     using L = Lay<n, m, HESS>;
     constexpr int NT = L::NT, w = L::w, LB = L::LB, THREADS = L::THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -424,7 +442,8 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
            *ys = sm + L::mV, *vs = ys + n, *dps = vs + n, *red = dps + n /* 4n */, *xs = red + 4 * n, *rsv = xs + w,
            *xps = rsv + w;
     uint64_t *bar = reinterpret_cast<uint64_t *>(sm + L::mBar);
-    __shared__ int flag;
+    __shared__ int flag3[3];
+    int &flag = flag3[0];
     const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int64_t inst = blockIdx.x;
     const double *db = data + inst * L::data_rows(N);
@@ -440,6 +459,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         flag = 0;
     }
+    int spread = 0;  // thread 0: largest log2 pivot ratio of any Sigma_k (conditioning estimate, see gj8_warp)
     if (tid < n) dps[tid] = 0.0;
     __syncthreads();
     uint32_t ph = 0;
@@ -475,11 +495,16 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         }
         if (tid < n) ys[tid] = dps[tid] - slot[L::hHg + tid];  // y = dp - hg_x  (d += next.r_[1])
         const double rho = tid < n ? slot[L::hRho + tid] : 0.0;
-        if (tid == 0) flag = 0;
+        if (tid == 0) {
+            flag = 0;
+            flag3[1] = 0x7fffffff;
+            flag3[2] = 0;
+        }
         __syncthreads();
         {
             const int bad = block_gj_inverse<NT>(S, pan, pis, colb, &flag, wp, lane);
             if (bad != 0 && st_all == 0) st_all = k == 0 ? 1000 + 100 + bad : k * 1000 + 200 + bad;
+            if (tid == 0) spread = max(spread, pivot_bits(flag3[1], flag3[2]));
         }
         SM_UNROLL
         for (int ct = 0; ct < NT; ++ct)
@@ -576,11 +601,16 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     }
     // ---- last block: mu_N' = Bl'^-1 y_mu   (Cp, dps hold Bl' and y_mu)
     {
-        if (tid == 0) flag = 0;
+        if (tid == 0) {
+            flag = 0;
+            flag3[1] = 0x7fffffff;
+            flag3[2] = 0;
+        }
         if (tid < n) ys[tid] = dps[tid];
         __syncthreads();
         const int bad = block_gj_inverse<NT>(Cp, pan, pis, colb, &flag, wp, lane);
         if (bad != 0 && st_all == 0) st_all = N * 1000 + 100 + bad;
+        if (tid == 0) atomicMax(cinfo + inst, max(spread, pivot_bits(flag3[1], flag3[2])));
         SM_UNROLL
         for (int ct = 0; ct < NT; ++ct)
             *reinterpret_cast<double2 *>(Ss + r0 * LB + 8 * ct + 2 * q) = make_double2(Cp[ct][0], Cp[ct][1]);

@@ -276,7 +276,8 @@ template <int n, int m, int HESS, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     kkt_hw_kernel(const double *__restrict__ data, const double *__restrict__ hinv, const int32_t *__restrict__ hinfo,
                   double *__restrict__ recs, double *__restrict__ dz, double *__restrict__ mult,
-                  double *__restrict__ res, int32_t *__restrict__ info, int N, int64_t batch, int soc) {
+                  double *__restrict__ res, int32_t *__restrict__ info, int32_t *__restrict__ cinfo, int N,
+                   int64_t batch, int soc) {
     using L = Lay<n, m, HESS>;
     const double gsc = soc ? 0.0 : 1.0;  // second-order correction: g = 0
     constexpr int w = L::w;
@@ -507,6 +508,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const int hcode = hinfo[inst];
         info[inst] = hcode != 0x7f7f7f7f ? hcode : st_all;
     }
+    if (active && hl == 0) cinfo[inst] = -1;  // the column-per-lane variant does not track conditioning
     if (active && hl < n) __stcs(mb + L::mult_rows(N) - n + hl, -xcur);  // mu_N
 
     // ---------------- backward sweep: k = N-1 .. 0     x_{k-1} = v_k - U_k x_k,  Lambda = -x
@@ -653,9 +655,12 @@ __device__ __forceinline__ void gemm_rr2(double (&acc1)[bs][bs], double (&acc2)[
 
 // In-place Gauss-Jordan inverse of the SPD matrix held as register blocks: lane (bi, bj) of the half-warp
 // owns rows bs*bi.., columns bs*bj...  Returns the 1-based index of the first non-positive pivot or 0.
+// `spread` collects the largest (max - min) of the pivots' high words met so far: positive doubles order like their
+// high words, so spread >> 20 is log2 of the pivot ratio — the conditioning estimate of the explicit inverse (integer
+// pipe only, nothing on the FP64 chain).
 template <int n, int bs>
-__device__ __forceinline__ int gj_block(double (&a)[bs][bs], int bi, int bj) {
-    int bad = 0;
+__device__ __forceinline__ int gj_block(double (&a)[bs][bs], int bi, int bj, int &spread) {
+    int bad = 0, lo = 0x7fffffff, hi = 0;
     SM_UNROLL
     for (int k = 0; k < n; ++k) {
         const int kb = k / bs, kr = k % bs;
@@ -666,6 +671,8 @@ __device__ __forceinline__ int gj_block(double (&a)[bs][bs], int bi, int bj) {
         for (int r = 0; r < bs; ++r) pcol[r] = __shfl_sync(0xffffffffu, a[r][kr], (bi << 2) | kb, 16);  // A[rows][k]
         const double piv = __shfl_sync(0xffffffffu, a[kr][kr], (kb << 2) | kb, 16);
         if (!(piv > 0.0) && bad == 0) bad = k + 1;
+        lo = min(lo, __double2hiint(piv));
+        hi = max(hi, __double2hiint(piv));
         const double p = fast_rcp(piv);
         const bool rowk = bi == kb, colk = bj == kb;
         SM_UNROLL
@@ -679,6 +686,7 @@ __device__ __forceinline__ int gj_block(double (&a)[bs][bs], int bi, int bj) {
             }
         }
     }
+    if (lo > 0 && hi >= lo) spread = max(spread, hi - lo);
     return bad;
 }
 
@@ -686,7 +694,8 @@ template <int n, int m, int HESS, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     kkt_hw2_kernel(const double *__restrict__ data, const double *__restrict__ hinv, const int32_t *__restrict__ hinfo,
                    double *__restrict__ recs, double *__restrict__ dz, double *__restrict__ mult,
-                   double *__restrict__ res, int32_t *__restrict__ info, int N, int64_t batch, int soc) {
+                   double *__restrict__ res, int32_t *__restrict__ info, int32_t *__restrict__ cinfo, int N,
+                   int64_t batch, int soc) {
     using L = Lay<n, m, HESS>;
     static_assert(n % 4 == 0, "4 x 4 lane grid");
     constexpr int bs = n / 4;
@@ -746,7 +755,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     issue_hi(0);
     issue_core(0);
 
-    int st_all = 0;
+    int st_all = 0, spread = 0;
     double Cp[bs][bs], dp = 0.0;  // pending Schur complement (this lane's block) and right-hand side (entry hl)
     SM_UNROLL
     for (int r = 0; r < bs; ++r)
@@ -908,7 +917,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             issue_core(k + 1);
         }
         {
-            const int bad = gj_block<n, bs>(Sb, bi, bj);
+            const int bad = gj_block<n, bs>(Sb, bi, bj, spread);
             if (bad != 0 && st_all == 0) st_all = first ? 1000 + 100 + bad : k * 1000 + 200 + bad;
         }
         SM_UNROLL
@@ -981,7 +990,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     // ---------------- last block: mu_N' = Bl'^-1 y_mu  (Cp, dp hold Bl' and y_mu)
     double xcur = 0.0;
     {
-        const int bad = gj_block<n, bs>(Cp, bi, bj);
+        const int bad = gj_block<n, bs>(Cp, bi, bj, spread);
         if (bad != 0 && st_all == 0) st_all = N * 1000 + 100 + bad;
         SM_UNROLL
         for (int r = 0; r < bs; ++r)
@@ -1005,6 +1014,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const int hcode = hinfo[inst];
         info[inst] = hcode != 0x7f7f7f7f ? hcode : st_all;
     }
+    if (active && hl == 0) cinfo[inst] = spread >> 20;  // log2 of the worst pivot ratio of any Sigma_k
     if (active && hl < n) __stcs(mb + L::mult_rows(N) - n + hl, -xcur);  // mu_N
 
     // ---------------- backward sweep: k = N-1 .. 0     x_{k-1} = v_k - U_k x_k,  Lambda = -x

@@ -84,6 +84,14 @@ function fp64_peak(h::Handle, kind::Integer=1; seconds::Real=0.4)
     return t[]
 end
 
+"(log2 pivot ratios of the last tuned KKT launch, instances re-solved by the Cholesky-based kernel)"
+function kkt_last_condition(h::Handle, count::Integer)
+    out = zeros(Int32, count)
+    n = Ref{Int64}(0)
+    check(h, ccall((:lqrb_kkt_last_condition, lib), Int32, (Ptr{Cvoid}, Int64, Ptr{Int32}, Ref{Int64}), h.ptr, count, out, n))
+    return out, n[]
+end
+
 ptr_or_null(a::Nothing) = Ptr{Float64}(C_NULL)
 ptr_or_null(a::Array{Float64}) = pointer(a)
 iptr_or_null(a::Nothing) = Ptr{Int32}(C_NULL)
@@ -593,6 +601,6 @@ export Handle, LQRBError, LQRProblem, LQRSolution, DPSolver, solve!, rollout!, n
        DubinsSQP, SqpOptions, riccati_pack!, riccati_solve_packed!, riccati_unpack!, kkt_pack!, kkt_solve_packed!,
        kkt_unpack!, pack_rows!, unpack_rows!, riccati_layout, kkt_data_rows, kkt_knot_offset, padded_batch, num_cons,
        riccati_tile_width, kkt_tile_width, set_stream!, set_option!, synchronize, launch_count, last_kernel_name,
-       fp64_peak, version, device_count
+       fp64_peak, version, device_count, kkt_last_condition
 
 end # module
