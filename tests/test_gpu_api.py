@@ -249,8 +249,8 @@ def test_edge_cases_empty_batch_shortest_horizon_and_argument_errors(handle, ora
 
 
 @pytest.mark.parametrize("n,m,N,b,mid_p,hess,d2x", [(4, 1, 12, 5, 0, 2, False), (6, 3, 9, 3, 1, 1, False),
-                                                    (5, 2, 8, 4, 2, 0, True), (12, 4, 10, 3, 0, 1, False),
-                                                    (3, 2, 2, 2, 0, 1, False)])
+                                                    (5, 2, 10, 4, 1, 0, True), (12, 4, 10, 3, 0, 1, False),
+                                                    (3, 3, 2, 2, 0, 1, False)])
 def test_factor_once_solve_many(handle, oracle_mod, n, m, N, b, mid_p, hess, d2x):
     """lqrb_kkt_factor_f64 once, lqrb_kkt_solve_factored_f64 for several right-hand sides; each
     must equal the fused solve of the same data (oracle and the tuned / cooperative kernels)."""
