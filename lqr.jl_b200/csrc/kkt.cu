@@ -8,8 +8,11 @@
 #include "kkt_kernels.cuh"
 
 // default of the `kkt_cond_bits` option: instances whose worst Schur-block pivot ratio reaches 2^bits are solved again
-// by the Cholesky-based kernel (see kkt_resolve_ill_conditioned; calibrated with tools/stress_scales.py)
-#define LQRB_KKT_COND_BITS 12
+// by the Cholesky-based kernel (see kkt_resolve_ill_conditioned).  Calibrated with tools/stress_scales.py
+// (profiles/r2_conditioning_calibration.txt): the error of the explicit-inverse kernels is about 2^bits times that of
+// the reference's U'U order; every grid case where they miss 1e-10 while the reference order meets it has bits >= 7,
+// the BASELINE configs at their own scaling have bits 2-3.
+#define LQRB_KKT_COND_BITS 6
 
 // ------------------------------------------------------------------ size classes --------------
 // thread-per-instance instantiations: (n, m, P1, PM, PN) with p = [P1, PM, ..., PM, PN].

@@ -1,0 +1,62 @@
+"""GPU: the conditioning hole of the explicit-inverse KKT kernels (kkt_hw2, kkt_cta) is closed on the DEFAULT
+dispatch.  tools/stress_scales.py as tests: cost blocks rescaled by 10^-3 .. 10^5, every size class with a tuned kernel.
+
+Tolerance, stated per case: the relative error of (dz, multipliers) against the extended-precision global KKT solve
+(oracle/dense_kkt.py) must be <= max(1e-10, 4 x the error the reference's own operation order makes on the same
+input) — the second term only matters where the PROBLEM is ill-conditioned (Q 10^5 lighter than R: the CPU oracle
+itself is 1e-7 off) and no block-Cholesky solver, the reference included, can reach 1e-10."""
+import numpy as np
+import pytest
+
+from lqr_b200 import ops, problems
+
+pytestmark = pytest.mark.gpu
+
+SCALES = [(1.0, 1.0), (1e3, 1e-3), (1e-3, 1e3), (1e5, 1.0), (1.0, 1e-5), (1e2, 1e-2), (1e4, 1e-1), (79.0, 1e-3)]
+SIZES = [(12, 4, 40, 4, "kkt_hw<12,4"), (8, 4, 30, 4, "kkt_hw<8,4"), (64, 16, 12, 2, "kkt_cta_dmma<64,16"),
+         (24, 8, 20, 2, "kkt_cta_dmma<24,8")]
+
+
+def _err(prob, dz, lam):
+    from oracle import dense_kkt
+    e = 0.0
+    for i in range(dz.shape[0]):
+        zt, lt = dense_kkt.kkt_truth(prob, i)
+        e = max(e, np.linalg.norm(dz[i] - zt) / np.linalg.norm(zt), np.linalg.norm(lam[i] - lt) / np.linalg.norm(lt))
+    return e
+
+
+@pytest.mark.parametrize("qs,rs", SCALES)
+@pytest.mark.parametrize("n,m,N,b,kern", SIZES)
+def test_default_dispatch_under_rescaled_costs(handle, oracle_mod, n, m, N, b, kern, qs, rs):
+    prob = problems.random_lqr_kkt(n, m, N, b, seed=200 + int(np.log10(qs) * 7 + np.log10(rs)), mid_p=0, hess_mode=1)
+    prob["Q"] = prob["Q"] * qs
+    prob["R"] = prob["R"] * rs
+    dz, lam, info = ops.kkt_solve_problem(prob, handle=handle)
+    assert handle.last_kernel.startswith(kern) and (info == 0).all()
+    bits, resolved = handle.kkt_last_condition(b)
+    dzo, lamo, _ = oracle_mod.kkt_solve(prob)
+    e, eo = _err(prob, dz, lam), _err(prob, dzo, lamo)
+    assert e <= max(1e-10, 4.0 * eo), (e, eo, bits.tolist(), resolved, handle.last_kernel)
+    # flagged instances went through the Cholesky-based kernel, the others did not
+    assert resolved == int((bits >= 6).sum())
+    assert ("+kkt_coop[" in handle.last_kernel) == (resolved > 0)
+
+
+def test_condition_estimate_and_switch(handle):
+    """kkt_refine = 0 leaves the tuned kernel alone; the estimate grows with the spread of the cost scaling."""
+    prob = problems.random_lqr_kkt(8, 4, 30, 4, seed=3, mid_p=0, hess_mode=1)
+    ops.kkt_solve_problem(prob, handle=handle)
+    b0, r0 = handle.kkt_last_condition(4)
+    prob["Q"] = prob["Q"] * 1e3
+    prob["R"] = prob["R"] * 1e-3
+    dz1, lam1, _ = ops.kkt_solve_problem(prob, handle=handle)
+    b1, r1 = handle.kkt_last_condition(4)
+    assert r0 == 0 and r1 == 4 and (b1 > b0).all() and (b0 >= 0).all()
+    handle.set_option("kkt_refine", 0)
+    try:
+        dz2, lam2, _ = ops.kkt_solve_problem(prob, handle=handle)
+        assert "+kkt_coop" not in handle.last_kernel
+    finally:
+        handle.set_option("kkt_refine", 1)
+    assert not np.array_equal(dz1, dz2)

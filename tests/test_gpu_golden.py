@@ -22,13 +22,17 @@ def _rel(a, b):
                                          ("large_kkt", "kkt_cta_dmma<64,16"), ("mid32_kkt", "kkt_cta_dmma<32,8"),
                                          ("mid24_kkt", "kkt_cta_dmma<24,8"), ("dubins_stage_kkt", "kkt_tpi<3,2,p=3/1/3"),
                                          ("explicit_d2_kkt", "kkt_coop")])
-def test_kkt_golden(handle, name, kernel):
+def test_kkt_golden(handle, oracle_mod, name, kernel):
     from tests.golden.make_golden import KKT_CASES
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
-    dz, lam, info = ops.kkt_solve_problem(KKT_CASES[name](), handle=handle)
+    prob = KKT_CASES[name]()
+    dz, lam, info = ops.kkt_solve_problem(prob, handle=handle)
     assert handle.last_kernel.startswith(kernel) and (info == 0).all()
-    tol = 1e-9 if name in ("large_kkt", "mid32_kkt", "mid24_kkt") else TOL   # n=64 at N=8: cond ~1e6 (same allowance as test_gpu_kkt.py)
-    assert _rel(dz[0], z["dz"]) <= tol and _rel(lam[0], z["mult"]) <= tol
+    # 1e-10 against the golden (extended-precision) vectors; where the reference's own operation order (the CPU
+    # oracle) is itself further than that from them (short-horizon n >= 24 cases, cond ~1e6), 4x its error
+    dzo, lamo, _ = oracle_mod.kkt_solve(prob)
+    tol = max(TOL, 4.0 * max(_rel(dzo[0], z["dz"]), _rel(lamo[0], z["mult"])))
+    assert _rel(dz[0], z["dz"]) <= tol and _rel(lam[0], z["mult"]) <= tol, (tol, handle.last_kernel)
 
 
 @pytest.mark.parametrize("name,kernel", [("cartpole_riccati", "riccati_tpi<4,1"), ("quad_riccati", "riccati_dmma<12,4"),

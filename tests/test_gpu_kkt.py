@@ -139,10 +139,19 @@ def test_irregular_stage_pattern(handle, oracle_mod):
 
 
 def test_large_dense_schur_variant(handle, oracle_mod):
-    """config 5b shape (n=64, m=16) at a short horizon (cond ~1e6: held to 1e-9)."""
+    """config 5b shape (n=64, m=16) at a short horizon: 1e-10 against the extended-precision solve, or 4x the error
+    the reference's own operation order (the CPU oracle) makes on this input if that is larger (measured here)."""
+    from oracle import dense_kkt
     prob = problems.random_lqr_kkt(64, 16, 6, 2, seed=4)
-    _check(prob, handle, oracle_mod, tol=1e-9, res_tol=1e-9)
-    assert handle.last_kernel.startswith("kkt_cta_dmma<64,16")
+    dz, lam, info = ops.kkt_solve_problem(prob, handle=handle)
+    assert handle.last_kernel.startswith("kkt_cta_dmma<64,16") and (info == 0).all()
+    dzo, lamo, _ = oracle_mod.kkt_solve(prob)
+    for i in range(2):
+        zt, lt = dense_kkt.kkt_truth(prob, i)
+        tol = max(TOL, 4.0 * max(_rel(dzo[i], zt), _rel(lamo[i], lt)))
+        assert _rel(dz[i], zt) <= tol and _rel(lam[i], lt) <= tol, (i, tol)
+        rs, rp = dense_kkt.kkt_residuals(prob, i, dz[i], lam[i])
+        assert rs <= TOL and rp <= TOL, (rs, rp)
 
 
 @pytest.mark.parametrize("N,batch", [(12, 3), (101, 2), (30, 5)])

@@ -16,6 +16,7 @@ from lqr_b200 import _lib, ops, problems  # noqa: E402
 from oracle import dense_kkt  # noqa: E402
 
 h = _lib.Handle(0)
+DEFAULT_BITS = 6   # LQRB_KKT_COND_BITS in csrc/kkt.cu
 
 
 def err_vs_truth(prob, dz, lam, insts):
@@ -36,10 +37,10 @@ for (n, m, N, b) in [(12, 4, 40, 4), (8, 4, 30, 4), (64, 16, 12, 2), (24, 8, 20,
         p["Q"] = p["Q"] * qs
         p["R"] = p["R"] * rs_
         insts = range(b)
-        h.set_option("kkt_refine", 0)
+        h.set_option("kkt_cond_bits", 99)  # estimates are read back, nothing is re-solved: the tuned kernel alone
         dz0, lam0, i0 = ops.kkt_solve_problem(p, handle=h)
         bits, _ = h.kkt_last_condition(b)
-        h.set_option("kkt_refine", 1)
+        h.set_option("kkt_cond_bits", DEFAULT_BITS)
         dz1, lam1, i1 = ops.kkt_solve_problem(p, handle=h)
         k1 = h.last_kernel
         _, nres = h.kkt_last_condition(b)
