@@ -155,6 +155,16 @@ int32_t lqrb_rollout_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, 
                          int32_t flags, const double *A, const double *B, const double *x0,
                          const double *U, double *X);
 
+/* Replaces solve!(sol, ::LeastSquaresSolver, prob) : src/least_squares.jl:158-190 — the condensed form of the
+ * unconstrained LTI problem: T (block Toeplitz, build_toeplitz :136-156), (T' Qbar T + Rbar) U = -T' Qbar L x0 by
+ * Cholesky (:176-178), then rollout! (:195-202).  O((N m)^3) work and (N m)^2 doubles per instance: for short
+ * horizons, and the reference's independent cross-check of the Riccati path (test/least_squares.jl:38).
+ *   A[n,n,batch] B[n,m,batch] Q[n,n,batch] R[m,m,batch] Qf[n,n,batch] x0[n,batch] (host or device)
+ *   -> Z[NN,batch] (Primals order), info[batch] | NULL (potrf info of the condensed Hessian).               */
+int32_t lqrb_lsq_solve_f64(lqrb_handle_t handle, int32_t n, int32_t m, int32_t N, int64_t batch,
+                           const double *A, const double *B, const double *Q, const double *R,
+                           const double *Qf, const double *x0, double *Z, int32_t *info);
+
 /* ---------------------------------------------------------------- BlockCholesky ------------- */
 /* Replaces cholesky!(chol, A, B[, C]) : src/block_cholesky.jl:55-91.  Instance-major:
  *   A[n,n,batch] B[m,m,batch] C[m,n,batch] (C NULL unless DENSE) -> M[(n+m),(n+m),batch]

@@ -32,7 +32,7 @@ from . import _lib, ops
 from ._lib import HESS_BLOCKDIAG, HESS_DENSE, HESS_DIAG, Handle, LqrbError
 
 __all__ = [
-    "LQRProblem", "Primals", "LQRSolution", "DPSolver", "solve_", "rollout_", "size", "num_vars",
+    "LQRProblem", "Primals", "LQRSolution", "DPSolver", "LeastSquaresSolver", "solve_", "rollout_", "size", "num_vars",
     "BlockCholesky", "cholesky_", "ldiv_", "ldiv", "InvertedQuadratic", "update_cost_", "update_cholesky_",
     "gradient", "ConstraintBlock", "ConstraintBlocks", "dims", "copy_blocks_", "num_constraints",
     "CholeskySolver", "build_shur_factors", "calculate_shur_factors_", "forward_substitution_",
@@ -174,12 +174,37 @@ class DPSolver:
         self.handle = handle or ops.default_handle(device)
 
 
+class LeastSquaresSolver:
+    """LeastSquaresSolver(prob) (src/least_squares.jl:1-59): the condensed form of the unconstrained LTI problem —
+    block-Toeplitz T, (T'QT + R) U = -T'Q L x0 by Cholesky, then rollout!.  The Toeplitz matrices live in a device
+    workspace (lqrb_lsq_solve_f64); O((N m)^3) per instance, for short horizons and as a cross-check of the Riccati
+    path (test/least_squares.jl:38)."""
+
+    def __init__(self, prob: LQRProblem, handle: Handle | None = None, device: int = 0):
+        if prob.ltv or prob.q is not None or prob.r is not None or prob.qf is not None:
+            raise LqrbError("LeastSquaresSolver takes the reference's time-invariant LQRProblem without affine terms")
+        self.n, self.m, self.N = size(prob)
+        self.handle = handle or ops.default_handle(device)
+        self.info = np.zeros(prob.batch, dtype=np.int32)
+
+
 def solve_(sol, solver, prob=None):
     """solve!(sol, solver::DPSolver, prob) (src/dynamic_programming.jl:54-72): backward Riccati pass then
-    forward rollout; or solve!(solver::CholeskySolver) (src/cholesky_solver.jl:109-120) when called with
-    a CholeskySolver."""
+    forward rollout; solve!(sol::Primals, solver::LeastSquaresSolver, prob) (src/least_squares.jl:158-190); or
+    solve!(solver::CholeskySolver) (src/cholesky_solver.jl:109-120) when called with a CholeskySolver."""
     if isinstance(sol, CholeskySolver):
         return sol.solve_()
+    if isinstance(solver, LeastSquaresSolver):
+        n, m, N = solver.n, solver.m, solver.N
+        Z = np.zeros((prob.batch, _lib.num_vars(n, m, N)))
+        ops.lsq_solve(solver.handle, n, m, N, prob.batch, ops.cm(prob.A), ops.cm(prob.B), ops.cm(prob.Q), ops.cm(prob.R),
+                      ops.cm(prob.Qf), ops.f64(prob.x0), Z, solver.info)
+        if isinstance(sol, Primals):
+            sol.Z[:] = Z
+        else:
+            sol.X[:], sol.U[:] = ops.split_primals(Z, n, m, N)
+            sol.info[:] = solver.info
+        return sol
     X, U, K, kff, info = ops.riccati_solve_problem(prob.as_dict(), want_gains=True, handle=solver.handle)
     sol.X[:], sol.U[:], sol.K[:], sol.d[:], sol.info[:] = X, U, K, kff, info
     return sol

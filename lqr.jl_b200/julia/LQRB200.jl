@@ -197,6 +197,27 @@ function rollout!(X::Array{Float64,3}, U::Array{Float64,3}, prob::LQRProblem, ha
     return X
 end
 
+# ------------------------------------------------------------------ LeastSquaresSolver (src/least_squares.jl)
+"LeastSquaresSolver(prob): the condensed (block-Toeplitz) form of the unconstrained LTI problem, src/least_squares.jl:1-59"
+struct LeastSquaresSolver
+    handle::Handle
+    info::Vector{Int32}
+end
+LeastSquaresSolver(prob::LQRProblem; device=0) = LeastSquaresSolver(Handle(device), zeros(Int32, batchsize(prob)))
+"solve!(sol, solver::LeastSquaresSolver, prob): src/least_squares.jl:158-190 ((T'QT + R) U = -T'Q L x0 by Cholesky, rollout!)"
+function solve!(sol::LQRSolution, solver::LeastSquaresSolver, prob::LQRProblem)
+    islti(prob) || throw(ArgumentError("LeastSquaresSolver takes the time-invariant LQRProblem"))
+    n, m, N = size(prob)
+    GC.@preserve sol prob solver begin
+        rc = ccall((:lqrb_lsq_solve_f64, lib), Int32,
+            (Ptr{Cvoid}, Int32, Int32, Int32, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+            solver.handle.ptr, n, m, N, batchsize(prob), prob.A, prob.B, prob.Q, prob.R, prob.Qf, prob.x0, sol.Z, solver.info)
+    end
+    check(solver.handle, rc)
+    return sol
+end
+
 # ------------------------------------------------------------------ BlockCholesky (src/block_cholesky.jl) -
 struct BlockCholesky
     handle::Handle
@@ -592,7 +613,7 @@ kkt_unpack!(h::Handle, n, m, N, batch, p::Vector{Int32}, hess_mode, explicit_d2,
          Ptr{Float64}, Ptr{Float64}),
         h.ptr, n, m, N, batch, p, hess_mode, explicit_d2, dzp, multp, resp, dz, mult, res))
 
-export Handle, LQRBError, LQRProblem, LQRSolution, DPSolver, solve!, rollout!, num_vars, state, control,
+export Handle, LQRBError, LQRProblem, LQRSolution, DPSolver, LeastSquaresSolver, solve!, rollout!, num_vars, state, control,
        BlockCholesky, InvertedQuadratic, update_cost!, update_cholesky!, gradient,
        ConstraintBlock, ConstraintBlocks, dims, copy_blocks!,
        CholeskySolver, build_shur_factors, calculate_shur_factors!, forward_substitution!, backward_substitution!,

@@ -63,6 +63,11 @@ def rollout(h: Handle, n, m, N, batch, flags, A, B, x0, U, X):
     h.call("lqrb_rollout_f64", n, m, N, batch, flags, ptr(A), ptr(B), ptr(x0), ptr(U), ptr(X))
 
 
+def lsq_solve(h: Handle, n, m, N, batch, A, B, Q, R, Qf, x0, Z, info=None):
+    """lqrb_lsq_solve_f64: condensed least-squares solve of the LTI problem (src/least_squares.jl:158-190)."""
+    h.call("lqrb_lsq_solve_f64", n, m, N, batch, ptr(A), ptr(B), ptr(Q), ptr(R), ptr(Qf), ptr(x0), ptr(Z), ptr(info))
+
+
 # ------------------------------------------------------------------ BlockCholesky
 def block_cholesky(h: Handle, n, m, batch, mode, A, B, C, M, info=None):
     h.call("lqrb_block_cholesky_f64", n, m, batch, mode, ptr(A), ptr(B), ptr(C), ptr(M), ptr(info))

@@ -303,3 +303,28 @@ def test_dense_extractors_on_other_shapes(handle, name):
         assert _rel(h[i], D @ np.linalg.solve(H, g) - d) < 1e-11
         assert _rel(U[i].T @ U[i], S[i]) < 1e-12
         assert _rel(lam[i], -np.linalg.solve(S[i], h[i])) < 1e-6
+
+
+@pytest.mark.parametrize("n,m,N,b", [(4, 1, 101, 3), (6, 3, 31, 4), (2, 1, 12, 5)])
+def test_least_squares_solver_matches_riccati(handle, n, m, N, b):
+    """solve!(sol::Primals, ::LeastSquaresSolver, prob) (src/least_squares.jl:158-190) on the device: the condensed
+    Cholesky solve lands on the Riccati solution (two independent device algorithms, same optimum), and its controls
+    zero the reference's own gradient identity A'(AU + b) + R U = 0 (test/least_squares.jl:38)."""
+    from conftest import condensed_least_squares_gradient
+    pr = problems.random_lqr_riccati(n, m, N, b, seed=5 + n, lti=True)
+    prob = LQR.LQRProblem(pr["Qf"], pr["Q"], pr["R"], pr["A"], pr["B"], pr["x0"], N=N)
+    sol = LQR.Primals(n, m, N, batch=b)
+    lsq = LQR.LeastSquaresSolver(prob, handle=handle)
+    LQR.solve_(sol, lsq, prob)
+    assert handle.last_kernel.startswith("lsq_solve") and (lsq.info == 0).all()
+    ref = LQR.LQRSolution(prob)
+    LQR.solve_(ref, LQR.DPSolver(prob, handle=handle), prob)
+    assert _rel(sol.X_, ref.X) < 1e-9 and _rel(sol.U_, ref.U) < 1e-9
+    for i in range(b):
+        grad, scale = condensed_least_squares_gradient(pr["A"][i], pr["B"][i], pr["Q"][i], pr["R"][i], pr["Qf"][i],
+                                                       pr["x0"][i], sol.U_[i])
+        assert np.abs(grad).max() < 1e-10 * max(1.0, scale)
+    # an affine or time-varying problem is refused (the reference's solver is LTI, src/least_squares.jl:61-104)
+    ltv = problems.random_lqr_riccati(n, m, N, b, seed=1)
+    with pytest.raises(LQR.LqrbError):
+        LQR.LeastSquaresSolver(LQR.LQRProblem(ltv["Qf"], ltv["Q"], ltv["R"], ltv["A"], ltv["B"], ltv["x0"], N=N))
