@@ -310,7 +310,7 @@ def test_least_squares_solver_matches_riccati(handle, n, m, N, b):
     """solve!(sol::Primals, ::LeastSquaresSolver, prob) (src/least_squares.jl:158-190) on the device: the condensed
     Cholesky solve lands on the Riccati solution (two independent device algorithms, same optimum), and its controls
     zero the reference's own gradient identity A'(AU + b) + R U = 0 (test/least_squares.jl:38)."""
-    from conftest import condensed_least_squares_gradient
+    from tests.conftest import condensed_least_squares_gradient
     pr = problems.random_lqr_riccati(n, m, N, b, seed=5 + n, lti=True)
     prob = LQR.LQRProblem(pr["Qf"], pr["Q"], pr["R"], pr["A"], pr["B"], pr["x0"], N=N)
     sol = LQR.Primals(n, m, N, batch=b)
