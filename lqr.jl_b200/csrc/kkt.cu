@@ -4,6 +4,7 @@
 
 #include "kkt_coop.cuh"
 #include "kkt_hw_kernels.cuh"
+#include "kkt_wp_kernels.cuh"
 #include "kkt_cta_kernels.cuh"
 #include "kkt_kernels.cuh"
 
@@ -55,6 +56,21 @@ static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_) return true;
     KKT_HW_SIZES(X)
+#undef X
+    return false;
+}
+
+// warp-per-instance FP64 tensor-core instantiations (kkt_wp_kernels.cuh; same stage pattern)
+#define KKT_WP_SIZES(X) X(12, 4) X(8, 4) X(12, 1) X(8, 1)
+
+static bool kkt_has_wp(const lqrb_context *h, const KktShape &s) {
+    const int64_t v = h->opt("kkt_variant", 0);
+    if (v == 2 || v == 3 || v == 4) return false;
+    if (!s.uniform || s.d2x || s.hess == LQRB_HESS_DENSE) return false;
+    if (s.N < 3 || s.P1 != s.n || s.PM != 0 || s.PN != s.n) return false;
+#define X(N_, M_) \
+    if (s.n == N_ && s.m == M_) return true;
+    KKT_WP_SIZES(X)
 #undef X
     return false;
 }
@@ -323,6 +339,44 @@ static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, 
     return 0;
 }
 
+// warp-per-instance FP64 tensor-core kernel (kkt_wp_kernels.cuh): the default for the half-warp size list; H^-1 is
+// formed in the kernel, so there is no pre-pass and no Hi array (scratch: the records and the two info arrays)
+template <int n, int m, int HESS>
+static int32_t launch_kkt_wp(lqrb_context *h, const KktShape &s, int64_t batch, int soc, const double *data,
+                             double *scratch, double *dz, double *mult, double *res, int32_t *info, cudaStream_t st) {
+    using L = kwp::Lay<n, m, HESS>;
+    using RW = kwp::RecW<n>;
+    const int N = s.N;
+    constexpr int WARPS = 4, MINB = 3;  // 168 registers (no spills): 12 warps per SM
+    constexpr size_t smem = (size_t)WARPS * (2 * L::FIRST + 128 + 4) * sizeof(double);
+    auto kern = kwp::kkt_wp_kernel<n, m, HESS, WARPS, MINB>;
+    LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
+    int64_t refined = 0;
+    for (int64_t first = 0; first < batch; first += chunk) {
+        const int64_t cb = std::min(chunk, batch - first);
+        // scratch (reused by every chunk): [records: cb x N x REC] [cinfo: cb]
+        double *recs = scratch;
+        int32_t *cinfo = reinterpret_cast<int32_t *>(recs + (size_t)cb * N * RW::REC);
+        const double *dc = data + first * L::data_rows(N);
+        kern<<<(unsigned)((cb + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(
+            dc, recs, dz + first * L::z_rows(N), mult + first * L::mult_rows(N), res ? res + first * L::z_rows(N) : nullptr,
+            info ? info + first : nullptr, cinfo, N, cb, soc);
+        LQRB_LAUNCH_CHECK(h, "kkt_wp_kernel");
+        int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * L::z_rows(N),
+                                                 mult + first * L::mult_rows(N), res ? res + first * L::z_rows(N) : nullptr,
+                                                 info ? info + first : nullptr, st);
+        if (rc) return rc;
+        refined += h->last_refined;
+    }
+    char nm[128];
+    snprintf(nm, sizeof nm, "kkt_wp_dmma<%d,%d,p=%d/0/%d,hess=%d%s>", n, m, n, n, HESS, soc ? ",soc" : "");
+    h->kernel_name = nm;
+    if (refined) h->kernel_name += "+kkt_coop[" + std::to_string(refined) + " ill-conditioned]";
+    h->last_refined = refined;
+    return 0;
+}
+
 template <int n, int m, int HESS>
 static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch, int soc, const double *data,
                               double *scratch, double *dz, double *mult, double *res, int32_t *info,
@@ -380,6 +434,10 @@ static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch) {
         return (size_t)batch * ((size_t)s.N * (khw::Lay<N_, M_>::REC + khw::Lay<N_, M_>::HI) + 1) + 2;
     KKT_HW_SIZES(X)
 #undef X
+#define X(N_, M_) \
+    if (s.n == N_ && s.m == M_) return (size_t)batch * ((size_t)s.N * kwp::RecW<N_>::REC + 1) + 2;
+    KKT_WP_SIZES(X)
+#undef X
     return 0;
 }
 
@@ -402,7 +460,7 @@ static size_t kkt_scratch_bytes(const lqrb_context *h, const KktShape &s, const 
     size_t bytes = (size_t)lqrb_padded_batch(batch) * z.rec_rows * 8;
     // the tuned kernels' records only when one of them will actually run for this shape (a dense Hessian, an
     // irregular stage pattern, explicit D2 or kkt_variant = 2 route the same (n, m) to the cooperative kernel)
-    if (!kkt_has_hw(h, s, 0) && !kkt_has_cta(h, s, 0)) return bytes;
+    if (!kkt_has_hw(h, s, 0) && !kkt_has_cta(h, s, 0) && !kkt_has_wp(h, s)) return bytes;
     const int64_t chunk = kkt_tuned_chunk(h, s);
     if (chunk > 0) bytes = std::max(bytes, kkt_hw_scratch_doubles(s, std::min(batch, chunk)) * 8 + 64);
     return bytes;
@@ -420,6 +478,17 @@ static int32_t kkt_solve_on(lqrb_context *h, const KktShape &s, int64_t batch, i
                    ? launch_kkt_cta<N_, M_, LQRB_HESS_DIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st)      \
                    : launch_kkt_cta<N_, M_, LQRB_HESS_BLOCKDIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st);
         KKT_CTA_SIZES(X)
+#undef X
+    }
+    // kkt_variant: 0 = warp-per-instance tensor-core kernel (default), 3 / 4 = the half-warp kernels (column / block layout)
+    if (kkt_has_wp(h, s) && ((uintptr_t)data & 15) == 0) {
+        const int soc = (flags & LQRB_FLAG_SOC) ? 1 : 0;
+#define X(N_, M_)                                                                                              \
+    if (s.n == N_ && s.m == M_)                                                                                \
+        return s.hess == LQRB_HESS_DIAG                                                                        \
+                   ? launch_kkt_wp<N_, M_, LQRB_HESS_DIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st)      \
+                   : launch_kkt_wp<N_, M_, LQRB_HESS_BLOCKDIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st);
+        KKT_WP_SIZES(X)
 #undef X
     }
     if (kkt_has_hw(h, s, flags) && ((uintptr_t)data & 15) == 0) {

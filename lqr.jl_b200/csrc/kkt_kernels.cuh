@@ -359,7 +359,8 @@ __device__ __forceinline__ int kkt_fwd_knot(const double *__restrict__ kp, doubl
 
 // ------------------------------------------------------------------ backward knot -------------
 // lam holds lam'_k (un-negated back-substitution value) on entry and lam'_{k-1} on exit.
-template <int n, int mk, int p1, int ps, int p2, int HESS, bool SOC, int KS = 32>
+// RS: stride between the record rows (32 = packed tile in global memory, 1 = a thread-local copy)
+template <int n, int mk, int p1, int ps, int p2, int HESS, bool SOC, int KS = 32, int RS = 32>
 __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
                                              const double *__restrict__ rec, double *lam,
                                              double *__restrict__ dz, double *__restrict__ mult_mu,
@@ -387,12 +388,12 @@ __device__ __forceinline__ void kkt_bwd_knot(const double *__restrict__ kp,
         for (int j = 0; j < p1; ++j)
             SM_UNROLL
             for (int i = 0; i <= j; ++i) {
-                const double v = rec[(RR::oC + tri_idx(i, j)) * 32];
+                const double v = rec[(RR::oC + tri_idx(i, j)) * RS];
                 if (i == j) Ahinv[i] = v;
                 Ah[tri_idx(i, j)] = v;
             }
         SM_UNROLL
-        for (int i = 0; i < p1; ++i) lamp[i] = rec[(RR::ol + i) * 32];
+        for (int i = 0; i < p1; ++i) lamp[i] = rec[(RR::ol + i) * RS];
     }
     RowFactor<n, mk, p1, ps, p2, HESS, SOC, false> R;
     R.template compute<KS>(kp, H, hg, Ah, Ahinv, lamp);

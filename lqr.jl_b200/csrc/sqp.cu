@@ -389,8 +389,22 @@ __device__ __forceinline__ void prefetch_row_l2(const double *p, int lane) {
     if ((lane & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-__global__ void __launch_bounds__(64, 8)  // 65,536 instances = 1,024 CTAs must fit in one wave (148 x 8)
-    dubins_sqp_step_kernel(double *__restrict__ Z, const double *__restrict__ x0, const double *__restrict__ xf,
+// Per-thread asynchronous prefetch ring in shared memory (cp.async, 8 bytes per row and thread): a thread copies the
+// rows IT will read two knots later, so only cp.async.wait_group orders the data — no barrier.  The kernel runs one
+// instance per thread with ~14 warps per SM (the batch is one wave), and ncu showed 4.5 long-scoreboard stall cycles
+// per issued instruction: the loads at the top of every knot were latency nothing else could cover.
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+
+// PF = true: cp.async ring (3 slots, 2 knots ahead) and 7 CTAs per SM (144 registers; 1,024 CTAs still fit in the one
+// wave of 148 x 7 = 1,036); PF = false: the round-1 kernel (L2 prefetch only, 8 CTAs per SM at 128 registers).
+template <bool PF>
+__device__ __forceinline__ void
+    dubins_sqp_step_body(double *__restrict__ Z, const double *__restrict__ x0, const double *__restrict__ xf,
                            double *__restrict__ mult_kept, double *__restrict__ cvals, double *__restrict__ scratch,
                            double *__restrict__ dz, int32_t *__restrict__ info, double *__restrict__ stats, Opts o,
                            int64_t batch, double eps_p, double eps_d, int full_step, int *__restrict__ counters) {
@@ -422,9 +436,31 @@ __global__ void __launch_bounds__(64, 8)  // 65,536 instances = 1,024 CTAs must 
     // ---------------- forward sweep: statistics at Z + elimination
     double f = 0.0, c1 = 0.0, cinf = 0.0, fd2 = 0.0, lam_prev[n] = {0.0, 0.0, 0.0};
     // knot with controls: g at kn[w..], D1 at kn[2w..], d after D1 (and C | c of the first knot after that)
+    // ---- prefetch ring: [slot][row][thread]; forward rows: x_{k+1} (n) | u_k (m) | kept lam_k (n); backward rows:
+    // x_k (n) | u_k (m) | record of knot k (RM::ROWS)
+    constexpr int PF_ROWS = n + m + (L::RM::ROWS > n ? L::RM::ROWS : n);
+    __shared__ double pfbuf[PF ? 3 * PF_ROWS * 64 : 1];
+    double *pft = pfbuf + threadIdx.x;
+    auto pf_issue_fwd = [&](int k) {  // rows of knot k (1 <= k <= N-2)
+        double *dst = pft + (k % 3) * PF_ROWS * 64;
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) cp_async8(dst + i * 64, zb + ((int64_t)(k + 1) * w + i) * 32);
+        SM_UNROLL
+        for (int i = 0; i < m; ++i) cp_async8(dst + (n + i) * 64, zb + ((int64_t)k * w + n + i) * 32);
+        SM_UNROLL
+        for (int i = 0; i < n; ++i) cp_async8(dst + (w + i) * 64, mb + (mult_row(k) + i) * 32);
+    };
+    auto pf_issue_bwd = [&](int k) {  // rows of knot k (1 <= k <= N-2)
+        double *dst = pft + (k % 3) * PF_ROWS * 64;
+        SM_UNROLL
+        for (int i = 0; i < w; ++i) cp_async8(dst + i * 64, zb + ((int64_t)k * w + i) * 32);
+        const double *rp = sb + ((int64_t)L::RF::ROWS + (int64_t)(k - 1) * L::RM::ROWS) * 32;
+        SM_UNROLL
+        for (int i = 0; i < L::RM::ROWS; ++i) cp_async8(dst + (w + i) * 64, rp + i * 32);
+    };
+    double lk[n];
     auto knot_stats = [&](int k) {
         const double *D1 = kn + 2 * w;
-        double lk[n];
         SM_UNROLL
         for (int i = 0; i < n; ++i) {
             const double e = x[i] - xg[i];
@@ -432,7 +468,6 @@ __global__ void __launch_bounds__(64, 8)  // 65,536 instances = 1,024 CTAs must 
             const double d = D1[n * w + i];
             c1 += fabs(d);
             cinf = fmax(cinf, fabs(d));
-            lk[i] = mb[(mult_row(k) + (k == 0 ? n : 0) + i) * 32];
         }
         SM_UNROLL
         for (int i = 0; i < m; ++i) f += 0.5 * rs * u[i] * u[i];
@@ -456,24 +491,41 @@ __global__ void __launch_bounds__(64, 8)  // 65,536 instances = 1,024 CTAs must 
         for (int i = 0; i < n; ++i) lam_prev[i] = lk[i];
     };
     FwdCarry<n> cy;
+    if constexpr (PF) {  // two knots ahead; empty groups keep the group count uniform
+        if (1 < N - 1) pf_issue_fwd(1);
+        cp_async_commit();
+        if (2 < N - 1) pf_issue_fwd(2);
+        cp_async_commit();
+    }
     SM_UNROLL
-    for (int i = 0; i < n; ++i) { x[i] = ldz(i); xn[i] = ldz(w + i); }
+    for (int i = 0; i < n; ++i) { x[i] = ldz(i); xn[i] = ldz(w + i); lk[i] = mb[(n + i) * 32]; }
     SM_UNROLL
     for (int i = 0; i < m; ++i) u[i] = ldz(n + i);
     dubins_build_knot<0, false>(kn, x, u, xn, x0v, xg, o, nullptr, nullptr);
     knot_stats(0);
     int s1 = kkt_fwd_knot<n, m, 0, n, n, HD, false, 1>(kn, sb, cy, 0);
     for (int k = 1; k < N - 1; ++k) {
-        if (k + 2 < N) {  // next knot: u_{k+1}, x_{k+2}, kept lam_{k+1}
+        if constexpr (PF) {
+            cp_async_wait<1>();  // the group of knot k has landed (at most the one of knot k+1 is pending)
+            const double *src = pft + (k % 3) * PF_ROWS * 64;
             SM_UNROLL
-            for (int i = 0; i < w; ++i) prefetch_row_l2(zb + ((int64_t)(k + 1) * w + n + i) * 32, lane);
+            for (int i = 0; i < n; ++i) { x[i] = xn[i]; xn[i] = src[i * 64]; lk[i] = src[(w + i) * 64]; }
             SM_UNROLL
-            for (int i = 0; i < n; ++i) prefetch_row_l2(mb + (mult_row(k + 1) + i) * 32, lane);
+            for (int i = 0; i < m; ++i) u[i] = src[(n + i) * 64];
+            if (k + 2 < N - 1) pf_issue_fwd(k + 2);  // slot (k+2) % 3: not the one just read, not the pending one
+            cp_async_commit();
+        } else {
+            if (k + 2 < N) {  // next knot: u_{k+1}, x_{k+2}, kept lam_{k+1}
+                SM_UNROLL
+                for (int i = 0; i < w; ++i) prefetch_row_l2(zb + ((int64_t)(k + 1) * w + n + i) * 32, lane);
+                SM_UNROLL
+                for (int i = 0; i < n; ++i) prefetch_row_l2(mb + (mult_row(k + 1) + i) * 32, lane);
+            }
+            SM_UNROLL
+            for (int i = 0; i < n; ++i) { x[i] = xn[i]; xn[i] = ldz((int64_t)(k + 1) * w + i); lk[i] = mb[(mult_row(k) + i) * 32]; }
+            SM_UNROLL
+            for (int i = 0; i < m; ++i) u[i] = ldz((int64_t)k * w + n + i);
         }
-        SM_UNROLL
-        for (int i = 0; i < n; ++i) { x[i] = xn[i]; xn[i] = ldz((int64_t)(k + 1) * w + i); }
-        SM_UNROLL
-        for (int i = 0; i < m; ++i) u[i] = ldz((int64_t)k * w + n + i);
         dubins_build_knot<1, false>(kn, x, u, xn, x0v, xg, o, nullptr, nullptr);
         knot_stats(k);
         const int s2 = kkt_fwd_knot<n, m, n, 0, n, HD, false, 1>(
@@ -509,6 +561,13 @@ __global__ void __launch_bounds__(64, 8)  // 65,536 instances = 1,024 CTAs must 
     }
 
     // ---------------- backward sweep: step, multipliers (kept for the next feas_d) and the alpha = 1 trial
+    if constexpr (PF) {
+        cp_async_wait<0>();
+        if (N - 2 >= 1) pf_issue_bwd(N - 2);
+        cp_async_commit();
+        if (N - 3 >= 1) pf_issue_bwd(N - 3);
+        cp_async_commit();
+    }
     double lam[n], dzr[w], xtn[n];
     double gdx = 0.0, linf = 0.0, ft = 0.0, c1t = 0.0;
     const int64_t mlast = (int64_t)n + n + (int64_t)(N - 2) * n;
@@ -551,24 +610,42 @@ __global__ void __launch_bounds__(64, 8)  // 65,536 instances = 1,024 CTAs must 
         }
     };
     for (int k = N - 2; k >= 1; --k) {
-        if (k >= 2) {  // previous knot: z_{k-1} and its record
-            SM_UNROLL
-            for (int i = 0; i < w; ++i) prefetch_row_l2(zb + ((int64_t)(k - 1) * w + i) * 32, lane);
-            const double *rp = sb + ((int64_t)L::RF::ROWS + (int64_t)(k - 2) * L::RM::ROWS) * 32;
-            SM_UNROLL
-            for (int i = 0; i < L::RM::ROWS; ++i) prefetch_row_l2(rp + i * 32, lane);
-        }
-        SM_UNROLL
-        for (int i = 0; i < n; ++i) { xn[i] = x[i]; x[i] = ldz((int64_t)k * w + i); }
-        SM_UNROLL
-        for (int i = 0; i < m; ++i) u[i] = ldz((int64_t)k * w + n + i);
-        dubins_build_knot<1, false>(kn, x, u, xn, x0v, xg, o, nullptr, nullptr);
         const int64_t mo = (int64_t)n + n + (int64_t)(k - 1) * n;
-        kkt_bwd_knot<n, m, n, 0, n, HD, false, 1>(kn, sb + ((int64_t)L::RF::ROWS + (int64_t)(k - 1) * L::RM::ROWS) * 32, lam,
-                                                  dzb + (int64_t)k * w * 32, mb + mo * 32, mb + (mo - n) * 32, nullptr,
-                                                  dzr, &linf);
+        if constexpr (PF) {
+            cp_async_wait<1>();
+            const double *src = pft + (k % 3) * PF_ROWS * 64;
+            double rl[L::RM::ROWS];
+            SM_UNROLL
+            for (int i = 0; i < n; ++i) { xn[i] = x[i]; x[i] = src[i * 64]; }
+            SM_UNROLL
+            for (int i = 0; i < m; ++i) u[i] = src[(n + i) * 64];
+            SM_UNROLL
+            for (int i = 0; i < L::RM::ROWS; ++i) rl[i] = src[(w + i) * 64];
+            if (k - 2 >= 1) pf_issue_bwd(k - 2);
+            cp_async_commit();
+            dubins_build_knot<1, false>(kn, x, u, xn, x0v, xg, o, nullptr, nullptr);
+            kkt_bwd_knot<n, m, n, 0, n, HD, false, 1, 1>(kn, rl, lam, dzb + (int64_t)k * w * 32, mb + mo * 32,
+                                                         mb + (mo - n) * 32, nullptr, dzr, &linf);
+        } else {
+            if (k >= 2) {  // previous knot: z_{k-1} and its record
+                SM_UNROLL
+                for (int i = 0; i < w; ++i) prefetch_row_l2(zb + ((int64_t)(k - 1) * w + i) * 32, lane);
+                const double *rp = sb + ((int64_t)L::RF::ROWS + (int64_t)(k - 2) * L::RM::ROWS) * 32;
+                SM_UNROLL
+                for (int i = 0; i < L::RM::ROWS; ++i) prefetch_row_l2(rp + i * 32, lane);
+            }
+            SM_UNROLL
+            for (int i = 0; i < n; ++i) { xn[i] = x[i]; x[i] = ldz((int64_t)k * w + i); }
+            SM_UNROLL
+            for (int i = 0; i < m; ++i) u[i] = ldz((int64_t)k * w + n + i);
+            dubins_build_knot<1, false>(kn, x, u, xn, x0v, xg, o, nullptr, nullptr);
+            kkt_bwd_knot<n, m, n, 0, n, HD, false, 1>(kn, sb + ((int64_t)L::RF::ROWS + (int64_t)(k - 1) * L::RM::ROWS) * 32, lam,
+                                                      dzb + (int64_t)k * w * 32, mb + mo * 32, mb + (mo - n) * 32, nullptr,
+                                                      dzr, &linf);
+        }
         knot_trial(k);
     }
+    if constexpr (PF) cp_async_wait<0>();
     SM_UNROLL
     for (int i = 0; i < n; ++i) { xn[i] = x[i]; x[i] = ldz(i); }
     SM_UNROLL
@@ -603,6 +680,23 @@ __global__ void __launch_bounds__(64, 8)  // 65,536 instances = 1,024 CTAs must 
         st[Stats::DONE * 32] = 0.0;
         atomicAdd(&counters[0], 1);  // needs the second-order correction solve
     }
+}
+
+// 65,536 instances = 1,024 CTAs of 64 threads must fit in ONE wave: 148 x 8 at 128 registers (round-1 kernel), or
+// 148 x 7 = 1,036 at 144 registers for the prefetching variant (its ring takes 21.5 KB of shared memory per CTA).
+__global__ void __launch_bounds__(64, 8)
+    dubins_sqp_step_kernel(double *__restrict__ Z, const double *__restrict__ x0, const double *__restrict__ xf,
+                           double *__restrict__ mult_kept, double *__restrict__ cvals, double *__restrict__ scratch,
+                           double *__restrict__ dz, int32_t *__restrict__ info, double *__restrict__ stats, Opts o,
+                           int64_t batch, double eps_p, double eps_d, int full_step, int *__restrict__ counters) {
+    dubins_sqp_step_body<false>(Z, x0, xf, mult_kept, cvals, scratch, dz, info, stats, o, batch, eps_p, eps_d, full_step, counters);
+}
+__global__ void __maxnreg__(144)
+    dubins_sqp_step_pf_kernel(double *__restrict__ Z, const double *__restrict__ x0, const double *__restrict__ xf,
+                              double *__restrict__ mult_kept, double *__restrict__ cvals, double *__restrict__ scratch,
+                              double *__restrict__ dz, int32_t *__restrict__ info, double *__restrict__ stats, Opts o,
+                              int64_t batch, double eps_p, double eps_d, int full_step, int *__restrict__ counters) {
+    dubins_sqp_step_body<true>(Z, x0, xf, mult_kept, cvals, scratch, dz, info, stats, o, batch, eps_p, eps_d, full_step, counters);
 }
 
 // Line search stages (src/sqp.jl:72-94).
@@ -815,8 +909,12 @@ extern "C" int32_t lqrb_sqp_dubins_f64(lqrb_handle_t h, int64_t batch, const lqr
         if (fused) {
             // update! + convergence check + _solve! + line-search stage 0 in one kernel
             LQRB_CUDA(h, cudaMemsetAsync(counters, 0, 8, s));
-            dubins_sqp_step_kernel<<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, data, frec, dz, dinfo, stats, o, batch,
-                                                       opts->eps_p, opts->eps_d, opts->line_search ? 0 : 1, counters);
+            if (h->opt("sqp_prefetch", 1))
+                dubins_sqp_step_pf_kernel<<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, data, frec, dz, dinfo, stats, o, batch,
+                                                                 opts->eps_p, opts->eps_d, opts->line_search ? 0 : 1, counters);
+            else
+                dubins_sqp_step_kernel<<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, data, frec, dz, dinfo, stats, o, batch,
+                                                                  opts->eps_p, opts->eps_d, opts->line_search ? 0 : 1, counters);
             h->kernel_name = "dubins_sqp_step<3,2,p=3/0/3,hess=2>";
             LQRB_LAUNCH_CHECK(h, "dubins_sqp_step_kernel");
         } else {

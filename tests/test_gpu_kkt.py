@@ -81,30 +81,46 @@ def test_cooperative_kernel(handle, oracle_mod, n, m, N, mid_p, d2x, hess):
     assert handle.last_kernel.startswith("kkt_coop")
 
 
+# kkt_variant: 0 = warp per instance on the FP64 tensor cores (default), 4 / 3 = half warp per instance (block / column layout)
+QUAD_VARIANTS = [(0, "kkt_wp_dmma<"), (4, "kkt_hw<"), (3, "kkt_hw<")]
+
+
+@pytest.mark.parametrize("variant,kern", QUAD_VARIANTS)
 @pytest.mark.parametrize("n,m,N,batch", [(12, 4, 40, 6), (12, 4, 8, 5), (12, 4, 6, 1), (8, 4, 25, 7), (8, 4, 4, 3), (12, 4, 301, 9),
                                          (12, 4, 1001, 2)])
-def test_half_warp_kernel(handle, oracle_mod, n, m, N, batch):
-    """config 5a-K shape: init + dynamics + goal, block-diagonal Hessian -> half-warp-per-instance kernel."""
+def test_half_warp_kernel(handle, oracle_mod, n, m, N, batch, variant, kern):
+    """config 5a-K shape: init + dynamics + goal, block-diagonal Hessian -> warp- / half-warp-per-instance kernels."""
     prob = problems.random_lqr_kkt(n, m, N, batch, seed=n + N, mid_p=0, hess_mode=1)
-    _check(prob, handle, oracle_mod, truth_instances=(0, batch - 1))
-    assert handle.last_kernel.startswith("kkt_hw<")
+    handle.set_option("kkt_variant", variant)
+    try:
+        _check(prob, handle, oracle_mod, truth_instances=(0, batch - 1))
+        assert handle.last_kernel.startswith(kern) and ("cols" in handle.last_kernel) == (variant == 3)
+    finally:
+        handle.set_option("kkt_variant", 0)
 
 
 @pytest.mark.parametrize("hess", [1, 2])
 @pytest.mark.parametrize("soc", [False, True])
-@pytest.mark.parametrize("n,m,N,batch,kern", [(12, 4, 40, 6, "kkt_hw<"), (8, 4, 21, 5, "kkt_hw<"), (64, 16, 12, 2, "kkt_cta_dmma<")])
-def test_tuned_kernels_hessian_modes_and_soc(handle, oracle_mod, n, m, N, batch, kern, hess, soc):
+@pytest.mark.parametrize("n,m,N,batch,kern,variant", [(12, 4, 40, 6, "kkt_wp_dmma<", 0), (8, 4, 21, 5, "kkt_wp_dmma<", 0),
+                                                      (12, 1, 40, 4, "kkt_wp_dmma<", 0), (8, 1, 25, 3, "kkt_wp_dmma<", 0),
+                                                      (12, 4, 40, 6, "kkt_hw<", 4), (8, 4, 21, 5, "kkt_hw<", 4),
+                                                      (64, 16, 12, 2, "kkt_cta_dmma<", 0)])
+def test_tuned_kernels_hessian_modes_and_soc(handle, oracle_mod, n, m, N, batch, kern, variant, hess, soc):
     """Diagonal / block-diagonal BlockCholesky modes (src/block_cholesky.jl:69-91) and the Ginv=false chain of
     second_order_correction! (src/cholesky_solver.jl:254-273) on the tuned large-size kernels."""
     prob = problems.random_lqr_kkt(n, m, N, batch, seed=3 * n + hess, mid_p=0, hess_mode=hess)
-    _check(prob, handle, oracle_mod, soc=soc, tol=1e-9 if soc else TOL, res_tol=1e-9 if soc else TOL)
-    assert handle.last_kernel.startswith(kern) and (",soc" in handle.last_kernel) == soc
+    handle.set_option("kkt_variant", variant)
+    try:
+        _check(prob, handle, oracle_mod, soc=soc, tol=1e-9 if soc else TOL, res_tol=1e-9 if soc else TOL)
+        assert handle.last_kernel.startswith(kern) and (",soc" in handle.last_kernel) == soc
+    finally:
+        handle.set_option("kkt_variant", 0)
 
 
 def test_half_warp_matches_cooperative_kernel(handle):
     prob = problems.random_lqr_kkt(12, 4, 120, 11, seed=5, mid_p=0, hess_mode=1)
     dz1, lam1, i1, r1 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
-    assert handle.last_kernel.startswith("kkt_hw<")
+    assert handle.last_kernel.startswith("kkt_wp_dmma<")
     handle.set_option("kkt_variant", 2)
     try:
         dz2, lam2, i2, r2 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
@@ -119,9 +135,14 @@ def test_half_warp_matches_cooperative_kernel(handle):
 def test_half_warp_info_flags(handle):
     prob = problems.random_lqr_kkt(12, 4, 30, 5, seed=9, mid_p=0, hess_mode=1)
     prob["R"][2, 7] = -np.eye(4)
-    _, _, info = ops.kkt_solve_problem(prob, handle=handle)
-    assert handle.last_kernel.startswith("kkt_hw<")
-    assert info[2] == 8 * 1000 + 12 + 1 and (np.delete(info, 2) == 0).all()
+    for variant, kern in ((0, "kkt_wp_dmma<"), (4, "kkt_hw<")):
+        handle.set_option("kkt_variant", variant)
+        try:
+            _, _, info = ops.kkt_solve_problem(prob, handle=handle)
+        finally:
+            handle.set_option("kkt_variant", 0)
+        assert handle.last_kernel.startswith(kern)
+        assert info[2] == 8 * 1000 + 12 + 1 and (np.delete(info, 2) == 0).all(), (kern, info)
 
 
 def test_irregular_stage_pattern(handle, oracle_mod):
@@ -252,7 +273,7 @@ def _kkt_residuals_all(prob, dz, lam):
     return max(np.abs(sx).max(), np.abs(su).max()) / scale, prim
 
 
-@pytest.mark.parametrize("n,m,N,batch,kern", [(12, 4, 101, 2049, "kkt_hw<"), (64, 16, 41, 300, "kkt_cta_dmma<")])
+@pytest.mark.parametrize("n,m,N,batch,kern", [(12, 4, 101, 2049, "kkt_wp_dmma<"), (64, 16, 41, 300, "kkt_cta_dmma<")])
 def test_tuned_kernels_kkt_conditions_at_scale(handle, n, m, N, batch, kern):
     """Size-independent property on a batch that spans many CTAs (and an odd tail): the returned step and
     multipliers satisfy the KKT conditions  H dz + g + D'lam = 0,  D dz + d = 0  for EVERY instance."""
