@@ -49,7 +49,7 @@ static bool kkt_has_tpi(const KktShape &s) {
 #define KKT_HW_SIZES(X) X(12, 4) X(8, 4)
 
 static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
-    if (h->opt("kkt_variant", 0) == 2) return false;
+    if (h->opt("kkt_variant", 0) == 2 || h->opt("kkt_variant", 0) == 5) return false;
     (void)flags;
     if (!s.uniform || s.d2x || s.hess == LQRB_HESS_DENSE) return false;
     if (s.N < 3 || s.P1 != s.n || s.PM != 0 || s.PN != s.n) return false;
@@ -63,10 +63,11 @@ static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
 // warp-per-instance FP64 tensor-core instantiations (kkt_wp_kernels.cuh; same stage pattern)
 #define KKT_WP_SIZES(X) X(12, 4) X(8, 4) X(12, 1) X(8, 1)
 
+// kkt_variant: 0 = default (half-warp kernel where it exists, else this one), 5 = force this kernel
 static bool kkt_has_wp(const lqrb_context *h, const KktShape &s) {
     const int64_t v = h->opt("kkt_variant", 0);
     if (v == 2 || v == 3 || v == 4) return false;
-    if (!s.uniform || s.d2x || s.hess == LQRB_HESS_DENSE) return false;
+    if (!s.uniform || s.d2x) return false;
     if (s.N < 3 || s.P1 != s.n || s.PM != 0 || s.PN != s.n) return false;
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_) return true;
@@ -481,13 +482,19 @@ static int32_t kkt_solve_on(lqrb_context *h, const KktShape &s, int64_t batch, i
 #undef X
     }
     // kkt_variant: 0 = warp-per-instance tensor-core kernel (default), 3 / 4 = the half-warp kernels (column / block layout)
-    if (kkt_has_wp(h, s) && ((uintptr_t)data & 15) == 0) {
+    // The warp-per-instance tensor-core kernel takes the shapes the half-warp kernel does not have (odd m, dense
+    // Hessian); for (12,4) / (8,4) block-diagonal it is the slower one (74.9 vs 49.1 ms on config 5a-K: its three
+    // serial 16 x 16 inversions per knot make it latency-bound at 12 warps per SM) and runs only when forced.
+    if (kkt_has_wp(h, s) && ((uintptr_t)data & 15) == 0 && (h->opt("kkt_variant", 0) == 5 || !kkt_has_hw(h, s, flags))) {
         const int soc = (flags & LQRB_FLAG_SOC) ? 1 : 0;
-#define X(N_, M_)                                                                                              \
-    if (s.n == N_ && s.m == M_)                                                                                \
-        return s.hess == LQRB_HESS_DIAG                                                                        \
-                   ? launch_kkt_wp<N_, M_, LQRB_HESS_DIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st)      \
-                   : launch_kkt_wp<N_, M_, LQRB_HESS_BLOCKDIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st);
+#define X(N_, M_)                                                                                                        \
+    if (s.n == N_ && s.m == M_) {                                                                                        \
+        if (s.hess == LQRB_HESS_DIAG)                                                                                    \
+            return launch_kkt_wp<N_, M_, LQRB_HESS_DIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st);      \
+        if (s.hess == LQRB_HESS_BLOCKDIAG)                                                                               \
+            return launch_kkt_wp<N_, M_, LQRB_HESS_BLOCKDIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st); \
+        return launch_kkt_wp<N_, M_, LQRB_HESS_DENSE>(h, s, batch, soc, data, scratch, dz, mult, res, info, st);         \
+    }
         KKT_WP_SIZES(X)
 #undef X
     }

@@ -3,7 +3,8 @@
 // in shared memory.
 //
 // Replaces _solve!(::CholeskySolver) : src/cholesky_solver.jl:166-182 for the stage pattern of the reference's own
-// fixtures (test/problems.jl:58-88: initial condition + dynamics + goal, p = [n, 0, ..., 0, n], D2 = [-I 0]):
+// fixtures (test/problems.jl:58-88: initial condition + dynamics + goal, p = [n, 0, ..., 0, n], D2 = [-I 0]; any of the
+// three BlockCholesky modes of the cost Hessian — the dense one too: H^-1 is a z-space inverse here):
 //   calculate_shur_factors!  src/jacobian_blocks.jl:220-286   S = D H^-1 D', h = D H^-1 g - d
 //   cholesky!(chol, shur)    src/cholesky_solve.jl:28-67
 //   forward_substitution!    :93-117        backward_substitution! :119-143   (Lambda = -S^-1 h)
@@ -41,8 +42,10 @@ using rdmma::mma884;
 template <int n, int m, int HESS = LQRB_HESS_BLOCKDIAG>
 struct Lay {
     static constexpr int w = n + m;
-    static_assert(HESS == LQRB_HESS_BLOCKDIAG || HESS == LQRB_HESS_DIAG, "block-diagonal or diagonal cost Hessian");
-    static constexpr int HQ = HESS == LQRB_HESS_DIAG ? n : tri(n), HR = HESS == LQRB_HESS_DIAG ? m : tri(m);
+    // H part: DIAG: w entries | BLOCKDIAG: tri(n) + tri(m) | DENSE: tri(w), upper packed over z = [x; u] (lqrb200.h);
+    // the last knot has no controls: n | tri(n) | tri(n)
+    static constexpr int HQ = HESS == LQRB_HESS_DIAG ? n : tri(n);
+    static constexpr int HR = HESS == LQRB_HESS_DIAG ? m : (HESS == LQRB_HESS_BLOCKDIAG ? tri(m) : tri(w) - tri(n));
     static constexpr int oQ = 0, oR = HQ, og = oR + HR, oD1 = og + w, od = oD1 + n * w, CORE = od + n;
     static constexpr int oC0 = CORE, FIRST = CORE + n * w + n, MID = CORE;
     static constexpr int oCl = HQ + n, LAST = oCl + n * n + n;
@@ -272,7 +275,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                     const int za = zrow(rt), zb_ = zcol(ct, e);
                     double v = is_diag(rt, ct, e) ? 1.0 : 0.0;
                     if (!soc && za >= 0 && zb_ >= 0 && za < wk && zb_ < wk) {
-                        if (za < n && zb_ < n)
+                        if (HESS == LQRB_HESS_DENSE)  // whole-matrix mode: cross terms Hux are part of H (src/block_cholesky.jl:55-66)
+                            v = kp[sym_idx(za, zb_)];
+                        else if (za < n && zb_ < n)
                             v = HESS == LQRB_HESS_DIAG ? (za == zb_ ? kp[L::oQ + za] : 0.0) : kp[L::oQ + sym_idx(za, zb_)];
                         else if (za >= n && zb_ >= n)
                             v = HESS == LQRB_HESS_DIAG ? (za == zb_ ? kp[L::oR + za - n] : 0.0) : kp[L::oR + sym_idx(za - n, zb_ - n)];

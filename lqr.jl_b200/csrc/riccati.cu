@@ -442,8 +442,42 @@ extern "C" int32_t lqrb_riccati_f64(lqrb_handle_t h, int32_t n, int32_t m, int32
 }
 
 // ------------------------------------------------------------------ rollout -------------------
-// rollout!(X, U) : src/least_squares.jl:195-202.  Instance-major, one thread per instance, the state
-// lives in the output array (not a hot path; used by callers that supply their own controls).
+// rollout!(X, U) : src/least_squares.jl:195-202, one WARP per instance (n <= 32): lane i owns row i of A_k, B_k, so
+// every load of a column of [A B] is one contiguous piece (the instance-major arrays are column-major), x_k and u_k
+// travel by shuffle, and X is written as contiguous n-double pieces.  The thread-per-instance kernel below read A
+// with a stride of Kn n^2 doubles between lanes (every lane its own 32-byte sector).
+__global__ void __launch_bounds__(128)
+    rollout_warp_kernel(const double *__restrict__ A, const double *__restrict__ B, const double *__restrict__ x0,
+                        const double *__restrict__ U, double *__restrict__ X, int n, int m, int N, int lti,
+                        int64_t batch) {
+    const int64_t inst = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (inst >= batch) return;
+    const int Kn = lti ? 1 : N - 1;
+    const double *Ai = A + inst * (int64_t)Kn * n * n, *Bi = B + inst * (int64_t)Kn * n * m;
+    const double *Ui = U + inst * (int64_t)(N - 1) * m;
+    double *Xi = X + inst * (int64_t)N * n;
+    double x = lane < n ? x0[inst * n + lane] : 0.0;
+    if (lane < n) Xi[lane] = x;
+    double un = lane < m ? Ui[lane] : 0.0;  // u_0, one knot ahead of its use
+    for (int k = 0; k < N - 1; ++k) {
+        const double *Ak = Ai + (int64_t)(lti ? 0 : k) * n * n, *Bk = Bi + (int64_t)(lti ? 0 : k) * n * m;
+        const double u = un;
+        if (k + 1 < N - 1) un = lane < m ? Ui[(int64_t)(k + 1) * m + lane] : 0.0;
+        double s0 = 0.0, s1 = 0.0;
+        for (int l = 0; l + 1 < n; l += 2) {
+            const double a0 = lane < n ? Ak[lane + l * n] : 0.0, a1 = lane < n ? Ak[lane + (l + 1) * n] : 0.0;
+            s0 = fma(a0, __shfl_sync(0xffffffffu, x, l), s0);
+            s1 = fma(a1, __shfl_sync(0xffffffffu, x, l + 1), s1);
+        }
+        if (n & 1) s0 = fma(lane < n ? Ak[lane + (n - 1) * n] : 0.0, __shfl_sync(0xffffffffu, x, n - 1), s0);
+        for (int l = 0; l < m; ++l) s1 = fma(lane < n ? Bk[lane + l * n] : 0.0, __shfl_sync(0xffffffffu, u, l), s1);
+        x = s0 + s1;
+        if (lane < n) Xi[(int64_t)(k + 1) * n + lane] = x;
+    }
+}
+
+// the same for n > 32: one thread per instance, the state lives in the output array
 __global__ void rollout_kernel(const double *__restrict__ A, const double *__restrict__ B,
                                const double *__restrict__ x0, const double *__restrict__ U,
                                double *__restrict__ X, int n, int m, int N, int lti, int64_t batch) {
@@ -496,7 +530,13 @@ extern "C" int32_t lqrb_rollout_f64(lqrb_handle_t h, int32_t n, int32_t m, int32
         LQRB_CUDA(h, cudaMemcpyAsync(u, U, (size_t)batch * (N - 1) * m * 8, cudaMemcpyHostToDevice, h->stream));
         dA = a; dB = b; dx0 = x; dU = u;
     }
-    rollout_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, h->stream>>>(dA, dB, dx0, dU, dX, n, m, N, lti, batch);
+    if (n <= 32) {
+        rollout_warp_kernel<<<(unsigned)((batch + 3) / 4), 128, 0, h->stream>>>(dA, dB, dx0, dU, dX, n, m, N, lti, batch);
+        h->kernel_name = "rollout_warp";
+    } else {
+        rollout_kernel<<<(unsigned)((batch + 127) / 128), 128, 0, h->stream>>>(dA, dB, dx0, dU, dX, n, m, N, lti, batch);
+        h->kernel_name = "rollout_tpi";
+    }
     LQRB_LAUNCH_CHECK(h, "rollout_kernel");
     if (!dev) {
         LQRB_CUDA(h, cudaMemcpyAsync(X, dX, (size_t)batch * N * n * 8, cudaMemcpyDeviceToHost, h->stream));

@@ -909,7 +909,8 @@ extern "C" int32_t lqrb_sqp_dubins_f64(lqrb_handle_t h, int64_t batch, const lqr
         if (fused) {
             // update! + convergence check + _solve! + line-search stage 0 in one kernel
             LQRB_CUDA(h, cudaMemsetAsync(counters, 0, 8, s));
-            if (h->opt("sqp_prefetch", 1))
+            // the cp.async ring measured SLOWER than the L2 prefetch (config 4: 23.9 vs 18.7 ms, same box): option only
+            if (h->opt("sqp_prefetch", 0))
                 dubins_sqp_step_pf_kernel<<<grid, 64, 0, s>>>(Zp, x0p, xfp, multk, data, frec, dz, dinfo, stats, o, batch,
                                                                  opts->eps_p, opts->eps_d, opts->line_search ? 0 : 1, counters);
             else

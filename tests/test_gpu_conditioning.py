@@ -13,7 +13,7 @@ from lqr_b200 import ops, problems
 pytestmark = pytest.mark.gpu
 
 SCALES = [(1.0, 1.0), (1e3, 1e-3), (1e-3, 1e3), (1e5, 1.0), (1.0, 1e-5), (1e2, 1e-2), (1e4, 1e-1), (79.0, 1e-3)]
-SIZES = [(12, 4, 40, 4, "kkt_wp_dmma<12,4"), (8, 4, 30, 4, "kkt_wp_dmma<8,4"), (64, 16, 12, 2, "kkt_cta_dmma<64,16"),
+SIZES = [(12, 4, 40, 4, "kkt_hw<12,4"), (8, 4, 30, 4, "kkt_hw<8,4"), (64, 16, 12, 2, "kkt_cta_dmma<64,16"),
          (24, 8, 20, 2, "kkt_cta_dmma<24,8")]
 
 

@@ -18,7 +18,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("name,kernel", [("cartpole_kkt", "kkt_tpi<4,1"), ("double_integrator_kkt", "kkt_tpi<6,3"),
-                                         ("dubins_kkt", "kkt_tpi<3,2"), ("quad_kkt", "kkt_wp_dmma<12,4"),
+                                         ("dubins_kkt", "kkt_tpi<3,2"), ("quad_kkt", "kkt_hw<12,4"),
                                          ("large_kkt", "kkt_cta_dmma<64,16"), ("mid32_kkt", "kkt_cta_dmma<32,8"),
                                          ("mid24_kkt", "kkt_cta_dmma<24,8"), ("dubins_stage_kkt", "kkt_tpi<3,2,p=3/1/3"),
                                          ("explicit_d2_kkt", "kkt_coop")])

@@ -81,8 +81,9 @@ def test_cooperative_kernel(handle, oracle_mod, n, m, N, mid_p, d2x, hess):
     assert handle.last_kernel.startswith("kkt_coop")
 
 
-# kkt_variant: 0 = warp per instance on the FP64 tensor cores (default), 4 / 3 = half warp per instance (block / column layout)
-QUAD_VARIANTS = [(0, "kkt_wp_dmma<"), (4, "kkt_hw<"), (3, "kkt_hw<")]
+# kkt_variant: 0 = default (half warp per instance, block layout), 3 = its column layout, 5 = warp per instance on the FP64
+# tensor cores (the default only for the shapes the half-warp kernel does not have: odd m, dense Hessian)
+QUAD_VARIANTS = [(0, "kkt_hw<"), (5, "kkt_wp_dmma<"), (3, "kkt_hw<")]
 
 
 @pytest.mark.parametrize("variant,kern", QUAD_VARIANTS)
@@ -101,9 +102,9 @@ def test_half_warp_kernel(handle, oracle_mod, n, m, N, batch, variant, kern):
 
 @pytest.mark.parametrize("hess", [1, 2])
 @pytest.mark.parametrize("soc", [False, True])
-@pytest.mark.parametrize("n,m,N,batch,kern,variant", [(12, 4, 40, 6, "kkt_wp_dmma<", 0), (8, 4, 21, 5, "kkt_wp_dmma<", 0),
+@pytest.mark.parametrize("n,m,N,batch,kern,variant", [(12, 4, 40, 6, "kkt_wp_dmma<", 5), (8, 4, 21, 5, "kkt_wp_dmma<", 5),
                                                       (12, 1, 40, 4, "kkt_wp_dmma<", 0), (8, 1, 25, 3, "kkt_wp_dmma<", 0),
-                                                      (12, 4, 40, 6, "kkt_hw<", 4), (8, 4, 21, 5, "kkt_hw<", 4),
+                                                      (12, 4, 40, 6, "kkt_hw<", 0), (8, 4, 21, 5, "kkt_hw<", 0),
                                                       (64, 16, 12, 2, "kkt_cta_dmma<", 0)])
 def test_tuned_kernels_hessian_modes_and_soc(handle, oracle_mod, n, m, N, batch, kern, variant, hess, soc):
     """Diagonal / block-diagonal BlockCholesky modes (src/block_cholesky.jl:69-91) and the Ginv=false chain of
@@ -120,7 +121,7 @@ def test_tuned_kernels_hessian_modes_and_soc(handle, oracle_mod, n, m, N, batch,
 def test_half_warp_matches_cooperative_kernel(handle):
     prob = problems.random_lqr_kkt(12, 4, 120, 11, seed=5, mid_p=0, hess_mode=1)
     dz1, lam1, i1, r1 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
-    assert handle.last_kernel.startswith("kkt_wp_dmma<")
+    assert handle.last_kernel.startswith("kkt_hw<")
     handle.set_option("kkt_variant", 2)
     try:
         dz2, lam2, i2, r2 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
@@ -135,7 +136,7 @@ def test_half_warp_matches_cooperative_kernel(handle):
 def test_half_warp_info_flags(handle):
     prob = problems.random_lqr_kkt(12, 4, 30, 5, seed=9, mid_p=0, hess_mode=1)
     prob["R"][2, 7] = -np.eye(4)
-    for variant, kern in ((0, "kkt_wp_dmma<"), (4, "kkt_hw<")):
+    for variant, kern in ((0, "kkt_hw<"), (5, "kkt_wp_dmma<")):
         handle.set_option("kkt_variant", variant)
         try:
             _, _, info = ops.kkt_solve_problem(prob, handle=handle)
@@ -273,7 +274,7 @@ def _kkt_residuals_all(prob, dz, lam):
     return max(np.abs(sx).max(), np.abs(su).max()) / scale, prim
 
 
-@pytest.mark.parametrize("n,m,N,batch,kern", [(12, 4, 101, 2049, "kkt_wp_dmma<"), (64, 16, 41, 300, "kkt_cta_dmma<")])
+@pytest.mark.parametrize("n,m,N,batch,kern", [(12, 4, 101, 2049, "kkt_hw<"), (64, 16, 41, 300, "kkt_cta_dmma<")])
 def test_tuned_kernels_kkt_conditions_at_scale(handle, n, m, N, batch, kern):
     """Size-independent property on a batch that spans many CTAs (and an odd tail): the returned step and
     multipliers satisfy the KKT conditions  H dz + g + D'lam = 0,  D dz + d = 0  for EVERY instance."""
@@ -303,3 +304,15 @@ def test_tuned_kernels_chunked_scratch(handle, n, m, N, batch):
     assert (i1 == 0).all() and (i2 == 0).all()
     assert np.array_equal(dz1, dz2) and np.array_equal(lam1, lam2)
     assert np.array_equal(dz1[:64], dz1[64:128])      # replicated instances give replicated answers
+
+
+@pytest.mark.parametrize("soc", [False, True])
+@pytest.mark.parametrize("n,m,N,batch", [(12, 4, 40, 6), (8, 4, 21, 5), (12, 1, 40, 3), (8, 1, 30, 4), (12, 4, 301, 2)])
+def test_dense_hessian_on_the_tensor_core_kernel(handle, oracle_mod, n, m, N, batch, soc):
+    """Whole-matrix BlockCholesky mode (Hux != 0, src/block_cholesky.jl:55-66) at the quadrotor sizes: lands on the
+    warp-per-instance tensor-core kernel (H^-1 is a z-space inverse there), not on the cooperative fallback."""
+    prob = problems.random_lqr_kkt(n, m, N, batch, seed=5 * n + m, mid_p=0, hess_mode=0)
+    assert np.abs(prob["Hux"]).max() > 0
+    _check(prob, handle, oracle_mod, soc=soc, tol=1e-9 if soc else TOL, res_tol=1e-9 if soc else TOL,
+           truth_instances=(0, batch - 1))
+    assert handle.last_kernel.startswith(f"kkt_wp_dmma<{n},{m}") and ",hess=0" in handle.last_kernel

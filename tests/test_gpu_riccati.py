@@ -208,7 +208,27 @@ def test_rollout_entry_point(handle, oracle_mod):
     f = ops.riccati_flatten(prob)
     Xr = np.zeros((50, 101, 4))
     ops.rollout(handle, 4, 1, 101, 50, 0, f["A"], f["B"], f["x0"], np.ascontiguousarray(U), Xr)
-    assert _rel(Xr, X) <= 1e-12
+    assert _rel(Xr, X) <= 1e-12 and handle.last_kernel == "rollout_warp"
+
+
+@pytest.mark.parametrize("n,m,N,b,lti,kern", [(12, 4, 60, 37, False, "rollout_warp"), (7, 3, 20, 5, True, "rollout_warp"),
+                                              (32, 8, 9, 3, False, "rollout_warp"), (40, 8, 7, 3, False, "rollout_tpi")])
+def test_rollout_kernels(handle, n, m, N, b, lti, kern):
+    """rollout! (src/least_squares.jl:195-202) against numpy for both kernels (warp per instance for n <= 32)."""
+    prob = problems.random_lqr_riccati(n, m, N, b, seed=n, lti=lti)
+    rng = np.random.default_rng(1)
+    U = rng.standard_normal((b, N - 1, m))
+    f = ops.riccati_flatten(prob)
+    X = np.zeros((b, N, n))
+    ops.rollout(handle, n, m, N, b, _lib.FLAG_LTI if lti else 0, f["A"], f["B"], f["x0"], U, X)
+    assert handle.last_kernel == kern
+    Xr = np.zeros_like(X)
+    Xr[:, 0] = prob["x0"]
+    for k in range(N - 1):
+        Ak = prob["A"] if lti else prob["A"][:, k]
+        Bk = prob["B"] if lti else prob["B"][:, k]
+        Xr[:, k + 1] = np.einsum("bij,bj->bi", Ak, Xr[:, k]) + np.einsum("bij,bj->bi", Bk, U[:, k])
+    assert _rel(X, Xr) <= 1e-13
 
 
 @pytest.mark.parametrize("n,m,N,batch,kern", [(12, 4, 201, 1027, "riccati_dmma"), (64, 16, 31, 301, "riccati_cta_dmma")])
