@@ -68,7 +68,7 @@ static bool kkt_has_wp(const lqrb_context *h, const KktShape &s) {
     const int64_t v = h->opt("kkt_variant", 0);
     if (v == 2 || v == 3 || v == 4) return false;
     if (!s.uniform || s.d2x) return false;
-    if (s.N < 3 || s.P1 != s.n || s.PM != 0 || s.PN != s.n) return false;
+    if (s.N < 3 || s.P1 != s.n || s.PM > 4 || s.PN != s.n) return false;  // up to 4 stage rows on the interior knots
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_) return true;
     KKT_WP_SIZES(X)
@@ -348,8 +348,9 @@ static int32_t launch_kkt_wp(lqrb_context *h, const KktShape &s, int64_t batch, 
     using L = kwp::Lay<n, m, HESS>;
     using RW = kwp::RecW<n>;
     const int N = s.N;
-    constexpr int WARPS = 4, MINB = 3;  // 168 registers (no spills): 12 warps per SM
-    constexpr size_t smem = (size_t)WARPS * (2 * L::FIRST + 128 + 4) * sizeof(double);
+    constexpr int WARPS = 4, MINB = 3;  // 168 registers: 12 warps per SM
+    constexpr size_t smem = (size_t)WARPS * kwp::warp_smem_doubles<n, m, HESS>() * sizeof(double);
+    const int ps = s.PM;
     auto kern = kwp::kkt_wp_kernel<n, m, HESS, WARPS, MINB>;
     LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
@@ -358,20 +359,20 @@ static int32_t launch_kkt_wp(lqrb_context *h, const KktShape &s, int64_t batch, 
         const int64_t cb = std::min(chunk, batch - first);
         // scratch (reused by every chunk): [records: cb x N x REC] [cinfo: cb]
         double *recs = scratch;
-        int32_t *cinfo = reinterpret_cast<int32_t *>(recs + (size_t)cb * N * RW::REC);
-        const double *dc = data + first * L::data_rows(N);
+        int32_t *cinfo = reinterpret_cast<int32_t *>(recs + (size_t)cb * N * RW::rec(ps));
+        const double *dc = data + first * L::data_rows(N, ps);
         kern<<<(unsigned)((cb + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(
-            dc, recs, dz + first * L::z_rows(N), mult + first * L::mult_rows(N), res ? res + first * L::z_rows(N) : nullptr,
-            info ? info + first : nullptr, cinfo, N, cb, soc);
+            dc, recs, dz + first * L::z_rows(N), mult + first * L::mult_rows(N, ps), res ? res + first * L::z_rows(N) : nullptr,
+            info ? info + first : nullptr, cinfo, N, cb, soc, ps);
         LQRB_LAUNCH_CHECK(h, "kkt_wp_kernel");
         int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * L::z_rows(N),
-                                                 mult + first * L::mult_rows(N), res ? res + first * L::z_rows(N) : nullptr,
+                                                 mult + first * L::mult_rows(N, ps), res ? res + first * L::z_rows(N) : nullptr,
                                                  info ? info + first : nullptr, st);
         if (rc) return rc;
         refined += h->last_refined;
     }
     char nm[128];
-    snprintf(nm, sizeof nm, "kkt_wp_dmma<%d,%d,p=%d/0/%d,hess=%d%s>", n, m, n, n, HESS, soc ? ",soc" : "");
+    snprintf(nm, sizeof nm, "kkt_wp_dmma<%d,%d,p=%d/%d/%d,hess=%d%s>", n, m, n, ps, n, HESS, soc ? ",soc" : "");
     h->kernel_name = nm;
     if (refined) h->kernel_name += "+kkt_coop[" + std::to_string(refined) + " ill-conditioned]";
     h->last_refined = refined;
@@ -436,7 +437,7 @@ static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch) {
     KKT_HW_SIZES(X)
 #undef X
 #define X(N_, M_) \
-    if (s.n == N_ && s.m == M_) return (size_t)batch * ((size_t)s.N * kwp::RecW<N_>::REC + 1) + 2;
+    if (s.n == N_ && s.m == M_) return (size_t)batch * ((size_t)s.N * kwp::RecW<N_>::rec(s.PM) + 1) + 2;
     KKT_WP_SIZES(X)
 #undef X
     return 0;

@@ -50,10 +50,15 @@ struct Lay {
     static constexpr int oC0 = CORE, FIRST = CORE + n * w + n, MID = CORE;
     static constexpr int oCl = HQ + n, LAST = oCl + n * n + n;
     static_assert(CORE % 2 == 0 && FIRST % 2 == 0 && LAST % 2 == 0, "whole knot records are moved by 16-byte bulk copies");
-    __host__ __device__ static constexpr int64_t data_rows(int N) { return FIRST + (int64_t)(N - 2) * MID + LAST; }
-    __host__ __device__ static constexpr int64_t knot_off(int k) { return k == 0 ? 0 : FIRST + (int64_t)(k - 1) * MID; }
-    __host__ __device__ static constexpr int64_t mult_rows(int N) { return 2 * n + (int64_t)(N - 1) * n; }
+    // ps = stage-constraint rows of every interior knot (C (ps x w) | c (ps) follow d in its record), 0 <= ps <= PSMAX
+    static constexpr int PSMAX = 4;
+    __host__ __device__ static constexpr int mid(int ps) { return MID + ps * w + ps; }
+    __host__ __device__ static constexpr int64_t data_rows(int N, int ps = 0) { return FIRST + (int64_t)(N - 2) * mid(ps) + LAST; }
+    __host__ __device__ static constexpr int64_t knot_off(int k, int ps = 0) { return k == 0 ? 0 : FIRST + (int64_t)(k - 1) * mid(ps); }
+    __host__ __device__ static constexpr int64_t mult_rows(int N, int ps = 0) { return 2 * n + (int64_t)(N - 1) * n + (int64_t)(N - 2) * ps; }
     __host__ __device__ static constexpr int64_t z_rows(int N) { return (int64_t)N * n + (int64_t)(N - 1) * m; }
+    // largest knot record, + 2 doubles: a record that starts on an odd double is copied from the even one before it
+    static constexpr int BUF = (FIRST > MID + PSMAX * (w + 1) ? FIRST : MID + PSMAX * (w + 1)) + 2;
 };
 
 struct Tile16 {
@@ -80,9 +85,11 @@ struct Phys {
 // record of one knot in the scratch array: the real entries of Z in fragment order + v (16 physical slots)
 //   [0,32) tile00 e0 | [32,64) tile00 e1 | [64,96) tile01 e0 | [96,112) tile10 e0 (even g) | [112,128) tile10 e1
 //   | [128,144) tile11 e0 (even g) | v
+// interior knots with ps stage rows add: sd_j (16) | E'_j (16) for j < ps | Bi (16) | c' (4)
 template <int n>
 struct RecW {
     static constexpr int ZR = n > 8 ? 144 : 64, REC = ZR + 16;
+    __host__ __device__ static constexpr int rec(int ps) { return REC + (ps > 0 ? 32 * ps + 20 : 0); }
 };
 
 // X Y' accumulated into out: KS contraction steps (4: z space, 3: x space); UPPER: tile (1,0) is not formed
@@ -209,27 +216,37 @@ __device__ __forceinline__ void matvec_col(double (&out)[2][2], const Tile16 &M,
         }
 }
 
+// per-warp shared memory in doubles (the launcher sizes the dynamic allocation with it)
+template <int n, int m, int HESS>
+__host__ __device__ constexpr int warp_smem_doubles() {
+    return 2 * Lay<n, m, HESS>::BUF + 496 + 4;
+}
+
 template <int n, int m, int HESS, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     kkt_wp_kernel(const double *__restrict__ data, double *__restrict__ recs, double *__restrict__ dz,
                   double *__restrict__ mult, double *__restrict__ res, int32_t *__restrict__ info,
-                  int32_t *__restrict__ cinfo, int N, int64_t batch, int soc) {
+                  int32_t *__restrict__ cinfo, int N, int64_t batch, int soc, int ps) {
     using L = Lay<n, m, HESS>;
     using PH = Phys<n, m>;
     using RW = RecW<n>;
     constexpr int w = L::w;
-    constexpr int BUF = L::FIRST;  // the largest knot record
+    constexpr int BUF = L::BUF;
     constexpr int STG = 2;
-    // per-warp shared memory (doubles): STG knot buffers | vectors (16 slots each) | STG mbarriers
+    // per-warp shared memory (doubles): STG knot buffers | vectors (16 slots each) | stage-constraint work | STG mbarriers
     constexpr int VG = 0, VHG = 16, VY = 32, VV = 48, VX = 64, VXP = 80, VR = 96, VD = 112, NVEC = 128;
-    constexpr int WSM = STG * BUF + NVEC + 2 * STG;
+    // stage rows j < 4: cz_j (C_j in z slots) | tc_j = Hi C_j' | E_j then E'_j | sd_j | W_j ; B (16) | Bi (16) | ct, c', bc, xi (4 each)
+    constexpr int SCZ = NVEC, STC = SCZ + 64, SE = STC + 64, SSD = SE + 64, SW = SSD + 64, SB = SW + 64, SBI = SB + 16,
+                  SCT = SBI + 16, SCP = SCT + 4, SBC = SCP + 4, SXI = SBC + 4, NWORK = SXI + 4;
+    constexpr int WSM = STG * BUF + NWORK + 2 * STG;
+    static_assert(WSM == warp_smem_doubles<n, m, HESS>(), "launcher and kernel disagree on the shared-memory size");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
     const int64_t inst = (int64_t)blockIdx.x * WARPS + warp;
     if (inst >= batch) return;  // whole warp leaves; no CTA-wide barrier is used below
     double *wsm = reinterpret_cast<double *>(smem_raw) + (size_t)warp * WSM;
     double *buf = wsm, *vec = wsm + STG * BUF;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(vec + NVEC);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(vec + NWORK);
     if (lane == 0) {
         SM_UNROLL
         for (int s = 0; s < STG; ++s) mbar_init(bars + s, 1);
@@ -237,18 +254,26 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     }
     __syncwarp();
 
-    const double *db = data + inst * L::data_rows(N);
-    double *rb = recs + inst * (int64_t)N * RW::REC;
+    const int64_t doff = inst * L::data_rows(N, ps);  // in doubles from `data` (16-byte aligned)
+    const int recw = RW::rec(ps);
+    double *rb = recs + inst * (int64_t)N * recw;
     double *zb = dz + inst * L::z_rows(N);
-    double *mb = mult + inst * L::mult_rows(N);
+    double *mb = mult + inst * L::mult_rows(N, ps);
     double *resb = res ? res + inst * L::z_rows(N) : nullptr;
+    const int lstride = n + ps;  // lam_j sits at n + j (n + ps) of the multiplier vector, mu of knot j + 1 right after it
 
-    auto knot_len = [&](int k) { return k == 0 ? L::FIRST : (k == N - 1 ? L::LAST : L::MID); };
-    auto issue = [&](int k, int st) {  // the whole record of knot k -> buffer st
+    auto knot_len = [&](int k) { return k == 0 ? L::FIRST : (k == N - 1 ? L::LAST : L::mid(ps)); };
+    // The whole record of knot k -> buffer st.  Bulk copies move 16-byte pieces: with an odd number of stage rows a
+    // record can start on an odd double, so the copy starts at the even double before it (shift 0 or 1) and may
+    // carry one double more at the end (the packed array is a whole number of 32-instance tiles: it stays inside).
+    auto knot_shift = [&](int k) { return (int)((doff + L::knot_off(k, ps)) & 1); };
+    auto issue = [&](int k, int st) {
         if (lane == 0) {
-            const uint32_t bytes = (uint32_t)knot_len(k) * 8u;
+            const int64_t g0 = doff + L::knot_off(k, ps);
+            const int sh = (int)(g0 & 1);
+            const uint32_t bytes = (uint32_t)((knot_len(k) + sh + 1) & ~1) * 8u;
             mbar_expect_tx(bars + st, bytes);
-            bulk_g2s(buf + st * BUF, db + L::knot_off(k), bytes, bars + st);
+            bulk_g2s(buf + st * BUF, data + (g0 - sh), bytes, bars + st);
         }
     };
 
@@ -344,14 +369,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const bool first = k == 0, last = k == N - 1;
         const int st = k & 1;
         mbar_wait(bars + st, (k >> 1) & 1);
-        const double *kp = buf + st * BUF;
+        const double *kp = buf + st * BUF + knot_shift(k);
         const int wk = last ? n : w;
+        const int psk = (first || last) ? 0 : ps;  // stage rows of this knot (the end knots have their own blocks)
         // g (z slots) -> vec; d (x slots)
         double dv = 0.0;
         if (lane < 16) {
             vec[VG + lane] = (!soc && zslot >= 0 && zslot < wk) ? kp[(last ? L::HQ : L::og) + zslot] : 0.0;
             if (xslot >= 0) dv = last ? kp[L::oCl + n * n + xslot] : kp[L::od + xslot];
         }
+        for (int j = 0; j < psk; ++j)  // C_j (row j of the ps x w block, column-major) in z slots
+            if (lane < 16) vec[SCZ + 16 * j + lane] = (zslot >= 0 && zslot < w) ? kp[L::CORE + j + psk * zslot] : 0.0;
         Tile16 Hi, F;
         load_H(Hi, kp, last);
         load_rows(F, last ? kp + L::oCl : kp + L::oD1, wk);
@@ -366,6 +394,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         double r2[2];
         matvec_row(r2, Hi, vec + VG, q);
         put_rows(vec + VHG, r2);  // hg = Hi g
+        for (int j = 0; j < psk; ++j) {  // tc_j = Hi C_j'
+            matvec_row(r2, Hi, vec + SCZ + 16 * j, q);
+            put_rows(vec + STC + 16 * j, r2);
+        }
         Tile16 TF, Gm;
         SM_UNROLL
         for (int rt = 0; rt < 2; ++rt)
@@ -379,6 +411,26 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         {
             const double rr = rows_to_slot(r2, lane);
             if (lane < 16 && xslot >= 0) rho = rr - dv;
+        }
+        if (psk > 0) {
+            // stage rows as vectors (shur! / copy_shur! for the ps rows, src/jacobian_blocks.jl:231-286):
+            //   E_j = F tc_j (x slots),  B = C Hi C',  ct = C hg - c
+            for (int j = 0; j < psk; ++j) {
+                matvec_row(r2, F, vec + STC + 16 * j, q);
+                const double rr = rows_to_slot(r2, lane);
+                if (lane < 16) vec[SE + 16 * j + lane] = xslot >= 0 ? rr : 0.0;
+            }
+            if (lane < psk * psk) {
+                const int j = lane / psk, jp = lane % psk;
+                double sB = 0.0;
+                for (int t = 0; t < 16; ++t) sB = fma(vec[SCZ + 16 * j + t], vec[STC + 16 * jp + t], sB);
+                vec[SB + 4 * j + jp] = sB;
+            } else if (lane >= 16 && lane < 16 + psk) {
+                const int j = lane - 16;
+                double sc = -kp[L::CORE + psk * w + j];
+                for (int t = 0; t < 16; ++t) sc = fma(vec[SCZ + 16 * j + t], vec[VHG + t], sc);
+                vec[SCT + j] = sc;
+            }
         }
         Tile16 Sig, T;
         if (first) {
@@ -448,9 +500,104 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             const double rr = rows_to_slot(r2, lane);
             if (lane < 16) vec[VD + lane] = xslot >= 0 ? rho + rr : 0.0;
         }
+        if (psk > 0) {
+            // eliminate lam_{k-1}:  sd_j = Si D_j (D_j = -(tc_j)_x),  B' = B - D'Si D,  E'_j = E_j + T_x sd_j,
+            // c'_j = ct_j - sd_j'y;   eliminate mu_k:  Bi = B'^-1,  Cp -= E'' Bi E',  dp -= E'' Bi c'
+            __syncwarp();
+            for (int j = 0; j < psk; ++j)
+                if (lane < 16) vec[SW + 16 * j + lane] = xslot >= 0 ? -vec[STC + 16 * j + lane] : 0.0;  // D_j (W_j slot as scratch)
+            __syncwarp();
+            for (int j = 0; j < psk; ++j) {
+                matvec_row(r2, Sig, vec + SW + 16 * j, q);
+                const double rr = rows_to_slot(r2, lane);
+                if (lane < 16) vec[SSD + 16 * j + lane] = xslot >= 0 ? rr : 0.0;
+            }
+            __syncwarp();
+            for (int j = 0; j < psk; ++j) {
+                matvec_row(r2, T, vec + SSD + 16 * j, q);
+                const double rr = rows_to_slot(r2, lane);
+                if (lane < 16) vec[SE + 16 * j + lane] += xslot >= 0 ? rr : 0.0;  // E'_j
+            }
+            if (lane < psk * psk) {
+                const int j = lane / psk, jp = lane % psk;
+                double sB = vec[SB + 4 * j + jp];
+                for (int t = 0; t < 16; ++t) sB = fma(-vec[SW + 16 * j + t], vec[SSD + 16 * jp + t], sB);
+                vec[SB + 4 * j + jp] = sB;  // B'
+            } else if (lane >= 16 && lane < 16 + psk) {
+                const int j = lane - 16;
+                double sc = vec[SCT + j];
+                for (int t = 0; t < 16; ++t) sc = fma(-vec[SSD + 16 * j + t], vec[VY + t], sc);
+                vec[SCP + j] = sc;  // c'
+            }
+            __syncwarp();
+            if (lane == 0) {  // Bi = B'^-1: Gauss-Jordan on at most 4 x 4, potrf sign test on the pivots
+                double bm[4][4];
+                for (int a = 0; a < 4; ++a)
+                    for (int b = 0; b < 4; ++b) bm[a][b] = (a < psk && b < psk) ? vec[SB + 4 * a + b] : (a == b ? 1.0 : 0.0);
+                int badp = 0;
+                for (int kk = 0; kk < 4; ++kk) {
+                    if (kk >= psk) break;
+                    const double piv = bm[kk][kk];
+                    if (!(piv > 0.0) && badp == 0) badp = kk + 1;
+                    const double pinv = 1.0 / piv;
+                    for (int b = 0; b < 4; ++b) bm[kk][b] = b == kk ? pinv : bm[kk][b] * pinv;
+                    for (int a = 0; a < 4; ++a) {
+                        if (a == kk) continue;
+                        const double f = bm[a][kk];
+                        for (int b = 0; b < 4; ++b) bm[a][b] = b == kk ? -f * pinv : fma(-f, bm[kk][b], bm[a][b]);
+                    }
+                }
+                for (int a = 0; a < 4; ++a)
+                    for (int b = 0; b < 4; ++b) vec[SBI + 4 * a + b] = bm[a][b];
+                vec[SXI] = (double)badp;
+            }
+            __syncwarp();
+            {
+                const int badp = (int)vec[SXI];
+                if (badp != 0 && st_all == 0) st_all = (k + 1) * 1000 + 100 + badp;
+            }
+            // W_j = sum_j' Bi[j][j'] E'_j' ;  bc = Bi c'
+            for (int j = 0; j < psk; ++j)
+                if (lane < 16) {
+                    double sW = 0.0;
+                    for (int jp = 0; jp < psk; ++jp) sW = fma(vec[SBI + 4 * j + jp], vec[SE + 16 * jp + lane], sW);
+                    vec[SW + 16 * j + lane] = sW;
+                }
+            if (lane >= 16 && lane < 16 + psk) {
+                const int j = lane - 16;
+                double sb = 0.0;
+                for (int jp = 0; jp < psk; ++jp) sb = fma(vec[SBI + 4 * j + jp], vec[SCP + jp], sb);
+                vec[SBC + j] = sb;
+            }
+            __syncwarp();
+            // Cp -= 1/2 (E'_j W_j' + W_j E'_j')  (products rounded separately: bitwise symmetric);  dp -= sum_j bc_j E'_j
+            for (int j = 0; j < psk; ++j) {
+                const double *E = vec + SE + 16 * j, *W = vec + SW + 16 * j;
+                SM_UNROLL
+                for (int rt = 0; rt < 2; ++rt)
+                    SM_UNROLL
+                    for (int ct = 0; ct < 2; ++ct)
+                        SM_UNROLL
+                        for (int e = 0; e < 2; ++e) {
+                            const int r = 8 * rt + g, c = 8 * ct + 2 * q + e;
+                            const double p1 = __dmul_rn(E[r], W[c]), p2 = __dmul_rn(W[r], E[c]);
+                            Cp.v[rt][ct][e] = __dadd_rn(Cp.v[rt][ct][e], -0.5 * __dadd_rn(p1, p2));
+                        }
+                if (lane < 16) vec[VD + lane] -= vec[SBC + j] * E[lane];
+            }
+            // record: sd_j | E'_j | Bi | c'
+            double *rs = rb + (int64_t)k * recw + RW::REC;
+            for (int j = 0; j < psk; ++j)
+                if (lane < 16) {
+                    __stcs(rs + 32 * j + lane, vec[SSD + 16 * j + lane]);
+                    __stcs(rs + 32 * j + 16 + lane, vec[SE + 16 * j + lane]);
+                }
+            if (lane < 16) __stcs(rs + 32 * psk + lane, vec[SBI + lane]);
+            if (lane < 4) __stcs(rs + 32 * psk + 16 + lane, vec[SCP + lane]);
+        }
         // record: the real entries of Z in fragment order, v
         {
-            double *rk = rb + (int64_t)k * RW::REC;
+            double *rk = rb + (int64_t)k * recw;
             __stcs(rk + lane, Zm.v[0][0][0]);
             __stcs(rk + 32 + lane, Zm.v[0][0][1]);
             if (n > 8) {
@@ -479,7 +626,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const double rr = rows_to_slot(r2, lane);
         if (lane < 16) {
             vec[VX + lane] = xslot >= 0 ? rr : 0.0;
-            if (xslot >= 0) __stcs(mb + L::mult_rows(N) - n + xslot, -rr);  // mu_N
+            if (xslot >= 0) __stcs(mb + L::mult_rows(N, ps) - n + xslot, -rr);  // mu_N
         }
     }
     if (lane == 0) {
@@ -500,7 +647,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const int st = it & 1;
         const int wk = last ? n : w;
         // record
-        const double *rk = rb + (int64_t)k * RW::REC;
+        const double *rk = rb + (int64_t)k * recw;
+        const int psk = (first || last) ? 0 : ps;
         Tile16 Zm;
         Zm.v[0][0][0] = rk[lane];
         Zm.v[0][0][1] = rk[32 + lane];
@@ -520,13 +668,32 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         matvec_col(c4, Zm, vec + VX, g);  // Z' x_k : lane (g, q) holds columns 8 ct + 2 q + e
         {
             const double zx = cols_to_slot(c4, lane);
-            if (lane < 16) vec[VXP + lane] = xslot >= 0 ? vk + zx : 0.0;  // x_{k-1} (k >= 1) or mu_1'
+            double xp = xslot >= 0 ? vk + zx : 0.0;  // x_{k-1} (k >= 1) or mu_1'
+            if (psk > 0) {
+                // xi = Bi (c' - E' x_k)   (mu_k' of the back-substitution);  x_{k-1} -= sum_j xi_j sd_j
+                const double *rs = rk + RW::REC;
+                if (lane < psk) {
+                    double sx = rs[32 * psk + 16 + lane];
+                    for (int t = 0; t < 16; ++t) sx = fma(-rs[32 * lane + 16 + t], vec[VX + t], sx);
+                    vec[SCP + lane] = sx;
+                }
+                __syncwarp();
+                if (lane < psk) {
+                    double sx = 0.0;
+                    for (int jp = 0; jp < psk; ++jp) sx = fma(rs[32 * psk + 4 * lane + jp], vec[SCP + jp], sx);
+                    vec[SXI + lane] = sx;
+                }
+                __syncwarp();
+                if (lane < 16 && xslot >= 0)
+                    for (int j = 0; j < psk; ++j) xp = fma(-vec[SXI + j], rs[32 * j + lane], xp);
+            }
+            if (lane < 16) vec[VXP + lane] = xp;
         }
         {
             const uint32_t par = (uint32_t)(((st == 0 ? uses0 : uses1) + (it >> 1)) & 1);
             mbar_wait(bars + st, par);
         }
-        const double *kp = buf + st * BUF;
+        const double *kp = buf + st * BUF + knot_shift(k);
         if (lane < 16) vec[VG + lane] = (!soc && zslot >= 0 && zslot < wk) ? kp[(last ? L::HQ : L::og) + zslot] : 0.0;
         Tile16 Hi, F;
         load_H(Hi, kp, last);
@@ -547,6 +714,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             rz = vec[VG + lane] - fx;
             if (first) rz -= cx;
             else if (xslot >= 0) rz += vec[VXP + lane];
+            for (int j = 0; j < psk; ++j) rz = fma(-vec[SXI + j], kp[L::CORE + j + psk * zslot], rz);  // C' mu_k, mu = -xi
         }
         if (lane < 16) vec[VR + lane] = rz;
         __syncwarp();  // the knot buffer is free, res is published
@@ -563,8 +731,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
                 __stcs(zb + (int64_t)k * w + zslot, -rr);
                 if (resb) __stcs(resb + (int64_t)k * w + zslot, rz);
             }
-            // multipliers: [mu_1 (n); lam_1 (n); ...; lam_{N-1}; mu_N]; this knot produces lam_{k-1} (k >= 1) or mu_1
-            if (lane < 16 && xslot >= 0) __stcs(mb + (int64_t)k * n + xslot, -vec[VXP + lane]);
+            // multipliers: [mu_1 (n); lam_1 (n); mu_2 (ps); lam_2; ...; lam_{N-1}; mu_N]; this knot produces lam_{k-1}
+            // (k >= 1) or mu_1, and its own stage multipliers mu_k
+            const int64_t lo_ = first ? 0 : (int64_t)n + (int64_t)(k - 1) * lstride;
+            if (lane < 16 && xslot >= 0) __stcs(mb + lo_ + xslot, -vec[VXP + lane]);
+            if (lane < psk) __stcs(mb + lo_ + n + lane, -vec[SXI + lane]);
         }
         __syncwarp();
         if (lane < 16) vec[VX + lane] = vec[VXP + lane];

@@ -316,3 +316,36 @@ def test_dense_hessian_on_the_tensor_core_kernel(handle, oracle_mod, n, m, N, ba
     _check(prob, handle, oracle_mod, soc=soc, tol=1e-9 if soc else TOL, res_tol=1e-9 if soc else TOL,
            truth_instances=(0, batch - 1))
     assert handle.last_kernel.startswith(f"kkt_wp_dmma<{n},{m}") and ",hess=0" in handle.last_kernel
+
+
+@pytest.mark.parametrize("hess,soc", [(1, False), (2, False), (0, False), (1, True)])
+@pytest.mark.parametrize("n,m,N,batch,mid_p", [(12, 4, 40, 7, 1), (12, 4, 41, 6, 2), (8, 4, 30, 5, 1), (12, 4, 25, 3, 3),
+                                               (8, 4, 31, 4, 2), (12, 4, 30, 2, 4)])
+def test_stage_constraints_on_the_tensor_core_kernel(handle, oracle_mod, n, m, N, batch, mid_p, hess, soc):
+    """Mid-horizon stage constraints (the reference's DoubleIntegrator pattern p = [n, ps, ..., ps, n],
+    test/problems.jl:39-43) at the quadrotor sizes run on the warp-per-instance tensor-core kernel — ps <= 4 rows per
+    knot as vector work next to the n x n blocks — not on the cooperative fallback.  Odd ps puts knot records on odd
+    doubles (the bulk copies then start one double early): batches > 1 and both parities of N cover that."""
+    prob = problems.random_lqr_kkt(n, m, N, batch, seed=11 * n + mid_p, mid_p=mid_p, hess_mode=hess)
+    _check(prob, handle, oracle_mod, soc=soc, tol=1e-9 if soc else TOL, res_tol=1e-9 if soc else TOL,
+           truth_instances=(0, batch - 1))
+    assert handle.last_kernel.startswith(f"kkt_wp_dmma<{n},{m},p={n}/{mid_p}/{n}"), handle.last_kernel
+
+
+def test_stage_constraints_match_cooperative_kernel_and_report_info(handle):
+    prob = problems.random_lqr_kkt(12, 4, 50, 9, seed=4, mid_p=2, hess_mode=1)
+    dz1, lam1, i1, r1 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
+    assert handle.last_kernel.startswith("kkt_wp_dmma<12,4,p=12/2/12")
+    handle.set_option("kkt_variant", 2)
+    try:
+        dz2, lam2, i2, r2 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
+        assert handle.last_kernel.startswith("kkt_coop")
+    finally:
+        handle.set_option("kkt_variant", 0)
+    assert (i1 == 0).all() and (i2 == 0).all()
+    assert _rel(dz1, dz2) <= 1e-10 and _rel(lam1, lam2) <= 1e-10
+    assert np.abs(r1 - r2).max() <= 1e-9 * max(1.0, np.abs(r2).max())
+    # two identical stage rows at knot 7 of instance 3: the stage block B' is singular -> info names knot 8, stage 1
+    prob["C"][7][3, 1] = prob["C"][7][3, 0]
+    _, _, info = ops.kkt_solve_problem(prob, handle=handle)
+    assert info[3] // 1000 == 8 and (info[3] % 1000) // 100 == 1 and (np.delete(info, 3) == 0).all(), info

@@ -182,7 +182,8 @@ def matvec_col(M, x):
 
 # ------------------------------------------------------------------ the solve
 def solve_instance(prob, i, soc=False):
-    """One instance of a KKT problem dict (p = [n, 0, ..., 0, n], block-diagonal or diagonal H, structural D2)."""
+    """One instance of a KKT problem dict (p = [n, ps, ..., ps, n] with ps <= 4 stage rows on the interior knots,
+    any Hessian mode, structural D2)."""
     n, m, N = prob["n"], prob["m"], prob["N"]
     mp = Map(n, m)
     zpos = [mp.zmap(p) for p in range(16)]
@@ -199,6 +200,9 @@ def solve_instance(prob, i, soc=False):
             H[:n, :n] = prob["Q"][i, k]
             if k < N - 1:
                 H[n:, n:] = prob["R"][i, k]
+                if prob.get("Hux") is not None and int(prob.get("hess_mode", 1)) == 0:
+                    H[n:, :n] = prob["Hux"][i, k]
+                    H[:n, n:] = prob["Hux"][i, k].T
         M = np.eye(16)
         for a in range(16):
             for b in range(16):
@@ -286,9 +290,38 @@ def solve_instance(prob, i, soc=False):
         P11 = transpose8(X[1][1], 0.5, acc=[0.5 * X[1][1][0], 0.5 * X[1][1][1]])
         P10 = transpose8(X[0][1], 1.0)
         Cp = [[P00, X[0][1]], [P10, P11]]
-        Tv = matvec_row(T, v) if not first else matvec_row(T, v)
+        Tv = matvec_row(T, v)
         dp = (rho + Tv) * xmask
-        recs.append((Z, v))
+        stage = None
+        ps = int(prob["p"][k]) if not (first or last) else 0
+        if ps:
+            # stage rows C (ps x w), c: vectors only.  tc_j = Hi C_j' (z space), B = C Hi C', E_j = F tc_j (x space),
+            # D_j = -(tc_j)_x;  eliminate lam_{k-1}: sd_j = Si D_j, B' = B - D'Si D, E'_j = E_j + T_x sd_j,
+            # c'_j = (C hg - c)_j - sd_j'y;  eliminate mu_k: Bi = B'^-1, Cp -= E'' Bi E', dp -= E'' Bi c'.
+            Cd = prob["C"][k][i]
+            cz = [phys_vec_z(Cd[j]) for j in range(ps)]
+            tc = [matvec_row(Hi, cz[j]) for j in range(ps)]
+            Bm = np.array([[cz[j] @ tc[jp] for jp in range(ps)] for j in range(ps)])
+            Ej = [matvec_row(F, tc[j]) * xmask for j in range(ps)]
+            Dj = [-tc[j] * xmask for j in range(ps)]
+            sd = [matvec_row(Si, Dj[j]) * xmask for j in range(ps)]
+            ct = np.array([cz[j] @ hg - prob["c"][k][i][j] for j in range(ps)])
+            Bp = Bm - np.array([[Dj[j] @ sd[jp] for jp in range(ps)] for j in range(ps)])
+            Ep = [Ej[j] + matvec_row(T, sd[j]) * xmask for j in range(ps)]
+            cp_ = ct - np.array([sd[j] @ y for j in range(ps)])
+            Bi = np.linalg.inv(Bp)              # ps <= 4: every lane does it redundantly in the kernel
+            if not np.all(np.linalg.eigvalsh(Bp) > 0) and not info:
+                info = (k + 1) * 1000 + 100 + 1
+            Wj = [sum(Bi[j, jp] * Ep[jp] for jp in range(ps)) for j in range(ps)]
+            Cd_ = dense_from_tiles(Cp)
+            for j in range(ps):
+                Cd_ -= np.outer(Ep[j], Wj[j])
+            Cd_ = 0.5 * (Cd_ + Cd_.T)
+            Cp = tiles_from_dense(Cd_)
+            bc = Bi @ cp_
+            dp = dp - sum(bc[j] * Ep[j] for j in range(ps))
+            stage = (sd, Bi, Ep, cp_, cz)
+        recs.append((Z, v, stage))
     # last block: mu_N' = Cp^-1 dp
     Cd = dense_from_tiles(Cp) + padx
     Bl, bad, piv = inv16(tiles_from_dense(Cd), x_space=True)
@@ -297,18 +330,29 @@ def solve_instance(prob, i, soc=False):
     xcur = matvec_row(Bl, dp) * xmask
 
     NN = N * n + (N - 1) * m
-    P = 2 * n + (N - 1) * n
+    psm = int(prob["p"][1]) if N > 2 else 0
+    P = 2 * n + (N - 1) * n + (N - 2) * psm
     dz, mult = np.zeros(NN), np.zeros(P)
+
+    def lam_off(kk):     # offset of lam_kk (0-based knot), kk = 0 .. N-2
+        return n + kk * (n + psm)
     xinv = [p for p in range(16) if xpos[p] >= 0]
     mult[P - n:] = -xcur[xinv]
     for k in range(N - 1, -1, -1):
         first, last = k == 0, k == N - 1
-        Z, v = recs[k]
+        Z, v, stage = recs[k]
         xprev = (v + matvec_col(Z, xcur)) * xmask      # x_{k-1} = v_k + Z_k' x_k
+        xi = None
+        if stage is not None:
+            sd, Bi, Ep, cp_, cz = stage
+            xi = Bi @ (cp_ - np.array([Ep[j] @ xcur for j in range(len(sd))]))   # mu_k' = B'^-1 (c' - E' x_k)
+            xprev = (xprev - sum(xi[j] * sd[j] for j in range(len(sd)))) * xmask
         gz = np.zeros(16) if soc else phys_vec_z(np.concatenate([prob["q"][i, k], prob["r"][i, k]]) if not last else prob["q"][i, k])
         Fd = prob["C"][k][i] if last else np.concatenate([prob["A"][i, k], prob["B"][i, k]], axis=1)
         F = tiles_from_dense(phys_rows_z(Fd))
         res = gz - matvec_col(F, xcur)                 # g + D1' lam_k,  lam = -x
+        if xi is not None:
+            res = res - sum(xi[j] * cz[j] for j in range(len(xi)))   # C' mu_k, mu = -xi
         if not first:
             res = res + xprev                          # D2' lam_{k-1} = +x_{k-1} on the state slots
         else:
@@ -321,7 +365,12 @@ def solve_instance(prob, i, soc=False):
             zz = zpos[ppos]
             if 0 <= zz < w:
                 dz[k * (n + m) + zz] = z[ppos]
-        mult[k * n: k * n + n] = -xprev[xinv]
+        if first:
+            mult[:n] = -xprev[xinv]
+        else:
+            mult[lam_off(k - 1): lam_off(k - 1) + n] = -xprev[xinv]
+        if xi is not None:
+            mult[lam_off(k - 1) + n: lam_off(k - 1) + n + psm] = -xi
         xcur = xprev
     return dz, mult, info, spread
 
@@ -331,8 +380,10 @@ def main():
     from lqr_b200 import problems
     oracle.build()
     worst = 0.0
-    for (n, m, N, b, hess) in [(12, 4, 9, 2, 1), (12, 4, 30, 2, 2), (8, 4, 12, 2, 1), (12, 2, 12, 1, 1), (8, 1, 14, 1, 1), (12, 4, 5, 1, 1)]:
-        prob = problems.random_lqr_kkt(n, m, N, b, seed=n + N, mid_p=0, hess_mode=hess)
+    for (n, m, N, b, hess, mid_p) in [(12, 4, 9, 2, 1, 0), (12, 4, 30, 2, 2, 0), (8, 4, 12, 2, 1, 0), (12, 2, 12, 1, 1, 0),
+                                      (8, 1, 14, 1, 1, 0), (12, 4, 5, 1, 1, 0), (12, 4, 12, 2, 0, 0), (12, 4, 12, 2, 1, 1),
+                                      (12, 4, 15, 1, 1, 2), (8, 4, 12, 1, 0, 1), (12, 4, 12, 1, 1, 3)]:
+        prob = problems.random_lqr_kkt(n, m, N, b, seed=n + N, mid_p=mid_p, hess_mode=hess)
         if hess == 2:
             for key in ("Q", "R"):
                 prob[key] = prob[key] * np.eye(prob[key].shape[-1])
@@ -342,7 +393,7 @@ def main():
                 dz, lam, info, spread = solve_instance(prob, i, soc=soc)
                 e = max(np.linalg.norm(dz - dzo[i]) / np.linalg.norm(dzo[i]), np.linalg.norm(lam - lamo[i]) / np.linalg.norm(lamo[i]))
                 worst = max(worst, e)
-                print(f"n={n} m={m} N={N} hess={hess} soc={soc} inst={i}: rel err {e:.2e} info {info} log2 pivot ratio {np.log2(spread):.1f}")
+                print(f"n={n} m={m} N={N} hess={hess} mid_p={mid_p} soc={soc} inst={i}: rel err {e:.2e} info {info} log2 pivot ratio {np.log2(spread):.1f}")
     assert worst < 1e-9, worst
     print("EMULATOR_OK worst", worst)
 
