@@ -33,7 +33,7 @@ def test_riccati_families_are_deterministic(handle, n, m, N, b, kern):
 @pytest.mark.parametrize("n,m,N,b,mid_p,kern", [(3, 2, 41, 97, 0, "kkt_tpi"), (6, 3, 20, 33, 1, "kkt_tpi"),
                                                 (12, 4, 60, 37, 0, "kkt_hw<"), (8, 4, 33, 21, 0, "kkt_hw<"), (12, 1, 60, 37, 0, "kkt_wp_dmma<"), (8, 1, 33, 21, 0, "kkt_wp_dmma<"),
                                                 (64, 16, 17, 5, 0, "kkt_cta_dmma"), (24, 8, 21, 7, 0, "kkt_cta_dmma"),
-                                                (12, 4, 12, 9, 2, "kkt_coop"), (40, 8, 9, 3, 1, "kkt_coop")])
+                                                (12, 4, 12, 9, 2, "kkt_wp_dmma<"), (20, 6, 12, 9, 2, "kkt_coop"), (40, 8, 9, 3, 1, "kkt_coop")])
 def test_kkt_families_are_deterministic(handle, n, m, N, b, mid_p, kern):
     prob = problems.random_lqr_kkt(n, m, N, b, seed=n + N, mid_p=mid_p, hess_mode=1)
     ref = ops.kkt_solve_problem(prob, want_res=True, handle=handle)

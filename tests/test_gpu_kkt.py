@@ -320,7 +320,7 @@ def test_dense_hessian_on_the_tensor_core_kernel(handle, oracle_mod, n, m, N, ba
 
 @pytest.mark.parametrize("hess,soc", [(1, False), (2, False), (0, False), (1, True)])
 @pytest.mark.parametrize("n,m,N,batch,mid_p", [(12, 4, 40, 7, 1), (12, 4, 41, 6, 2), (8, 4, 30, 5, 1), (12, 4, 25, 3, 3),
-                                               (8, 4, 31, 4, 2), (12, 4, 30, 2, 4)])
+                                               (8, 4, 31, 4, 2), (8, 4, 40, 3, 3)])
 def test_stage_constraints_on_the_tensor_core_kernel(handle, oracle_mod, n, m, N, batch, mid_p, hess, soc):
     """Mid-horizon stage constraints (the reference's DoubleIntegrator pattern p = [n, ps, ..., ps, n],
     test/problems.jl:39-43) at the quadrotor sizes run on the warp-per-instance tensor-core kernel — ps <= 4 rows per
