@@ -13,8 +13,9 @@
 // work is products):  with F = [A B] (or C_N at the last knot), Hi = H_k^-1, T = F Hi,
 //   G = T F',   Sigma = Cp + Hi_xx,   Si = Sigma^-1,   Z = T_x Si (the record, = -U'),   v = Si y,
 //   Cp <- G - Z T_x' (symmetrised exactly),   dp <- (F hg - d) + T_x v,
-// backward  x_{k-1} = v_k + Z_k' x_k,  Lambda = -x,  res_k,  dz_k = -Hi res_k  (Hi is re-formed: cheaper than a
-// round trip through HBM).
+// backward  x_{k-1} = v_k + Z_k' x_k,  Lambda = -x,  res_k,  dz_k = -Hi res_k  (Hi comes back from the record: the
+// kernel is bound by its serial pivot chains, not by HBM; for the same reason H_{k+1} is inverted in lock step with
+// Sigma_k in the forward sweep).
 //
 // Layout.  A 16 x 16 "physical" index space, tile 0 = x0..x7, tile 1 = [x8 u0 x9 u1 x10 u2 x11 u3] (the map of
 // riccati_dmma_kernels.cuh): z-space matrices (H, Hi, F, T) use every slot, x-space matrices (Sigma, Si, Cp, G, Z:
@@ -86,9 +87,12 @@ struct Phys {
 //   [0,32) tile00 e0 | [32,64) tile00 e1 | [64,96) tile01 e0 | [96,112) tile10 e0 (even g) | [112,128) tile10 e1
 //   | [128,144) tile11 e0 (even g) | v
 // interior knots with ps stage rows add: sd_j (16) | E'_j (16) for j < ps | Bi (16) | c' (4)
+// then Hi = H_k^-1 (z space, tiles 00 | 01 | 11 in fragment order, 6 x 32 doubles): the backward sweep reads it back
+// instead of inverting H_k a second time (the serial pivot chains, not HBM, bound this kernel);
+// interior knots with ps stage rows add: sd_j (16) | E'_j (16) for j < ps | Bi (16) | c' (4)
 template <int n>
 struct RecW {
-    static constexpr int ZR = n > 8 ? 144 : 64, REC = ZR + 16;
+    static constexpr int ZR = n > 8 ? 144 : 64, HIO = ZR + 16, REC = HIO + 192;
     __host__ __device__ static constexpr int rec(int ps) { return REC + (ps > 0 ? 32 * ps + 20 : 0); }
 };
 
@@ -147,6 +151,70 @@ __device__ __forceinline__ int gj8c(double (&a)[2], int g, int q, int &lo, int &
         a[1] = rowk ? (c1 ? p : prow1 * p) : (c1 ? -f : u1);
     }
     return bad;
+}
+
+// one pivot step of gj8c (kk is a compile-time constant after unrolling)
+__device__ __forceinline__ void gj_step(double (&a)[2], int kk, int g, int q, int &lo, int &hi, int &bad) {
+    const double prow0 = __shfl_sync(0xffffffffu, a[0], 4 * kk + q);
+    const double prow1 = __shfl_sync(0xffffffffu, a[1], 4 * kk + q);
+    const double src = (kk & 1) ? a[1] : a[0];
+    const double pcol = __shfl_sync(0xffffffffu, src, 4 * g + (kk >> 1));
+    const double piv = __shfl_sync(0xffffffffu, src, 4 * kk + (kk >> 1));
+    if (!(piv > 0.0) && bad == 0) bad = kk + 1;
+    lo = min(lo, __double2hiint(piv));
+    hi = max(hi, __double2hiint(piv));
+    const double p = fast_rcp(piv);
+    const double f = pcol * p;
+    const bool rowk = g == kk, c0 = 2 * q == kk, c1 = 2 * q + 1 == kk;
+    const double u0 = fma(-f, prow0, a[0]), u1 = fma(-f, prow1, a[1]);
+    a[0] = rowk ? (c0 ? p : prow0 * p) : (c0 ? -f : u0);
+    a[1] = rowk ? (c1 ? p : prow1 * p) : (c1 ? -f : u1);
+}
+
+// Two independent 8 x 8 inversions pivot by pivot in lock step: the serial chain shuffle -> reciprocal -> FMA of one
+// tile fills the latency of the other (the kernel is bound by these chains, not by issue slots).  Tile a is full
+// (z space), tile b is an x-space tile 1 with NEVEN real even slots when SKIPB.
+template <bool SKIPB, int NEVEN>
+__device__ __forceinline__ void gj8c_pair(double (&a)[2], double (&b)[2], int g, int q, int &loa, int &hia, int &bada,
+                                          int &lob, int &hib, int &badb) {
+    SM_UNROLL
+    for (int kk = 0; kk < 8; ++kk) {
+        gj_step(a, kk, g, q, loa, hia, bada);
+        if (!(SKIPB && ((kk & 1) || (kk >> 1) >= NEVEN))) gj_step(b, kk, g, q, lob, hib, badb);
+    }
+}
+
+// inv16 of A (z space) and of B (x space) interleaved step by step; returns the bad-pivot positions (1-based) or 0
+template <int NX1>
+__device__ __forceinline__ void inv16_pair(Tile16 &A, Tile16 &B, int g, int q, int &loa, int &hia, int &bada, int &lob,
+                                           int &hib, int &badb) {
+    int a0 = 0, b0 = 0, a1 = 0, b1 = 0;
+    gj8c_pair<false, 4>(A.v[0][0], B.v[0][0], g, q, loa, hia, a0, lob, hib, b0);
+    double Ta[2] = {0.0, 0.0}, Tta[2] = {0.0, 0.0}, Tb[2] = {0.0, 0.0}, Ttb[2] = {0.0, 0.0};
+    prod8(Ta, A.v[0][0], A.v[1][0], 1.0);
+    prod8(Tb, B.v[0][0], B.v[1][0], 1.0);
+    prod8(Tta, A.v[1][0], A.v[0][0], 1.0);
+    prod8(Ttb, B.v[1][0], B.v[0][0], 1.0);
+    prod8(A.v[1][1], A.v[1][0], Tta, -1.0);
+    prod8(B.v[1][1], B.v[1][0], Ttb, -1.0);
+    gj8c_pair<true, NX1>(A.v[1][1], B.v[1][1], g, q, loa, hia, a1, lob, hib, b1);
+    double Na01[2] = {0.0, 0.0}, Na10[2] = {0.0, 0.0}, Nb01[2] = {0.0, 0.0}, Nb10[2] = {0.0, 0.0};
+    prod8(Na01, Ta, A.v[1][1], -1.0);
+    prod8(Nb01, Tb, B.v[1][1], -1.0);
+    prod8(Na10, A.v[1][1], Ta, -1.0);
+    prod8(Nb10, B.v[1][1], Tb, -1.0);
+    prod8(A.v[0][0], Na01, Ta, -1.0);
+    prod8(B.v[0][0], Nb01, Tb, -1.0);
+    A.v[0][1][0] = Na01[0];
+    A.v[0][1][1] = Na01[1];
+    A.v[1][0][0] = Na10[0];
+    A.v[1][0][1] = Na10[1];
+    B.v[0][1][0] = Nb01[0];
+    B.v[0][1][1] = Nb01[1];
+    B.v[1][0][0] = Nb10[0];
+    B.v[1][0][1] = Nb10[1];
+    bada = a0 != 0 ? a0 : (a1 != 0 ? 8 + a1 : 0);
+    badb = b0 != 0 ? b0 : (b1 != 0 ? 8 + b1 : 0);
 }
 
 // Inverse of a symmetric positive definite 16 x 16 physical matrix (identity on its pad slots), in place, by 2 x 2
@@ -363,6 +431,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         for (int ct = 0; ct < 2; ++ct) Cp.v[rt][ct][0] = Cp.v[rt][ct][1] = 0.0;
     if (lane < 16) vec[VD + lane] = 0.0;  // dp
     __syncwarp();
+    // H_0^-1; from then on H_{k+1} is inverted in lock step with Sigma_k (they are independent: two serial pivot
+    // chains in flight instead of one)
+    Tile16 Hnext;
+    {
+        mbar_wait(bars, 0);
+        load_H(Hnext, buf + knot_shift(0), N == 1);
+        const int bad = inv16<false, 4>(Hnext, g, q, hlo, hhi);
+        if (bad != 0) st_all = 1000 + PH::zmap(bad - 1) + 1;
+    }
 
     // ---------------- forward sweep: k = 0 .. N-1
     for (int k = 0; k < N; ++k) {
@@ -380,17 +457,18 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         }
         for (int j = 0; j < psk; ++j)  // C_j (row j of the ps x w block, column-major) in z slots
             if (lane < 16) vec[SCZ + 16 * j + lane] = (zslot >= 0 && zslot < w) ? kp[L::CORE + j + psk * zslot] : 0.0;
-        Tile16 Hi, F;
-        load_H(Hi, kp, last);
+        Tile16 Hi = Hnext, F;  // H_k^-1 was formed during the previous knot
         load_rows(F, last ? kp + L::oCl : kp + L::oD1, wk);
-        __syncwarp();
-        {
-            const int bad = inv16<false, 4>(Hi, g, q, hlo, hhi);
-            if (bad != 0 && st_all == 0) {
-                const int z = PH::zmap(bad - 1);
-                st_all = (k + 1) * 1000 + z + 1;
-            }
+        {   // Hi -> record (the backward sweep reads it back instead of inverting H_k again)
+            double *rh = rb + (int64_t)k * recw + RW::HIO;
+            __stcs(rh + lane, Hi.v[0][0][0]);
+            __stcs(rh + 32 + lane, Hi.v[0][0][1]);
+            __stcs(rh + 64 + lane, Hi.v[0][1][0]);
+            __stcs(rh + 96 + lane, Hi.v[0][1][1]);
+            __stcs(rh + 128 + lane, Hi.v[1][1][0]);
+            __stcs(rh + 160 + lane, Hi.v[1][1][1]);
         }
+        __syncwarp();
         double r2[2];
         matvec_row(r2, Hi, vec + VG, q);
         put_rows(vec + VHG, r2);  // hg = Hi g
@@ -464,11 +542,20 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         {
             lo = 0x7fffffff;
             hi = 0;
-            const int bad = inv16<true, n - 8>(Sig, g, q, lo, hi);
+            int bad = 0, badh = 0;
+            if (!last) {
+                // H_{k+1} sits in the other buffer (copied two knots ahead); waiting again on a completed phase is free
+                mbar_wait(bars + (st ^ 1), ((k + 1) >> 1) & 1);
+                load_H(Hnext, buf + (st ^ 1) * BUF + knot_shift(k + 1), k + 1 == N - 1);
+                inv16_pair<n - 8>(Hnext, Sig, g, q, hlo, hhi, badh, lo, hi, bad);
+            } else {
+                bad = inv16<true, n - 8>(Sig, g, q, lo, hi);
+            }
             if (bad != 0 && st_all == 0) {
                 const int x = PH::xmap(bad - 1);
                 st_all = first ? 1000 + 100 + x + 1 : k * 1000 + 200 + x + 1;
             }
+            if (badh != 0 && st_all == 0) st_all = (k + 2) * 1000 + PH::zmap(badh - 1) + 1;
             if (lo > 0 && hi >= lo) spread = max(spread, hi - lo);
         }
         Tile16 Zm;
@@ -696,7 +783,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const double *kp = buf + st * BUF + knot_shift(k);
         if (lane < 16) vec[VG + lane] = (!soc && zslot >= 0 && zslot < wk) ? kp[(last ? L::HQ : L::og) + zslot] : 0.0;
         Tile16 Hi, F;
-        load_H(Hi, kp, last);
+        {   // H_k^-1 from the record (upper tiles; tile (1,0) is the transpose of tile (0,1))
+            const double *rh = rk + RW::HIO;
+            Hi.v[0][0][0] = rh[lane];
+            Hi.v[0][0][1] = rh[32 + lane];
+            Hi.v[0][1][0] = rh[64 + lane];
+            Hi.v[0][1][1] = rh[96 + lane];
+            Hi.v[1][1][0] = rh[128 + lane];
+            Hi.v[1][1][1] = rh[160 + lane];
+            Hi.v[1][0][0] = Hi.v[1][0][1] = 0.0;
+            transpose8(Hi.v[1][0], Hi.v[0][1], 1.0, g, q);
+        }
         load_rows(F, last ? kp + L::oCl : kp + L::oD1, wk);
         __syncwarp();  // x_{k-1}, g are published
         // res_k = g_k + D1' lam_k + D2' lam_{k-1} (+ C_1' mu_1)  with Lambda = -x   (calc_residual! :201-236)
@@ -719,10 +816,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         if (lane < 16) vec[VR + lane] = rz;
         __syncwarp();  // the knot buffer is free, res is published
         if (it + 2 < N) issue_b(it + 2);
-        {
-            int dl = 0x7fffffff, dh = 0;
-            inv16<false, 4>(Hi, g, q, dl, dh);
-        }
         double r2[2];
         matvec_row(r2, Hi, vec + VR, q);  // dz_k = -Hi res_k   (calc_primals! :195-199)
         {
