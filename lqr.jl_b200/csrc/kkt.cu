@@ -425,22 +425,25 @@ static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch,
     return 0;
 }
 
+// scratch of the tuned kernels in doubles: the largest need of the families that have this (n, m) — which one runs
+// also depends on options (kkt_variant) and on the Hessian mode / stage rows
 static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch) {
+    size_t per = 0;
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_)   \
-        return (size_t)batch * ((size_t)s.N * kcta::Lay<N_, M_>::REC + kcta::Lay<N_, M_>::prep_rows(s.N) + 1) + 2;
+        per = std::max(per, (size_t)s.N * kcta::Lay<N_, M_>::REC + kcta::Lay<N_, M_>::prep_rows(s.N) + 1);
     KKT_CTA_SIZES(X)
 #undef X
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_)   \
-        return (size_t)batch * ((size_t)s.N * (khw::Lay<N_, M_>::REC + khw::Lay<N_, M_>::HI) + 1) + 2;
+        per = std::max(per, (size_t)s.N * (khw::Lay<N_, M_>::REC + khw::Lay<N_, M_>::HI) + 1);
     KKT_HW_SIZES(X)
 #undef X
 #define X(N_, M_) \
-    if (s.n == N_ && s.m == M_) return (size_t)batch * ((size_t)s.N * kwp::RecW<N_>::rec(s.PM) + 1) + 2;
+    if (s.n == N_ && s.m == M_) per = std::max(per, (size_t)s.N * kwp::RecW<N_>::rec(s.PM) + 1);
     KKT_WP_SIZES(X)
 #undef X
-    return 0;
+    return per == 0 ? 0 : (size_t)batch * per + 2;
 }
 
 // The tuned large-size kernels keep records and pre-pass results in scratch (2.5 MB per instance for n=12,
