@@ -34,7 +34,7 @@ from ._lib import HESS_BLOCKDIAG, HESS_DENSE, HESS_DIAG, Handle, LqrbError
 __all__ = [
     "LQRProblem", "Primals", "LQRSolution", "DPSolver", "LeastSquaresSolver", "solve_", "rollout_", "size", "num_vars",
     "BlockCholesky", "cholesky_", "ldiv_", "ldiv", "InvertedQuadratic", "update_cost_", "update_cholesky_",
-    "gradient", "ConstraintBlock", "ConstraintBlocks", "dims", "copy_blocks_", "num_constraints",
+    "gradient", "ConstraintBlock", "ConstraintBlocks", "dims", "copy_blocks_", "gen_con_inds", "num_constraints",
     "CholeskySolver", "build_shur_factors", "calculate_shur_factors_", "forward_substitution_",
     "backward_substitution_", "calculate_primals_", "residual", "second_order_correction_", "get_step",
     "get_multipliers", "get_residual", "get_linearized_constraints", "get_cost_expansion", "step_",
@@ -343,6 +343,38 @@ def ConstraintBlocks(n, m, N, p, batch=1):
             blk.D2[:, :, :n] = -np.eye(n)
         blocks.append(blk)
     return blocks
+
+
+def gen_con_inds(cons, N, structure="by_knotpoint"):
+    """gen_con_inds(conSet, structure) (src/conblocks.jl:122-166): index ranges of every constraint at every knot it
+    applies to, in the concatenated constraint vector.  `cons` stands in for TrajOptCore's ConstraintList (un-vendored):
+    a list of (length, knots) with `knots` a range of 0-based knot indices.  Returns cons_inds[i][j] = range for
+    constraint i at its j-th knot.  structure: "by_constraint" | "by_knotpoint" | "by_block" (per-knot offsets, the order
+    BlockConstraintSet uses, :186)."""
+    out = [[range(0, 0) for _ in knots] for _, knots in cons]
+    if structure == "by_constraint":
+        idx = 0
+        for i, (ln, knots) in enumerate(cons):
+            for j, _ in enumerate(knots):
+                out[i][j] = range(idx, idx + ln)
+                idx += ln
+    elif structure == "by_knotpoint":
+        idx = 0
+        for k in range(N):
+            for i, (ln, knots) in enumerate(cons):
+                if k in knots:
+                    out[i][k - knots[0]] = range(idx, idx + ln)
+                    idx += ln
+    elif structure == "by_block":
+        idx = [0] * N
+        for k in range(N):
+            for i, (ln, knots) in enumerate(cons):
+                if k in knots:
+                    out[i][k - knots[0]] = range(idx[k], idx[k] + ln)
+                    idx[k] += ln
+    else:
+        raise ValueError(f"unknown structure {structure!r}")
+    return out
 
 
 def num_constraints(blocks):

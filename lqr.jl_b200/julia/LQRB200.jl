@@ -334,6 +334,35 @@ function copy_blocks!(D, d, blocks::Vector{ConstraintBlock}, i::Int=1)
     return D, d
 end
 
+"gen_con_inds(cons, N, structure): src/conblocks.jl:122-166.  `cons` stands in for TrajOptCore's ConstraintList: a vector
+of (length, knots::UnitRange) pairs; returns cons[i][j] = index range of constraint i at its j-th knot."
+function gen_con_inds(cons::Vector{<:Tuple{Int,UnitRange{Int}}}, N::Int, structure::Symbol=:by_knotpoint)
+    out = [[1:0 for _ in knots] for (_, knots) in cons]
+    if structure == :by_constraint
+        idx = 0
+        for (i, (len, knots)) in enumerate(cons), j in eachindex(knots)
+            out[i][j] = idx .+ (1:len); idx += len
+        end
+    elseif structure == :by_knotpoint
+        idx = 0
+        for k = 1:N, (i, (len, knots)) in enumerate(cons)
+            if k in knots
+                out[i][k - first(knots) + 1] = idx .+ (1:len); idx += len
+            end
+        end
+    elseif structure == :by_block
+        idx = zeros(Int, N)
+        for k = 1:N, (i, (len, knots)) in enumerate(cons)
+            if k in knots
+                out[i][k - first(knots) + 1] = idx[k] .+ (1:len); idx[k] += len
+            end
+        end
+    else
+        throw(ArgumentError("unknown structure $structure"))
+    end
+    return out
+end
+
 # ------------------------------------------------------------------ CholeskySolver (src/cholesky_solver.jl)
 # The reference fills Jinv / conSet.blocks through TrajOptCore (update!, :155-164).  A batched caller supplies a
 # `linearize!(solver)` callback that writes the same linearised blocks (Q, R, Hux, q, r, A, B, d, C, c) as plain
@@ -615,7 +644,7 @@ kkt_unpack!(h::Handle, n, m, N, batch, p::Vector{Int32}, hess_mode, explicit_d2,
 
 export Handle, LQRBError, LQRProblem, LQRSolution, DPSolver, LeastSquaresSolver, solve!, rollout!, num_vars, state, control,
        BlockCholesky, InvertedQuadratic, update_cost!, update_cholesky!, gradient,
-       ConstraintBlock, ConstraintBlocks, dims, copy_blocks!,
+       ConstraintBlock, ConstraintBlocks, dims, copy_blocks!, gen_con_inds,
        CholeskySolver, build_shur_factors, calculate_shur_factors!, forward_substitution!, backward_substitution!,
        calculate_primals!, solve_factored!, copy_shur_factors!, get_shur_factors, get_cholesky,
        _solve!, step!, update!, second_order_correction!, residual, get_step, get_multipliers, get_residual,

@@ -203,3 +203,21 @@ def test_julia_shim_binds_every_header_symbol():
                  "get_step", "get_multipliers", "get_shur_factors", "get_cholesky", "copy_shur_factors!", "rollout!",
                  "second_order_correction!", "num_vars"):
         assert re.search(r"\b" + re.escape(name) + r"(?![A-Za-z0-9_])", jl.split("export", 1)[1]), name
+
+
+def test_gen_con_inds_orderings():
+    """gen_con_inds (src/conblocks.jl:122-166) on the DoubleIntegrator constraint list of test/problems.jl:39-48:
+    goal (n rows at knot N), a 1-row plane constraint on knots 2..N-1, the dynamics (n rows on knots 1..N-1)."""
+    n, N = 6, 5
+    cons = [(n, range(N - 1, N)), (1, range(1, N - 1)), (n, range(0, N - 1))]
+    byc = lqr_b200.gen_con_inds(cons, N, "by_constraint")
+    assert byc[0][0] == range(0, 6) and byc[1][0] == range(6, 7) and byc[1][2] == range(8, 9) and byc[2][0] == range(9, 15)
+    byk = lqr_b200.gen_con_inds(cons, N, "by_knotpoint")
+    # knot 0: dynamics; knot 1: plane then dynamics; ...; knot 4: goal
+    assert byk[2][0] == range(0, 6) and byk[1][0] == range(6, 7) and byk[2][1] == range(7, 13) and byk[0][0] == range(27, 33)
+    assert sum(len(r) for rows in byk for r in rows) == n + (N - 2) + n * (N - 1)
+    byb = lqr_b200.gen_con_inds(cons, N, "by_block")
+    # per-knot offsets: at an interior knot the stage row comes first, then the dynamics rows
+    assert byb[1][0] == range(0, 1) and byb[2][1] == range(1, 7) and byb[2][0] == range(0, 6) and byb[0][0] == range(0, 6)
+    with pytest.raises(ValueError):
+        lqr_b200.gen_con_inds(cons, N, "nope")
