@@ -61,7 +61,7 @@ static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
 }
 
 // warp-per-instance FP64 tensor-core instantiations (kkt_wp_kernels.cuh; same stage pattern)
-#define KKT_WP_SIZES(X) X(12, 4) X(8, 4) X(12, 1) X(8, 1)
+#define KKT_WP_SIZES(X) X(12, 4) X(8, 4) X(12, 3) X(8, 3) X(12, 2) X(8, 2) X(12, 1) X(8, 1)
 
 // kkt_variant: 0 = default (half-warp kernel where it exists, else this one), 5 = force this kernel
 static bool kkt_has_wp(const lqrb_context *h, const KktShape &s) {

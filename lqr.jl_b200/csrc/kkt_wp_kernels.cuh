@@ -50,7 +50,8 @@ struct Lay {
     static constexpr int oQ = 0, oR = HQ, og = oR + HR, oD1 = og + w, od = oD1 + n * w, CORE = od + n;
     static constexpr int oC0 = CORE, FIRST = CORE + n * w + n, MID = CORE;
     static constexpr int oCl = HQ + n, LAST = oCl + n * n + n;
-    static_assert(CORE % 2 == 0 && FIRST % 2 == 0 && LAST % 2 == 0, "whole knot records are moved by 16-byte bulk copies");
+    // records may have odd lengths and start on odd doubles: the bulk copies (16-byte pieces) start at the even double
+    // before the record and end at the even double after it, see issue() in the kernel
     // ps = stage-constraint rows of every interior knot (C (ps x w) | c (ps) follow d in its record), 0 <= ps <= PSMAX
     static constexpr int PSMAX = 4;
     __host__ __device__ static constexpr int mid(int ps) { return MID + ps * w + ps; }
@@ -59,7 +60,8 @@ struct Lay {
     __host__ __device__ static constexpr int64_t mult_rows(int N, int ps = 0) { return 2 * n + (int64_t)(N - 1) * n + (int64_t)(N - 2) * ps; }
     __host__ __device__ static constexpr int64_t z_rows(int N) { return (int64_t)N * n + (int64_t)(N - 1) * m; }
     // largest knot record, + 2 doubles: a record that starts on an odd double is copied from the even one before it
-    static constexpr int BUF = (FIRST > MID + PSMAX * (w + 1) ? FIRST : MID + PSMAX * (w + 1)) + 2;
+    // (rounded up to an even count: every stage of the ring is a 16-byte aligned bulk-copy destination)
+    static constexpr int BUF = ((FIRST > MID + PSMAX * (w + 1) ? FIRST : MID + PSMAX * (w + 1)) + 3) & ~1;
 };
 
 struct Tile16 {

@@ -332,6 +332,18 @@ def test_stage_constraints_on_the_tensor_core_kernel(handle, oracle_mod, n, m, N
     assert handle.last_kernel.startswith(f"kkt_wp_dmma<{n},{m},p={n}/{mid_p}/{n}"), handle.last_kernel
 
 
+@pytest.mark.parametrize("hess", [0, 1, 2])
+@pytest.mark.parametrize("n,m,N,batch,mid_p", [(12, 3, 40, 6, 0), (12, 3, 33, 5, 1), (12, 3, 30, 33, 2), (8, 3, 25, 7, 0),
+                                               (8, 3, 30, 4, 2), (12, 2, 41, 6, 0), (12, 2, 40, 34, 1), (8, 2, 30, 5, 0),
+                                               (8, 2, 31, 3, 1)])
+def test_every_control_count_up_to_four_on_the_tensor_core_kernel(handle, oracle_mod, n, m, N, batch, mid_p, hess):
+    """m = 2, 3 at n = 8, 12: knot records of odd length (the bulk copies start / end on the even doubles around
+    them) — every m <= 4 is on the warp-per-instance kernel, not on the cooperative fallback."""
+    prob = problems.random_lqr_kkt(n, m, N, batch, seed=13 * n + 3 * m + mid_p, mid_p=mid_p, hess_mode=hess)
+    _check(prob, handle, oracle_mod, truth_instances=(0, batch - 1))
+    assert handle.last_kernel.startswith(f"kkt_wp_dmma<{n},{m},p={n}/{mid_p}/{n}"), handle.last_kernel
+
+
 def test_stage_constraints_match_cooperative_kernel_and_report_info(handle):
     prob = problems.random_lqr_kkt(12, 4, 50, 9, seed=4, mid_p=2, hess_mode=1)
     dz1, lam1, i1, r1 = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
