@@ -27,12 +27,15 @@ struct KktShape {
     const int32_t *p;
     bool uniform;  // p = [P1, PM.., PN]
     int P1, PM, PN;
+    int PMAX;  // largest interior count
 };
 
 static KktShape make_shape(int n, int m, int N, const int32_t *p, int hess, int d2x) {
-    KktShape s{n, m, N, hess, d2x, p, true, p[0], N > 2 ? p[1] : 0, p[N - 1]};
-    for (int k = 1; k < N - 1; ++k)
+    KktShape s{n, m, N, hess, d2x, p, true, p[0], N > 2 ? p[1] : 0, p[N - 1], 0};
+    for (int k = 1; k < N - 1; ++k) {
         if (p[k] != s.PM) s.uniform = false;
+        s.PMAX = std::max(s.PMAX, (int)p[k]);
+    }
     return s;
 }
 
@@ -67,8 +70,8 @@ static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
 static bool kkt_has_wp(const lqrb_context *h, const KktShape &s) {
     const int64_t v = h->opt("kkt_variant", 0);
     if (v == 2 || v == 3 || v == 4) return false;
-    if (!s.uniform || s.d2x) return false;
-    if (s.N < 3 || s.P1 != s.n || s.PM > 4 || s.PN != s.n) return false;  // up to 4 stage rows on the interior knots
+    if (s.d2x) return false;
+    if (s.N < 3 || s.P1 != s.n || s.PMAX > 4 || s.PN != s.n) return false;  // up to 4 stage rows on every interior knot
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_) return true;
     KKT_WP_SIZES(X)
@@ -83,7 +86,7 @@ static bool kkt_has_cta(const lqrb_context *h, const KktShape &s, int flags) {
     if (h->opt("kkt_variant", 0) == 2) return false;
     (void)flags;
     if (!s.uniform || s.d2x || s.hess == LQRB_HESS_DENSE) return false;
-    if (s.N < 3 || s.P1 != s.n || s.PM != 0 || s.PN != s.n) return false;
+    if (s.N < 3 || s.P1 != s.n || s.PM > 4 || s.PN != s.n) return false;  // up to 4 stage rows on every interior knot
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_) return true;
     KKT_CTA_SIZES(X)
@@ -350,7 +353,14 @@ static int32_t launch_kkt_wp(lqrb_context *h, const KktShape &s, int64_t batch, 
     const int N = s.N;
     constexpr int WARPS = 4, MINB = 3;  // 168 registers: 12 warps per SM
     constexpr size_t smem = (size_t)WARPS * kwp::warp_smem_doubles<n, m, HESS>() * sizeof(double);
-    const int ps = s.PM;
+    const int ps = s.PMAX;
+    // uniform interior pattern: offsets are closed forms; else the per-knot tables of the general path
+    KktTables tb{};
+    if (!s.uniform) {
+        int32_t trc = lqrb_kkt_tables(h, n, m, N, s.p, HESS, 0, &tb);
+        if (trc) return trc;
+    }
+    const int64_t drows = lqrb_kkt_data_rows(n, m, N, s.p, HESS, 0), zrows = L::z_rows(N), mrows = lqrb_num_cons(n, N, s.p);
     auto kern = kwp::kkt_wp_kernel<n, m, HESS, WARPS, MINB>;
     LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
@@ -360,19 +370,23 @@ static int32_t launch_kkt_wp(lqrb_context *h, const KktShape &s, int64_t batch, 
         // scratch (reused by every chunk): [records: cb x N x REC] [cinfo: cb]
         double *recs = scratch;
         int32_t *cinfo = reinterpret_cast<int32_t *>(recs + (size_t)cb * N * RW::rec(ps));
-        const double *dc = data + first * L::data_rows(N, ps);
+        const double *dc = data + first * drows;
         kern<<<(unsigned)((cb + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(
-            dc, recs, dz + first * L::z_rows(N), mult + first * L::mult_rows(N, ps), res ? res + first * L::z_rows(N) : nullptr,
-            info ? info + first : nullptr, cinfo, N, cb, soc, ps);
+            dc, recs, dz + first * zrows, mult + first * mrows, res ? res + first * zrows : nullptr,
+            info ? info + first : nullptr, cinfo, N, cb, soc, ps, s.uniform ? nullptr : tb.p,
+            s.uniform ? nullptr : tb.knot_off, s.uniform ? nullptr : tb.mult_off);
         LQRB_LAUNCH_CHECK(h, "kkt_wp_kernel");
-        int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * L::z_rows(N),
-                                                 mult + first * L::mult_rows(N, ps), res ? res + first * L::z_rows(N) : nullptr,
+        int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * zrows,
+                                                 mult + first * mrows, res ? res + first * zrows : nullptr,
                                                  info ? info + first : nullptr, st);
         if (rc) return rc;
         refined += h->last_refined;
     }
     char nm[128];
-    snprintf(nm, sizeof nm, "kkt_wp_dmma<%d,%d,p=%d/%d/%d,hess=%d%s>", n, m, n, ps, n, HESS, soc ? ",soc" : "");
+    if (s.uniform)
+        snprintf(nm, sizeof nm, "kkt_wp_dmma<%d,%d,p=%d/%d/%d,hess=%d%s>", n, m, n, ps, n, HESS, soc ? ",soc" : "");
+    else
+        snprintf(nm, sizeof nm, "kkt_wp_dmma<%d,%d,p=%d/per-knot<=%d/%d,hess=%d%s>", n, m, n, ps, n, HESS, soc ? ",soc" : "");
     h->kernel_name = nm;
     if (refined) h->kernel_name += "+kkt_coop[" + std::to_string(refined) + " ill-conditioned]";
     h->last_refined = refined;
@@ -384,41 +398,43 @@ static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch,
                               double *scratch, double *dz, double *mult, double *res, int32_t *info,
                               cudaStream_t st) {
     using L = kcta::Lay<n, m, HESS>;
-    const int N = s.N;
-    const size_t psm = (size_t)L::PREP_TOTAL * sizeof(double), msm = (size_t)L::MAIN_TOTAL * sizeof(double);
-    auto pk = kcta::kkt_cta_prep_kernel<n, m, HESS>;
-    auto mk = kcta::kkt_cta_kernel<n, m, HESS>;
+    const int N = s.N, ps = s.PM;
+    // the stage-row work areas are allocated only when there are stage rows (config 5b-K keeps its footprint)
+    const size_t psm = (size_t)(ps ? L::PREP_TOTAL_ST : L::PREP_TOTAL) * sizeof(double),
+                 msm = (size_t)(ps ? L::MAIN_TOTAL_ST : L::MAIN_TOTAL) * sizeof(double);
+    auto pk = ps ? kcta::kkt_cta_prep_kernel<n, m, HESS, true> : kcta::kkt_cta_prep_kernel<n, m, HESS, false>;
+    auto mk = ps ? kcta::kkt_cta_kernel<n, m, HESS, true> : kcta::kkt_cta_kernel<n, m, HESS, false>;
     LQRB_CUDA(h, cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
     LQRB_CUDA(h, cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
     const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
+    const int64_t drows = L::data_rows(N, ps), zrows = L::z_rows(N), mrows = L::mult_rows(N, ps);
     int64_t refined = 0;
     for (int64_t first = 0; first < batch; first += chunk) {
         const int64_t cb = std::min(chunk, batch - first);
         // scratch (reused by every chunk): [records: cb x N x REC] [pre-pass slots: cb x prep_rows] [hinfo: cb] [cinfo: cb]
         double *recs = scratch;
-        double *prep = recs + (size_t)cb * N * L::REC;
-        int32_t *hinfo = reinterpret_cast<int32_t *>(prep + (size_t)cb * L::prep_rows(N));
+        double *prep = recs + (size_t)cb * N * L::rec(ps);
+        int32_t *hinfo = reinterpret_cast<int32_t *>(prep + (size_t)cb * L::prep_rows(N, ps));
         int32_t *cinfo = hinfo + cb;  // conditioning estimates (the "+ 1" double per instance holds both)
-        const double *dc = data + first * L::data_rows(N);
+        const double *dc = data + first * drows;
         LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)cb * sizeof(int32_t), st));
         LQRB_CUDA(h, cudaMemsetAsync(cinfo, 0, (size_t)cb * sizeof(int32_t), st));
-        kcta::kkt_cta_ri_kernel<n, m, HESS><<<(unsigned)((cb * (N - 1) + 7) / 8), 128, 0, st>>>(dc, prep, hinfo, N, cb, soc);
+        kcta::kkt_cta_ri_kernel<n, m, HESS><<<(unsigned)((cb * (N - 1) + 7) / 8), 128, 0, st>>>(dc, prep, hinfo, N, cb, soc, ps);
         LQRB_LAUNCH_CHECK(h, "kkt_cta_ri_kernel");
-        pk<<<(unsigned)(cb * N), L::THREADS, psm, st>>>(dc, prep, hinfo, cinfo, N, cb, soc);
+        pk<<<(unsigned)(cb * N), L::THREADS, psm, st>>>(dc, prep, hinfo, cinfo, N, cb, soc, ps);
         LQRB_LAUNCH_CHECK(h, "kkt_cta_prep_kernel");
-        mk<<<(unsigned)cb, L::THREADS, msm, st>>>(dc, prep, hinfo, recs, dz + first * L::z_rows(N),
-                                                  mult + first * L::mult_rows(N),
-                                                  res ? res + first * L::z_rows(N) : nullptr,
-                                                  info ? info + first : nullptr, cinfo, N, cb, soc);
+        mk<<<(unsigned)cb, L::THREADS, msm, st>>>(dc, prep, hinfo, recs, dz + first * zrows, mult + first * mrows,
+                                                  res ? res + first * zrows : nullptr,
+                                                  info ? info + first : nullptr, cinfo, N, cb, soc, ps);
         LQRB_LAUNCH_CHECK(h, "kkt_cta_kernel");
-        int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * L::z_rows(N),
-                                                 mult + first * L::mult_rows(N), res ? res + first * L::z_rows(N) : nullptr,
+        int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * zrows,
+                                                 mult + first * mrows, res ? res + first * zrows : nullptr,
                                                  info ? info + first : nullptr, st);
         if (rc) return rc;
         refined += h->last_refined;
     }
     char nm[128];
-    snprintf(nm, sizeof nm, "kkt_cta_dmma<%d,%d,p=%d/0/%d,hess=%d%s>", n, m, n, n, HESS, soc ? ",soc" : "");
+    snprintf(nm, sizeof nm, "kkt_cta_dmma<%d,%d,p=%d/%d/%d,hess=%d%s>", n, m, n, ps, n, HESS, soc ? ",soc" : "");
     h->kernel_name = nm;
     if (refined) h->kernel_name += "+kkt_coop[" + std::to_string(refined) + " ill-conditioned]";
     h->last_refined = refined;
@@ -431,7 +447,7 @@ static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch) {
     size_t per = 0;
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_)   \
-        per = std::max(per, (size_t)s.N * kcta::Lay<N_, M_>::REC + kcta::Lay<N_, M_>::prep_rows(s.N) + 1);
+        per = std::max(per, (size_t)s.N * kcta::Lay<N_, M_>::rec(s.PMAX) + kcta::Lay<N_, M_>::prep_rows(s.N, s.PMAX) + 1);
     KKT_CTA_SIZES(X)
 #undef X
 #define X(N_, M_) \
@@ -440,7 +456,7 @@ static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch) {
     KKT_HW_SIZES(X)
 #undef X
 #define X(N_, M_) \
-    if (s.n == N_ && s.m == M_) per = std::max(per, (size_t)s.N * kwp::RecW<N_>::rec(s.PM) + 1);
+    if (s.n == N_ && s.m == M_) per = std::max(per, (size_t)s.N * kwp::RecW<N_>::rec(s.PMAX) + 1);
     KKT_WP_SIZES(X)
 #undef X
     return per == 0 ? 0 : (size_t)batch * per + 2;

@@ -344,11 +344,13 @@ __global__ void __launch_bounds__(THREADS) kkt_coop_kernel(KktCoopArgs a) {
 }
 
 // device copies of the per-shape offset tables, cached on the handle
-struct CoopTables {
-    const int32_t *p;
-    const int64_t *knot_off, *rec_off, *mult_off;
-    int P;
-};
+using CoopTables = KktTables;
+
+static int32_t get_tables(lqrb_context *h, int n, int m, int N, const int32_t *p, int hess, int d2x,
+                          CoopTables *out);
+int32_t lqrb_kkt_tables(lqrb_context *h, int n, int m, int N, const int32_t *p, int hess, int d2x, KktTables *out) {
+    return get_tables(h, n, m, N, p, hess, d2x, out);
+}
 
 static int32_t get_tables(lqrb_context *h, int n, int m, int N, const int32_t *p, int hess, int d2x,
                           CoopTables *out) {

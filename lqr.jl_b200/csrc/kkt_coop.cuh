@@ -34,3 +34,12 @@ int32_t launch_kkt_coop(lqrb_context *h, int n, int m, int N, const int32_t *p, 
                         int flags, int64_t batch, const double *data, double *scratch, double *dz,
                         double *mult, double *res, int32_t *info, cudaStream_t st,
                         const KktCoopExtra *extra = nullptr);
+
+// device copies of the per-shape tables (cached on the handle): p[N], and N + 1 prefix offsets of the knot records in the
+// packed data (T = 1 layout), of the factor records and of the multiplier groups [mu_k; lam_k]
+struct KktTables {
+    const int32_t *p;
+    const int64_t *knot_off, *rec_off, *mult_off;
+    int P;  // max p[k]
+};
+int32_t lqrb_kkt_tables(lqrb_context *h, int n, int m, int N, const int32_t *p, int hess, int d2x, KktTables *out);

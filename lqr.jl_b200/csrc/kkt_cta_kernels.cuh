@@ -37,25 +37,37 @@ struct Lay {
     static constexpr int oQ = 0, oR = HQ, og = oR + HR, oD1 = og + w, od = oD1 + n * w, CORE = od + n;
     static constexpr int oC0 = CORE, FIRST = CORE + n * w + n, MID = CORE;
     static constexpr int oCl = HQ + n, LAST = oCl + n * n + n;
-    __host__ __device__ static constexpr int64_t data_rows(int N) { return FIRST + (int64_t)(N - 2) * MID + LAST; }
-    __host__ __device__ static constexpr int64_t knot_off(int k) { return k == 0 ? 0 : FIRST + (int64_t)(k - 1) * MID; }
-    __host__ __device__ static constexpr int64_t mult_rows(int N) { return 2 * n + (int64_t)(N - 1) * n; }
+    // ps = stage-constraint rows of every interior knot (C (ps x w, column-major) | c (ps) follow d in its record),
+    // 0 <= ps <= PSMAX; with an odd ps knot records can start on odd doubles (see the alignment notes in the kernels)
+    static constexpr int PSMAX = 4;
+    __host__ __device__ static constexpr int mid(int ps) { return MID + ps * (w + 1); }
+    __host__ __device__ static constexpr int64_t data_rows(int N, int ps = 0) { return FIRST + (int64_t)(N - 2) * mid(ps) + LAST; }
+    __host__ __device__ static constexpr int64_t knot_off(int k, int ps = 0) { return k == 0 ? 0 : FIRST + (int64_t)(k - 1) * mid(ps); }
+    __host__ __device__ static constexpr int64_t mult_rows(int N, int ps = 0) { return 2 * n + (int64_t)(N - 1) * n + (int64_t)(N - 2) * ps; }
     __host__ __device__ static constexpr int64_t z_rows(int N) { return (int64_t)N * n + (int64_t)(N - 1) * m; }
     // pre-pass output slot of one knot (doubles): Qi | T | G | hg (w) | rho (n) | Ri (m*m)
     static constexpr int hQi = 0, hT = n * n, hG = 2 * n * n, hHg = 3 * n * n, hRho = hHg + w, hRi = hRho + n,
                          HS = hRi + m * m;
     static_assert(HS % 2 == 0 && hHg % 2 == 0, "16-byte pieces");
+    // with stage rows the slot continues: [D_j (n) | E_j (n)] for j < 4 | B (4 x 4) | ct (4)
+    //   D_j = -(Hi C_j')_x,  E_j = D1 Hi C_j',  B = C Hi C',  ct = C hg - c      (shur! for the stage rows)
+    static constexpr int sB = 8 * n, sCt = sB + 16, HSS = sCt + 4;
+    __host__ __device__ static constexpr int hs(int ps) { return HS + (ps > 0 ? HSS : 0); }
     // per instance: N slots + the true Qi of the first knot (its slot holds B0)
-    __host__ __device__ static constexpr int64_t prep_rows(int N) { return (int64_t)N * HS + n * n; }
+    __host__ __device__ static constexpr int64_t prep_rows(int N, int ps = 0) { return (int64_t)N * hs(ps) + n * n; }
     static constexpr int REC = n * n + n;  // Z (row-major) | v
+    // with stage rows the record continues: [sd_j (n) | E'_j (n)] for j < 4 | Bi (4 x 4) | c' (4)
+    __host__ __device__ static constexpr int rec(int ps) { return REC + (ps > 0 ? HSS : 0); }
     // shared memory of the pre-pass (doubles)
     static constexpr int LA = n + 4;  // k-major operand loads: leading dimension = 4 (mod 16)
     static constexpr int pA = 0, pQ = pA + w * LA, pPan = pQ + n * LA, pPi = pPan + 2 * NT * 64, pCol = pPi + 128,
-                         pRi = pCol + 2 * m, pV = pRi + m * (m + 4), PREP_TOTAL = pV + 4 * w + 64;
+                         pRi = pCol + 2 * m, pV = pRi + m * (m + 4), PREP_TOTAL = pV + 4 * w + 64,
+                         pSt = PREP_TOTAL, PREP_TOTAL_ST = pSt + 8 * w;  // stage rows: C_j and Hi C_j' (4 x w each)
     // shared memory of the main kernel (doubles)
     static constexpr int LB = n + 8;  // paired (16-byte) operand loads: leading dimension = 8 (mod 16)
     static constexpr int mT = 0, mS = mT + n * LB, mPan = mS + n * LB, mPi = mPan + 2 * NT * 64, mCol = mPi + 128,
-                         mV = mCol + 16, mBar = mV + 8 * n + 4 * w, MAIN_TOTAL = mBar + 2;
+                         mV = mCol + 16, mBar = mV + 8 * n + 4 * w, MAIN_TOTAL = mBar + 2,
+                         mSt = MAIN_TOTAL, MAIN_TOTAL_ST = mSt + 16 * n + 48;  // stage rows: D, sd, E', W (4 x n each) | B, Bi | ct, c', bc, xi
 };
 
 // ------------------------------------------------------------------ 8 x 8 pivot block ------------------
@@ -189,7 +201,7 @@ __device__ __forceinline__ int block_gj_inverse(double (&S)[NT][2], double *pan,
 template <int n, int m, int HESS>
 __global__ void __launch_bounds__(128)
     kkt_cta_ri_kernel(const double *__restrict__ data, double *__restrict__ prep, int32_t *__restrict__ hinfo, int N,
-                      int64_t batch, int soc) {
+                      int64_t batch, int soc, int ps) {
     using L = Lay<n, m, HESS>;
     static_assert(m <= 16, "one half-warp per R");
     __shared__ __align__(16) double colb_all[8][2 * m];
@@ -201,8 +213,8 @@ __global__ void __launch_bounds__(128)
     const int64_t idx = active ? pair + hh : total - 1;
     const int64_t inst = idx / (N - 1);
     const int k = (int)(idx % (N - 1));
-    const double *kp = data + inst * L::data_rows(N) + L::knot_off(k);
-    double *out = prep + inst * L::prep_rows(N) + (int64_t)k * L::HS + L::hRi;
+    const double *kp = data + inst * L::data_rows(N, ps) + L::knot_off(k, ps);
+    double *out = prep + inst * L::prep_rows(N, ps) + (int64_t)k * L::hs(ps) + L::hRi;
     double a[m];
     const int j = hl < m ? hl : 0;
     SM_UNROLL
@@ -221,11 +233,13 @@ __global__ void __launch_bounds__(128)
 
 // ------------------------------------------------------------------ pre-pass --------------------------
 // grid = batch * N CTAs of THREADS threads.  knot 0: generic scalar code for the C_1 blocks (once per instance).
-template <int n, int m, int HESS>
+// ST = false: no stage rows (ps is ignored; the instantiation config 5b-K runs); true: ps <= 4 rows on every interior knot
+template <int n, int m, int HESS, bool ST>
 __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     kkt_cta_prep_kernel(const double *__restrict__ data, double *__restrict__ prep, int32_t *__restrict__ hinfo,
-                        int32_t *__restrict__ cinfo, int N, int64_t batch, int soc) {
+                        int32_t *__restrict__ cinfo, int N, int64_t batch, int soc, int ps_arg) {
     using L = Lay<n, m, HESS>;
+    const int ps = ST ? ps_arg : 0;
     constexpr int NT = L::NT, UT = L::UT, w = L::w, LA = L::LA, THREADS = L::THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sm = reinterpret_cast<double *>(smem_raw);
@@ -238,8 +252,8 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     const int k = (int)(blockIdx.x % N);
     const bool first = k == 0, last = k == N - 1;
     const int mk = last ? 0 : m, wk = n + mk;
-    const double *kp = data + inst * L::data_rows(N) + L::knot_off(k);
-    double *out = prep + inst * L::prep_rows(N) + (int64_t)k * L::HS;
+    const double *kp = data + inst * L::data_rows(N, ps) + L::knot_off(k, ps);
+    double *out = prep + inst * L::prep_rows(N, ps) + (int64_t)k * L::hs(ps);
     constexpr int LR = m + 4;
     __shared__ __align__(8) uint64_t xbar;
     if (tid == 0) {
@@ -255,10 +269,17 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     // in flight while Q is inverted (plain loads here put the whole HBM latency in front of the first barrier);
     // g, d wait in registers
     const double *Xg = last ? kp + L::oCl : kp + L::oD1;
-    if (wp == 0) {
-        if (lane == 0) mbar_expect_tx(&xbar, (uint32_t)(n * wk * 8));
-        __syncwarp();
-        for (int j = lane; j < wk; j += 32) bulk_g2s(As + j * LA, Xg + (int64_t)j * n, n * 8, &xbar);
+    // (an odd number of stage rows puts every other knot record on an odd double: bulk copies need 16-byte aligned
+    // sources, so those knots use plain loads, published by the barriers below)
+    const bool xal = !ST || (reinterpret_cast<uintptr_t>(Xg) & 15) == 0;
+    if (xal) {
+        if (wp == 0) {
+            if (lane == 0) mbar_expect_tx(&xbar, (uint32_t)(n * wk * 8));
+            __syncwarp();
+            for (int j = lane; j < wk; j += 32) bulk_g2s(As + j * LA, Xg + (int64_t)j * n, n * 8, &xbar);
+        }
+    } else {
+        for (int e = tid; e < n * wk; e += THREADS) As[(e / n) * LA + (e % n)] = Xg[e];
     }
     static_assert(THREADS >= w, "one thread per entry of g");
     const double gq_reg = (tid < wk && !soc) ? kp[(last ? L::HQ : L::og) + tid] : 0.0;  // SOC: g = 0
@@ -282,10 +303,10 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     int bad = block_gj_inverse<NT>(S, pan, pis, colb, &flag, wp, lane);
     if (tid < wk) vq[tid] = gq_reg;
     if (tid < n) vd[tid] = vd_reg;
-    mbar_wait(&xbar, 0);  // X has landed (every thread observes the barrier: the bulk writes are then visible)
+    if (xal) mbar_wait(&xbar, 0);  // X has landed (every thread observes the barrier: the bulk writes are then visible)
     // Qi -> shared (operand) and global (slot, or the extra block for the first knot)
     {
-        double *qo = first ? prep + inst * L::prep_rows(N) + (int64_t)N * L::HS : out + L::hQi;
+        double *qo = first ? prep + inst * L::prep_rows(N, ps) + (int64_t)N * L::hs(ps) : out + L::hQi;
         SM_UNROLL
         for (int ct = 0; ct < NT; ++ct) {
             const int r = 8 * wp + g, c = 8 * ct + 2 * q;
@@ -331,6 +352,55 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         }
         for (int l = 0; l < mk; ++l) s0 = fma(As[(n + l) * LA + tid], vhg[n + l], s0);
         out[L::hRho + tid] = s0 + s1;
+    }
+    // ---- stage rows of an interior knot (shur! for the ps rows, src/jacobian_blocks.jl:231-286), as vectors:
+    //   tc_j = Hi C_j',  D_j = -(tc_j)_x,  E_j = [A B] tc_j,  B = C tc,  ct = C hg - c
+    if (ST && ps > 0 && !first && !last) {
+        double *vc = sm + L::pSt, *tcs = vc + 4 * w;
+        const double *Cg = kp + L::CORE;  // ps x w column-major, then c (ps)
+        for (int e = tid; e < ps * w; e += THREADS) vc[(e % ps) * w + e / ps] = Cg[e];
+        __syncthreads();
+        for (int j = 0; j < ps; ++j) {
+            if (tid < n) {
+                double s0 = 0.0, s1 = 0.0;
+                SM_UNROLL
+                for (int l = 0; l < n; l += 2) {
+                    s0 = fma(Qs[l * LA + tid], vc[j * w + l], s0);
+                    s1 = fma(Qs[(l + 1) * LA + tid], vc[j * w + l + 1], s1);
+                }
+                tcs[j * w + tid] = s0 + s1;
+            } else if (tid < w) {
+                double s0 = 0.0;
+                for (int l = 0; l < m; ++l) s0 = fma(Ris[l * LR + tid - n], vc[j * w + n + l], s0);
+                tcs[j * w + tid] = s0;
+            }
+        }
+        __syncthreads();
+        double *so = out + L::HS;
+        if (tid < n) {
+            for (int j = 0; j < ps; ++j) {
+                double s0 = 0.0, s1 = 0.0;
+                SM_UNROLL
+                for (int l = 0; l < n; l += 2) {
+                    s0 = fma(As[l * LA + tid], tcs[j * w + l], s0);
+                    s1 = fma(As[(l + 1) * LA + tid], tcs[j * w + l + 1], s1);
+                }
+                for (int l = 0; l < m; ++l) s0 = fma(As[(n + l) * LA + tid], tcs[j * w + n + l], s0);
+                so[j * 2 * n + tid] = -tcs[j * w + tid];
+                so[j * 2 * n + n + tid] = s0 + s1;
+            }
+        }
+        if (tid < ps * ps) {
+            const int j = tid / ps, jp = tid % ps;
+            double s0 = 0.0;
+            for (int l = 0; l < w; ++l) s0 = fma(vc[j * w + l], tcs[jp * w + l], s0);
+            so[L::sB + 4 * j + jp] = s0;
+        } else if (tid >= 32 && tid < 32 + ps) {
+            const int j = tid - 32;
+            double s0 = -Cg[ps * w + j];
+            for (int l = 0; l < w; ++l) s0 = fma(vc[j * w + l], vhg[l], s0);
+            so[L::sCt + j] = s0;
+        }
     }
     // ---- T strip = X[rows] Qi   (A operand: X[8wp+g][4s+q], B operand: Qi[4s+q][8ct+g], k-major loads)
     double T[NT][2];
@@ -428,29 +498,35 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
 }
 
 // ------------------------------------------------------------------ main kernel -----------------------
-template <int n, int m, int HESS>
+template <int n, int m, int HESS, bool ST>
 __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     kkt_cta_kernel(const double *__restrict__ data, const double *__restrict__ prep, const int32_t *__restrict__ hinfo,
                    double *__restrict__ recs, double *__restrict__ dz, double *__restrict__ mult,
                    double *__restrict__ res, int32_t *__restrict__ info, int32_t *__restrict__ cinfo, int N,
-                   int64_t batch, int soc) {
+                   int64_t batch, int soc, int ps_arg) {
     using L = Lay<n, m, HESS>;
     constexpr int NT = L::NT, w = L::w, LB = L::LB, THREADS = L::THREADS;
+    static_assert(THREADS == 4 * n, "four partial sums per row in the mat-vecs");
+    const int ps = ST ? ps_arg : 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sm = reinterpret_cast<double *>(smem_raw);
     double *Ts = sm + L::mT, *Ss = sm + L::mS, *pan = sm + L::mPan, *pis = sm + L::mPi, *colb = sm + L::mCol,
            *ys = sm + L::mV, *vs = ys + n, *dps = vs + n, *red = dps + n /* 4n */, *xs = red + 4 * n, *rsv = xs + w,
            *xps = rsv + w;
     uint64_t *bar = reinterpret_cast<uint64_t *>(sm + L::mBar);
+    // stage rows (allocated only when ps > 0): D_j, sd_j, E'_j, W_j (4 x n each) | B (16) | Bi (16) | ct, c', bc, xi (4 each)
+    double *Dv = sm + L::mSt, *sdv = Dv + 4 * n, *Ev = sdv + 4 * n, *Wv = Ev + 4 * n, *Bm = Wv + 4 * n, *Bi = Bm + 16,
+           *ctv = Bi + 16, *cpv = ctv + 4, *bcv = cpv + 4, *xiv = bcv + 4;
     __shared__ int flag3[3];
     int &flag = flag3[0];
     const int tid = threadIdx.x, wp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int64_t inst = blockIdx.x;
-    const double *db = data + inst * L::data_rows(N);
-    const double *pb = prep + inst * L::prep_rows(N);
-    double *rb = recs + inst * (int64_t)N * L::REC;
+    const int hs = L::hs(ps), recw = L::rec(ps);
+    const double *db = data + inst * L::data_rows(N, ps);
+    const double *pb = prep + inst * L::prep_rows(N, ps);
+    double *rb = recs + inst * (int64_t)N * recw;
     double *zb = dz + inst * L::z_rows(N);
-    double *mb = mult + inst * L::mult_rows(N);
+    double *mb = mult + inst * L::mult_rows(N, ps);
     double *resb = res ? res + inst * L::z_rows(N) : nullptr;
     const int r0 = 8 * wp + g;  // the row of this lane's accumulator entries
 
@@ -466,7 +542,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     // T_k (n x n row-major in the slot) -> Ts with padded rows, one 512-byte bulk copy per row
     auto issue_T = [&](int k) {
         if (wp == 0) {
-            const double *src = pb + (int64_t)k * L::HS + L::hT;
+            const double *src = pb + (int64_t)k * hs + L::hT;
             if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n * n * 8));
             __syncwarp();
             for (int r = lane; r < n; r += 32) bulk_g2s(Ts + r * LB, src + r * n, n * 8, bar);
@@ -481,7 +557,8 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
 
     // one elimination step: (Cp, dps) of the previous row + slot k  ->  record k, new (Cp, dps)
     for (int k = 0; k < N; ++k) {
-        const double *slot = pb + (int64_t)k * L::HS;
+        const double *slot = pb + (int64_t)k * hs;
+        const int psk = (ST && k > 0 && k < N - 1) ? ps : 0;  // stage rows of this knot
         // Sigma strip = Cp + Qi (slot), G strip (prefetched)
         double S[NT][2], G[NT][2];
         SM_UNROLL
@@ -524,7 +601,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         if (tid < n) {
             const double v = (red[tid] + red[n + tid]) + (red[2 * n + tid] + red[3 * n + tid]);
             vs[tid] = v;
-            rb[(int64_t)k * L::REC + n * n + tid] = v;
+            rb[(int64_t)k * recw + n * n + tid] = v;
         }
         // Z strip = T[rows] Si   (A operand: T[8wp+g][8cp+2q+e], B operand: Si[8cp+2q+e][8ct+g] = Si[8ct+g][..])
         double Z[NT][2];
@@ -545,7 +622,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
             }
         }
         {
-            double *rk = rb + (int64_t)k * L::REC;
+            double *rk = rb + (int64_t)k * recw;
             SM_UNROLL
             for (int ct = 0; ct < NT; ++ct)
                 *reinterpret_cast<double2 *>(rk + r0 * n + 8 * ct + 2 * q) = make_double2(Z[ct][0], Z[ct][1]);
@@ -585,9 +662,130 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
             }
             if (lane < 8) red[8 * wp + lane] = mine;
         }
+        if (psk > 0) {
+            // Stage rows of knot k as vectors beside the tile algebra (same elimination as kkt_wp_kernels.cuh).
+            // Eliminate lam_{k-1}:  sd_j = Si D_j,  B' = B - D' sd,  E'_j = E_j + T sd_j,  c'_j = ct_j - sd_j' y;
+            // eliminate mu_k:  Bi = B'^-1,  W = Bi E',  Cp -= sym(E' W'),  dp -= E' Bi c'   (pan is free here)
+            const double *so = slot + L::HS;
+            for (int e = tid; e < psk * 2 * n; e += THREADS) {
+                const int j = e / (2 * n), r = e % (2 * n);
+                if (r < n) Dv[j * n + r] = so[e];
+                else Ev[j * n + r - n] = so[e];
+            }
+            if (tid < 16) Bm[tid] = so[L::sB + tid];
+            else if (tid < 20) ctv[tid - 16] = so[L::sCt + tid - 16];
+            __syncthreads();
+            {
+                const int i = tid % n, part = tid / n;
+                double sj[L::PSMAX];
+                SM_UNROLL
+                for (int j = 0; j < L::PSMAX; ++j) sj[j] = 0.0;
+                SM_UNROLL
+                for (int l = 0; l < n / 4; ++l) {
+                    const int r = part * (n / 4) + l;
+                    const double sv = Ss[r * LB + i];
+                    SM_UNROLL
+                    for (int j = 0; j < L::PSMAX; ++j)
+                        if (j < psk) sj[j] = fma(sv, Dv[j * n + r], sj[j]);
+                }
+                SM_UNROLL
+                for (int j = 0; j < L::PSMAX; ++j)
+                    if (j < psk) pan[j * 4 * n + part * n + i] = sj[j];
+            }
+            __syncthreads();
+            if (tid < n)
+                for (int j = 0; j < psk; ++j) {
+                    const double *pj = pan + j * 4 * n;
+                    sdv[j * n + tid] = (pj[tid] + pj[n + tid]) + (pj[2 * n + tid] + pj[3 * n + tid]);
+                }
+            __syncthreads();
+            {
+                constexpr int NC = (n + 31) / 32;
+                for (int j = 0; j < psk; ++j) {
+                    double vv[NC];
+                    SM_UNROLL
+                    for (int c = 0; c < NC; ++c) vv[c] = lane + 32 * c < n ? sdv[j * n + lane + 32 * c] : 0.0;
+                    double mine = 0.0;
+                    SM_UNROLL
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const double *row = Ts + (8 * wp + rr) * LB;
+                        double t = 0.0;
+                        SM_UNROLL
+                        for (int c = 0; c < NC; ++c)
+                            if (lane + 32 * c < n) t = fma(row[lane + 32 * c], vv[c], t);
+                        SM_UNROLL
+                        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                        if (lane == rr) mine = t;
+                    }
+                    if (lane < 8) Ev[j * n + 8 * wp + lane] += mine;
+                }
+            }
+            if (tid < psk * psk) {
+                const int j = tid / psk, jp = tid % psk;
+                double t = Bm[4 * j + jp];
+                for (int l = 0; l < n; ++l) t = fma(-Dv[j * n + l], sdv[jp * n + l], t);
+                Bm[4 * j + jp] = t;
+            } else if (tid >= 32 && tid < 32 + psk) {
+                const int j = tid - 32;
+                double t = ctv[j];
+                for (int l = 0; l < n; ++l) t = fma(-sdv[j * n + l], ys[l], t);
+                cpv[j] = t;
+            }
+            __syncthreads();
+            if (tid == 0) {  // Bi = B'^-1: Gauss-Jordan on at most 4 x 4, potrf sign test on the pivots
+                double bm[4][4];
+                for (int a = 0; a < 4; ++a)
+                    for (int b = 0; b < 4; ++b) bm[a][b] = (a < psk && b < psk) ? Bm[4 * a + b] : (a == b ? 1.0 : 0.0);
+                int badp = 0;
+                for (int kk = 0; kk < 4; ++kk) {
+                    if (kk >= psk) break;
+                    const double piv = bm[kk][kk];
+                    if (!(piv > 0.0) && badp == 0) badp = kk + 1;
+                    const double pinv = 1.0 / piv;
+                    for (int b = 0; b < 4; ++b) bm[kk][b] = b == kk ? pinv : bm[kk][b] * pinv;
+                    for (int a = 0; a < 4; ++a) {
+                        if (a == kk) continue;
+                        const double f = bm[a][kk];
+                        for (int b = 0; b < 4; ++b) bm[a][b] = b == kk ? -f * pinv : fma(-f, bm[kk][b], bm[a][b]);
+                    }
+                }
+                for (int a = 0; a < 4; ++a)
+                    for (int b = 0; b < 4; ++b) Bi[4 * a + b] = bm[a][b];
+                xiv[0] = (double)badp;
+            }
+            __syncthreads();
+            {
+                const int badp = (int)xiv[0];
+                if (badp != 0 && st_all == 0) st_all = (k + 1) * 1000 + 100 + badp;
+            }
+            if (tid < n) {
+                for (int j = 0; j < psk; ++j) {
+                    double t = 0.0;
+                    for (int jp = 0; jp < psk; ++jp) t = fma(Bi[4 * j + jp], Ev[jp * n + tid], t);
+                    Wv[j * n + tid] = t;
+                }
+            } else if (tid < n + psk) {
+                const int j = tid - n;
+                double t = 0.0;
+                for (int jp = 0; jp < psk; ++jp) t = fma(Bi[4 * j + jp], cpv[jp], t);
+                bcv[j] = t;
+            }
+            // record: [sd_j | E'_j] | Bi | c'
+            double *rs = rb + (int64_t)k * recw + L::REC;
+            for (int e = tid; e < psk * 2 * n; e += THREADS) {
+                const int j = e / (2 * n), r = e % (2 * n);
+                rs[e] = r < n ? sdv[j * n + r] : Ev[j * n + r - n];
+            }
+            if (tid < 16) rs[L::sB + tid] = Bi[tid];
+            else if (tid < 20) rs[L::sCt + tid - 16] = cpv[tid - 16];
+        }
         __syncthreads();  // every warp is done with Ts and Ss
         if (k + 1 < N) issue_T(k + 1);
-        if (tid < n) dps[tid] = rho + red[tid];
+        if (tid < n) {
+            double t = rho + red[tid];
+            for (int j = 0; j < psk; ++j) t = fma(-bcv[j], Ev[j * n + tid], t);
+            dps[tid] = t;
+        }
         // exact symmetrisation of Cp' through Ss
         SM_UNROLL
         for (int ct = 0; ct < NT; ++ct)
@@ -597,7 +795,20 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         for (int ct = 0; ct < NT; ++ct)
             SM_UNROLL
             for (int e = 0; e < 2; ++e) Cp[ct][e] = 0.5 * (G[ct][e] + Ss[(8 * ct + 2 * q + e) * LB + r0]);
-        // no barrier here: Ss is next written after the barriers of the following Gauss-Jordan
+        // Cp -= 1/2 (E'_j W_j' + W_j E'_j')   (products rounded separately: bitwise symmetric)
+        for (int j = 0; j < psk; ++j) {
+            const double *E = Ev + j * n, *W = Wv + j * n;
+            const double er = E[r0], wr = W[r0];
+            SM_UNROLL
+            for (int ct = 0; ct < NT; ++ct)
+                SM_UNROLL
+                for (int e = 0; e < 2; ++e) {
+                    const int c = 8 * ct + 2 * q + e;
+                    const double p1 = __dmul_rn(er, W[c]), p2 = __dmul_rn(wr, E[c]);
+                    Cp[ct][e] = __dadd_rn(Cp[ct][e], -0.5 * __dadd_rn(p1, p2));
+                }
+        }
+        // no barrier here: Ss / the stage vectors are next written after the barriers of the following Gauss-Jordan
     }
     // ---- last block: mu_N' = Bl'^-1 y_mu   (Cp, dps hold Bl' and y_mu)
     {
@@ -623,7 +834,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
                 s1 = fma(Ss[(l + 1) * LB + tid], ys[l + 1], s1);
             }
             xs[tid] = s0 + s1;
-            __stcs(mb + L::mult_rows(N) - n + tid, -(s0 + s1));  // mu_N
+            __stcs(mb + L::mult_rows(N, ps) - n + tid, -(s0 + s1));  // mu_N
         }
         if (info && tid == 0) {
             const int hcode = hinfo[inst];
@@ -636,18 +847,20 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     for (int k = N - 1; k >= 0; --k) {
         const bool first = k == 0, last = k == N - 1;
         const int mk = last ? 0 : m, wk = n + mk;
-        const double *rk = rb + (int64_t)k * L::REC;
-        const double *slot = pb + (int64_t)k * L::HS;
-        const double *kp = db + L::knot_off(k);
+        const double *rk = rb + (int64_t)k * recw;
+        const double *slot = pb + (int64_t)k * hs;
+        const double *kp = db + L::knot_off(k, ps);
+        const int psk = (ST && k > 0 && k < N - 1) ? ps : 0;
         const double *D1g = last ? kp + L::oCl : kp + L::oD1;  // [A B] or C_N, column-major n x wk
         // the three operands of the NEXT step (record, [g | A B], Hi slot) go to L2 now: the mat-vecs below read
         // straight from global memory and every step is three dependent load phases
         if (k > 0 && tid == 0) {
-            const double *rn = rb + (int64_t)(k - 1) * L::REC;
-            const double *sn = pb + (int64_t)(k - 1) * L::HS;
-            const double *kn = db + L::knot_off(k - 1);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rn), "r"(L::REC * 8) : "memory");
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kn + L::og), "r"((L::CORE - L::og) * 8) : "memory");
+            const double *rn = rb + (int64_t)(k - 1) * recw;
+            const double *sn = pb + (int64_t)(k - 1) * hs;
+            // (16-byte aligned start, whole 16-byte pieces: with an odd number of stage rows a knot can start on an odd double)
+            const double *kn = reinterpret_cast<const double *>(reinterpret_cast<uintptr_t>(db + L::knot_off(k - 1, ps) + L::og) & ~(uintptr_t)15);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rn), "r"(recw * 8) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(kn), "r"((L::CORE - L::og) / 2 * 16) : "memory");
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sn + L::hQi), "r"(n * n * 8) : "memory");
             asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sn + L::hRi), "r"(m * m * 8) : "memory");
         }
@@ -663,8 +876,32 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
             for (int l = 0; l < n / 4; ++l) s = fma(zv[l], xs[part * (n / 4) + l], s);
             red[part * n + i] = s;
         }
+        const double *rs = rk + L::REC;  // stage part of the record: [sd_j | E'_j] | Bi | c'
+        if (psk > 0) {
+            // xi = Bi (c' - E' x_k)   (mu_k = -xi);  x_{k-1} -= sum_j xi_j sd_j
+            constexpr int NC = (n + 31) / 32;
+            for (int j = wp; j < psk; j += L::WARPS) {
+                double t = 0.0;
+                SM_UNROLL
+                for (int c = 0; c < NC; ++c)
+                    if (lane + 32 * c < n) t = fma(rs[j * 2 * n + n + lane + 32 * c], xs[lane + 32 * c], t);
+                SM_UNROLL
+                for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+                if (lane == 0) cpv[j] = rs[L::sCt + j] - t;
+            }
+            __syncthreads();
+            if (tid < psk) {
+                double t = 0.0;
+                for (int jp = 0; jp < psk; ++jp) t = fma(rs[L::sB + 4 * tid + jp], cpv[jp], t);
+                xiv[tid] = t;
+            }
+        }
         __syncthreads();
-        if (tid < n) xps[tid] = rk[n * n + tid] + (red[tid] + red[n + tid]) + (red[2 * n + tid] + red[3 * n + tid]);
+        if (tid < n) {
+            double xp = rk[n * n + tid] + (red[tid] + red[n + tid]) + (red[2 * n + tid] + red[3 * n + tid]);
+            for (int j = 0; j < psk; ++j) xp = fma(-xiv[j], rs[j * 2 * n + tid], xp);
+            xps[tid] = xp;
+        }
         __syncthreads();
         // res_j = g_j - sum_i D1[i][j] x_i (+ x_prev_j) (- sum_i C_1[i][j] mu1'_i at the first knot)
         {
@@ -696,6 +933,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
                 if (lane == 0) {
                     double r = gj[jj] - s;
                     if (!first && j < n) r += xps[j];
+                    for (int jp = 0; jp < psk; ++jp) r = fma(-xiv[jp], kp[L::CORE + jp + psk * j], r);  // C' mu_k, mu = -xi
                     rsv[j] = r;
                 }
             }
@@ -703,7 +941,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         __syncthreads();
         // dz = -Hi res
         {
-            const double *Qi = first ? pb + (int64_t)N * L::HS : slot + L::hQi;
+            const double *Qi = first ? pb + (int64_t)N * hs : slot + L::hQi;
             const int i = tid % n, part = tid / n;  // THREADS = 4 n
             double qv[n / 4];
             SM_UNROLL
@@ -718,7 +956,11 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
             const double z = -((red[tid] + red[n + tid]) + (red[2 * n + tid] + red[3 * n + tid]));
             __stcs(zb + (int64_t)k * w + tid, z);
             if (resb) __stcs(resb + (int64_t)k * w + tid, rsv[tid]);
-            __stcs(mb + (int64_t)k * n + tid, -xps[tid]);  // lam_{k-1} (k >= 1) or mu_1
+            // multipliers: [mu_1 (n); lam_1 (n); mu_2 (ps); lam_2; ...; lam_{N-1}; mu_N]: this knot writes lam_{k-1} (or mu_1)
+            // and its own stage multipliers mu_k
+            const int64_t lo_ = first ? 0 : (int64_t)n + (int64_t)(k - 1) * (n + ps);
+            __stcs(mb + lo_ + tid, -xps[tid]);
+            if (tid < psk) __stcs(mb + lo_ + n + tid, -xiv[tid]);
         } else if (tid < wk) {
             const double *Ri = slot + L::hRi;
             double s = 0.0;

@@ -296,7 +296,10 @@ template <int n, int m, int HESS, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     kkt_wp_kernel(const double *__restrict__ data, double *__restrict__ recs, double *__restrict__ dz,
                   double *__restrict__ mult, double *__restrict__ res, int32_t *__restrict__ info,
-                  int32_t *__restrict__ cinfo, int N, int64_t batch, int soc, int ps) {
+                  int32_t *__restrict__ cinfo, int N, int64_t batch, int soc, int ps,
+                  const int32_t *__restrict__ pk, const int64_t *__restrict__ koff, const int64_t *__restrict__ moff) {
+    // ps = stage rows of every interior knot; or, with pk / koff / moff (stage rows per knot, offsets of the knot records
+    // and of the multiplier groups [mu_k; lam_k], N + 1 entries each), ps = the largest interior count
     using L = Lay<n, m, HESS>;
     using PH = Phys<n, m>;
     using RW = RecW<n>;
@@ -324,22 +327,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     }
     __syncwarp();
 
-    const int64_t doff = inst * L::data_rows(N, ps);  // in doubles from `data` (16-byte aligned)
+    const int64_t mrows = moff ? moff[N] : L::mult_rows(N, ps);
+    const int64_t doff = inst * (koff ? koff[N] : L::data_rows(N, ps));  // in doubles from `data` (16-byte aligned)
     const int recw = RW::rec(ps);
     double *rb = recs + inst * (int64_t)N * recw;
     double *zb = dz + inst * L::z_rows(N);
-    double *mb = mult + inst * L::mult_rows(N, ps);
+    double *mb = mult + inst * mrows;
     double *resb = res ? res + inst * L::z_rows(N) : nullptr;
     const int lstride = n + ps;  // lam_j sits at n + j (n + ps) of the multiplier vector, mu of knot j + 1 right after it
 
-    auto knot_len = [&](int k) { return k == 0 ? L::FIRST : (k == N - 1 ? L::LAST : L::mid(ps)); };
+    auto knot_ps = [&](int k) { return (k == 0 || k == N - 1) ? 0 : (pk ? (int)pk[k] : ps); };
+    auto knot_off = [&](int k) { return koff ? koff[k] : L::knot_off(k, ps); };
+    auto knot_len = [&](int k) { return k == 0 ? L::FIRST : (k == N - 1 ? L::LAST : L::mid(knot_ps(k))); };
     // The whole record of knot k -> buffer st.  Bulk copies move 16-byte pieces: with an odd number of stage rows a
     // record can start on an odd double, so the copy starts at the even double before it (shift 0 or 1) and may
     // carry one double more at the end (the packed array is a whole number of 32-instance tiles: it stays inside).
-    auto knot_shift = [&](int k) { return (int)((doff + L::knot_off(k, ps)) & 1); };
+    auto knot_shift = [&](int k) { return (int)((doff + knot_off(k)) & 1); };
     auto issue = [&](int k, int st) {
         if (lane == 0) {
-            const int64_t g0 = doff + L::knot_off(k, ps);
+            const int64_t g0 = doff + knot_off(k);
             const int sh = (int)(g0 & 1);
             const uint32_t bytes = (uint32_t)((knot_len(k) + sh + 1) & ~1) * 8u;
             mbar_expect_tx(bars + st, bytes);
@@ -450,7 +456,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         mbar_wait(bars + st, (k >> 1) & 1);
         const double *kp = buf + st * BUF + knot_shift(k);
         const int wk = last ? n : w;
-        const int psk = (first || last) ? 0 : ps;  // stage rows of this knot (the end knots have their own blocks)
+        const int psk = knot_ps(k);  // stage rows of this knot (the end knots have their own blocks)
         // g (z slots) -> vec; d (x slots)
         double dv = 0.0;
         if (lane < 16) {
@@ -715,7 +721,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const double rr = rows_to_slot(r2, lane);
         if (lane < 16) {
             vec[VX + lane] = xslot >= 0 ? rr : 0.0;
-            if (xslot >= 0) __stcs(mb + L::mult_rows(N, ps) - n + xslot, -rr);  // mu_N
+            if (xslot >= 0) __stcs(mb + mrows - n + xslot, -rr);  // mu_N
         }
     }
     if (lane == 0) {
@@ -737,7 +743,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         const int wk = last ? n : w;
         // record
         const double *rk = rb + (int64_t)k * recw;
-        const int psk = (first || last) ? 0 : ps;
+        const int psk = knot_ps(k);
         Tile16 Zm;
         Zm.v[0][0][0] = rk[lane];
         Zm.v[0][0][1] = rk[32 + lane];
@@ -828,7 +834,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
             }
             // multipliers: [mu_1 (n); lam_1 (n); mu_2 (ps); lam_2; ...; lam_{N-1}; mu_N]; this knot produces lam_{k-1}
             // (k >= 1) or mu_1, and its own stage multipliers mu_k
-            const int64_t lo_ = first ? 0 : (int64_t)n + (int64_t)(k - 1) * lstride;
+            const int64_t lo_ = first ? 0 : (moff ? moff[k] - n : (int64_t)n + (int64_t)(k - 1) * lstride);
             if (lane < 16 && xslot >= 0) __stcs(mb + lo_ + xslot, -vec[VXP + lane]);
             if (lane < psk) __stcs(mb + lo_ + n + lane, -vec[SXI + lane]);
         }

@@ -73,7 +73,7 @@ def test_tpi_hessian_modes(handle, oracle_mod, n, m, N, mid_p, hess):
 
 @pytest.mark.parametrize("hess", [0, 1, 2])
 @pytest.mark.parametrize("n,m,N,mid_p,d2x", [(5, 2, 10, 1, False), (4, 1, 12, 0, True), (3, 2, 8, 1, True),
-                                            (12, 3, 40, 0, False), (12, 4, 9, 2, True), (20, 6, 6, 0, False),
+                                            (10, 3, 40, 0, False), (12, 4, 9, 2, True), (20, 6, 6, 0, False),
                                             (3, 3, 2, 0, False)])
 def test_cooperative_kernel(handle, oracle_mod, n, m, N, mid_p, d2x, hess):
     prob = problems.random_lqr_kkt(n, m, N, 6, seed=n + hess, mid_p=mid_p, hess_mode=hess, explicit_D2=d2x)
@@ -342,6 +342,58 @@ def test_every_control_count_up_to_four_on_the_tensor_core_kernel(handle, oracle
     prob = problems.random_lqr_kkt(n, m, N, batch, seed=13 * n + 3 * m + mid_p, mid_p=mid_p, hess_mode=hess)
     _check(prob, handle, oracle_mod, truth_instances=(0, batch - 1))
     assert handle.last_kernel.startswith(f"kkt_wp_dmma<{n},{m},p={n}/{mid_p}/{n}"), handle.last_kernel
+
+
+@pytest.mark.parametrize("hess,soc", [(1, False), (2, False), (1, True)])
+@pytest.mark.parametrize("n,m,N,batch,mid_p", [(64, 16, 12, 3, 1), (64, 16, 13, 2, 2), (64, 16, 30, 2, 3), (48, 16, 12, 3, 1),
+                                               (32, 8, 14, 3, 1), (32, 8, 15, 2, 4), (24, 8, 21, 4, 3), (16, 8, 20, 5, 1),
+                                               (16, 8, 21, 3, 2), (16, 8, 30, 2, 4)])
+def test_stage_constraints_on_the_cta_kernels(handle, oracle_mod, n, m, N, batch, mid_p, hess, soc):
+    """Mid-horizon stage constraints (p = [n, ps, ..., ps, n], test/problems.jl:39-43) at the large-state sizes stay on the
+    CTA-per-instance tensor-core kernels: ps <= 4 rows per knot as vector work beside the tile algebra.  Odd ps puts
+    knot records on odd doubles (the pre-pass then stages [A B] with plain loads): batches > 1, both parities of N.
+    Tolerance: 1e-10, or 4x the error the reference's own operation order (the oracle) makes on the input if larger."""
+    from oracle import dense_kkt
+    prob = problems.random_lqr_kkt(n, m, N, batch, seed=7 * n + mid_p, mid_p=mid_p, hess_mode=hess)
+    dz, lam, info, res = ops.kkt_solve_problem(prob, soc=soc, want_res=True, handle=handle)
+    assert handle.last_kernel.startswith(f"kkt_cta_dmma<{n},{m},p={n}/{mid_p}/{n}"), handle.last_kernel
+    dzo, lamo, infoo, reso = oracle_mod.kkt_solve(prob, soc=soc, want_res=True)
+    assert (info == 0).all() and (infoo == 0).all()
+    base = 1e-9 if soc else TOL
+    for i in range(batch):
+        zt, lt = dense_kkt.kkt_truth(prob, i, soc=soc)
+        tol = max(base, 4.0 * max(_rel(dzo[i], zt), _rel(lamo[i], lt)))
+        assert _rel(dz[i], zt) <= tol and _rel(lam[i], lt) <= tol, (i, tol, _rel(dz[i], zt), _rel(lam[i], lt))
+        assert _rel(dz[i], dzo[i]) <= 2 * tol and _rel(lam[i], lamo[i]) <= 2 * tol
+        assert np.linalg.norm(res[i] - reso[i]) <= 2 * tol * max(1.0, np.linalg.norm(reso[i]))
+        rs, rp = dense_kkt.kkt_residuals(prob, i, dz[i], lam[i], soc=soc)
+        assert rs <= 10 * base and rp <= 10 * base, (rs, rp)
+
+
+def _per_knot_pattern(prob, seed, hi):
+    """Keep a random number (0..hi) of the stage rows of every interior knot."""
+    rng = np.random.default_rng(seed)
+    p = prob["p"].copy()
+    for k in range(1, prob["N"] - 1):
+        p[k] = int(rng.integers(0, hi + 1))
+        prob["C"][k] = prob["C"][k][:, :p[k]]
+        prob["c"][k] = prob["c"][k][:, :p[k]]
+    prob["p"] = p
+    return prob
+
+
+@pytest.mark.parametrize("hess,soc", [(1, False), (2, False), (0, False), (1, True)])
+@pytest.mark.parametrize("n,m,N,batch,hi", [(12, 4, 40, 7, 3), (12, 4, 31, 33, 2), (8, 4, 30, 5, 3), (12, 3, 33, 6, 2),
+                                            (8, 2, 30, 34, 1), (12, 2, 25, 3, 1)])
+def test_per_knot_stage_rows_on_the_tensor_core_kernel(handle, oracle_mod, n, m, N, batch, hi, hess, soc):
+    """The reference sizes every knot freely (src/conblocks.jl:74-96): a different number of stage rows on every
+    interior knot (<= 4) stays on the warp-per-instance kernel; record and multiplier offsets come from the per-knot
+    tables of the general path."""
+    prob = _per_knot_pattern(problems.random_lqr_kkt(n, m, N, batch, seed=17 * n + hi, mid_p=hi, hess_mode=hess), N + hi, hi)
+    assert len(set(prob["p"][1:-1].tolist())) > 1
+    _check(prob, handle, oracle_mod, soc=soc, tol=1e-9 if soc else TOL, res_tol=1e-9 if soc else TOL,
+           truth_instances=(0, batch - 1))
+    assert handle.last_kernel.startswith(f"kkt_wp_dmma<{n},{m},p={n}/per-knot<={max(prob['p'][1:-1])}/{n}"), handle.last_kernel
 
 
 def test_stage_constraints_match_cooperative_kernel_and_report_info(handle):

@@ -147,6 +147,10 @@ def main():
             r = probe_riccati(h, stream, 64, 16, 101, int(4096 * S), 32, args.steps, args.warmup, peak)
         elif w == "5bK":
             r = probe_kkt(h, stream, 64, 16, 101, int(4096 * S), 32, args.steps, args.warmup, peak)
+        elif w in ("5bKp1", "5bKp2", "5bKp4"):  # 5b-K with 1 / 2 / 4 stage rows on every interior knot
+            r = probe_kkt(h, stream, 64, 16, 101, int(4096 * S), 32, args.steps, args.warmup, peak, mid_p=int(w[-1]))
+        elif w in ("5aKp1", "5aKp3"):
+            r = probe_kkt(h, stream, 12, 4, 1001, int(16384 * S), 32, args.steps, args.warmup, peak, mid_p=int(w[-1]))
         else:
             continue
         r["config"] = w
