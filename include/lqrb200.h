@@ -85,7 +85,8 @@ int64_t lqrb_num_cons(int32_t n, int32_t N, const int32_t *p);
 
 /* Riccati packed rows.
  *   knots : [(LTI ? 1 : N-1)][F][ldb]  per knot: A (n*n col-major) | B (n*m) | Q (upper packed,
- *           idx(i,j)=j(j+1)/2+i) | R (upper packed) | q (n) | r (m);  F = rows_per_knot
+ *           idx(i,j)=j(j+1)/2+i) | R (upper packed) | q (n) | r (m);  F = rows_per_knot (for n = 8, 12 with
+ *           m = 2, 3 one padding row follows r so that F is even: take F from lqrb_riccati_layout)
  *   term  : [n(n+1)/2 + 2n][ldb]       Qf (upper packed) | qf (n) | x0 (n)
  *   Z     : [N*n+(N-1)*m][ldb]         Primals order [x1;u1;x2;u2;...;xN] (src/lqr_problem.jl:46-73)
  *   K     : [(N-1)*(m*n+m)][ldb]       per knot: K (m*n col-major) | kff (m)                      */

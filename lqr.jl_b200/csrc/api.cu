@@ -189,7 +189,7 @@ extern "C" int32_t lqrb_riccati_layout(int32_t n, int32_t m, int32_t N, int32_t 
     if (m < 1) return -2;
     if (N < 2) return -3;
     if (!out) return -5;
-    out->rows_per_knot = (int64_t)n * n + n * m + tri(n) + tri(m) + n + m;
+    out->rows_per_knot = lqrb_riccati_knot_rows(n, m);  // one padding double for (8 | 12, 2 | 3)
     out->knot_count = (flags & LQRB_FLAG_LTI) ? 1 : N - 1;
     out->term_rows = tri(n) + 2 * n;
     out->z_rows = lqrb_num_vars(n, m, N);

@@ -116,6 +116,14 @@ static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * 
 
 // ------------------------------------------------------------------ gather/scatter maps -------
 // One packed row = one element of one instance-major source array.
+// Doubles per knot record of the packed Riccati layout: A | B | Q (upper packed) | R (upper packed) | q | r, plus one
+// padding double for the warp-per-instance tensor-core size class (n = 8, 12, m <= 4) when that count is odd — its
+// records travel by 16-byte bulk copies and are read with 16-byte shared loads (m = 2, 3 at both n).
+__host__ __device__ constexpr int lqrb_riccati_knot_rows(int n, int m) {
+    const int f = n * n + n * m + n * (n + 1) / 2 + m * (m + 1) / 2 + n + m;
+    return ((n == 8 || n == 12) && m <= 4) ? ((f + 1) & ~1) : f;
+}
+
 struct RowMap {
     int32_t array;   // index into the source pointer table (-1: constant fill)
     int32_t offset;  // element offset inside that array's per-instance record

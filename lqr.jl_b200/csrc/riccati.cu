@@ -19,7 +19,7 @@ static bool riccati_has_tpi(int n, int m) {
 }
 
 // warp-per-instance FP64 tensor-core (DMMA) instantiations: n in {8,12}, m <= 4, even record length
-#define RICCATI_DMMA_SIZES(X) X(8, 1) X(8, 4) X(12, 1) X(12, 4)
+#define RICCATI_DMMA_SIZES(X) X(8, 1) X(8, 2) X(8, 3) X(8, 4) X(12, 1) X(12, 2) X(12, 3) X(12, 4)
 
 static bool riccati_has_dmma(int n, int m) {
 #define X(N_, M_) \
@@ -61,6 +61,7 @@ static std::vector<RowMap> riccati_knot_map(int n, int m, int N, int flags) {
             for (int i = 0; i <= j; ++i) map.push_back({3, k * m * m + i + j * m, 0.0});
         for (int e = 0; e < n; ++e) map.push_back({4, k * n + e, 0.0});
         for (int e = 0; e < m; ++e) map.push_back({5, k * m + e, 0.0});
+        if (lqrb_riccati_knot_rows(n, m) > n * n + n * m + tri(n) + tri(m) + n + m) map.push_back({-1, 0, 0.0});  // padding
     }
     return map;
 }

@@ -67,7 +67,7 @@ struct Map {
     static constexpr int w = n + m;
     static constexpr int KS = n / 4;  // contraction steps over the state index
     static constexpr int oQ = n * w, oR = oQ + tri(n), oq = oR + tri(m), orr = oq + n;
-    static constexpr int F = orr + m;      // doubles per knot record
+    static constexpr int F = lqrb_riccati_knot_rows(n, m);  // doubles per knot record (orr + m, padded to even)
     static constexpr int TR = tri(n) + 2 * n;
     static constexpr int GR = m * n + m;
     static_assert(F % 2 == 0, "bulk copies need 16-byte records");

@@ -21,7 +21,7 @@
 template <int n, int m>
 struct RiccatiRows {
     static constexpr int oA = 0, oB = n * n, oQ = oB + n * m, oR = oQ + tri(n), oq = oR + tri(m),
-                         orr = oq + n, F = orr + m;
+                         orr = oq + n, F = lqrb_riccati_knot_rows(n, m);
     static constexpr int TR = tri(n) + 2 * n;  // Qf | qf | x0
     static constexpr int GR = m * n + m;       // K | kff
     static constexpr int W = n + m;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(THREADS)
     const bool active = inst_raw < batch;
     const int64_t inst = active ? inst_raw : batch - 1;  // idle groups shadow a valid instance
     const int nn = n * n, nm = n * m, tn = tri(n), tm = tri(m);
-    const int F = nn + nm + tn + tm + n + m, TR = tn + 2 * n, GR = m * n + m, W = n + m;
+    const int F = lqrb_riccati_knot_rows(n, m), TR = tn + 2 * n, GR = m * n + m, W = n + m;
     const int Kn = lti ? 1 : N - 1;
     double *s = smem + (size_t)g * riccati_coop_smem_doubles(n, m);
     double *P = s, *Pn = P + nn, *PA = Pn + nn, *A = PA + nn, *B = A + nn, *PB = B + nm,

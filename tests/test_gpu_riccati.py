@@ -53,7 +53,7 @@ def test_tpi_sizes(handle, oracle_mod, n, m, N, lti):
     assert handle.last_kernel.startswith("riccati_tpi")
 
 
-@pytest.mark.parametrize("n,m,N,batch", [(5, 2, 20, 9), (12, 3, 101, 10), (7, 7, 15, 5), (32, 7, 12, 3), (40, 12, 11, 2)])
+@pytest.mark.parametrize("n,m,N,batch", [(5, 2, 20, 9), (10, 3, 101, 10), (7, 7, 15, 5), (32, 7, 12, 3), (40, 12, 11, 2)])
 def test_cooperative_sizes(handle, oracle_mod, n, m, N, batch):
     prob = problems.random_lqr_riccati(n, m, N, batch, seed=n)
     _check(prob, handle, oracle_mod)
@@ -61,7 +61,8 @@ def test_cooperative_sizes(handle, oracle_mod, n, m, N, batch):
 
 
 @pytest.mark.parametrize("n,m,N,batch", [(12, 4, 101, 10), (12, 4, 2, 3), (12, 4, 7, 133), (8, 4, 60, 9), (12, 1, 40, 5),
-                                         (8, 1, 33, 6), (12, 4, 1001, 4)])
+                                         (8, 1, 33, 6), (12, 4, 1001, 4), (12, 2, 50, 7), (12, 3, 41, 34), (8, 2, 30, 5),
+                                         (8, 3, 33, 33), (12, 3, 2, 3)])
 @pytest.mark.parametrize("lti", [False, True])
 def test_dmma_sizes(handle, oracle_mod, n, m, N, batch, lti):
     """warp-per-instance FP64 tensor-core kernel (config 5a shape and its siblings)."""
