@@ -2,42 +2,7 @@
 #include <algorithm>
 #include <cstdio>
 
-#include "kkt_coop.cuh"
-#include "kkt_hw_kernels.cuh"
-#include "kkt_wp_kernels.cuh"
-#include "kkt_cta_kernels.cuh"
-#include "kkt_kernels.cuh"
-
-// default of the `kkt_cond_bits` option: instances whose worst Schur-block pivot ratio reaches 2^bits are solved again
-// by the Cholesky-based kernel (see kkt_resolve_ill_conditioned).  Calibrated with tools/stress_scales.py
-// (profiles/r2_conditioning_calibration.txt): the error of the explicit-inverse kernels is about 2^bits times that of
-// the reference's U'U order; every grid case where they miss 1e-10 while the reference order meets it has bits >= 7,
-// the BASELINE configs at their own scaling have bits 2-3.
-#define LQRB_KKT_COND_BITS 6
-
-// ------------------------------------------------------------------ size classes --------------
-// thread-per-instance instantiations: (n, m, P1, PM, PN) with p = [P1, PM, ..., PM, PN].
-//   cartpole (test/problems.jl:58-88): 4,1 init+goal          dubins: 3,2 init+goal (+1 mid row)
-//   DoubleIntegrator(3) (test/problems.jl:14-56): 6,3 init, 1 mid row, goal;  D=2: 4,2
-#define KKT_TPI_SIZES(X) \
-    X(4, 1, 4, 0, 4) X(3, 2, 3, 0, 3) X(3, 2, 3, 1, 3) X(2, 1, 2, 0, 2) X(4, 2, 4, 1, 4) X(6, 3, 6, 1, 6)
-
-struct KktShape {
-    int n, m, N, hess, d2x;
-    const int32_t *p;
-    bool uniform;  // p = [P1, PM.., PN]
-    int P1, PM, PN;
-    int PMAX;  // largest interior count
-};
-
-static KktShape make_shape(int n, int m, int N, const int32_t *p, int hess, int d2x) {
-    KktShape s{n, m, N, hess, d2x, p, true, p[0], N > 2 ? p[1] : 0, p[N - 1], 0};
-    for (int k = 1; k < N - 1; ++k) {
-        if (p[k] != s.PM) s.uniform = false;
-        s.PMAX = std::max(s.PMAX, (int)p[k]);
-    }
-    return s;
-}
+#include "kkt_dispatch.cuh"
 
 static bool kkt_has_tpi(const KktShape &s) {
     if (!s.uniform || s.d2x) return false;
@@ -48,8 +13,6 @@ static bool kkt_has_tpi(const KktShape &s) {
     return false;
 }
 
-// half-warp-per-instance instantiations: p = [n, 0, ..., 0, n], block-diagonal Hessian, structural D2
-#define KKT_HW_SIZES(X) X(12, 4) X(8, 4)
 
 static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
     if (h->opt("kkt_variant", 0) == 2 || h->opt("kkt_variant", 0) == 5) return false;
@@ -63,8 +26,6 @@ static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
     return false;
 }
 
-// warp-per-instance FP64 tensor-core instantiations (kkt_wp_kernels.cuh; same stage pattern)
-#define KKT_WP_SIZES(X) X(12, 4) X(8, 4) X(12, 3) X(8, 3) X(12, 2) X(8, 2) X(12, 1) X(8, 1)
 
 // kkt_variant: 0 = default (half-warp kernel where it exists, else this one), 5 = force this kernel
 static bool kkt_has_wp(const lqrb_context *h, const KktShape &s) {
@@ -79,8 +40,6 @@ static bool kkt_has_wp(const lqrb_context *h, const KktShape &s) {
     return false;
 }
 
-// CTA-per-instance FP64 tensor-core instantiations (same stage pattern)
-#define KKT_CTA_SIZES(X) X(64, 16) X(48, 16) X(32, 8) X(24, 8) X(16, 8)
 
 static bool kkt_has_cta(const lqrb_context *h, const KktShape &s, int flags) {
     if (h->opt("kkt_variant", 0) == 2) return false;
@@ -201,63 +160,15 @@ static int32_t check_kkt(lqrb_context *h, int n, int m, int N, int64_t batch, co
 }
 
 static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch);
-static int64_t kkt_tuned_chunk(const lqrb_context *h, const KktShape &s);
-
-struct KktSizes {
-    int64_t NN, P, data_rows, rec_rows;
-    int64_t sC, sc, sD2;
-};
-
-static KktSizes kkt_sizes(const KktShape &s) {
-    KktSizes z{};
-    z.NN = lqrb_num_vars(s.n, s.m, s.N);
-    z.P = lqrb_num_cons(s.n, s.N, s.p);
-    z.data_rows = lqrb_kkt_data_rows(s.n, s.m, s.N, s.p, s.hess, s.d2x);
-    for (int k = 0; k < s.N; ++k) {
-        const int w = s.n + (k < s.N - 1 ? s.m : 0);
-        z.sC += (int64_t)s.p[k] * w;
-        z.sc += s.p[k];
-        if (k > 0) z.sD2 += (int64_t)s.n * w;
-    }
-    z.rec_rows = kkt_coop_rec_rows(s.n, s.m, s.N, s.p);  // an upper bound that also fits the TPI records
-    return z;
-}
 
 // ------------------------------------------------------------------ solve (packed, device) ----
-template <int n, int m, int P1, int PM, int PN>
-static int32_t launch_kkt_tpi(lqrb_context *h, const KktShape &s, int64_t batch, int flags,
-                              const double *data, double *scratch, double *dz, double *mult,
-                              double *res, int32_t *info, cudaStream_t st) {
-    constexpr int THREADS = 64;
-    const unsigned grid = (unsigned)((batch + THREADS - 1) / THREADS);
-    const bool soc = (flags & LQRB_FLAG_SOC) != 0;
-#define LAUNCH(HESS, SOC) \
-    kkt_tpi_kernel<n, m, P1, PM, PN, HESS, SOC, THREADS><<<grid, THREADS, 0, st>>>(data, scratch, dz, mult, res, info, s.N, batch)
-    if (soc) {
-        // H and g are ignored: any HESS instantiation reads the same rows layout it was packed with
-        if (s.hess == LQRB_HESS_DIAG) LAUNCH(LQRB_HESS_DIAG, true);
-        else if (s.hess == LQRB_HESS_BLOCKDIAG) LAUNCH(LQRB_HESS_BLOCKDIAG, true);
-        else LAUNCH(LQRB_HESS_DENSE, true);
-    } else {
-        if (s.hess == LQRB_HESS_DIAG) LAUNCH(LQRB_HESS_DIAG, false);
-        else if (s.hess == LQRB_HESS_BLOCKDIAG) LAUNCH(LQRB_HESS_BLOCKDIAG, false);
-        else LAUNCH(LQRB_HESS_DENSE, false);
-    }
-#undef LAUNCH
-    char nm[96];
-    snprintf(nm, sizeof nm, "kkt_tpi<%d,%d,p=%d/%d/%d,hess=%d%s>", n, m, P1, PM, PN, s.hess, soc ? ",soc" : "");
-    h->kernel_name = nm;
-    LQRB_LAUNCH_CHECK(h, "kkt_tpi_kernel");
-    return 0;
-}
-
 // The tuned large-size kernels (kkt_hw2, kkt_cta) carry the block elimination with explicit SPD inverses (products
 // instead of the reference's sequential triangular solves); their error grows with cond(Sigma_k) where the reference's
 // U'U form (src/cholesky_solve.jl:47-67) does not.  Both kernels report, per instance, log2 of the worst pivot ratio
 // met in any Sigma_k (free: integer compares of the pivots' high words).  Instances above `kkt_cond_bits` are solved
 // again by the Cholesky-based general kernel — the reference's own operation order — which overwrites their outputs.
 // `kkt_refine` = 0 switches this off.  Costs one 4-byte-per-instance read-back and a stream synchronisation.
-static int32_t kkt_resolve_ill_conditioned(lqrb_context *h, const KktShape &s, int64_t cb, int flags, const double *dc,
+int32_t kkt_resolve_ill_conditioned(lqrb_context *h, const KktShape &s, int64_t cb, int flags, const double *dc,
                                            const int32_t *cinfo_dev, double *dz, double *mult, double *res, int32_t *info,
                                            cudaStream_t st) {
     h->last_refined = 0;
@@ -296,169 +207,10 @@ static int32_t kkt_resolve_ill_conditioned(lqrb_context *h, const KktShape &s, i
     return 0;
 }
 
-template <int n, int m, int HESS>
-static int32_t launch_kkt_hw(lqrb_context *h, const KktShape &s, int64_t batch, int soc, const double *data,
-                             double *scratch, double *dz, double *mult, double *res, int32_t *info,
-                             cudaStream_t st) {
-    using L = khw::Lay<n, m, HESS>;
-    const int N = s.N;
-    // default: the block-layout kernel (4 x 4 lane grid per instance); kkt_variant = 3 keeps the column-per-lane one.
-    // Three 4-warp CTAs per SM at 168 registers: eight 2-warp CTAs at 128 registers (16 warps, a few spills) were
-    // 3.5 % slower in an A/B on one box (48.95 vs 47.2 ms) — the kernel is not latency-bound.
-    constexpr int WARPS = 4, MINB = 3;
-    const bool blocks = h->opt("kkt_variant", 0) != 3;
-    const size_t smem = (size_t)WARPS * (2 * (blocks ? L::INST2 : L::INST) + 4) * sizeof(double);
-    auto kern = blocks ? khw::kkt_hw2_kernel<n, m, HESS, WARPS, MINB> : khw::kkt_hw_kernel<n, m, HESS, WARPS, MINB>;
-    LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
-    int64_t refined = 0;
-    for (int64_t first = 0; first < batch; first += chunk) {
-        const int64_t cb = std::min(chunk, batch - first);
-        // scratch (reused by every chunk): [records: cb x N x REC] [Hi: cb x N x HI] [hinfo: cb] [cinfo: cb]
-        double *recs = scratch;
-        double *hinv = recs + (size_t)cb * N * L::REC;
-        int32_t *hinfo = reinterpret_cast<int32_t *>(hinv + (size_t)cb * N * L::HI);
-        int32_t *cinfo = hinfo + cb;  // conditioning estimates (the "+ 1" double per instance holds both)
-        const double *dc = data + first * L::data_rows(N);
-        LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)cb * sizeof(int32_t), st));
-        const int64_t total = cb * N;
-        khw::kkt_hinv_kernel<n, m, HESS><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(dc, hinv, hinfo, N, cb, soc);
-        LQRB_LAUNCH_CHECK(h, "kkt_hinv_kernel");
-        const int64_t pairs = (cb + 1) / 2;
-        kern<<<(unsigned)((pairs + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(
-            dc, hinv, hinfo, recs, dz + first * L::z_rows(N), mult + first * L::mult_rows(N),
-            res ? res + first * L::z_rows(N) : nullptr, info ? info + first : nullptr, cinfo, N, cb, soc);
-        LQRB_LAUNCH_CHECK(h, "kkt_hw_kernel");
-        int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * L::z_rows(N),
-                                                 mult + first * L::mult_rows(N), res ? res + first * L::z_rows(N) : nullptr,
-                                                 info ? info + first : nullptr, st);
-        if (rc) return rc;
-        refined += h->last_refined;
-    }
-    char nm[128];
-    snprintf(nm, sizeof nm, "kkt_hw<%d,%d,p=%d/0/%d,hess=%d%s%s>", n, m, n, n, HESS, soc ? ",soc" : "", blocks ? "" : ",cols");
-    h->kernel_name = nm;
-    if (refined) h->kernel_name += "+kkt_coop[" + std::to_string(refined) + " ill-conditioned]";
-    h->last_refined = refined;
-    return 0;
-}
-
-// warp-per-instance FP64 tensor-core kernel (kkt_wp_kernels.cuh): the default for the half-warp size list; H^-1 is
-// formed in the kernel, so there is no pre-pass and no Hi array (scratch: the records and the two info arrays)
-template <int n, int m, int HESS>
-static int32_t launch_kkt_wp(lqrb_context *h, const KktShape &s, int64_t batch, int soc, const double *data,
-                             double *scratch, double *dz, double *mult, double *res, int32_t *info, cudaStream_t st) {
-    using L = kwp::Lay<n, m, HESS>;
-    using RW = kwp::RecW<n>;
-    const int N = s.N;
-    constexpr int WARPS = 4, MINB = 3;  // 168 registers: 12 warps per SM
-    constexpr size_t smem = (size_t)WARPS * kwp::warp_smem_doubles<n, m, HESS>() * sizeof(double);
-    const int ps = s.PMAX;
-    // uniform interior pattern: offsets are closed forms; else the per-knot tables of the general path
-    KktTables tb{};
-    if (!s.uniform) {
-        int32_t trc = lqrb_kkt_tables(h, n, m, N, s.p, HESS, 0, &tb);
-        if (trc) return trc;
-    }
-    const int64_t drows = lqrb_kkt_data_rows(n, m, N, s.p, HESS, 0), zrows = L::z_rows(N), mrows = lqrb_num_cons(n, N, s.p);
-    auto kern = kwp::kkt_wp_kernel<n, m, HESS, WARPS, MINB>;
-    LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
-    int64_t refined = 0;
-    for (int64_t first = 0; first < batch; first += chunk) {
-        const int64_t cb = std::min(chunk, batch - first);
-        // scratch (reused by every chunk): [records: cb x N x REC] [cinfo: cb]
-        double *recs = scratch;
-        int32_t *cinfo = reinterpret_cast<int32_t *>(recs + (size_t)cb * N * RW::rec(ps));
-        const double *dc = data + first * drows;
-        kern<<<(unsigned)((cb + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(
-            dc, recs, dz + first * zrows, mult + first * mrows, res ? res + first * zrows : nullptr,
-            info ? info + first : nullptr, cinfo, N, cb, soc, ps, s.uniform ? nullptr : tb.p,
-            s.uniform ? nullptr : tb.knot_off, s.uniform ? nullptr : tb.mult_off);
-        LQRB_LAUNCH_CHECK(h, "kkt_wp_kernel");
-        int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * zrows,
-                                                 mult + first * mrows, res ? res + first * zrows : nullptr,
-                                                 info ? info + first : nullptr, st);
-        if (rc) return rc;
-        refined += h->last_refined;
-    }
-    char nm[128];
-    if (s.uniform)
-        snprintf(nm, sizeof nm, "kkt_wp_dmma<%d,%d,p=%d/%d/%d,hess=%d%s>", n, m, n, ps, n, HESS, soc ? ",soc" : "");
-    else
-        snprintf(nm, sizeof nm, "kkt_wp_dmma<%d,%d,p=%d/per-knot<=%d/%d,hess=%d%s>", n, m, n, ps, n, HESS, soc ? ",soc" : "");
-    h->kernel_name = nm;
-    if (refined) h->kernel_name += "+kkt_coop[" + std::to_string(refined) + " ill-conditioned]";
-    h->last_refined = refined;
-    return 0;
-}
-
-template <int n, int m, int HESS>
-static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch, int soc, const double *data,
-                              double *scratch, double *dz, double *mult, double *res, int32_t *info,
-                              cudaStream_t st) {
-    using L = kcta::Lay<n, m, HESS>;
-    const int N = s.N, ps = s.PM;
-    // the stage-row work areas are allocated only when there are stage rows (config 5b-K keeps its footprint)
-    const size_t psm = (size_t)(ps ? L::PREP_TOTAL_ST : L::PREP_TOTAL) * sizeof(double),
-                 msm = (size_t)(ps ? L::MAIN_TOTAL_ST : L::MAIN_TOTAL) * sizeof(double);
-    auto pk = ps ? kcta::kkt_cta_prep_kernel<n, m, HESS, true> : kcta::kkt_cta_prep_kernel<n, m, HESS, false>;
-    auto mk = ps ? kcta::kkt_cta_kernel<n, m, HESS, true> : kcta::kkt_cta_kernel<n, m, HESS, false>;
-    LQRB_CUDA(h, cudaFuncSetAttribute(pk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-    LQRB_CUDA(h, cudaFuncSetAttribute(mk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msm));
-    const int64_t chunk = std::min(batch, kkt_tuned_chunk(h, s));
-    const int64_t drows = L::data_rows(N, ps), zrows = L::z_rows(N), mrows = L::mult_rows(N, ps);
-    int64_t refined = 0;
-    for (int64_t first = 0; first < batch; first += chunk) {
-        const int64_t cb = std::min(chunk, batch - first);
-        // scratch (reused by every chunk): [records: cb x N x REC] [pre-pass slots: cb x prep_rows] [hinfo: cb] [cinfo: cb]
-        double *recs = scratch;
-        double *prep = recs + (size_t)cb * N * L::rec(ps);
-        int32_t *hinfo = reinterpret_cast<int32_t *>(prep + (size_t)cb * L::prep_rows(N, ps));
-        int32_t *cinfo = hinfo + cb;  // conditioning estimates (the "+ 1" double per instance holds both)
-        const double *dc = data + first * drows;
-        LQRB_CUDA(h, cudaMemsetAsync(hinfo, 0x7f, (size_t)cb * sizeof(int32_t), st));
-        LQRB_CUDA(h, cudaMemsetAsync(cinfo, 0, (size_t)cb * sizeof(int32_t), st));
-        kcta::kkt_cta_ri_kernel<n, m, HESS><<<(unsigned)((cb * (N - 1) + 7) / 8), 128, 0, st>>>(dc, prep, hinfo, N, cb, soc, ps);
-        LQRB_LAUNCH_CHECK(h, "kkt_cta_ri_kernel");
-        pk<<<(unsigned)(cb * N), L::THREADS, psm, st>>>(dc, prep, hinfo, cinfo, N, cb, soc, ps);
-        LQRB_LAUNCH_CHECK(h, "kkt_cta_prep_kernel");
-        mk<<<(unsigned)cb, L::THREADS, msm, st>>>(dc, prep, hinfo, recs, dz + first * zrows, mult + first * mrows,
-                                                  res ? res + first * zrows : nullptr,
-                                                  info ? info + first : nullptr, cinfo, N, cb, soc, ps);
-        LQRB_LAUNCH_CHECK(h, "kkt_cta_kernel");
-        int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * zrows,
-                                                 mult + first * mrows, res ? res + first * zrows : nullptr,
-                                                 info ? info + first : nullptr, st);
-        if (rc) return rc;
-        refined += h->last_refined;
-    }
-    char nm[128];
-    snprintf(nm, sizeof nm, "kkt_cta_dmma<%d,%d,p=%d/%d/%d,hess=%d%s>", n, m, n, ps, n, HESS, soc ? ",soc" : "");
-    h->kernel_name = nm;
-    if (refined) h->kernel_name += "+kkt_coop[" + std::to_string(refined) + " ill-conditioned]";
-    h->last_refined = refined;
-    return 0;
-}
-
 // scratch of the tuned kernels in doubles: the largest need of the families that have this (n, m) — which one runs
 // also depends on options (kkt_variant) and on the Hessian mode / stage rows
 static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch) {
-    size_t per = 0;
-#define X(N_, M_) \
-    if (s.n == N_ && s.m == M_)   \
-        per = std::max(per, (size_t)s.N * kcta::Lay<N_, M_>::rec(s.PMAX) + kcta::Lay<N_, M_>::prep_rows(s.N, s.PMAX) + 1);
-    KKT_CTA_SIZES(X)
-#undef X
-#define X(N_, M_) \
-    if (s.n == N_ && s.m == M_)   \
-        per = std::max(per, (size_t)s.N * (khw::Lay<N_, M_>::REC + khw::Lay<N_, M_>::HI) + 1);
-    KKT_HW_SIZES(X)
-#undef X
-#define X(N_, M_) \
-    if (s.n == N_ && s.m == M_) per = std::max(per, (size_t)s.N * kwp::RecW<N_>::rec(s.PMAX) + 1);
-    KKT_WP_SIZES(X)
-#undef X
+    const size_t per = std::max(kkt_cta_scratch_per_instance(s), std::max(kkt_hw_scratch_per_instance(s), kkt_wp_scratch_per_instance(s)));
     return per == 0 ? 0 : (size_t)batch * per + 2;
 }
 
@@ -466,7 +218,7 @@ static size_t kkt_hw_scratch_doubles(const KktShape &s, int64_t batch) {
 // N=1001; 13.7 MB for n=64, N=101).  Batches are processed in chunks so that the scratch stays under
 // `scratch_budget_mb` (default 48 GB of the 180 GB) whatever the batch size.  A chunk is a whole number of
 // resident waves of the sequential kernel (its CTAs live for the whole horizon, so a partial wave is a tail).
-static int64_t kkt_tuned_chunk(const lqrb_context *h, const KktShape &s) {
+int64_t kkt_tuned_chunk(const lqrb_context *h, const KktShape &s) {
     const size_t per = kkt_hw_scratch_doubles(s, 1);
     if (per == 0) return 0;
     const size_t budget = (size_t)h->opt("scratch_budget_mb", 49152) << 20;
@@ -491,50 +243,19 @@ static int32_t kkt_solve_on(lqrb_context *h, const KktShape &s, int64_t batch, i
                             const double *data, double *scratch, double *dz, double *mult, double *res,
                             int32_t *info, cudaStream_t st) {
     if (batch == 0) return 0;
-    if (kkt_has_cta(h, s, flags) && ((uintptr_t)data & 15) == 0 && ((uintptr_t)scratch & 15) == 0) {
-        const int soc = (flags & LQRB_FLAG_SOC) ? 1 : 0;
-#define X(N_, M_)                                                                                               \
-    if (s.n == N_ && s.m == M_)                                                                                 \
-        return s.hess == LQRB_HESS_DIAG                                                                         \
-                   ? launch_kkt_cta<N_, M_, LQRB_HESS_DIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st)      \
-                   : launch_kkt_cta<N_, M_, LQRB_HESS_BLOCKDIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st);
-        KKT_CTA_SIZES(X)
-#undef X
-    }
-    // kkt_variant: 0 = warp-per-instance tensor-core kernel (default), 3 / 4 = the half-warp kernels (column / block layout)
-    // The warp-per-instance tensor-core kernel takes the shapes the half-warp kernel does not have (odd m, dense
-    // Hessian); for (12,4) / (8,4) block-diagonal it is the slower one (74.9 vs 49.1 ms on config 5a-K: its three
-    // serial 16 x 16 inversions per knot make it latency-bound at 12 warps per SM) and runs only when forced.
-    if (kkt_has_wp(h, s) && ((uintptr_t)data & 15) == 0 && (h->opt("kkt_variant", 0) == 5 || !kkt_has_hw(h, s, flags))) {
-        const int soc = (flags & LQRB_FLAG_SOC) ? 1 : 0;
-#define X(N_, M_)                                                                                                        \
-    if (s.n == N_ && s.m == M_) {                                                                                        \
-        if (s.hess == LQRB_HESS_DIAG)                                                                                    \
-            return launch_kkt_wp<N_, M_, LQRB_HESS_DIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st);      \
-        if (s.hess == LQRB_HESS_BLOCKDIAG)                                                                               \
-            return launch_kkt_wp<N_, M_, LQRB_HESS_BLOCKDIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st); \
-        return launch_kkt_wp<N_, M_, LQRB_HESS_DENSE>(h, s, batch, soc, data, scratch, dz, mult, res, info, st);         \
-    }
-        KKT_WP_SIZES(X)
-#undef X
-    }
-    if (kkt_has_hw(h, s, flags) && ((uintptr_t)data & 15) == 0) {
-        const int soc = (flags & LQRB_FLAG_SOC) ? 1 : 0;
-#define X(N_, M_)                                                                                              \
-    if (s.n == N_ && s.m == M_)                                                                                \
-        return s.hess == LQRB_HESS_DIAG                                                                        \
-                   ? launch_kkt_hw<N_, M_, LQRB_HESS_DIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st)      \
-                   : launch_kkt_hw<N_, M_, LQRB_HESS_BLOCKDIAG>(h, s, batch, soc, data, scratch, dz, mult, res, info, st);
-        KKT_HW_SIZES(X)
-#undef X
-    }
-    if (lqrb_kkt_tile(h, s.n, s.m, s.N, s.p, s.hess, s.d2x) == LQRB_TILE) {
-#define X(N_, M_, A_, B_, C_)                                                                       \
-    if (s.n == N_ && s.m == M_ && s.P1 == A_ && (s.N == 2 || s.PM == B_) && s.PN == C_)            \
-        return launch_kkt_tpi<N_, M_, A_, B_, C_>(h, s, batch, flags, data, scratch, dz, mult, res, info, st);
-        KKT_TPI_SIZES(X)
-#undef X
-    }
+    int32_t rc = LQRB_NO_KERNEL;
+    if (kkt_has_cta(h, s, flags) && ((uintptr_t)data & 15) == 0 && ((uintptr_t)scratch & 15) == 0)
+        rc = kkt_launch_cta(h, s, batch, flags, data, scratch, dz, mult, res, info, st);
+    // The warp-per-instance tensor-core kernel takes the shapes the half-warp kernel does not have (m < 4, dense
+    // Hessian, stage rows); for (12,4) / (8,4) block-diagonal it is the slower one (65.5 vs 49.0 ms on config 5a-K) and
+    // runs only when forced (kkt_variant = 5; 3 = the column layout of the half-warp kernel).
+    else if (kkt_has_wp(h, s) && ((uintptr_t)data & 15) == 0 && (h->opt("kkt_variant", 0) == 5 || !kkt_has_hw(h, s, flags)))
+        rc = kkt_launch_wp(h, s, batch, flags, data, scratch, dz, mult, res, info, st);
+    else if (kkt_has_hw(h, s, flags) && ((uintptr_t)data & 15) == 0)
+        rc = kkt_launch_hw(h, s, batch, flags, data, scratch, dz, mult, res, info, st);
+    else if (lqrb_kkt_tile(h, s.n, s.m, s.N, s.p, s.hess, s.d2x) == LQRB_TILE)
+        rc = kkt_launch_tpi(h, s, batch, flags, data, scratch, dz, mult, res, info, st);
+    if (rc != LQRB_NO_KERNEL) return rc;
     return launch_kkt_coop(h, s.n, s.m, s.N, s.p, s.hess, s.d2x, flags, batch, data, scratch, dz, mult, res,
                            info, st);
 }

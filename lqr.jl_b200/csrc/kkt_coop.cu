@@ -94,8 +94,12 @@ __global__ void __launch_bounds__(THREADS) kkt_coop_kernel(KktCoopArgs a) {
            *Dh = Bh + P * P, *Eh = Dh + n * P, *dp = Eh + n * P, *lamp = dp + n, *lam = lamp + n,
            *lprev = lam + n, *mut = lprev + n, *mu = mut + P, *cvec = mu + P;
 
-    for (int64_t inst = (int64_t)blockIdx.x * IPC + g; inst < a.batch;
-         inst += (int64_t)gridDim.x * IPC) {
+    // Groups narrower than a warp synchronise with __syncwarp(): the groups of one warp make the same number of trips,
+    // and a group without an instance of its own shadows the last one (same bits written twice).
+    constexpr int GPW = G < 32 ? 32 / G : 1;
+    for (int64_t base = (int64_t)blockIdx.x * IPC + (g / GPW) * GPW; base < a.batch;
+         base += (int64_t)gridDim.x * IPC) {
+        const int64_t inst = base + g % GPW < a.batch ? base + g % GPW : a.batch - 1;
         const bool active = true;
         const int64_t ii = a.list ? (int64_t)a.list[inst] : inst;  // optional instance list (re-solve of a subset)
         const int64_t data_rows = a.knot_off[N], rec_rows = a.rec_off[N], mult_rows = a.mult_off[N];
@@ -432,10 +436,18 @@ int32_t launch_kkt_coop(lqrb_context *h, int n, int m, int N, const int32_t *p, 
     const size_t smem_cap = 200 * 1024;
     char nm[96];
     if (n + m <= 24) {
-        constexpr int G = 32, THREADS = 128, IPC = THREADS / G;
+        // lanes per instance, measured (N = 101, 8-16 k instances, solves/s at G = 4 / 8 / 16 / 32): (3,2) 1.56e6 / 1.18e6 /
+        // 7.6e5 / 4.0e5; (5,2) 5.0e5 / 8.5e5 / 8.3e5 / 5.1e5; (6,3) 3.0e5 / 4.1e5 / 4.7e5 / 2.9e5; (10,3) 1.5e5 / 1.6e5 /
+        // 1.75e5 / 1.4e5; (13,4) 5.1e4 / 8.4e4 / 6.2e4 / 7.4e4.  `coop_group` forces one of them.
+        int G = n + m <= 5 ? 4 : (n + m <= 7 ? 8 : (n + m <= 13 ? 16 : 32));
+        const int64_t force = h->opt("coop_group", 0);
+        if (force == 4 || force == 8 || force == 16 || force == 32) G = (int)force;
+        constexpr int THREADS = 128;
+        const int IPC = THREADS / G;
         size_t smem = wsd * 8 * IPC;
         unsigned grid = (unsigned)std::min<int64_t>((batch + IPC - 1) / IPC, (int64_t)h->sm_count * 64);
-        auto kern = kkt_coop_kernel<G, THREADS>;
+        auto kern = G == 4 ? kkt_coop_kernel<4, THREADS>
+                           : (G == 8 ? kkt_coop_kernel<8, THREADS> : (G == 16 ? kkt_coop_kernel<16, THREADS> : kkt_coop_kernel<32, THREADS>));
         if (smem > smem_cap) {
             grid = std::min<unsigned>(grid, (unsigned)h->sm_count * 8);  // instances are strided over the grid
             a.gws = coop_global_ws(h, st, (size_t)h->sm_count * 8 * IPC * wsd * 8);
@@ -445,7 +457,7 @@ int32_t launch_kkt_coop(lqrb_context *h, int n, int m, int N, const int32_t *p, 
             LQRB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
         kern<<<grid, THREADS, smem, st>>>(a);
-        snprintf(nm, sizeof nm, "kkt_coop<G=32>(n=%d,m=%d,%s)", n, m, a.gws ? "gmem-ws" : "smem-ws");
+        snprintf(nm, sizeof nm, "kkt_coop<G=%d>(n=%d,m=%d,%s)", G, n, m, a.gws ? "gmem-ws" : "smem-ws");
     } else {
         constexpr int G = 256, THREADS = 256;
         size_t smem = wsd * 8;

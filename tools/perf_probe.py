@@ -151,6 +151,12 @@ def main():
             r = probe_kkt(h, stream, 64, 16, 101, int(4096 * S), 32, args.steps, args.warmup, peak, mid_p=int(w[-1]))
         elif w in ("5aKp1", "5aKp3"):
             r = probe_kkt(h, stream, 12, 4, 1001, int(16384 * S), 32, args.steps, args.warmup, peak, mid_p=int(w[-1]))
+        elif w.startswith("kkt:"):  # kkt:n:m:N:batch[:mid_p]
+            f = [int(x) for x in w.split(":")[1:]]
+            r = probe_kkt(h, stream, f[0], f[1], f[2], f[3], 32, args.steps, args.warmup, peak, mid_p=f[4] if len(f) > 4 else 0)
+        elif w.startswith("ric:"):  # ric:n:m:N:batch
+            f = [int(x) for x in w.split(":")[1:]]
+            r = probe_riccati(h, stream, f[0], f[1], f[2], f[3], 32, args.steps, args.warmup, peak)
         else:
             continue
         r["config"] = w
