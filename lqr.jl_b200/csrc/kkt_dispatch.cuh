@@ -20,8 +20,15 @@
 // thread-per-instance instantiations: (n, m, P1, PM, PN) with p = [P1, PM, ..., PM, PN].
 //   cartpole (test/problems.jl:58-88): 4,1 init+goal          dubins: 3,2 init+goal (+1 mid row)
 //   DoubleIntegrator(3) (test/problems.jl:14-56): 6,3 init, 1 mid row, goal;  D=2: 4,2
-#define KKT_TPI_SIZES(X) \
+#define KKT_TPI_SIZES_A(X) \
     X(4, 1, 4, 0, 4) X(3, 2, 3, 0, 3) X(3, 2, 3, 1, 3) X(2, 1, 2, 0, 2) X(4, 2, 4, 1, 4) X(6, 3, 6, 1, 6)
+// the other small shapes (n <= 6, m <= 3), init + goal rows and 0 or 1 stage row per interior knot
+#define KKT_TPI_SIZES_B(X)                                                                                          \
+    X(4, 2, 4, 0, 4) X(6, 3, 6, 0, 6) X(2, 2, 2, 0, 2) X(2, 2, 2, 1, 2) X(3, 1, 3, 0, 3) X(3, 3, 3, 0, 3) X(3, 3, 3, 1, 3) \
+    X(5, 1, 5, 0, 5) X(6, 1, 6, 0, 6)
+#define KKT_TPI_SIZES_C(X) \
+    X(5, 2, 5, 0, 5) X(5, 2, 5, 1, 5) X(6, 2, 6, 0, 6) X(6, 2, 6, 1, 6) X(4, 3, 4, 0, 4) X(4, 3, 4, 1, 4) X(5, 3, 5, 0, 5) X(5, 3, 5, 1, 5)
+#define KKT_TPI_SIZES(X) KKT_TPI_SIZES_A(X) KKT_TPI_SIZES_B(X) KKT_TPI_SIZES_C(X)
 
 struct KktShape {
     int n, m, N, hess, d2x;

@@ -1,40 +1,17 @@
-// kkt_tpi.cu — launcher of the thread-per-instance KKT kernels (kkt_kernels.cuh); size list in kkt_dispatch.cuh.
-#include "kkt_dispatch.cuh"
-#include "kkt_kernels.cuh"
+// kkt_tpi.cu — thread-per-instance KKT kernels, part A of the size list (the reference's fixtures and BASELINE configs).
+#define KKT_TPI_PART_SIZES KKT_TPI_SIZES_A
+#define KKT_TPI_PART_NAME kkt_launch_tpi_a
+#include "kkt_tpi_part.cuh"
 
-template <int n, int m, int P1, int PM, int PN>
-static int32_t launch_kkt_tpi(lqrb_context *h, const KktShape &s, int64_t batch, int flags,
-                              const double *data, double *scratch, double *dz, double *mult,
-                              double *res, int32_t *info, cudaStream_t st) {
-    constexpr int THREADS = 64;
-    const unsigned grid = (unsigned)((batch + THREADS - 1) / THREADS);
-    const bool soc = (flags & LQRB_FLAG_SOC) != 0;
-#define LAUNCH(HESS, SOC) \
-    kkt_tpi_kernel<n, m, P1, PM, PN, HESS, SOC, THREADS><<<grid, THREADS, 0, st>>>(data, scratch, dz, mult, res, info, s.N, batch)
-    if (soc) {
-        // H and g are ignored: any HESS instantiation reads the same rows layout it was packed with
-        if (s.hess == LQRB_HESS_DIAG) LAUNCH(LQRB_HESS_DIAG, true);
-        else if (s.hess == LQRB_HESS_BLOCKDIAG) LAUNCH(LQRB_HESS_BLOCKDIAG, true);
-        else LAUNCH(LQRB_HESS_DENSE, true);
-    } else {
-        if (s.hess == LQRB_HESS_DIAG) LAUNCH(LQRB_HESS_DIAG, false);
-        else if (s.hess == LQRB_HESS_BLOCKDIAG) LAUNCH(LQRB_HESS_BLOCKDIAG, false);
-        else LAUNCH(LQRB_HESS_DENSE, false);
-    }
-#undef LAUNCH
-    char nm[96];
-    snprintf(nm, sizeof nm, "kkt_tpi<%d,%d,p=%d/%d/%d,hess=%d%s>", n, m, P1, PM, PN, s.hess, soc ? ",soc" : "");
-    h->kernel_name = nm;
-    LQRB_LAUNCH_CHECK(h, "kkt_tpi_kernel");
-    return 0;
-}
+int32_t kkt_launch_tpi_b(lqrb_context *h, const KktShape &s, int64_t batch, int flags, const double *data, double *scratch,
+                         double *dz, double *mult, double *res, int32_t *info, cudaStream_t st);
+int32_t kkt_launch_tpi_c(lqrb_context *h, const KktShape &s, int64_t batch, int flags, const double *data, double *scratch,
+                         double *dz, double *mult, double *res, int32_t *info, cudaStream_t st);
 
 int32_t kkt_launch_tpi(lqrb_context *h, const KktShape &s, int64_t batch, int flags, const double *data, double *scratch,
                        double *dz, double *mult, double *res, int32_t *info, cudaStream_t st) {
-#define X(N_, M_, A_, B_, C_)                                                            \
-    if (s.n == N_ && s.m == M_ && s.P1 == A_ && (s.N == 2 || s.PM == B_) && s.PN == C_) \
-        return launch_kkt_tpi<N_, M_, A_, B_, C_>(h, s, batch, flags, data, scratch, dz, mult, res, info, st);
-    KKT_TPI_SIZES(X)
-#undef X
-    return LQRB_NO_KERNEL;
+    int32_t rc = kkt_launch_tpi_a(h, s, batch, flags, data, scratch, dz, mult, res, info, st);
+    if (rc == LQRB_NO_KERNEL) rc = kkt_launch_tpi_b(h, s, batch, flags, data, scratch, dz, mult, res, info, st);
+    if (rc == LQRB_NO_KERNEL) rc = kkt_launch_tpi_c(h, s, batch, flags, data, scratch, dz, mult, res, info, st);
+    return rc;
 }

@@ -8,7 +8,8 @@
 
 // ------------------------------------------------------------------ size classes --------------
 // thread-per-instance instantiations (registers only).  Everything else -> cooperative kernel.
-#define RICCATI_TPI_SIZES(X) X(2, 1) X(3, 2) X(4, 1) X(4, 2) X(6, 3)
+#define RICCATI_TPI_SIZES(X) \
+    X(2, 1) X(3, 2) X(4, 1) X(4, 2) X(6, 3) X(2, 2) X(3, 1) X(3, 3) X(4, 3) X(5, 1) X(5, 2) X(5, 3) X(6, 1) X(6, 2)
 
 static bool riccati_has_tpi(int n, int m) {
 #define X(N_, M_) \

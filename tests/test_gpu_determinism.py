@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("n,m,N,b,kern", [(4, 1, 40, 97, "riccati_tpi"), (12, 4, 60, 37, "riccati_dmma"), (8, 4, 33, 21, "riccati_dmma"),
                                           (64, 16, 17, 9, "riccati_cta_dmma"), (24, 8, 21, 7, "riccati_cta_dmma"),
-                                          (5, 2, 20, 13, "riccati_coop")])
+                                          (7, 2, 20, 13, "riccati_coop")])
 def test_riccati_families_are_deterministic(handle, n, m, N, b, kern):
     prob = problems.random_lqr_riccati(n, m, N, b, seed=n + N)
     ref = ops.riccati_solve_problem(prob, handle=handle)

@@ -14,7 +14,7 @@ def _dev(f, keys):
     return {k: (None if f[k] is None else torch.from_numpy(np.ascontiguousarray(f[k])).cuda()) for k in keys}
 
 
-@pytest.mark.parametrize("n,m,N,b,tile", [(4, 1, 30, 70, 32), (12, 4, 25, 37, 1), (64, 16, 9, 5, 1), (5, 2, 12, 33, 1)])
+@pytest.mark.parametrize("n,m,N,b,tile", [(4, 1, 30, 70, 32), (12, 4, 25, 37, 1), (64, 16, 9, 5, 1), (7, 2, 12, 33, 1), (5, 2, 12, 33, 32)])
 def test_riccati_device_resident_all_size_classes(handle, n, m, N, b, tile):
     import torch
     prob = problems.random_lqr_riccati(n, m, N, b, seed=n + N)

@@ -64,7 +64,10 @@ def test_config3_dubins(handle, oracle_mod, mid_p, batch):
 
 
 @pytest.mark.parametrize("hess", [0, 1, 2])
-@pytest.mark.parametrize("n,m,N,mid_p", [(2, 1, 9, 0), (4, 2, 9, 1), (4, 1, 30, 0), (3, 2, 6, 0), (6, 3, 12, 1)])
+@pytest.mark.parametrize("n,m,N,mid_p", [(2, 1, 9, 0), (4, 2, 9, 1), (4, 1, 30, 0), (3, 2, 6, 0), (6, 3, 12, 1), (4, 2, 12, 0),
+                                        (6, 3, 14, 0), (2, 2, 9, 0), (2, 2, 10, 1), (3, 1, 12, 0), (3, 3, 9, 0), (3, 3, 11, 1),
+                                        (5, 1, 14, 0), (6, 1, 15, 0), (5, 2, 12, 0), (5, 2, 13, 1), (6, 2, 14, 0), (6, 2, 15, 1),
+                                        (4, 3, 9, 0), (4, 3, 10, 1), (5, 3, 11, 0), (5, 3, 12, 1)])
 def test_tpi_hessian_modes(handle, oracle_mod, n, m, N, mid_p, hess):
     prob = problems.random_lqr_kkt(n, m, N, 37, seed=7 * n + hess, mid_p=mid_p, hess_mode=hess)
     _check(prob, handle, oracle_mod)
@@ -72,9 +75,9 @@ def test_tpi_hessian_modes(handle, oracle_mod, n, m, N, mid_p, hess):
 
 
 @pytest.mark.parametrize("hess", [0, 1, 2])
-@pytest.mark.parametrize("n,m,N,mid_p,d2x", [(5, 2, 10, 1, False), (4, 1, 12, 0, True), (3, 2, 8, 1, True),
+@pytest.mark.parametrize("n,m,N,mid_p,d2x", [(7, 2, 10, 1, False), (4, 1, 12, 0, True), (3, 2, 8, 1, True),
                                             (10, 3, 40, 0, False), (12, 4, 9, 2, True), (20, 6, 6, 0, False),
-                                            (3, 3, 2, 0, False)])
+                                            (4, 4, 2, 0, False)])
 def test_cooperative_kernel(handle, oracle_mod, n, m, N, mid_p, d2x, hess):
     prob = problems.random_lqr_kkt(n, m, N, 6, seed=n + hess, mid_p=mid_p, hess_mode=hess, explicit_D2=d2x)
     _check(prob, handle, oracle_mod)

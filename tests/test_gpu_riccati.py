@@ -45,7 +45,8 @@ def test_cartpole_vs_refined_kkt_truth(handle, oracle_mod):
         assert _rel(X[i], Xt[0]) <= TOL and _rel(U[i], Ut[0]) <= TOL
 
 
-@pytest.mark.parametrize("n,m,N", [(2, 1, 11), (3, 2, 201), (4, 2, 50), (6, 3, 31)])
+@pytest.mark.parametrize("n,m,N", [(2, 1, 11), (3, 2, 201), (4, 2, 50), (6, 3, 31), (2, 2, 20), (3, 1, 33), (3, 3, 25), (4, 3, 30),
+                                   (5, 1, 40), (5, 2, 31), (5, 3, 22), (6, 1, 35), (6, 2, 41)])
 @pytest.mark.parametrize("lti", [False, True])
 def test_tpi_sizes(handle, oracle_mod, n, m, N, lti):
     prob = problems.random_lqr_riccati(n, m, N, 70, seed=n * 10 + m, lti=lti)
@@ -53,7 +54,7 @@ def test_tpi_sizes(handle, oracle_mod, n, m, N, lti):
     assert handle.last_kernel.startswith("riccati_tpi")
 
 
-@pytest.mark.parametrize("n,m,N,batch", [(5, 2, 20, 9), (10, 3, 101, 10), (7, 7, 15, 5), (32, 7, 12, 3), (40, 12, 11, 2)])
+@pytest.mark.parametrize("n,m,N,batch", [(7, 2, 20, 9), (10, 3, 101, 10), (7, 7, 15, 5), (32, 7, 12, 3), (40, 12, 11, 2)])
 def test_cooperative_sizes(handle, oracle_mod, n, m, N, batch):
     prob = problems.random_lqr_riccati(n, m, N, batch, seed=n)
     _check(prob, handle, oracle_mod)

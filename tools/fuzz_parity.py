@@ -68,12 +68,13 @@ def sample_pattern(rng, n, m, N):
 KKT_SIZES = [(1, 1), (2, 1), (3, 2), (4, 1), (4, 2), (5, 2), (6, 3), (7, 2), (8, 1), (8, 2), (8, 3), (8, 4), (9, 3),
              (10, 4), (12, 1), (12, 2), (12, 3), (12, 4), (12, 5), (13, 4), (16, 8), (16, 4), (24, 8), (24, 16),
              (32, 8), (32, 16), (40, 8), (48, 16), (64, 16), (64, 8), (20, 6)]
-RIC_SIZES = [(1, 1), (2, 1), (3, 2), (4, 1), (4, 2), (6, 3), (7, 3), (8, 2), (8, 4), (9, 2), (12, 4), (12, 3),
+RIC_SIZES = [(1, 1), (2, 1), (3, 2), (4, 1), (4, 2), (6, 3), (7, 3), (2, 2), (3, 1), (3, 3), (4, 3), (5, 1), (5, 2), (5, 3), (6, 1), (6, 2), (8, 2), (8, 4), (9, 2), (12, 4), (12, 3),
              (12, 1), (13, 4), (16, 8), (16, 16), (24, 8), (32, 16), (40, 8), (48, 16), (64, 16), (64, 8), (20, 5)]
 
 
 # shapes with a tuned kernel (csrc/kkt.cu: KKT_TPI_SIZES, KKT_HW_SIZES, KKT_WP_SIZES, KKT_CTA_SIZES): (n, m, interior rows)
-TUNED = [(4, 1, 0), (3, 2, 0), (3, 2, 1), (2, 1, 0), (4, 2, 1), (6, 3, 1),
+TUNED = [(4, 1, 0), (3, 2, 0), (3, 2, 1), (2, 1, 0), (4, 2, 1), (6, 3, 1), (4, 2, 0), (6, 3, 0), (2, 2, 0), (2, 2, 1), (3, 1, 0),
+         (3, 3, 0), (3, 3, 1), (5, 1, 0), (6, 1, 0), (5, 2, 0), (5, 2, 1), (6, 2, 0), (6, 2, 1), (4, 3, 0), (4, 3, 1), (5, 3, 0), (5, 3, 1),
          (12, 4, 0), (8, 4, 0), (12, 4, 1), (12, 4, 2), (12, 4, 3), (8, 4, 1), (8, 4, 3), (12, 3, 0), (12, 3, 1),
          (12, 3, 2), (8, 3, 0), (8, 3, 2), (12, 2, 0), (12, 2, 1), (8, 2, 0), (8, 2, 1), (12, 1, 0), (8, 1, 0),
          (64, 16, 0), (48, 16, 0), (32, 8, 0), (24, 8, 0), (16, 8, 0), (64, 16, 1), (48, 16, 3), (32, 8, 2), (24, 8, 1),
