@@ -229,7 +229,230 @@ int64_t kkt_tuned_chunk(const lqrb_context *h, const KktShape &s) {
     return c;
 }
 
+// ------------------------------------------------------------------ padding into a tuned size class ----
+// A shape without a tuned kernel of its own (n = 7, 9..11, 13.., m > 4, ...) is embedded in the next tuned size class
+// (n2, m2) instead of falling to the general kernel (14-50x slower): pad states xp with cost I, dynamics
+// xp_{k+1} = xp_k + (pad control c drives pad state (k mp + c) mod np at knot k: every pad state is driven at some knot,
+// so the pad part of the goal rows stays independent of the dynamics rows), init / goal rows xp_1 = xp_N = 0, pad
+// controls with cost I.  The pad
+// variables and their multipliers are exactly zero at the optimum and the original variables see the same KKT system.
+// The packed data (layout of s) is expanded on the device into the layout of the padded shape, the tuned kernel runs,
+// and dz, mult, res are compacted back: two extra passes over the data, a few percent of what the padding saves.
+static bool kkt_pad_target(const lqrb_context *h, const KktShape &s, int *n2, int *m2) {
+    if (h->opt("kkt_pad", 1) == 0 || h->opt("kkt_variant", 0) == 2) return false;
+    if (s.d2x || s.N < 3 || s.P1 != s.n || s.PN != s.n || s.PMAX > 4) return false;
+    if (kkt_has_tpi(s) || kkt_has_hw(h, s, 0) || kkt_has_wp(h, s) || kkt_has_cta(h, s, 0)) return false;
+    auto fits = [&](int N2, int M2) {
+        if (N2 < s.n || M2 < s.m) return false;
+        const int np = N2 - s.n, mp = M2 - s.m;
+        if (np > 0 && mp < 1) return false;  // no pad control to drive the pad states
+        if (np > (int64_t)(s.N - 1) * std::min(mp, np)) return false;  // every pad state must be driven at some knot
+        return true;
+    };
+    // warp-per-instance class: any Hessian mode, any stage-row count per knot
+#define X(N_, M_) \
+    if (fits(N_, M_)) { *n2 = N_; *m2 = M_; return true; }
+    X(8, 1) X(8, 2) X(8, 3) X(8, 4) X(12, 1) X(12, 2) X(12, 3) X(12, 4)
+    if (s.hess == LQRB_HESS_DENSE || !s.uniform) return false;
+    X(16, 8) X(24, 8) X(32, 8) X(48, 16) X(64, 16)
+#undef X
+    return false;
+}
+
+namespace {
+struct PadMaps {
+    std::vector<RowMap> data, dz, mult;  // rows of the padded layout -> offset in the original one (or fill / skip)
+};
+}
+
+static PadMaps kkt_pad_maps(const KktShape &s, int n2, int m2) {
+    const int n = s.n, m = s.m, N = s.N, np = n2 - n, mpe = std::min(m2 - m, np);  // pad controls in use
+    PadMaps M;
+    int64_t base = 0;  // start of knot k in the original packed record
+    int64_t moff = 0;  // original multiplier offset
+    for (int k = 0; k < N; ++k) {
+        const bool first = k == 0, last = k == N - 1;
+        const int mk = last ? 0 : m, w = n + mk, p2 = last ? 0 : n, ps = s.p[k];
+        const int mk2 = last ? 0 : m2, w2 = n2 + mk2;
+        const int64_t oH = base, og = oH + hess_rows(n, mk, s.hess), oD1 = og + w, od = oD1 + (int64_t)p2 * w, oC = od + p2,
+                      oc = oC + (int64_t)ps * w;
+        // padded z index -> original z index (-1: pad)
+        auto zmap = [&](int j) { return j < n ? j : (j < n2 ? -1 : (j - n2 < mk ? n + (j - n2) : -1)); };
+        auto src = [&](int64_t off) { M.data.push_back(RowMap{0, (int32_t)off, 0.0}); };
+        auto fill = [&](double v) { M.data.push_back(RowMap{-1, 0, v}); };
+        // H
+        if (s.hess == LQRB_HESS_DIAG) {
+            for (int j = 0; j < w2; ++j) {
+                const int o = zmap(j);
+                if (o >= 0) src(oH + o); else fill(1.0);
+            }
+        } else if (s.hess == LQRB_HESS_BLOCKDIAG) {
+            for (int j = 0; j < n2; ++j)
+                for (int i = 0; i <= j; ++i) {
+                    if (j < n) src(oH + (int64_t)j * (j + 1) / 2 + i); else fill(i == j ? 1.0 : 0.0);
+                }
+            for (int j = 0; j < mk2; ++j)
+                for (int i = 0; i <= j; ++i) {
+                    if (j < mk) src(oH + tri(n) + (int64_t)j * (j + 1) / 2 + i); else fill(i == j ? 1.0 : 0.0);
+                }
+        } else {
+            for (int j = 0; j < w2; ++j)
+                for (int i = 0; i <= j; ++i) {
+                    const int oi = zmap(i), oj = zmap(j);
+                    if (oi >= 0 && oj >= 0) src(oH + (int64_t)oj * (oj + 1) / 2 + oi); else fill(i == j ? 1.0 : 0.0);
+                }
+        }
+        // g
+        for (int j = 0; j < w2; ++j) {
+            const int o = zmap(j);
+            if (o >= 0) src(og + o); else fill(0.0);
+        }
+        // D1 = [A B] (n2 x w2 column-major), d
+        if (!last) {
+            for (int j = 0; j < w2; ++j)
+                for (int i = 0; i < n2; ++i) {
+                    const int o = zmap(j);
+                    if (i < n) {
+                        if (o >= 0) src(oD1 + i + (int64_t)o * n); else fill(0.0);
+                    } else {
+                        const int r = i - n, c = j - n2 - m;  // pad state r, pad control c (if 0 <= c < mpe)
+                        fill((j == i || (c >= 0 && c < mpe && (k * mpe + c) % np == r)) ? 1.0 : 0.0);
+                    }
+                }
+            for (int i = 0; i < n2; ++i) {
+                if (i < n) src(od + i); else fill(0.0);
+            }
+        }
+        // C, c : the end knots have n rows (+ identity rows on the pad states), the interior ones their ps rows
+        const int ps2 = (first || last) ? n2 : ps;
+        for (int j = 0; j < w2; ++j)
+            for (int i = 0; i < ps2; ++i) {
+                const int o = zmap(j);
+                if (i < ps) {
+                    if (o >= 0) src(oC + i + (int64_t)o * ps); else fill(0.0);
+                } else {
+                    fill(j == n + (i - ps) ? 1.0 : 0.0);  // (first / last knot only: ps = n) pad state i - n pinned to 0
+                }
+            }
+        for (int i = 0; i < ps2; ++i) {
+            if (i < ps) src(oc + i); else fill(0.0);
+        }
+        base = oc + ps;
+        // outputs: dz / res rows of knot k
+        for (int j = 0; j < w2; ++j) {
+            const int o = zmap(j);
+            M.dz.push_back(o >= 0 ? RowMap{0, (int32_t)((int64_t)k * (n + m) + o), 0.0} : RowMap{-1, 0, 0.0});
+        }
+        // multipliers: [mu_k (ps2); lam_k (n2)]
+        for (int i = 0; i < ps2; ++i) M.mult.push_back(i < ps ? RowMap{0, (int32_t)(moff + i), 0.0} : RowMap{-1, 0, 0.0});
+        moff += ps;
+        if (!last) {
+            for (int i = 0; i < n2; ++i) M.mult.push_back(i < n ? RowMap{0, (int32_t)(moff + i), 0.0} : RowMap{-1, 0, 0.0});
+            moff += n;
+        }
+    }
+    return M;
+}
+
+static size_t kkt_scratch_bytes(const lqrb_context *h, const KktShape &s, const KktSizes &z, int64_t batch);
+static int32_t kkt_solve_on(lqrb_context *h, const KktShape &s, int64_t batch, int flags, const double *data, double *scratch,
+                            double *dz, double *mult, double *res, int32_t *info, cudaStream_t st);
+
+struct PadPlan {
+    std::vector<int32_t> p2;
+    KktShape s2;
+    KktSizes z2;
+    int64_t chunk;
+    size_t data_b, out_b, scr_b;  // bytes per chunk: padded data | dz2, mult2, res2 | scratch of the tuned kernel
+};
+
+static void kkt_pad_plan(const lqrb_context *h, const KktShape &s, int n2, int m2, int64_t batch, PadPlan *P) {
+    P->p2.assign(s.p, s.p + s.N);
+    P->p2[0] = n2;
+    P->p2[s.N - 1] = n2;
+    P->s2 = make_shape(n2, m2, s.N, P->p2.data(), s.hess, 0);
+    P->z2 = kkt_sizes(P->s2);
+    P->chunk = std::max<int64_t>(1, std::min(batch, kkt_tuned_chunk(h, P->s2)));
+    const size_t ldb = (size_t)lqrb_padded_batch(P->chunk);
+    P->data_b = (ldb * P->z2.data_rows * 8 + 255) / 256 * 256;
+    P->out_b = (ldb * (2 * P->z2.NN + P->z2.P) * 8 + 255) / 256 * 256;
+    P->scr_b = (kkt_scratch_bytes(h, P->s2, P->z2, P->chunk) + 255) / 256 * 256;
+}
+
+static int32_t kkt_solve_padded(lqrb_context *h, const KktShape &s, int n2, int m2, int64_t batch, int flags,
+                                const double *data, double *scratch, double *dz, double *mult, double *res, int32_t *info,
+                                cudaStream_t st) {
+    PadPlan P;
+    kkt_pad_plan(h, s, n2, m2, batch, &P);
+    const KktSizes z = kkt_sizes(s);
+    char key[64];
+    snprintf(key, sizeof key, "->%d,%d", n2, m2);
+    const std::string k0 = shape_key("pad", s) + key;
+    DevMap md, mz, mm;
+    if (h->maps.find(k0 + ":m") == h->maps.end()) {  // first use of this shape: build and upload the three maps
+        const PadMaps M = kkt_pad_maps(s, n2, m2);
+        md = lqrb_get_map(h, k0 + ":d", M.data);
+        mz = lqrb_get_map(h, k0 + ":z", M.dz);
+        mm = lqrb_get_map(h, k0 + ":m", M.mult);
+    } else {
+        md = h->maps[k0 + ":d"];
+        mz = h->maps[k0 + ":z"];
+        mm = h->maps[k0 + ":m"];
+    }
+    if (md.rows != P.z2.data_rows || mz.rows != P.z2.NN || mm.rows != P.z2.P) return lqrb_fail(h, 1, "pad map size mismatch");
+    char *base = reinterpret_cast<char *>(scratch);
+    double *data2 = reinterpret_cast<double *>(base);
+    double *dz2 = reinterpret_cast<double *>(base + P.data_b);
+    const size_t ldb = (size_t)lqrb_padded_batch(P.chunk);
+    double *mult2 = dz2 + ldb * P.z2.NN, *res2 = mult2 + ldb * P.z2.P;
+    double *scr2 = reinterpret_cast<double *>(base + P.data_b + P.out_b);
+    std::string name;
+    int64_t refined = 0;
+    std::vector<int32_t> cond;
+    for (int64_t first = 0; first < batch; first += P.chunk) {
+        const int64_t cb = std::min(P.chunk, batch - first);
+        ArrayTable src = {};
+        src.ptr[0] = data + first * z.data_rows;
+        src.stride[0] = z.data_rows;
+        int32_t rc = lqrb_gather_pack(h, md, src, cb, 1, data2, st);
+        if (rc) return rc;
+        rc = kkt_solve_on(h, P.s2, cb, flags, data2, scr2, dz2, mult2, res ? res2 : nullptr, info ? info + first : nullptr, st);
+        if (rc) return rc;
+        name = h->kernel_name;
+        refined += h->last_refined;
+        cond.insert(cond.end(), h->last_cond.begin(), h->last_cond.end());
+        ArrayTableOut o = {};
+        o.ptr[0] = dz + first * z.NN;
+        o.stride[0] = z.NN;
+        rc = lqrb_scatter_unpack(h, mz, o, cb, 1, dz2, st);
+        if (rc) return rc;
+        if (res) {
+            o.ptr[0] = res + first * z.NN;
+            rc = lqrb_scatter_unpack(h, mz, o, cb, 1, res2, st);
+            if (rc) return rc;
+        }
+        o.ptr[0] = mult + first * z.P;
+        o.stride[0] = z.P;
+        rc = lqrb_scatter_unpack(h, mm, o, cb, 1, mult2, st);
+        if (rc) return rc;
+    }
+    char nm[64];
+    snprintf(nm, sizeof nm, " <- (%d,%d) padded", s.n, s.m);
+    h->kernel_name = name + nm;
+    h->last_refined = refined;
+    h->last_cond = cond;
+    return 0;
+}
+
 static size_t kkt_scratch_bytes(const lqrb_context *h, const KktShape &s, const KktSizes &z, int64_t batch) {
+    {
+        int n2, m2;
+        if (kkt_pad_target(h, s, &n2, &m2)) {
+            PadPlan P;
+            kkt_pad_plan(h, s, n2, m2, batch, &P);
+            return P.data_b + P.out_b + P.scr_b;
+        }
+    }
     size_t bytes = (size_t)lqrb_padded_batch(batch) * z.rec_rows * 8;
     // the tuned kernels' records only when one of them will actually run for this shape (a dense Hessian, an
     // irregular stage pattern, explicit D2 or kkt_variant = 2 route the same (n, m) to the cooperative kernel)
@@ -243,6 +466,11 @@ static int32_t kkt_solve_on(lqrb_context *h, const KktShape &s, int64_t batch, i
                             const double *data, double *scratch, double *dz, double *mult, double *res,
                             int32_t *info, cudaStream_t st) {
     if (batch == 0) return 0;
+    {
+        int n2, m2;
+        if (((uintptr_t)data & 15) == 0 && ((uintptr_t)scratch & 255) == 0 && kkt_pad_target(h, s, &n2, &m2))
+            return kkt_solve_padded(h, s, n2, m2, batch, flags, data, scratch, dz, mult, res, info, st);
+    }
     int32_t rc = LQRB_NO_KERNEL;
     if (kkt_has_cta(h, s, flags) && ((uintptr_t)data & 15) == 0 && ((uintptr_t)scratch & 15) == 0)
         rc = kkt_launch_cta(h, s, batch, flags, data, scratch, dz, mult, res, info, st);

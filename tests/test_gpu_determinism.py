@@ -33,18 +33,23 @@ def test_riccati_families_are_deterministic(handle, n, m, N, b, kern):
 @pytest.mark.parametrize("n,m,N,b,mid_p,kern", [(3, 2, 41, 97, 0, "kkt_tpi"), (6, 3, 20, 33, 1, "kkt_tpi"),
                                                 (12, 4, 60, 37, 0, "kkt_hw<"), (8, 4, 33, 21, 0, "kkt_hw<"), (12, 1, 60, 37, 0, "kkt_wp_dmma<"), (8, 1, 33, 21, 0, "kkt_wp_dmma<"),
                                                 (64, 16, 17, 5, 0, "kkt_cta_dmma"), (24, 8, 21, 7, 0, "kkt_cta_dmma"),
-                                                (12, 4, 12, 9, 2, "kkt_wp_dmma<"), (20, 6, 12, 9, 2, "kkt_coop"), (40, 8, 9, 3, 1, "kkt_coop")])
+                                                (12, 4, 12, 9, 2, "kkt_wp_dmma<"), (20, 6, 12, 9, 2, "kkt_cta_dmma<24,8"), (40, 8, 9, 3, 1, "kkt_cta_dmma<48,16"),
+                                                (20, 6, 12, 9, 2, "kkt_coop"), (40, 8, 9, 3, 1, "kkt_coop")])
 def test_kkt_families_are_deterministic(handle, n, m, N, b, mid_p, kern):
     prob = problems.random_lqr_kkt(n, m, N, b, seed=n + N, mid_p=mid_p, hess_mode=1)
-    ref = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
-    assert handle.last_kernel.startswith(kern) and (ref[2] == 0).all()
+    pad = 0 if kern == "kkt_coop" else 1  # the general kernel itself: without the embedding into a tuned size class
+    handle.set_option("kkt_pad", pad)
     h2 = _lib.Handle(0)
+    h2.set_option("kkt_pad", pad)
     try:
+        ref = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
+        assert handle.last_kernel.startswith(kern) and (ref[2] == 0).all()
         for i in range(5):
             out = ops.kkt_solve_problem(prob, want_res=True, handle=h2 if i == 4 else handle)
             for a, c in zip((out[0], out[1], out[3]), (ref[0], ref[1], ref[3])):
                 assert np.array_equal(a, c), (kern, i)
     finally:
+        handle.set_option("kkt_pad", 1)
         h2.close()
 
 

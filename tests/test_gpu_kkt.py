@@ -80,8 +80,42 @@ def test_tpi_hessian_modes(handle, oracle_mod, n, m, N, mid_p, hess):
                                             (4, 4, 2, 0, False)])
 def test_cooperative_kernel(handle, oracle_mod, n, m, N, mid_p, d2x, hess):
     prob = problems.random_lqr_kkt(n, m, N, 6, seed=n + hess, mid_p=mid_p, hess_mode=hess, explicit_D2=d2x)
-    _check(prob, handle, oracle_mod)
+    handle.set_option("kkt_pad", 0)  # (without it most of these shapes are embedded in a tuned size class, see below)
+    try:
+        _check(prob, handle, oracle_mod)
+    finally:
+        handle.set_option("kkt_pad", 1)
     assert handle.last_kernel.startswith("kkt_coop")
+
+
+@pytest.mark.parametrize("hess", [0, 1, 2])
+@pytest.mark.parametrize("n,m,N,batch,mid_p,kern", [
+    (7, 2, 12, 6, 1, "kkt_wp_dmma<8,3"), (10, 3, 40, 33, 0, "kkt_wp_dmma<12,4|kkt_hw<12,4"), (9, 2, 30, 5, 1, "kkt_wp_dmma<12,3"),
+    (5, 3, 14, 7, 2, "kkt_wp_dmma<8,4"), (7, 3, 21, 34, 2, "kkt_wp_dmma<8,4"), (11, 1, 25, 4, 0, "kkt_wp_dmma<12,2"),
+    (14, 7, 12, 5, 0, "kkt_cta_dmma<16,8"), (20, 6, 14, 3, 2, "kkt_cta_dmma<24,8"), (13, 4, 20, 6, 1, "kkt_cta_dmma<16,8"),
+    (30, 8, 12, 3, 0, "kkt_cta_dmma<48,16"), (40, 12, 11, 2, 1, "kkt_cta_dmma<48,16"), (60, 10, 12, 2, 0, "kkt_cta_dmma<64,16"),
+    (16, 5, 18, 4, 3, "kkt_cta_dmma<16,8")])
+def test_shapes_without_a_tuned_kernel_are_padded_into_one(handle, oracle_mod, n, m, N, batch, mid_p, kern, hess):
+    """A shape that has no tuned kernel of its own is embedded in the next tuned size class (decoupled pad states and
+    controls whose solution is exactly zero) instead of falling to the general kernel; the outputs are the original
+    problem's.  Dense Hessians stay on the general kernel above n = 12 (the CTA kernels do not have that mode)."""
+    from oracle import dense_kkt
+    prob = problems.random_lqr_kkt(n, m, N, batch, seed=5 * n + m + hess, mid_p=mid_p, hess_mode=hess)
+    dz, lam, info, res = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
+    if hess == 0 and n > 12:
+        assert handle.last_kernel.startswith("kkt_coop")
+    else:
+        assert any(handle.last_kernel.startswith(k) for k in kern.split("|")), handle.last_kernel
+        assert handle.last_kernel.endswith(f"<- ({n},{m}) padded"), handle.last_kernel
+    dzo, lamo, infoo, reso = oracle_mod.kkt_solve(prob, want_res=True)
+    assert (info == 0).all() and (infoo == 0).all()
+    for i in range(batch):
+        zt, lt = dense_kkt.kkt_truth(prob, i)
+        tol = max(TOL, 4.0 * max(_rel(dzo[i], zt), _rel(lamo[i], lt)))
+        assert _rel(dz[i], zt) <= tol and _rel(lam[i], lt) <= tol, (i, tol, _rel(dz[i], zt), _rel(lam[i], lt))
+        assert np.linalg.norm(res[i] - reso[i]) <= 2 * tol * max(1.0, np.linalg.norm(reso[i]))
+        rs, rp = dense_kkt.kkt_residuals(prob, i, dz[i], lam[i])
+        assert rs <= 10 * TOL and rp <= 10 * TOL, (rs, rp)
 
 
 # kkt_variant: 0 = default (half warp per instance, block layout), 3 = its column layout, 5 = warp per instance on the FP64
@@ -150,7 +184,8 @@ def test_half_warp_info_flags(handle):
 
 
 def test_irregular_stage_pattern(handle, oracle_mod):
-    """A waypoint constraint on a single interior knot: p is not [P1, PM.., PN] -> cooperative kernel."""
+    """A waypoint constraint on a single interior knot: p is not [P1, PM.., PN] -> padded into the warp-per-instance
+    kernel (per-knot stage rows); with kkt_pad = 0 the cooperative kernel."""
     prob = problems.random_lqr_kkt(4, 1, 16, 5, seed=3, mid_p=1)
     p = prob["p"].copy()
     for k in range(1, 15):
@@ -160,6 +195,12 @@ def test_irregular_stage_pattern(handle, oracle_mod):
             prob["c"][k] = np.zeros((5, 0))
     prob["p"] = p
     _check(prob, handle, oracle_mod)
+    assert handle.last_kernel.startswith("kkt_wp_dmma<8,2,p=8/per-knot<=1/8") and "(4,1) padded" in handle.last_kernel
+    handle.set_option("kkt_pad", 0)
+    try:
+        _check(prob, handle, oracle_mod)
+    finally:
+        handle.set_option("kkt_pad", 1)
     assert handle.last_kernel.startswith("kkt_coop")
 
 
