@@ -55,6 +55,7 @@ enum ScratchSlot {
     SCR_KEEP_REC,   //                      block rows of U (BlockUpperTriangular3 records)
     SCR_REFINE,       // records of the instances re-solved by the Cholesky-based kernel (ill-conditioned blocks)
     SCR_REFINE_LIST,  // their indices
+    SCR_RICCATI_PAD,  // Riccati problems embedded in a tuned size class: padded knots, term, Z, gains (one slice per stream)
     SCR_COUNT
 };
 

@@ -197,10 +197,144 @@ static int32_t launch_cta(lqrb_context *h, int N, int64_t batch, int lti, const 
     return 0;
 }
 
+// ------------------------------------------------------------------ padding into a tuned size class ----
+// A size without a tensor-core kernel of its own (n = 7, 9..11, 13.., or m > 4 at n <= 12, ...) is embedded in the next
+// tuned size class (n2, m2): pad states with A = 0, B = 0, Q = Qf = I, x0 = 0 and pad controls with R = I stay exactly
+// zero and leave the original recursion untouched.  The packed arrays are expanded on the device, the tuned kernel runs,
+// Z and the gains are compacted back.
+static bool riccati_pad_target(const lqrb_context *h, int n, int m, int *n2, int *m2) {
+    if (h->opt("riccati_pad", 1) == 0 || h->opt("riccati_variant", 0) != 0) return false;
+    if (lqrb_riccati_tile(h, n, m) == LQRB_TILE || riccati_has_dmma(n, m) || riccati_has_cta(n, m)) return false;
+#define X(N_, M_) \
+    if (n <= N_ && m <= M_) { *n2 = N_; *m2 = M_; return true; }
+    RICCATI_DMMA_SIZES(X)
+    RICCATI_CTA_SIZES(X)
+#undef X
+    return false;
+}
+
+namespace {
+struct RiccatiPadMaps {
+    std::vector<RowMap> knots, term, z, gains;
+};
+}
+
+static RiccatiPadMaps riccati_pad_maps(int n, int m, int N, int Kn, int n2, int m2) {
+    RiccatiPadMaps M;
+    const int F = lqrb_riccati_knot_rows(n, m), F2 = lqrb_riccati_knot_rows(n2, m2);
+    const int nn = n * n, nm = n * m, tn = tri(n), tm = tri(m);
+    for (int k = 0; k < Kn; ++k) {
+        const int32_t b = k * F;
+        const size_t start = M.knots.size();
+        for (int j = 0; j < n2; ++j)  // A' = blkdiag(A, 0)
+            for (int i = 0; i < n2; ++i) M.knots.push_back((i < n && j < n) ? RowMap{0, b + i + j * n, 0.0} : RowMap{-1, 0, 0.0});
+        for (int j = 0; j < m2; ++j)  // B' = [B 0; 0 0]
+            for (int i = 0; i < n2; ++i)
+                M.knots.push_back((i < n && j < m) ? RowMap{0, b + nn + i + j * n, 0.0} : RowMap{-1, 0, 0.0});
+        for (int j = 0; j < n2; ++j)  // Q' = blkdiag(Q, I), upper packed
+            for (int i = 0; i <= j; ++i)
+                M.knots.push_back(j < n ? RowMap{0, b + nn + nm + j * (j + 1) / 2 + i, 0.0} : RowMap{-1, 0, i == j ? 1.0 : 0.0});
+        for (int j = 0; j < m2; ++j)  // R' = blkdiag(R, I)
+            for (int i = 0; i <= j; ++i)
+                M.knots.push_back(j < m ? RowMap{0, b + nn + nm + tn + j * (j + 1) / 2 + i, 0.0} : RowMap{-1, 0, i == j ? 1.0 : 0.0});
+        for (int i = 0; i < n2; ++i) M.knots.push_back(i < n ? RowMap{0, b + nn + nm + tn + tm + i, 0.0} : RowMap{-1, 0, 0.0});
+        for (int i = 0; i < m2; ++i) M.knots.push_back(i < m ? RowMap{0, b + nn + nm + tn + tm + n + i, 0.0} : RowMap{-1, 0, 0.0});
+        while (M.knots.size() - start < (size_t)F2) M.knots.push_back(RowMap{-1, 0, 0.0});  // record padding
+    }
+    for (int j = 0; j < n2; ++j)  // Qf' = blkdiag(Qf, I)
+        for (int i = 0; i <= j; ++i) M.term.push_back(j < n ? RowMap{0, j * (j + 1) / 2 + i, 0.0} : RowMap{-1, 0, i == j ? 1.0 : 0.0});
+    for (int i = 0; i < n2; ++i) M.term.push_back(i < n ? RowMap{0, tn + i, 0.0} : RowMap{-1, 0, 0.0});
+    for (int i = 0; i < n2; ++i) M.term.push_back(i < n ? RowMap{0, tn + n + i, 0.0} : RowMap{-1, 0, 0.0});
+    // outputs: rows of the padded arrays -> offsets in the original ones (skipped when pad)
+    for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < n2; ++i) M.z.push_back(i < n ? RowMap{0, k * (n + m) + i, 0.0} : RowMap{-1, 0, 0.0});
+        if (k < N - 1)
+            for (int i = 0; i < m2; ++i) M.z.push_back(i < m ? RowMap{0, k * (n + m) + n + i, 0.0} : RowMap{-1, 0, 0.0});
+    }
+    const int GR = m * n + m;
+    for (int k = 0; k < N - 1; ++k) {
+        for (int j = 0; j < n2; ++j)
+            for (int c = 0; c < m2; ++c) M.gains.push_back((c < m && j < n) ? RowMap{0, k * GR + c + m * j, 0.0} : RowMap{-1, 0, 0.0});
+        for (int c = 0; c < m2; ++c) M.gains.push_back(c < m ? RowMap{0, k * GR + m * n + c, 0.0} : RowMap{-1, 0, 0.0});
+    }
+    return M;
+}
+
+static int32_t riccati_solve_on(lqrb_context *h, int n, int m, int N, int64_t batch, int flags, const double *knots,
+                                const double *term, double *Z, double *gains, int32_t *info, cudaStream_t s);
+
+static int32_t riccati_solve_padded(lqrb_context *h, int n, int m, int N, int n2, int m2, int64_t batch, int flags,
+                                    const double *knots, const double *term, double *Z, double *gains, int32_t *info,
+                                    cudaStream_t st) {
+    const int Kn = (flags & LQRB_FLAG_LTI) ? 1 : N - 1;
+    const int64_t F = lqrb_riccati_knot_rows(n, m), F2 = lqrb_riccati_knot_rows(n2, m2);
+    const int64_t TR = tri(n) + 2 * n, TR2 = tri(n2) + 2 * n2;
+    const int64_t ZR = (int64_t)N * n + (int64_t)(N - 1) * m, ZR2 = (int64_t)N * n2 + (int64_t)(N - 1) * m2;
+    const int64_t GR = (int64_t)(N - 1) * (m * n + m), GR2 = (int64_t)(N - 1) * (m2 * n2 + m2);
+    const std::string k0 = key("rpad", n, m, N, Kn) + key("->", n2, m2, 0, 0);
+    DevMap mk, mt, mz, mg;
+    if (h->maps.find(k0 + ":g") == h->maps.end()) {
+        const RiccatiPadMaps M = riccati_pad_maps(n, m, N, Kn, n2, m2);
+        mk = lqrb_get_map(h, k0 + ":k", M.knots);
+        mt = lqrb_get_map(h, k0 + ":t", M.term);
+        mz = lqrb_get_map(h, k0 + ":z", M.z);
+        mg = lqrb_get_map(h, k0 + ":g", M.gains);
+    } else {
+        mk = h->maps[k0 + ":k"];
+        mt = h->maps[k0 + ":t"];
+        mz = h->maps[k0 + ":z"];
+        mg = h->maps[k0 + ":g"];
+    }
+    if (mk.rows != Kn * F2 || mt.rows != TR2 || mz.rows != ZR2 || mg.rows != GR2) return lqrb_fail(h, 1, "pad map size mismatch");
+    // chunks of at most ~2 GB of padded arrays; one slice of the scratch per stream (the host path has two in flight)
+    const int64_t per = Kn * F2 + TR2 + ZR2 + GR2;
+    int64_t chunk = std::max<int64_t>(LQRB_TILE, ((int64_t)2 << 30) / (per * 8) / LQRB_TILE * LQRB_TILE);
+    chunk = std::min(chunk, lqrb_padded_batch(batch));
+    const size_t slice = ((size_t)chunk * per * 8 + 255) / 256 * 256;
+    char *base = (char *)lqrb_scratch(h, SCR_RICCATI_PAD, 2 * slice);
+    if (!base) return 1000 + (int)cudaErrorMemoryAllocation;
+    base += (st == h->copy_stream[1] ? 1 : 0) * slice;
+    double *knots2 = (double *)base, *term2 = knots2 + chunk * Kn * F2, *Z2 = term2 + chunk * TR2, *gains2 = Z2 + chunk * ZR2;
+    std::string name;
+    for (int64_t first = 0; first < batch; first += chunk) {
+        const int64_t cb = std::min(chunk, batch - first);
+        ArrayTable src = {};
+        src.ptr[0] = knots + first * Kn * F;
+        src.stride[0] = Kn * F;
+        int32_t rc = lqrb_gather_pack(h, mk, src, cb, 1, knots2, st);
+        if (rc) return rc;
+        src.ptr[0] = term + first * TR;
+        src.stride[0] = TR;
+        rc = lqrb_gather_pack(h, mt, src, cb, 1, term2, st);
+        if (rc) return rc;
+        rc = riccati_solve_on(h, n2, m2, N, cb, flags, knots2, term2, Z2, gains2, info ? info + first : nullptr, st);
+        if (rc) return rc;
+        name = h->kernel_name;
+        ArrayTableOut o = {};
+        o.ptr[0] = Z + first * ZR;
+        o.stride[0] = ZR;
+        rc = lqrb_scatter_unpack(h, mz, o, cb, 1, Z2, st);
+        if (rc) return rc;
+        o.ptr[0] = gains + first * GR;
+        o.stride[0] = GR;
+        rc = lqrb_scatter_unpack(h, mg, o, cb, 1, gains2, st);
+        if (rc) return rc;
+    }
+    char nm[64];
+    snprintf(nm, sizeof nm, " <- (%d,%d) padded", n, m);
+    h->kernel_name = name + nm;
+    return 0;
+}
+
 static int32_t riccati_solve_on(lqrb_context *h, int n, int m, int N, int64_t batch, int flags,
                                 const double *knots, const double *term, double *Z, double *gains,
                                 int32_t *info, cudaStream_t s) {
     if (batch == 0) return 0;
+    {
+        int n2, m2;
+        if (((uintptr_t)knots & 15) == 0 && riccati_pad_target(h, n, m, &n2, &m2))
+            return riccati_solve_padded(h, n, m, N, n2, m2, batch, flags, knots, term, Z, gains, info, s);
+    }
     const int lti = (flags & LQRB_FLAG_LTI) ? 1 : 0;
     const int tile = lqrb_riccati_tile(h, n, m);
     if (tile == LQRB_TILE) {

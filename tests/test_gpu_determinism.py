@@ -15,18 +15,22 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("n,m,N,b,kern", [(4, 1, 40, 97, "riccati_tpi"), (12, 4, 60, 37, "riccati_dmma"), (8, 4, 33, 21, "riccati_dmma"),
                                           (64, 16, 17, 9, "riccati_cta_dmma"), (24, 8, 21, 7, "riccati_cta_dmma"),
-                                          (7, 2, 20, 13, "riccati_coop")])
+                                          (7, 2, 20, 13, "riccati_coop"), (7, 2, 20, 13, "riccati_dmma<8,2>"), (20, 6, 15, 5, "riccati_cta_dmma<24,8>")])
 def test_riccati_families_are_deterministic(handle, n, m, N, b, kern):
     prob = problems.random_lqr_riccati(n, m, N, b, seed=n + N)
-    ref = ops.riccati_solve_problem(prob, handle=handle)
-    assert handle.last_kernel.startswith(kern) and (ref[4] == 0).all()
+    pad = 0 if kern == "riccati_coop" else 1  # the general kernel itself, not the embedding into a tuned size class
+    handle.set_option("riccati_pad", pad)
     h2 = _lib.Handle(0)
+    h2.set_option("riccati_pad", pad)
     try:
+        ref = ops.riccati_solve_problem(prob, handle=handle)
+        assert handle.last_kernel.startswith(kern) and (ref[4] == 0).all()
         for i in range(5):
             out = ops.riccati_solve_problem(prob, handle=h2 if i == 4 else handle)
             for a, c in zip(out[:4], ref[:4]):
                 assert np.array_equal(a, c), (kern, i)
     finally:
+        handle.set_option("riccati_pad", 1)
         h2.close()
 
 

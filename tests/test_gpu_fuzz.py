@@ -1,6 +1,6 @@
 """GPU parity: a seeded random sweep over the whole dispatch (tools/fuzz_parity.py) — sizes, horizons, batch widths,
 per-knot stage-row patterns, Hessian modes, explicit D2, SOC and LTI flags — against the oracle and the refined truth.
-Round 2 ran 30,500 cases of it (profiles/r2_fuzz_summary.txt); the suite keeps 250."""
+Round 2 ran 50,000 cases of it (profiles/r2_fuzz_summary.txt); the suite keeps 250."""
 import os
 import sys
 
@@ -28,4 +28,4 @@ def test_random_sweep_of_the_dispatch(handle, oracle_mod, seed):
         if "fail" in d:
             fails.append(d)
     assert not fails, fails[:3]
-    assert {"kkt_coop", "kkt_tpi", "kkt_wp_dmma", "riccati_tpi", "riccati_coop"} <= kernels, kernels
+    assert {"kkt_coop", "kkt_tpi", "kkt_wp_dmma", "riccati_tpi", "riccati_dmma", "riccati_cta_dmma"} <= kernels, kernels

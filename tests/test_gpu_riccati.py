@@ -57,8 +57,26 @@ def test_tpi_sizes(handle, oracle_mod, n, m, N, lti):
 @pytest.mark.parametrize("n,m,N,batch", [(7, 2, 20, 9), (10, 3, 101, 10), (7, 7, 15, 5), (32, 7, 12, 3), (40, 12, 11, 2)])
 def test_cooperative_sizes(handle, oracle_mod, n, m, N, batch):
     prob = problems.random_lqr_riccati(n, m, N, batch, seed=n)
-    _check(prob, handle, oracle_mod)
+    handle.set_option("riccati_pad", 0)  # (without it these sizes are embedded in a tuned size class, next test)
+    try:
+        _check(prob, handle, oracle_mod)
+    finally:
+        handle.set_option("riccati_pad", 1)
     assert handle.last_kernel.startswith("riccati_coop")
+
+
+@pytest.mark.parametrize("lti", [False, True])
+@pytest.mark.parametrize("n,m,N,batch,kern", [(7, 2, 20, 9, "riccati_dmma<8,2>"), (10, 3, 101, 33, "riccati_dmma<12,3>"),
+                                              (5, 4, 30, 7, "riccati_dmma<8,4>"), (11, 1, 40, 5, "riccati_dmma<12,1>"),
+                                              (7, 7, 15, 5, "riccati_cta_dmma<16,8>"), (14, 7, 25, 34, "riccati_cta_dmma<16,8>"),
+                                              (20, 6, 21, 4, "riccati_cta_dmma<24,8>"), (32, 7, 12, 3, "riccati_cta_dmma<32,8>"),
+                                              (40, 12, 11, 2, "riccati_cta_dmma<48,16>"), (60, 10, 9, 2, "riccati_cta_dmma<64,16>")])
+def test_sizes_without_a_tuned_kernel_are_padded_into_one(handle, oracle_mod, n, m, N, batch, kern, lti):
+    """A size with no tensor-core kernel of its own is embedded in the next tuned size class (pad states and controls that
+    stay exactly zero); X, U, K, kff are the original problem's."""
+    prob = problems.random_lqr_riccati(n, m, N, batch, seed=3 * n + m, lti=lti)
+    _check(prob, handle, oracle_mod)
+    assert handle.last_kernel.startswith(kern) and handle.last_kernel.endswith(f"<- ({n},{m}) padded"), handle.last_kernel
 
 
 @pytest.mark.parametrize("n,m,N,batch", [(12, 4, 101, 10), (12, 4, 2, 3), (12, 4, 7, 133), (8, 4, 60, 9), (12, 1, 40, 5),

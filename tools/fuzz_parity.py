@@ -69,7 +69,7 @@ KKT_SIZES = [(1, 1), (2, 1), (3, 2), (4, 1), (4, 2), (5, 2), (6, 3), (7, 2), (8,
              (10, 4), (12, 1), (12, 2), (12, 3), (12, 4), (12, 5), (13, 4), (16, 8), (16, 4), (24, 8), (24, 16),
              (32, 8), (32, 16), (40, 8), (48, 16), (64, 16), (64, 8), (20, 6)]
 RIC_SIZES = [(1, 1), (2, 1), (3, 2), (4, 1), (4, 2), (6, 3), (7, 3), (2, 2), (3, 1), (3, 3), (4, 3), (5, 1), (5, 2), (5, 3), (6, 1), (6, 2), (8, 2), (8, 4), (9, 2), (12, 4), (12, 3),
-             (12, 1), (13, 4), (16, 8), (16, 16), (24, 8), (32, 16), (40, 8), (48, 16), (64, 16), (64, 8), (20, 5)]
+             (12, 1), (13, 4), (16, 8), (16, 16), (24, 8), (32, 16), (40, 8), (48, 16), (64, 16), (64, 8), (20, 5), (70, 9)]
 
 
 # shapes with a tuned kernel (csrc/kkt.cu: KKT_TPI_SIZES, KKT_HW_SIZES, KKT_WP_SIZES, KKT_CTA_SIZES): (n, m, interior rows)
