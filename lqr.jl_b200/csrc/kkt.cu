@@ -254,7 +254,7 @@ static bool kkt_pad_target(const lqrb_context *h, const KktShape &s, int *n2, in
     if (fits(N_, M_)) { *n2 = N_; *m2 = M_; return true; }
     X(8, 1) X(8, 2) X(8, 3) X(8, 4) X(12, 1) X(12, 2) X(12, 3) X(12, 4)
     if (s.hess == LQRB_HESS_DENSE || !s.uniform) return false;
-    X(16, 8) X(24, 8) X(32, 8) X(48, 16) X(64, 16)
+    X(16, 8) X(16, 16) X(24, 8) X(24, 16) X(32, 8) X(32, 16) X(48, 16) X(64, 16)
 #undef X
     return false;
 }

@@ -54,7 +54,7 @@ inline KktShape make_shape(int n, int m, int N, const int32_t *p, int hess, int 
 #define KKT_WP_SIZES(X) X(12, 4) X(8, 4) X(12, 3) X(8, 3) X(12, 2) X(8, 2) X(12, 1) X(8, 1)
 
 // CTA-per-instance FP64 tensor-core instantiations (same stage pattern)
-#define KKT_CTA_SIZES(X) X(64, 16) X(48, 16) X(32, 8) X(24, 8) X(16, 8)
+#define KKT_CTA_SIZES(X) X(64, 16) X(48, 16) X(32, 16) X(32, 8) X(24, 16) X(24, 8) X(16, 16) X(16, 8)
 
 struct KktSizes {
     int64_t NN, P, data_rows, rec_rows;

@@ -31,7 +31,7 @@ static bool riccati_has_dmma(int n, int m) {
 }
 
 // CTA-per-instance FP64 tensor-core instantiations (large state)
-#define RICCATI_CTA_SIZES(X) X(16, 8) X(24, 8) X(32, 8) X(48, 16) X(64, 16)
+#define RICCATI_CTA_SIZES(X) X(16, 8) X(16, 16) X(24, 8) X(24, 16) X(32, 8) X(32, 16) X(48, 16) X(64, 16)
 
 static bool riccati_has_cta(int n, int m) {
 #define X(N_, M_) \

@@ -93,7 +93,7 @@ def test_cooperative_kernel(handle, oracle_mod, n, m, N, mid_p, d2x, hess):
     (7, 2, 12, 6, 1, "kkt_wp_dmma<8,3"), (10, 3, 40, 33, 0, "kkt_wp_dmma<12,4|kkt_hw<12,4"), (9, 2, 30, 5, 1, "kkt_wp_dmma<12,3"),
     (5, 3, 14, 7, 2, "kkt_wp_dmma<8,4"), (7, 3, 21, 34, 2, "kkt_wp_dmma<8,4"), (11, 1, 25, 4, 0, "kkt_wp_dmma<12,2"),
     (14, 7, 12, 5, 0, "kkt_cta_dmma<16,8"), (20, 6, 14, 3, 2, "kkt_cta_dmma<24,8"), (13, 4, 20, 6, 1, "kkt_cta_dmma<16,8"),
-    (30, 8, 12, 3, 0, "kkt_cta_dmma<48,16"), (40, 12, 11, 2, 1, "kkt_cta_dmma<48,16"), (60, 10, 12, 2, 0, "kkt_cta_dmma<64,16"),
+    (30, 8, 12, 3, 0, "kkt_cta_dmma<32,16"), (40, 12, 11, 2, 1, "kkt_cta_dmma<48,16"), (60, 10, 12, 2, 0, "kkt_cta_dmma<64,16"),
     (16, 5, 18, 4, 3, "kkt_cta_dmma<16,8")])
 def test_shapes_without_a_tuned_kernel_are_padded_into_one(handle, oracle_mod, n, m, N, batch, mid_p, kern, hess):
     """A shape that has no tuned kernel of its own is embedded in the next tuned size class (decoupled pad states and
@@ -229,7 +229,8 @@ def test_cta_dmma_kernel(handle, oracle_mod, N, batch):
 
 
 @pytest.mark.parametrize("hess,soc", [(1, False), (2, False), (1, True)])
-@pytest.mark.parametrize("n,m,N,batch", [(16, 8, 24, 5), (24, 8, 18, 3), (32, 8, 30, 4), (48, 16, 16, 3)])
+@pytest.mark.parametrize("n,m,N,batch", [(16, 8, 24, 5), (24, 8, 18, 3), (32, 8, 30, 4), (48, 16, 16, 3), (16, 16, 12, 5),
+                                         (24, 16, 14, 3), (32, 16, 15, 4)])
 def test_cta_dmma_other_sizes(handle, oracle_mod, n, m, N, batch, hess, soc):
     """The CTA-per-instance tensor-core KKT kernel at the other sizes of the Riccati CTA family
     (n = 16, 24, 32, 48: 2, 3, 4, 6 warps), against the oracle and against the cooperative kernel."""

@@ -91,7 +91,7 @@ def test_dmma_sizes(handle, oracle_mod, n, m, N, batch, lti):
 
 
 @pytest.mark.parametrize("n,m,N,batch", [(32, 8, 12, 3), (64, 16, 11, 2), (64, 16, 2, 3), (64, 16, 101, 5), (32, 8, 300, 7),
-                                         (16, 8, 40, 5), (24, 8, 30, 4), (48, 16, 25, 3)])
+                                         (16, 8, 40, 5), (24, 8, 30, 4), (48, 16, 25, 3), (16, 16, 30, 5), (24, 16, 21, 4), (32, 16, 26, 3)])
 @pytest.mark.parametrize("lti", [False, True])
 def test_cta_dmma_sizes(handle, oracle_mod, n, m, N, batch, lti):
     """CTA-per-instance FP64 tensor-core kernel (config 5b shape and its smaller sibling)."""

@@ -78,7 +78,7 @@ TUNED = [(4, 1, 0), (3, 2, 0), (3, 2, 1), (2, 1, 0), (4, 2, 1), (6, 3, 1), (4, 2
          (12, 4, 0), (8, 4, 0), (12, 4, 1), (12, 4, 2), (12, 4, 3), (8, 4, 1), (8, 4, 3), (12, 3, 0), (12, 3, 1),
          (12, 3, 2), (8, 3, 0), (8, 3, 2), (12, 2, 0), (12, 2, 1), (8, 2, 0), (8, 2, 1), (12, 1, 0), (8, 1, 0),
          (64, 16, 0), (48, 16, 0), (32, 8, 0), (24, 8, 0), (16, 8, 0), (64, 16, 1), (48, 16, 3), (32, 8, 2), (24, 8, 1),
-         (16, 8, 4), (16, 8, 1)]
+         (16, 8, 4), (16, 8, 1), (16, 16, 0), (24, 16, 2), (32, 16, 1)]
 
 
 def draw_kkt_case(rng, case):
