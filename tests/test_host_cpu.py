@@ -34,6 +34,11 @@ def test_layout_queries_need_no_gpu():
     L = _lib.riccati_layout(4, 1, 101)
     assert (L.rows_per_knot, L.knot_count, L.term_rows, L.z_rows, L.gain_rows) == (36, 100, 18, 504, 500)
     assert _lib.riccati_layout(4, 1, 101, _lib.FLAG_LTI).knot_count == 1
+    # knot records of the warp-per-instance size class travel by 16-byte bulk copies: odd lengths get one padding row
+    for n, m in [(12, 4), (12, 3), (12, 2), (8, 3), (8, 2), (8, 1)]:
+        raw = n * n + n * m + n * (n + 1) // 2 + m * (m + 1) // 2 + n + m
+        assert _lib.riccati_layout(n, m, 11).rows_per_knot == raw + raw % 2
+    assert _lib.riccati_layout(7, 3, 11).rows_per_knot == 49 + 21 + 28 + 6 + 7 + 3  # other sizes: no padding
     # SURVEY §8d algorithmic bytes of config 2: 8 * (rows in + rows out) = 32,976
     assert 8 * (L.rows_per_knot * L.knot_count + L.term_rows + L.z_rows) == 32976
     p = np.array([3] + [0] * 199 + [3], dtype=np.int32)
