@@ -53,9 +53,14 @@ enum ScratchSlot {
     SCR_SQP3,
     SCR_KEEP_DATA,  // lqrb_kkt_factor_f64: packed matrices of the kept factorisation
     SCR_KEEP_REC,   //                      block rows of U (BlockUpperTriangular3 records)
+    // one slot per stream for everything the host-buffer paths use from inside a chunk (two chunks are in flight, and
+    // chunk sizes differ: slices of one allocation at a size-dependent offset could overlap)
     SCR_REFINE,       // records of the instances re-solved by the Cholesky-based kernel (ill-conditioned blocks)
+    SCR_REFINE_B,
     SCR_REFINE_LIST,  // their indices
-    SCR_RICCATI_PAD,  // Riccati problems embedded in a tuned size class: padded knots, term, Z, gains (one slice per stream)
+    SCR_REFINE_LIST_B,
+    SCR_RICCATI_PAD,  // Riccati problems embedded in a tuned size class: padded knots, term, Z, gains
+    SCR_RICCATI_PAD_B,
     SCR_COUNT
 };
 

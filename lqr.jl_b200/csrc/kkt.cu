@@ -190,12 +190,10 @@ int32_t kkt_resolve_ill_conditioned(lqrb_context *h, const KktShape &s, int64_t 
     const int64_t piece = std::max<int64_t>(1, (int64_t)(((size_t)h->opt("scratch_budget_mb", 49152) << 20) / 4 / per));
     for (size_t first = 0; first < list.size(); first += (size_t)piece) {
         const int64_t cnt = std::min<int64_t>(piece, (int64_t)(list.size() - first));
-        // separate slices per stream: the host-buffer path has two of these in flight
-        int32_t *dl = (int32_t *)lqrb_scratch(h, SCR_REFINE_LIST, 2 * (size_t)cb * sizeof(int32_t));
-        double *rec = (double *)lqrb_scratch(h, SCR_REFINE, 2 * (size_t)std::min<int64_t>(piece, cb) * per);
+        // separate allocations per stream: the host-buffer path has two of these in flight
+        int32_t *dl = (int32_t *)lqrb_scratch(h, slot ? SCR_REFINE_LIST_B : SCR_REFINE_LIST, (size_t)cb * sizeof(int32_t));
+        double *rec = (double *)lqrb_scratch(h, slot ? SCR_REFINE_B : SCR_REFINE, (size_t)std::min<int64_t>(piece, cb) * per);
         if (!dl || !rec) return 1000 + (int)cudaErrorMemoryAllocation;
-        dl += slot * cb;
-        rec += (size_t)slot * std::min<int64_t>(piece, cb) * z.rec_rows;
         LQRB_CUDA(h, cudaMemcpyAsync(dl, list.data() + first, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         KktCoopExtra ex;
         ex.list = dl;

@@ -286,14 +286,13 @@ static int32_t riccati_solve_padded(lqrb_context *h, int n, int m, int N, int n2
         mg = h->maps[k0 + ":g"];
     }
     if (mk.rows != Kn * F2 || mt.rows != TR2 || mz.rows != ZR2 || mg.rows != GR2) return lqrb_fail(h, 1, "pad map size mismatch");
-    // chunks of at most ~2 GB of padded arrays; one slice of the scratch per stream (the host path has two in flight)
+    // chunks of at most ~2 GB of padded arrays; one allocation per stream (the host path has two in flight)
     const int64_t per = Kn * F2 + TR2 + ZR2 + GR2;
     int64_t chunk = std::max<int64_t>(LQRB_TILE, ((int64_t)2 << 30) / (per * 8) / LQRB_TILE * LQRB_TILE);
     chunk = std::min(chunk, lqrb_padded_batch(batch));
     const size_t slice = ((size_t)chunk * per * 8 + 255) / 256 * 256;
-    char *base = (char *)lqrb_scratch(h, SCR_RICCATI_PAD, 2 * slice);
+    char *base = (char *)lqrb_scratch(h, st == h->copy_stream[1] ? SCR_RICCATI_PAD_B : SCR_RICCATI_PAD, slice);
     if (!base) return 1000 + (int)cudaErrorMemoryAllocation;
-    base += (st == h->copy_stream[1] ? 1 : 0) * slice;
     double *knots2 = (double *)base, *term2 = knots2 + chunk * Kn * F2, *Z2 = term2 + chunk * TR2, *gains2 = Z2 + chunk * ZR2;
     std::string name;
     for (int64_t first = 0; first < batch; first += chunk) {

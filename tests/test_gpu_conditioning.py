@@ -60,3 +60,40 @@ def test_condition_estimate_and_switch(handle):
     finally:
         handle.set_option("kkt_refine", 1)
     assert not np.array_equal(dz1, dz2)
+
+
+@pytest.mark.parametrize("n,m,N,kind", [(12, 4, 30, "kkt"), (10, 3, 30, "kkt"), (14, 7, 12, "kkt"), (10, 3, 40, "riccati"),
+                                        (20, 6, 25, "riccati")])
+def test_host_path_with_uneven_chunks(handle, oracle_mod, n, m, N, kind):
+    """Host buffers go through two streams in chunks; the last chunk is smaller than the others.  Everything a chunk
+    allocates from inside (re-solve lists and records, padded arrays) has one allocation per stream, so the chunks in
+    flight cannot overlap whatever their sizes: 70 instances in chunks of 32 (32 + 32 + 6), half of them rescaled so
+    that the re-solve path runs in every chunk."""
+    b = 70
+    handle.set_option("host_chunk", 32)
+    try:
+        if kind == "kkt":
+            prob = problems.random_lqr_kkt(n, m, N, b, seed=31 + n, mid_p=0, hess_mode=1)
+            prob["Q"][::2] *= 1e3
+            prob["R"][::2] *= 1e-3
+            dz, lam, info = ops.kkt_solve_problem(prob, handle=handle)
+            dzo, lamo, infoo = oracle_mod.kkt_solve(prob)
+            assert (info == 0).all() and (infoo == 0).all()
+            e, eo = _err(prob, dz, lam), _err(prob, dzo, lamo)
+            assert e <= max(1e-10, 4.0 * eo), (e, eo, handle.last_kernel)
+            # the same call in one chunk gives the same bits
+            handle.set_option("host_chunk", 0)
+            dz1, lam1, _ = ops.kkt_solve_problem(prob, handle=handle)
+            assert np.array_equal(dz, dz1) and np.array_equal(lam, lam1)
+        else:
+            prob = problems.random_lqr_riccati(n, m, N, b, seed=31 + n)
+            X, U, K, kff, info = ops.riccati_solve_problem(prob, handle=handle)
+            assert "padded" in handle.last_kernel
+            Xo, Uo, Ko, kffo, _ = oracle_mod.riccati(prob)
+            for a, c in ((X, Xo), (U, Uo), (K, Ko), (kff, kffo)):
+                assert np.linalg.norm(a - c) / np.linalg.norm(c) <= 1e-10
+            handle.set_option("host_chunk", 0)
+            X1, U1, K1, kff1, _ = ops.riccati_solve_problem(prob, handle=handle)
+            assert np.array_equal(X, X1) and np.array_equal(U, U1) and np.array_equal(K, K1)
+    finally:
+        handle.set_option("host_chunk", 0)
