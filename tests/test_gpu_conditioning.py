@@ -97,3 +97,36 @@ def test_host_path_with_uneven_chunks(handle, oracle_mod, n, m, N, kind):
             assert np.array_equal(X, X1) and np.array_equal(U, U1) and np.array_equal(K, K1)
     finally:
         handle.set_option("host_chunk", 0)
+
+
+def test_general_kernel_grid_stride_with_narrow_groups(handle, oracle_mod):
+    """The general KKT kernel at 4 lanes per instance caps its grid and strides over the instances; the groups of one warp
+    must make the same number of trips (idle ones shadow the last instance).  310,001 tiny problems with explicit D2."""
+    b = 310001
+    prob = problems.random_lqr_kkt(3, 2, 4, b, seed=77, mid_p=0, hess_mode=1, explicit_D2=True)
+    dz, lam, info = ops.kkt_solve_problem(prob, handle=handle)
+    assert handle.last_kernel.startswith("kkt_coop<G=4>")
+    dzo, lamo, infoo = oracle_mod.kkt_solve(prob)
+    assert (info == 0).all() and (infoo == 0).all()
+    ez = np.linalg.norm(dz - dzo, axis=1) / np.linalg.norm(dzo, axis=1)
+    el = np.linalg.norm(lam - lamo, axis=1) / np.linalg.norm(lamo, axis=1)
+    assert ez.max() <= 1e-9 and el.max() <= 1e-9 and np.median(ez) <= 1e-13, (ez.max(), el.max())
+
+
+@pytest.mark.parametrize("n,m,N,mid_p,kern", [(10, 3, 12, 1, "kkt_wp_dmma<12,4"), (14, 7, 12, 0, "kkt_cta_dmma<16,8")])
+def test_padded_path_in_several_chunks(handle, oracle_mod, n, m, N, mid_p, kern):
+    """A small scratch budget makes the padded path (expand -> tuned kernel -> compact) run in several chunks."""
+    b = 8001
+    prob = problems.random_lqr_kkt(n, m, N, b, seed=5 + n, mid_p=mid_p, hess_mode=1)
+    handle.set_option("scratch_budget_mb", 8)
+    try:
+        dz, lam, info, res = ops.kkt_solve_problem(prob, want_res=True, handle=handle)
+    finally:
+        handle.set_option("scratch_budget_mb", 49152)
+    assert handle.last_kernel.startswith(kern) and "padded" in handle.last_kernel
+    dzo, lamo, infoo, reso = oracle_mod.kkt_solve(prob, want_res=True)
+    assert (info == 0).all() and (infoo == 0).all()
+    ez = np.linalg.norm(dz - dzo, axis=1) / np.linalg.norm(dzo, axis=1)
+    el = np.linalg.norm(lam - lamo, axis=1) / np.linalg.norm(lamo, axis=1)
+    assert np.median(ez) <= 1e-11 and np.median(el) <= 1e-11 and ez.max() <= 1e-8 and el.max() <= 1e-8, (ez.max(), el.max())
+    assert np.abs(res - reso).max() <= 1e-8 * max(1.0, np.abs(reso).max())
