@@ -5,7 +5,7 @@
 #include "kkt_dispatch.cuh"
 
 static bool kkt_has_tpi(const KktShape &s) {
-    if (!s.uniform || s.d2x) return false;
+    if (!s.uniform || s.d2x || s.free_final) return false;
 #define X(N_, M_, A_, B_, C_) \
     if (s.n == N_ && s.m == M_ && s.P1 == A_ && (s.N == 2 || s.PM == B_) && s.PN == C_) return true;
     KKT_TPI_SIZES(X)
@@ -17,7 +17,7 @@ static bool kkt_has_tpi(const KktShape &s) {
 static bool kkt_has_hw(const lqrb_context *h, const KktShape &s, int flags) {
     if (h->opt("kkt_variant", 0) == 2 || h->opt("kkt_variant", 0) == 5) return false;
     (void)flags;
-    if (!s.uniform || s.d2x || s.hess == LQRB_HESS_DENSE) return false;
+    if (!s.uniform || s.d2x || s.hess == LQRB_HESS_DENSE || s.free_final) return false;
     if (s.N < 3 || s.P1 != s.n || s.PM != 0 || s.PN != s.n) return false;
 #define X(N_, M_) \
     if (s.n == N_ && s.m == M_) return true;
@@ -197,7 +197,16 @@ int32_t kkt_resolve_ill_conditioned(lqrb_context *h, const KktShape &s, int64_t 
         LQRB_CUDA(h, cudaMemcpyAsync(dl, list.data() + first, (size_t)cnt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
         KktCoopExtra ex;
         ex.list = dl;
-        int32_t rc = launch_kkt_coop(h, s.n, s.m, s.N, s.p, s.hess, s.d2x, flags, cnt, dc, rec, dz, mult, res, info, st, &ex);
+        std::vector<int32_t> pf;
+        const int32_t *pp = s.p;
+        if (s.free_final) {  // the general kernel solves the problem as it is (no goal rows) inside the tuned kernel's layout
+            pf.assign(s.p, s.p + s.N);
+            pf[s.N - 1] = 0;
+            pp = pf.data();
+            ex.data_stride = z.data_rows;
+            ex.mult_stride = z.P;
+        }
+        int32_t rc = launch_kkt_coop(h, s.n, s.m, s.N, pp, s.hess, s.d2x, flags, cnt, dc, rec, dz, mult, res, info, st, &ex);
         if (rc) return rc;
         LQRB_CUDA(h, cudaStreamSynchronize(st));  // `list` (pageable) must outlive the copy
     }
@@ -238,7 +247,8 @@ int64_t kkt_tuned_chunk(const lqrb_context *h, const KktShape &s) {
 // and dz, mult, res are compacted back: two extra passes over the data, a few percent of what the padding saves.
 static bool kkt_pad_target(const lqrb_context *h, const KktShape &s, int *n2, int *m2) {
     if (h->opt("kkt_pad", 1) == 0 || h->opt("kkt_variant", 0) == 2) return false;
-    if (s.d2x || s.N < 3 || s.P1 != s.n || s.PN != s.n || s.PMAX > 4) return false;
+    // goal rows on the whole final state, or none at all (free final state: embedded with a zero goal block)
+    if (s.d2x || s.N < 3 || s.P1 != s.n || (s.PN != s.n && s.PN != 0) || s.PMAX > 4) return false;
     if (kkt_has_tpi(s) || kkt_has_hw(h, s, 0) || kkt_has_wp(h, s) || kkt_has_cta(h, s, 0)) return false;
     auto fits = [&](int N2, int M2) {
         if (N2 < s.n || M2 < s.m) return false;
@@ -323,13 +333,14 @@ static PadMaps kkt_pad_maps(const KktShape &s, int n2, int m2) {
         }
         // C, c : the end knots have n rows (+ identity rows on the pad states), the interior ones their ps rows
         const int ps2 = (first || last) ? n2 : ps;
+        const bool nogoal = last && ps == 0;  // free final state: a zero goal block (the kernel leaves mu_N = 0)
         for (int j = 0; j < w2; ++j)
             for (int i = 0; i < ps2; ++i) {
                 const int o = zmap(j);
                 if (i < ps) {
                     if (o >= 0) src(oC + i + (int64_t)o * ps); else fill(0.0);
                 } else {
-                    fill(j == n + (i - ps) ? 1.0 : 0.0);  // (first / last knot only: ps = n) pad state i - n pinned to 0
+                    fill((!nogoal && j == n + (i - ps)) ? 1.0 : 0.0);  // (first / last knot: ps = n) pad state i - n pinned to 0
                 }
             }
         for (int i = 0; i < ps2; ++i) {
@@ -369,6 +380,7 @@ static void kkt_pad_plan(const lqrb_context *h, const KktShape &s, int n2, int m
     P->p2[0] = n2;
     P->p2[s.N - 1] = n2;
     P->s2 = make_shape(n2, m2, s.N, P->p2.data(), s.hess, 0);
+    P->s2.free_final = s.PN == 0;
     P->z2 = kkt_sizes(P->s2);
     P->chunk = std::max<int64_t>(1, std::min(batch, kkt_tuned_chunk(h, P->s2)));
     const size_t ldb = (size_t)lqrb_padded_batch(P->chunk);
@@ -435,7 +447,7 @@ static int32_t kkt_solve_padded(lqrb_context *h, const KktShape &s, int n2, int 
         if (rc) return rc;
     }
     char nm[64];
-    snprintf(nm, sizeof nm, " <- (%d,%d) padded", s.n, s.m);
+    snprintf(nm, sizeof nm, " <- (%d,%d)%s padded", s.n, s.m, s.PN == 0 ? " free final state" : "");
     h->kernel_name = name + nm;
     h->last_refined = refined;
     h->last_cond = cond;

@@ -73,6 +73,7 @@ struct KktCoopArgs {
     const double *rhs;        // phase 2: per instance [per knot: g (w) | d (p2) | c (ps)], tile width 1
     double *sdump;            // optional: raw Schur blocks S (before cholesky!) in the record layout
     int phase;                // 0 fused, 1 factor only, 2 solve with the kept factor
+    int64_t data_stride, mult_stride;  // per-instance strides of data / mult when they are not the shape's own (0: own)
     int n, m, N, hess, d2x, soc;
     int64_t batch;
     int P;  // max p_k
@@ -102,7 +103,8 @@ __global__ void __launch_bounds__(THREADS) kkt_coop_kernel(KktCoopArgs a) {
         const int64_t inst = base + g % GPW < a.batch ? base + g % GPW : a.batch - 1;
         const bool active = true;
         const int64_t ii = a.list ? (int64_t)a.list[inst] : inst;  // optional instance list (re-solve of a subset)
-        const int64_t data_rows = a.knot_off[N], rec_rows = a.rec_off[N], mult_rows = a.mult_off[N];
+        const int64_t data_rows = a.data_stride ? a.data_stride : a.knot_off[N], rec_rows = a.rec_off[N],
+                      mult_rows = a.mult_stride ? a.mult_stride : a.mult_off[N];
         const int64_t NN = (int64_t)N * n + (int64_t)(N - 1) * m;
         const double *db = a.data + ii * data_rows;
         double *sb = a.scratch + inst * rec_rows;  // records by position: a list needs only its own slots
@@ -430,6 +432,8 @@ int32_t launch_kkt_coop(lqrb_context *h, int n, int m, int N, const int32_t *p, 
     a.rhs = extra ? extra->rhs : nullptr;
     a.sdump = extra ? extra->sdump : nullptr;
     a.phase = extra ? extra->phase : 0;
+    a.data_stride = extra ? extra->data_stride : 0;
+    a.mult_stride = extra ? extra->mult_stride : 0;
     a.n = n; a.m = m; a.N = N; a.hess = hess; a.d2x = d2x; a.soc = (flags & LQRB_FLAG_SOC) ? 1 : 0;
     a.batch = batch; a.P = tb.P;
     const size_t wsd = kkt_coop_ws_doubles(n, m, tb.P);

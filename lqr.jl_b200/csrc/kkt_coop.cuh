@@ -28,6 +28,9 @@ struct KktCoopExtra {
     const double *rhs = nullptr;
     double *sdump = nullptr;
     const int32_t *list = nullptr;  // device list of instance indices to process (batch = its length)
+    // per-instance strides (doubles) of `data` and `mult` when the arrays belong to a larger layout than this shape's
+    // (the re-solve of a free-final-state problem that a tuned kernel ran with a zero goal block); 0: the shape's own
+    int64_t data_stride = 0, mult_stride = 0;
 };
 
 int32_t launch_kkt_coop(lqrb_context *h, int n, int m, int N, const int32_t *p, int hess, int d2x,

@@ -34,7 +34,7 @@ static int32_t launch_kkt_cta(lqrb_context *h, const KktShape &s, int64_t batch,
         LQRB_LAUNCH_CHECK(h, "kkt_cta_prep_kernel");
         mk<<<(unsigned)cb, L::THREADS, msm, st>>>(dc, prep, hinfo, recs, dz + first * zrows, mult + first * mrows,
                                                   res ? res + first * zrows : nullptr,
-                                                  info ? info + first : nullptr, cinfo, N, cb, soc, ps);
+                                                  info ? info + first : nullptr, cinfo, N, cb, soc, ps, s.free_final ? 1 : 0);
         LQRB_LAUNCH_CHECK(h, "kkt_cta_kernel");
         int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * zrows,
                                                  mult + first * mrows, res ? res + first * zrows : nullptr,

@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
     kkt_cta_kernel(const double *__restrict__ data, const double *__restrict__ prep, const int32_t *__restrict__ hinfo,
                    double *__restrict__ recs, double *__restrict__ dz, double *__restrict__ mult,
                    double *__restrict__ res, int32_t *__restrict__ info, int32_t *__restrict__ cinfo, int N,
-                   int64_t batch, int soc, int ps_arg) {
+                   int64_t batch, int soc, int ps_arg, int free_final) {
     using L = Lay<n, m, HESS>;
     constexpr int NT = L::NT, w = L::w, LB = L::LB, THREADS = L::THREADS;
     static_assert(THREADS == 4 * n, "four partial sums per row in the mat-vecs");
@@ -811,7 +811,18 @@ __global__ void __launch_bounds__(Lay<n, m, HESS>::THREADS, 2)
         // no barrier here: Ss / the stage vectors are next written after the barriers of the following Gauss-Jordan
     }
     // ---- last block: mu_N' = Bl'^-1 y_mu   (Cp, dps hold Bl' and y_mu)
-    {
+    if (free_final) {  // no goal rows (the last knot carried a zero block): mu_N = 0, nothing to invert
+        if (tid == 0) atomicMax(cinfo + inst, spread);
+        if (tid < n) {
+            xs[tid] = 0.0;
+            __stcs(mb + L::mult_rows(N, ps) - n + tid, 0.0);
+        }
+        if (info && tid == 0) {
+            const int hcode = hinfo[inst];
+            info[inst] = hcode != 0x7f7f7f7f ? hcode : st_all;
+        }
+        __syncthreads();
+    } else {
         if (tid == 0) {
             flag = 0;
             flag3[1] = 0x7fffffff;

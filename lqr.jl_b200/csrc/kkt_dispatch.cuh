@@ -36,6 +36,9 @@ struct KktShape {
     bool uniform;  // p = [P1, PM.., PN]
     int P1, PM, PN;
     int PMAX;  // largest interior count
+    // set on the padded shape of a problem WITHOUT goal rows (p_N = 0): its last knot carries a zero goal block
+    // (PN = n), the tuned kernel leaves mu_N = 0 instead of inverting the (zero) last Schur block
+    bool free_final = false;
 };
 
 inline KktShape make_shape(int n, int m, int N, const int32_t *p, int hess, int d2x) {

@@ -33,7 +33,7 @@ static int32_t launch_kkt_wp(lqrb_context *h, const KktShape &s, int64_t batch, 
         kern<<<(unsigned)((cb + WARPS - 1) / WARPS), WARPS * 32, smem, st>>>(
             dc, recs, dz + first * zrows, mult + first * mrows, res ? res + first * zrows : nullptr,
             info ? info + first : nullptr, cinfo, N, cb, soc, ps, s.uniform ? nullptr : tb.p,
-            s.uniform ? nullptr : tb.knot_off, s.uniform ? nullptr : tb.mult_off);
+            s.uniform ? nullptr : tb.knot_off, s.uniform ? nullptr : tb.mult_off, s.free_final ? 1 : 0);
         LQRB_LAUNCH_CHECK(h, "kkt_wp_kernel");
         int32_t rc = kkt_resolve_ill_conditioned(h, s, cb, soc ? LQRB_FLAG_SOC : 0, dc, cinfo, dz + first * zrows,
                                                  mult + first * mrows, res ? res + first * zrows : nullptr,

@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     kkt_wp_kernel(const double *__restrict__ data, double *__restrict__ recs, double *__restrict__ dz,
                   double *__restrict__ mult, double *__restrict__ res, int32_t *__restrict__ info,
                   int32_t *__restrict__ cinfo, int N, int64_t batch, int soc, int ps,
-                  const int32_t *__restrict__ pk, const int64_t *__restrict__ koff, const int64_t *__restrict__ moff) {
+                  const int32_t *__restrict__ pk, const int64_t *__restrict__ koff, const int64_t *__restrict__ moff,
+                  int free_final) {
     // ps = stage rows of every interior knot; or, with pk / koff / moff (stage rows per knot, offsets of the knot records
     // and of the multiplier groups [mu_k; lam_k], N + 1 entries each), ps = the largest interior count
     using L = Lay<n, m, HESS>;
@@ -709,7 +710,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
         __syncwarp();
     }
     // ---------------- last block: mu_N' = Bl'^-1 y_mu   (Cp, dp hold Bl' and y_mu)
-    {
+    if (free_final) {  // no goal rows (the last knot carried a zero block): mu_N = 0, nothing to invert
+        if (lane < 16) {
+            vec[VX + lane] = 0.0;
+            if (xslot >= 0) __stcs(mb + mrows - n + xslot, 0.0);
+        }
+    } else {
         pad_identity(Cp);
         lo = 0x7fffffff;
         hi = 0;

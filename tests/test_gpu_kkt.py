@@ -458,3 +458,55 @@ def test_stage_constraints_match_cooperative_kernel_and_report_info(handle):
     prob["C"][7][3, 1] = prob["C"][7][3, 0]
     _, _, info = ops.kkt_solve_problem(prob, handle=handle)
     assert info[3] // 1000 == 8 and (info[3] % 1000) // 100 == 1 and (np.delete(info, 3) == 0).all(), info
+
+
+def _free_final(prob):
+    """Drop the goal rows: p_N = 0 (the MPC form: initial condition, dynamics, stage rows, free final state)."""
+    prob["p"] = prob["p"].copy()
+    prob["p"][-1] = 0
+    b = prob["q"].shape[0]
+    prob["C"][-1] = np.zeros((b, 0, prob["n"]))
+    prob["c"][-1] = np.zeros((b, 0))
+    return prob
+
+
+@pytest.mark.parametrize("hess,soc", [(1, False), (2, False), (0, False), (1, True)])
+@pytest.mark.parametrize("n,m,N,batch,mid_p,kern", [
+    (12, 4, 30, 7, 0, "kkt_wp_dmma<12,4"), (12, 4, 31, 5, 2, "kkt_wp_dmma<12,4"), (8, 2, 20, 33, 1, "kkt_wp_dmma<8,2"),
+    (4, 1, 25, 9, 0, "kkt_wp_dmma<8,2"), (6, 3, 20, 6, 1, "kkt_wp_dmma<8,4"), (10, 3, 25, 4, 0, "kkt_wp_dmma<12,4"),
+    (14, 7, 12, 5, 1, "kkt_cta_dmma<16,8"), (64, 16, 9, 2, 0, "kkt_cta_dmma<64,16"), (24, 8, 12, 3, 2, "kkt_cta_dmma<24,8")])
+def test_free_final_state_on_the_tuned_kernels(handle, oracle_mod, n, m, N, batch, mid_p, kern, hess, soc):
+    """No goal rows (p_N = 0): the problem is embedded with a ZERO goal block and the tuned kernel leaves mu_N = 0 instead
+    of inverting the last Schur block; the multiplier vector that comes back has no mu_N entries."""
+    from oracle import dense_kkt
+    prob = _free_final(problems.random_lqr_kkt(n, m, N, batch, seed=3 * n + m + mid_p, mid_p=mid_p, hess_mode=hess))
+    dz, lam, info, res = ops.kkt_solve_problem(prob, soc=soc, want_res=True, handle=handle)
+    if hess == 0 and n > 12:
+        assert handle.last_kernel.startswith("kkt_coop")
+    else:
+        assert handle.last_kernel.startswith(kern) and "free final state padded" in handle.last_kernel, handle.last_kernel
+    dzo, lamo, infoo, reso = oracle_mod.kkt_solve(prob, soc=soc, want_res=True)
+    assert (info == 0).all() and (infoo == 0).all() and lam.shape == lamo.shape
+    base = 1e-9 if soc else TOL
+    for i in range(batch):
+        zt, lt = dense_kkt.kkt_truth(prob, i, soc=soc)
+        tol = max(base, 4.0 * max(_rel(dzo[i], zt), _rel(lamo[i], lt)))
+        assert _rel(dz[i], zt) <= tol and _rel(lam[i], lt) <= tol, (i, tol, _rel(dz[i], zt), _rel(lam[i], lt))
+        assert np.linalg.norm(res[i] - reso[i]) <= 2 * tol * max(1.0, np.linalg.norm(reso[i]))
+
+
+def test_free_final_state_resolve_of_ill_conditioned_instances(handle, oracle_mod):
+    """The re-solve of flagged instances runs the general kernel on the problem as it is (no goal rows) inside the tuned
+    kernel's padded layout (its own per-instance strides)."""
+    from oracle import dense_kkt
+    prob = _free_final(problems.random_lqr_kkt(12, 4, 30, 9, seed=8, mid_p=1, hess_mode=1))
+    prob["Q"][::2] *= 1e3
+    prob["R"][::2] *= 1e-3
+    dz, lam, info = ops.kkt_solve_problem(prob, handle=handle)
+    assert "+kkt_coop[" in handle.last_kernel and "free final state" in handle.last_kernel, handle.last_kernel
+    dzo, lamo, infoo = oracle_mod.kkt_solve(prob)
+    assert (info == 0).all() and (infoo == 0).all()
+    for i in range(9):
+        zt, lt = dense_kkt.kkt_truth(prob, i)
+        tol = max(TOL, 4.0 * max(_rel(dzo[i], zt), _rel(lamo[i], lt)))
+        assert _rel(dz[i], zt) <= tol and _rel(lam[i], lt) <= tol, (i, tol)

@@ -94,6 +94,8 @@ def draw_kkt_case(rng, case):
         soc = bool(rng.integers(0, 6) == 0)
         p = np.full(N, pm, dtype=np.int32)
         p[0] = p[-1] = n
+        if rng.integers(0, 4) == 0:
+            p[-1] = 0  # free final state
     else:
         n, m = KKT_SIZES[int(rng.integers(len(KKT_SIZES)))]
         big = n >= 16
