@@ -28,7 +28,14 @@
     X(5, 1, 5, 0, 5) X(6, 1, 6, 0, 6)
 #define KKT_TPI_SIZES_C(X) \
     X(5, 2, 5, 0, 5) X(5, 2, 5, 1, 5) X(6, 2, 6, 0, 6) X(6, 2, 6, 1, 6) X(4, 3, 4, 0, 4) X(4, 3, 4, 1, 4) X(5, 3, 5, 0, 5) X(5, 3, 5, 1, 5)
-#define KKT_TPI_SIZES(X) KKT_TPI_SIZES_A(X) KKT_TPI_SIZES_B(X) KKT_TPI_SIZES_C(X)
+// the same shapes without goal rows (p_N = 0: free final state, the MPC form)
+#define KKT_TPI_SIZES_D(X)                                                                                          \
+    X(4, 1, 4, 0, 0) X(3, 2, 3, 0, 0) X(3, 2, 3, 1, 0) X(2, 1, 2, 0, 0) X(4, 2, 4, 0, 0) X(4, 2, 4, 1, 0) X(6, 3, 6, 0, 0) \
+    X(6, 3, 6, 1, 0) X(2, 2, 2, 0, 0) X(2, 2, 2, 1, 0) X(3, 1, 3, 0, 0) X(3, 3, 3, 0, 0) X(3, 3, 3, 1, 0)
+#define KKT_TPI_SIZES_E(X)                                                                                          \
+    X(5, 1, 5, 0, 0) X(6, 1, 6, 0, 0) X(5, 2, 5, 0, 0) X(5, 2, 5, 1, 0) X(6, 2, 6, 0, 0) X(6, 2, 6, 1, 0) X(4, 3, 4, 0, 0) \
+    X(4, 3, 4, 1, 0) X(5, 3, 5, 0, 0) X(5, 3, 5, 1, 0)
+#define KKT_TPI_SIZES(X) KKT_TPI_SIZES_A(X) KKT_TPI_SIZES_B(X) KKT_TPI_SIZES_C(X) KKT_TPI_SIZES_D(X) KKT_TPI_SIZES_E(X)
 
 struct KktShape {
     int n, m, N, hess, d2x;

@@ -473,18 +473,21 @@ def _free_final(prob):
 @pytest.mark.parametrize("hess,soc", [(1, False), (2, False), (0, False), (1, True)])
 @pytest.mark.parametrize("n,m,N,batch,mid_p,kern", [
     (12, 4, 30, 7, 0, "kkt_wp_dmma<12,4"), (12, 4, 31, 5, 2, "kkt_wp_dmma<12,4"), (8, 2, 20, 33, 1, "kkt_wp_dmma<8,2"),
-    (4, 1, 25, 9, 0, "kkt_wp_dmma<8,2"), (6, 3, 20, 6, 1, "kkt_wp_dmma<8,4"), (10, 3, 25, 4, 0, "kkt_wp_dmma<12,4"),
+    (4, 1, 25, 70, 0, "kkt_tpi<4,1,p=4/0/0"), (6, 3, 20, 33, 1, "kkt_tpi<6,3,p=6/1/0"), (3, 2, 41, 9, 0, "kkt_tpi<3,2,p=3/0/0"),
+    (5, 2, 20, 6, 1, "kkt_tpi<5,2,p=5/1/0"), (6, 3, 20, 6, 2, "kkt_wp_dmma<8,4"), (10, 3, 25, 4, 0, "kkt_wp_dmma<12,4"),
     (14, 7, 12, 5, 1, "kkt_cta_dmma<16,8"), (64, 16, 9, 2, 0, "kkt_cta_dmma<64,16"), (24, 8, 12, 3, 2, "kkt_cta_dmma<24,8")])
 def test_free_final_state_on_the_tuned_kernels(handle, oracle_mod, n, m, N, batch, mid_p, kern, hess, soc):
-    """No goal rows (p_N = 0): the problem is embedded with a ZERO goal block and the tuned kernel leaves mu_N = 0 instead
-    of inverting the last Schur block; the multiplier vector that comes back has no mu_N entries."""
+    """No goal rows (p_N = 0).  Small shapes have thread-per-instance instantiations of their own; above them the problem
+    is embedded with a ZERO goal block and the tuned kernel leaves mu_N = 0 instead of inverting the last Schur block;
+    the multiplier vector that comes back has no mu_N entries."""
     from oracle import dense_kkt
     prob = _free_final(problems.random_lqr_kkt(n, m, N, batch, seed=3 * n + m + mid_p, mid_p=mid_p, hess_mode=hess))
     dz, lam, info, res = ops.kkt_solve_problem(prob, soc=soc, want_res=True, handle=handle)
     if hess == 0 and n > 12:
         assert handle.last_kernel.startswith("kkt_coop")
     else:
-        assert handle.last_kernel.startswith(kern) and "free final state padded" in handle.last_kernel, handle.last_kernel
+        assert handle.last_kernel.startswith(kern), handle.last_kernel
+        assert ("free final state padded" in handle.last_kernel) == (not kern.startswith("kkt_tpi")), handle.last_kernel
     dzo, lamo, infoo, reso = oracle_mod.kkt_solve(prob, soc=soc, want_res=True)
     assert (info == 0).all() and (infoo == 0).all() and lam.shape == lamo.shape
     base = 1e-9 if soc else TOL
