@@ -460,7 +460,8 @@ static size_t kkt_scratch_bytes(const lqrb_context *h, const KktShape &s, const 
         if (kkt_pad_target(h, s, &n2, &m2)) {
             PadPlan P;
             kkt_pad_plan(h, s, n2, m2, batch, &P);
-            return P.data_b + P.out_b + P.scr_b;
+            // (never less than the general kernel needs: it is what runs if the padded path is not taken after all)
+            return std::max(P.data_b + P.out_b + P.scr_b, (size_t)lqrb_padded_batch(batch) * z.rec_rows * 8);
         }
     }
     size_t bytes = (size_t)lqrb_padded_batch(batch) * z.rec_rows * 8;
