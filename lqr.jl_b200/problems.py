@@ -200,6 +200,21 @@ def random_lqr_riccati(n, m, N, batch, seed=3, dt=0.01, lti=False):
     return dict(n=n, m=m, N=N, lti=lti, A=A, B=B, Q=Q, R=R, q=q, r=r, Qf=Qf, qf=qf, x0=x0)
 
 
+def dare_lti_riccati(n, m, N, batch, seed=1):
+    """LTI problem with a well-damped optimal closed loop (A = 0.9 I + 0.2 J / sqrt(n), B ~ N(0,1) / sqrt(n), SPD Q, R, no
+    affine terms, Qf = Q): the gain of the first knot of a long horizon converges to the gain of the discrete algebraic
+    Riccati equation, which scipy.linalg.solve_discrete_are computes independently (tests)."""
+    rng = np.random.default_rng(seed)
+    A = 0.9 * np.eye(n) + 0.2 * rng.standard_normal((batch, n, n)) / np.sqrt(n)
+    B = rng.standard_normal((batch, n, m)) / np.sqrt(n)
+    L = rng.standard_normal((batch, n, n))
+    Q = np.einsum("bij,bkj->bik", L, L) / n + np.eye(n)
+    L = rng.standard_normal((batch, m, m))
+    R = np.einsum("bij,bkj->bik", L, L) / m + 0.5 * np.eye(m)
+    return dict(n=n, m=m, N=N, lti=True, A=A, B=B, Q=Q, R=R, q=np.zeros((batch, n)), r=np.zeros((batch, m)), Qf=Q.copy(),
+                qf=np.zeros((batch, n)), x0=rng.standard_normal((batch, n)))
+
+
 def random_lqr_kkt(n, m, N, batch, seed=3, dt=0.01, mid_p=0, hess_mode=HESS_BLOCKDIAG,
                    explicit_D2=False):
     """Configs 5a-K/5b-K and generic test problems: random LTV dynamics, SPD cost blocks, init + goal

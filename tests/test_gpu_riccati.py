@@ -270,3 +270,22 @@ def test_tuned_kernels_closed_loop_at_scale(handle, n, m, N, batch, kern):
         p2[key] = 2.0 * prob[key]
     X2, U2, _, _, _ = ops.riccati_solve_problem(p2, want_gains=False, handle=handle)
     assert np.abs(X2 - 2 * X).max() <= 1e-9 * s and np.abs(U2 - 2 * U).max() <= 1e-9 * max(1.0, np.abs(U).max())
+
+
+@pytest.mark.parametrize("n,m,N,kern", [(4, 1, 401, "riccati_tpi<4,1>"), (6, 3, 401, "riccati_tpi<6,3>"), (12, 4, 401, "riccati_dmma<12,4>"),
+                                        (10, 3, 401, "riccati_dmma<12,3>"), (64, 16, 401, "riccati_cta_dmma<64,16>"),
+                                        (20, 6, 401, "riccati_cta_dmma<24,8>")])
+def test_gain_converges_to_scipy_dare(handle, n, m, N, kern):
+    """Independent of the oracle: the first gain of a long LTI horizon against scipy.linalg.solve_discrete_are
+    (tests/test_oracle.py::test_riccati_gain_converges_to_scipy_dare holds the oracle to the same number)."""
+    import scipy.linalg as sl
+    prob = problems.dare_lti_riccati(n, m, N, 5, seed=n)
+    X, U, K, kff, info = ops.riccati_solve_problem(prob, handle=handle)
+    assert (info == 0).all() and handle.last_kernel.startswith(kern), handle.last_kernel
+    for i in range(5):
+        A, B, Q, R = prob["A"][i], prob["B"][i], prob["Q"][i], prob["R"][i]
+        P = sl.solve_discrete_are(A, B, Q, R)
+        Kd = np.linalg.solve(R + B.T @ P @ B, B.T @ P @ A)
+        rho = np.abs(np.linalg.eigvals(A - B @ Kd)).max()
+        tol = max(1e-9, 100.0 * rho ** (2 * (N - 1)))
+        assert np.linalg.norm(K[i, 0] - Kd) / np.linalg.norm(Kd) <= tol, (i, rho, tol)
