@@ -200,13 +200,18 @@ def random_lqr_riccati(n, m, N, batch, seed=3, dt=0.01, lti=False):
     return dict(n=n, m=m, N=N, lti=lti, A=A, B=B, Q=Q, R=R, q=q, r=r, Qf=Qf, qf=qf, x0=x0)
 
 
-def dare_lti_riccati(n, m, N, batch, seed=1):
+def dare_lti_riccati(n, m, N, batch, seed=1, unstable=False):
     """LTI problem with a well-damped optimal closed loop (A = 0.9 I + 0.2 J / sqrt(n), B ~ N(0,1) / sqrt(n), SPD Q, R, no
     affine terms, Qf = Q): the gain of the first knot of a long horizon converges to the gain of the discrete algebraic
-    Riccati equation, which scipy.linalg.solve_discrete_are computes independently (tests)."""
+    Riccati equation, which scipy.linalg.solve_discrete_are computes independently (tests).  ``unstable``: an open-loop
+    unstable A — the recursion in the reference's form (no symmetrisation of P) then breaks down, the kernels do not."""
     rng = np.random.default_rng(seed)
-    A = 0.9 * np.eye(n) + 0.2 * rng.standard_normal((batch, n, n)) / np.sqrt(n)
-    B = rng.standard_normal((batch, n, m)) / np.sqrt(n)
+    if unstable:  # open-loop spectral radius 1.2-1.3, strong actuation
+        A = np.eye(n) + 0.3 * rng.standard_normal((batch, n, n)) / np.sqrt(n)
+        B = rng.standard_normal((batch, n, m))
+    else:
+        A = 0.9 * np.eye(n) + 0.2 * rng.standard_normal((batch, n, n)) / np.sqrt(n)
+        B = rng.standard_normal((batch, n, m)) / np.sqrt(n)
     L = rng.standard_normal((batch, n, n))
     Q = np.einsum("bij,bkj->bik", L, L) / n + np.eye(n)
     L = rng.standard_normal((batch, m, m))

@@ -289,3 +289,29 @@ def test_gain_converges_to_scipy_dare(handle, n, m, N, kern):
         rho = np.abs(np.linalg.eigvals(A - B @ Kd)).max()
         tol = max(1e-9, 100.0 * rho ** (2 * (N - 1)))
         assert np.linalg.norm(K[i, 0] - Kd) / np.linalg.norm(Kd) <= tol, (i, rho, tol)
+
+
+@pytest.mark.parametrize("n,m,N,kern", [(6, 3, 201, "riccati_tpi<6,3>"), (12, 4, 201, "riccati_dmma<12,4>"), (10, 3, 201, "riccati_dmma<12,3>"),
+                                        (64, 16, 201, "riccati_cta_dmma<64,16>"), (20, 6, 201, "riccati_cta_dmma<24,8>"),
+                                        (9, 5, 201, "riccati_cta_dmma<16,8>")])
+def test_open_loop_unstable_systems(handle, oracle_mod, n, m, N, kern):
+    """Where the kernels are deliberately NOT the reference's operation order: `P_ = Q + A'PA - A'PB K`
+    (src/dynamic_programming.jl:46-51) does not symmetrise P, and with an open-loop unstable A (spectral radius 1.2-1.3)
+    the antisymmetric rounding residue grows by |A|^2 per knot until potrf fails or the gains are wrong — the CPU oracle,
+    which follows the reference, shows exactly that on these inputs.  Every kernel family symmetrises the cost-to-go
+    exactly each knot and matches scipy's DARE gain."""
+    import scipy.linalg as sl
+    prob = problems.dare_lti_riccati(n, m, N, 4, seed=1, unstable=True)
+    X, U, K, kff, info = ops.riccati_solve_problem(prob, handle=handle)
+    assert (info == 0).all() and handle.last_kernel.startswith(kern), handle.last_kernel
+    worst_oracle = 0.0
+    Xo, Uo, Ko, kffo, infoo = oracle_mod.riccati(prob)
+    for i in range(4):
+        A, B, Q, R = prob["A"][i], prob["B"][i], prob["Q"][i], prob["R"][i]
+        P = sl.solve_discrete_are(A, B, Q, R)
+        Kd = np.linalg.solve(R + B.T @ P @ B, B.T @ P @ A)
+        rho = np.abs(np.linalg.eigvals(A - B @ Kd)).max()
+        tol = max(1e-9, 100.0 * rho ** (2 * (N - 1)))
+        assert np.linalg.norm(K[i, 0] - Kd) / np.linalg.norm(Kd) <= tol, (i, rho, tol)
+        worst_oracle = max(worst_oracle, np.linalg.norm(Ko[i, 0] - Kd) / np.linalg.norm(Kd) if infoo[i] == 0 else 1.0)
+    assert worst_oracle > 1e-6  # the reference's own order has lost the answer on at least one of these instances
