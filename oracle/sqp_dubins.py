@@ -187,3 +187,20 @@ def turn90_problem(batch, N=11, seed=2):
     body[:, :, :n], body[:, :, n:] = X[:, :-1], U
     Z[:, (N - 1) * (n + m):] = X[:, -1]
     return Z, x0, xf, o
+
+
+def slsqp_solution(Z0, x0, xf, o, i):
+    """Instance i of the same nonlinear program solved by SciPy's SLSQP (a third-party solver, finite-difference
+    derivatives): an independent pin of the SQP driver's end point.  Returns (z, cost, max |constraint|)."""
+    from scipy.optimize import minimize
+
+    def f(z):
+        return float(cost(z[None], xf[i:i + 1], o)[0])
+
+    def c(z):
+        c1, d, cN = constraints(z[None], x0[i:i + 1], xf[i:i + 1], o)
+        return np.concatenate([c1.ravel(), d.ravel(), cN.ravel()])
+
+    r = minimize(f, Z0[i], method="SLSQP", constraints=[dict(type="eq", fun=c)], options=dict(maxiter=1000, ftol=1e-15))
+    assert r.success, r.message
+    return r.x, float(r.fun), float(np.abs(c(r.x)).max())

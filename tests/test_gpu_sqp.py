@@ -75,3 +75,16 @@ def test_fused_path_matches_three_kernel_path(handle):
         handle.set_option("sqp_fused", 1)
     assert s1.kkt_solves == s2.kkt_solves and np.array_equal(s1.iters, s2.iters)
     assert _rel(Z1, Z2) <= 1e-9
+
+
+def test_end_point_matches_scipy_slsqp(handle):
+    """Independent of the oracle's SQP loop: SciPy's SLSQP on the same nonlinear program, from the same initial guess."""
+    from oracle import sqp_dubins as S
+    Z0, x0, xf, o = S.turn90_problem(3, N=11, seed=2)
+    s = DubinsSQP(x0, xf, N=11, tf=3.0, handle=handle)
+    Z = s.solve_(Z0)
+    assert (s.feas_p < 1e-5).all()
+    for i in range(3):
+        z, f, cv = S.slsqp_solution(Z0, x0, xf, o, i)
+        assert abs(f - S.cost(Z[i:i + 1], xf[i:i + 1], o)[0]) <= 1e-6 * abs(f)
+        assert np.linalg.norm(z - Z[i]) <= 1e-4 * np.linalg.norm(z)
