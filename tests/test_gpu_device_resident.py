@@ -49,7 +49,7 @@ def test_riccati_device_resident_all_size_classes(handle, n, m, N, b, tile):
 
 
 @pytest.mark.parametrize("n,m,N,b,mid_p,tile", [(3, 2, 21, 70, 0, 32), (12, 4, 25, 37, 0, 1), (64, 16, 9, 5, 0, 1),
-                                                (12, 4, 10, 9, 2, 1)])
+                                                (12, 4, 10, 9, 2, 1), (10, 3, 14, 33, 1, 1), (14, 7, 12, 6, 0, 1), (5, 2, 15, 40, 1, 32)])
 def test_kkt_device_resident_all_size_classes(handle, n, m, N, b, mid_p, tile):
     import torch
     prob = problems.random_lqr_kkt(n, m, N, b, seed=n + N, mid_p=mid_p, hess_mode=1)
