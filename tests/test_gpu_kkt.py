@@ -91,7 +91,7 @@ def test_cooperative_kernel(handle, oracle_mod, n, m, N, mid_p, d2x, hess):
 @pytest.mark.parametrize("hess", [0, 1, 2])
 @pytest.mark.parametrize("n,m,N,batch,mid_p,kern", [
     (7, 2, 12, 6, 1, "kkt_wp_dmma<8,3"), (10, 3, 40, 33, 0, "kkt_wp_dmma<12,4|kkt_hw<12,4"), (9, 2, 30, 5, 1, "kkt_wp_dmma<12,3"),
-    (5, 3, 14, 7, 2, "kkt_wp_dmma<8,4"), (7, 3, 21, 34, 2, "kkt_wp_dmma<8,4"), (11, 1, 25, 4, 0, "kkt_wp_dmma<12,2"),
+    (5, 3, 14, 7, 2, "kkt_wp_dmma<8,4"), (7, 3, 21, 34, 2, "kkt_wp_dmma<8,4"), (11, 1, 25, 4, 0, "kkt_wp_dmma<12,2|kkt_hw<12,4"),
     (14, 7, 12, 5, 0, "kkt_cta_dmma<16,8"), (20, 6, 14, 3, 2, "kkt_cta_dmma<24,8"), (13, 4, 20, 6, 1, "kkt_cta_dmma<16,8"),
     (30, 8, 12, 3, 0, "kkt_cta_dmma<32,16"), (40, 12, 11, 2, 1, "kkt_cta_dmma<48,16"), (60, 10, 12, 2, 0, "kkt_cta_dmma<64,16"),
     (16, 5, 18, 4, 3, "kkt_cta_dmma<16,8")])
