@@ -28,7 +28,23 @@ KKT_CASES = {
     "mid24_kkt": lambda: problems.random_lqr_kkt(24, 8, 12, 2, seed=36, mid_p=0, hess_mode=2),
     "dubins_stage_kkt": lambda: problems.dubins_kkt_batch(2, seed=5, N=61, mid_p=1),
     "explicit_d2_kkt": lambda: problems.random_lqr_kkt(5, 2, 12, 2, seed=37, mid_p=1, hess_mode=0, explicit_D2=True),
+    # round 2: stage rows on the tensor-core kernels, a size embedded in the next tuned class, a free final state
+    "quad_stage_kkt": lambda: problems.random_lqr_kkt(12, 4, 30, 2, seed=41, mid_p=2, hess_mode=0),
+    "large_stage_kkt": lambda: problems.random_lqr_kkt(64, 16, 10, 2, seed=42, mid_p=1, hess_mode=1),
+    "arm_padded_kkt": lambda: problems.random_lqr_kkt(14, 7, 14, 2, seed=43, mid_p=1, hess_mode=1),
+    "free_final_kkt": lambda: _free_final(problems.random_lqr_kkt(12, 4, 25, 2, seed=44, mid_p=1, hess_mode=1)),
 }
+
+
+def _free_final(prob):
+    """No goal rows: p_N = 0."""
+    prob["p"] = prob["p"].copy()
+    prob["p"][-1] = 0
+    b = prob["q"].shape[0]
+    prob["C"][-1] = np.zeros((b, 0, prob["n"]))
+    prob["c"][-1] = np.zeros((b, 0))
+    return prob
+
 
 RICCATI_CASES = {
     "cartpole_riccati": lambda: problems.riccati_cartpole_batch(4, seed=0),
@@ -36,17 +52,23 @@ RICCATI_CASES = {
     "large_riccati": lambda: problems.random_lqr_riccati(64, 16, 8, 2, seed=34),
     "mid24_riccati": lambda: problems.random_lqr_riccati(24, 8, 30, 2, seed=38),
     "lti_riccati": lambda: problems.random_lqr_riccati(8, 4, 60, 2, seed=39, lti=True),
+    "padded_riccati": lambda: problems.random_lqr_riccati(10, 3, 40, 2, seed=45),
 }
 
 
 def main():
     from oracle import dense_kkt
     here = os.path.dirname(os.path.abspath(__file__))
+    only = set(sys.argv[1:])  # optional: the names to (re)generate; default all
     for name, make in KKT_CASES.items():
+        if only and name not in only:
+            continue
         prob = make()
         dz, lam = dense_kkt.kkt_truth(prob, 0)
         np.savez_compressed(os.path.join(here, name + ".npz"), dz=dz, mult=lam)
     for name, make in RICCATI_CASES.items():
+        if only and name not in only:
+            continue
         prob = make()
         kp = dense_kkt.riccati_as_kkt(prob)
         n, m, N, b = prob["n"], prob["m"], prob["N"], prob["x0"].shape[0]

@@ -21,7 +21,10 @@ def _rel(a, b):
                                          ("dubins_kkt", "kkt_tpi<3,2"), ("quad_kkt", "kkt_hw<12,4"),
                                          ("large_kkt", "kkt_cta_dmma<64,16"), ("mid32_kkt", "kkt_cta_dmma<32,8"),
                                          ("mid24_kkt", "kkt_cta_dmma<24,8"), ("dubins_stage_kkt", "kkt_tpi<3,2,p=3/1/3"),
-                                         ("explicit_d2_kkt", "kkt_coop")])
+                                         ("explicit_d2_kkt", "kkt_coop"), ("quad_stage_kkt", "kkt_wp_dmma<12,4,p=12/2/12,hess=0"),
+                                         ("large_stage_kkt", "kkt_cta_dmma<64,16,p=64/1/64"),
+                                         ("arm_padded_kkt", "kkt_cta_dmma<16,8,p=16/1/16"),
+                                         ("free_final_kkt", "kkt_wp_dmma<12,4,p=12/1/12")])
 def test_kkt_golden(handle, oracle_mod, name, kernel):
     from tests.golden.make_golden import KKT_CASES
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
@@ -37,7 +40,7 @@ def test_kkt_golden(handle, oracle_mod, name, kernel):
 
 @pytest.mark.parametrize("name,kernel", [("cartpole_riccati", "riccati_tpi<4,1"), ("quad_riccati", "riccati_dmma<12,4"),
                                          ("large_riccati", "riccati_cta_dmma<64,16"), ("mid24_riccati", "riccati_cta_dmma<24,8"),
-                                         ("lti_riccati", "riccati_dmma<8,4")])
+                                         ("lti_riccati", "riccati_dmma<8,4"), ("padded_riccati", "riccati_dmma<12,3")])
 def test_riccati_golden(handle, name, kernel):
     from tests.golden.make_golden import RICCATI_CASES
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
