@@ -1,6 +1,6 @@
 """GPU parity: a seeded random sweep over the whole dispatch (tools/fuzz_parity.py) — sizes, horizons, batch widths,
 per-knot stage-row patterns, Hessian modes, explicit D2, SOC and LTI flags — against the oracle and the refined truth.
-Round 2 ran 90,000 cases of it (profiles/r2_fuzz_summary.txt); the suite keeps 250."""
+Round 2 ran 120,000 cases of it (profiles/r2_fuzz_summary.txt); the suite keeps 250."""
 import os
 import sys
 
